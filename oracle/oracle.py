@@ -1,0 +1,262 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE: ctypes loaders for the two CPU oracles.
+
+* Oracle B  (`liboracle_b.so`, oracle_b.c): header-free integer restatement; always available.
+* Oracle A  (`_ref/libacdsp_ref.so`, ref_driver_*.cpp): the UNMODIFIED reference templates
+  compiled from /root/reference over the clean-room shim; compile-time configurations only
+  (ref_configs.py).  Built in the dev container; the .so travels to the GPU box.
+
+All values are raw two's-complement integers in numpy int64 arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import ref_configs as rc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+Q_MODES = ["AC_TRN", "AC_RND", "AC_TRN_ZERO", "AC_RND_ZERO", "AC_RND_INF", "AC_RND_MIN_INF", "AC_RND_CONV", "AC_RND_CONV_ODD"]
+O_MODES = ["AC_WRAP", "AC_SAT", "AC_SAT_ZERO", "AC_SAT_SYM"]
+FTYPES = ["SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED", "FOLD_EVEN_ANTI", "FOLD_ODD_ANTI"]
+FIR_CLASSES = ["const", "load", "prog"]
+
+
+class ObFmt(C.Structure):
+    _fields_ = [("W", C.c_int), ("I", C.c_int), ("S", C.c_int), ("Q", C.c_int), ("O", C.c_int)]
+
+
+def normfmt(f):
+    """(W, I[, S[, Q[, O]]]) with Q/O as names or ints -> (W, I, bool S, Qname, Oname)."""
+    f = tuple(f)
+    W, I = int(f[0]), int(f[1])
+    S = bool(f[2]) if len(f) > 2 else True
+    Q = f[3] if len(f) > 3 else "AC_TRN"
+    O = f[4] if len(f) > 4 else "AC_WRAP"
+    if not isinstance(Q, str):
+        Q = Q_MODES[int(Q)]
+    if not isinstance(O, str):
+        O = O_MODES[int(O)]
+    return (W, I, S, Q, O)
+
+
+def _obfmt(f):
+    W, I, S, Q, O = normfmt(f)
+    return ObFmt(W, I, int(S), Q_MODES.index(Q), O_MODES.index(O))
+
+
+def _i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def build(force=False):
+    """Compile Oracle B (and Oracle A when /root/reference is present). Building the checker is not using it."""
+    need = force or not os.path.exists(os.path.join(HERE, "liboracle_b.so"))
+    ref_here = os.path.exists(os.environ.get("AC_DSP_REF", "/root/reference") + "/include/ac_dsp/ac_fir_load_coeffs.h")
+    if ref_here and not os.path.exists(os.path.join(HERE, "_ref", "libacdsp_ref.so")):
+        need = True
+    if need:
+        subprocess.check_call(["make", "-s", "-C", HERE, "-j8"], stdout=subprocess.DEVNULL)
+
+
+_lib_b = None
+_lib_a = None
+
+
+def lib_b():
+    global _lib_b
+    if _lib_b is None:
+        path = os.path.join(HERE, "liboracle_b.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.ob_fir_create.restype = C.c_void_p
+        L.ob_fir_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int, C.c_int]
+        L.ob_fir_destroy.argtypes = [C.c_void_p]
+        L.ob_fir_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.ob_fir_run.restype = C.c_long
+        L.ob_fir_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.ob_cic_create.restype = C.c_void_p
+        L.ob_cic_create.argtypes = [C.c_int, C.POINTER(ObFmt), C.POINTER(ObFmt), C.c_int, C.c_int, C.c_int]
+        L.ob_cic_destroy.argtypes = [C.c_void_p]
+        L.ob_cic_run.restype = C.c_long
+        L.ob_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.ob_cic_int_width.restype = C.c_int
+        L.ob_cic_int_width.argtypes = [C.c_int, C.POINTER(ObFmt), C.c_int, C.c_int, C.c_int]
+        _lib_b = L
+    return _lib_b
+
+
+def have_ref():
+    return os.path.exists(os.path.join(HERE, "_ref", "libacdsp_ref.so"))
+
+
+def lib_a():
+    global _lib_a
+    if _lib_a is None:
+        L = C.CDLL(os.path.join(HERE, "_ref", "libacdsp_ref.so"))
+        L.acref_fir_create.restype = C.c_void_p
+        L.acref_fir_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.acref_fir_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.acref_fir_run.restype = C.c_long
+        L.acref_fir_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.acref_fir_destroy.argtypes = [C.c_void_p]
+        for fn in (L.acref_cic_dec_create, L.acref_cic_intr_create):
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_int]
+        L.acref_cic_run.restype = C.c_long
+        L.acref_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.acref_cic_destroy.argtypes = [C.c_void_p]
+        _lib_a = L
+    return _lib_a
+
+
+# --------------------------------------------------------------------------- Oracle B objects
+class FirB:
+    """Oracle B FIR object: load(coeffs) then run(samples) any number of times (state persists)."""
+
+    def __init__(self, fin, fcoeff, facc, fout, n_taps, ftype):
+        self.L = lib_b()
+        ft = FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        a, b, c, d = _obfmt(fin), _obfmt(fcoeff), _obfmt(facc), _obfmt(fout)
+        self.h = self.L.ob_fir_create(C.byref(a), C.byref(b), C.byref(c), C.byref(d), int(n_taps), ft)
+        self.n_taps = int(n_taps)
+
+    def load(self, coeffs):
+        c = _i64(coeffs)
+        assert c.size == self.n_taps
+        self.L.ob_fir_load(self.h, _p(c))
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size, dtype=np.int64)
+        n = self.L.ob_fir_run(self.h, _p(x), x.size, _p(out))
+        if n < 0:
+            raise ValueError("unsupported ftype")
+        return out[:n]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_fir_destroy(self.h)
+            self.h = None
+
+
+class CicB:
+    def __init__(self, mode, fin, fout, R, M, N):
+        self.L = lib_b()
+        self.intr = 1 if mode == "intr" else 0
+        a, b = _obfmt(fin), _obfmt(fout)
+        self.h = self.L.ob_cic_create(self.intr, C.byref(a), C.byref(b), int(R), int(M), int(N))
+        self.R, self.M, self.N = int(R), int(M), int(N)
+
+    def run(self, x):
+        x = _i64(x)
+        cap = x.size * self.R + self.R + 8 if self.intr else x.size // self.R + 2
+        out = np.empty(max(cap, 1), dtype=np.int64)
+        n = self.L.ob_cic_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_cic_destroy(self.h)
+            self.h = None
+
+
+def cic_int_width(mode, fin, R, M, N):
+    a = _obfmt(fin)
+    return lib_b().ob_cic_int_width(1 if mode == "intr" else 0, C.byref(a), R, M, N)
+
+
+# --------------------------------------------------------------------------- Oracle A objects
+def ref_fir_cfg_id(fin, fcoeff, facc, fout, n_taps):
+    key = (normfmt(fin), normfmt(fcoeff), normfmt(facc), normfmt(fout), int(n_taps))
+    for cid, _name, fi, fc, fa, fo, t in rc.fir_configs():
+        if (fi, fc, fa, fo, t) == key:
+            return cid
+    return None
+
+
+def ref_cic_cfg_id(mode, fin, fout, R, M, N):
+    key = (mode, int(R), int(M), int(N), normfmt(fin), normfmt(fout))
+    for cid, c in enumerate(rc.CIC_CONFIGS):
+        if c == key:
+            return cid
+    return None
+
+
+class FirA:
+    """The real reference class (const / load / prog) for one compiled-in configuration."""
+
+    def __init__(self, cls, fin, fcoeff, facc, fout, n_taps, ftype):
+        self.L = lib_a()
+        cid = ref_fir_cfg_id(fin, fcoeff, facc, fout, n_taps)
+        if cid is None:
+            raise KeyError("configuration not instantiated in oracle/_ref (add it to ref_configs.py)")
+        ft = FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        k = FIR_CLASSES.index(cls) if isinstance(cls, str) else int(cls)
+        self.h = self.L.acref_fir_create(cid, k, ft)
+        if not self.h:
+            raise ValueError("reference does not dispatch this ftype")
+        self.n_taps = int(n_taps)
+
+    def load(self, coeffs):
+        c = _i64(coeffs)
+        assert c.size == self.n_taps
+        if self.L.acref_fir_load(self.h, _p(c)) != 0:
+            raise RuntimeError("constant-coefficient filter: coefficients are fixed at construction")
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size, dtype=np.int64)
+        n = self.L.acref_fir_run(self.h, _p(x), x.size, _p(out))
+        if n < 0:
+            raise RuntimeError("coefficients not set")
+        return out[:n]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_fir_destroy(self.h)
+            self.h = None
+
+
+class CicA:
+    def __init__(self, mode, fin, fout, R, M, N):
+        self.L = lib_a()
+        cid = ref_cic_cfg_id(mode, fin, fout, R, M, N)
+        if cid is None:
+            raise KeyError("configuration not instantiated in oracle/_ref (add it to ref_configs.py)")
+        self.h = (self.L.acref_cic_intr_create if mode == "intr" else self.L.acref_cic_dec_create)(cid)
+        self.intr = mode == "intr"
+        self.R = int(R)
+
+    def run(self, x):
+        x = _i64(x)
+        cap = x.size * self.R + self.R + 8 if self.intr else x.size // self.R + 2
+        out = np.empty(max(cap, 1), dtype=np.int64)
+        n = self.L.acref_cic_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_cic_destroy(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------- helpers
+def rand_raw(rng, f, n, kind="uniform"):
+    """Full-range random raw values for format f."""
+    W, _I, S, _Q, _O = normfmt(f)
+    lo, hi = (-(1 << (W - 1)), (1 << (W - 1)) - 1) if S else (0, (1 << W) - 1)
+    if kind == "min":
+        return np.full(n, lo, dtype=np.int64)
+    if kind == "max":
+        return np.full(n, hi, dtype=np.int64)
+    if kind == "alt":
+        a = np.full(n, hi, dtype=np.int64)
+        a[1::2] = lo
+        return a
+    return rng.integers(lo, hi, size=n, endpoint=True, dtype=np.int64)

@@ -1,0 +1,291 @@
+/* oracle/oracle_b.c -- TEST INFRASTRUCTURE (Oracle B), not product code.
+ *
+ * Header-free CPU restatement, on raw two's-complement integers, of the reference's FIR
+ * and CIC run() paths.  Every function cites the reference lines it restates
+ * (paths relative to /root/reference/include/ac_dsp/).  The ac_fixed arithmetic itself
+ * lives in hlslibs/ac_types (not vendored by the reference, unpinned -- SURVEY.md 8c);
+ * its published rules are restated in ob_convert()/ob_macc():
+ *   product : exact, F = F1 + F2
+ *   sum     : exact, F = max(F1, F2)
+ *   assign  : drop fraction bits with quantisation mode Q, then integer bits with overflow mode O
+ *   a += b  : a = convert(a + b)
+ * Pinned against: the five reference benches via Oracle A (reference headers over the
+ * clean-room shim), the two CIC golden vectors, and randomised A == B sweeps
+ * (tests/test_oracle_*.py).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef __int128 w128;
+typedef unsigned __int128 u128;
+
+typedef struct { int W, I, S, Q, O; } ob_fmt;  /* ac_fixed<W,I,S,Q,O>; Q/O use the ac_q_mode / ac_o_mode order */
+enum { Q_TRN, Q_RND, Q_TRN_ZERO, Q_RND_ZERO, Q_RND_INF, Q_RND_MIN_INF, Q_RND_CONV, Q_RND_CONV_ODD };
+enum { O_WRAP, O_SAT, O_SAT_ZERO, O_SAT_SYM };
+enum { FT_SHIFT_REG, FT_ROTATE_SHIFT, FT_C_BUFF, FT_FOLD_EVEN, FT_FOLD_ODD, FT_TRANSPOSED, FT_FOLD_EVEN_ANTI, FT_FOLD_ODD_ANTI };
+
+static int F_of(const ob_fmt *f) { return f->W - f->I; }
+
+static w128 ob_wrap(w128 v, int W, int S) {
+  if (W >= 128) return v;
+  u128 m = (((u128)1) << W) - 1;
+  u128 u = ((u128)v) & m;
+  if (S && ((u >> (W - 1)) & 1)) u |= ~m;
+  return (w128)u;
+}
+
+/* value with F2 fraction bits -> format f (quantise, then overflow) */
+static w128 ob_convert(w128 v, int F2, const ob_fmt *f) {
+  int F = F_of(f);
+  if (F2 > F) {
+    int sh = F2 - F;
+    w128 q = v >> sh;
+    w128 rem = v - (q << sh);
+    int msb = (int)((rem >> (sh - 1)) & 1);
+    int rest = (rem & ((((w128)1) << (sh - 1)) - 1)) != 0;
+    int neg = v < 0;
+    switch (f->Q) {
+      case Q_TRN: break;
+      case Q_RND: q += msb; break;
+      case Q_TRN_ZERO: q += (neg && rem != 0); break;
+      case Q_RND_INF: q += (msb && (rest || !neg)); break;
+      case Q_RND_ZERO: q += (msb && (rest || neg)); break;
+      case Q_RND_MIN_INF: q += (msb && rest); break;
+      case Q_RND_CONV: q += (msb && (rest || (q & 1))); break;
+      case Q_RND_CONV_ODD: q += (msb && (rest || !(q & 1))); break;
+    }
+    v = q;
+  } else if (F > F2) {
+    v = v << (F - F2);
+  }
+  {
+    w128 hi = f->S ? ((((w128)1) << (f->W - 1)) - 1) : ((((w128)1) << f->W) - 1);
+    w128 lo = f->S ? -(((w128)1) << (f->W - 1)) : 0;
+    switch (f->O) {
+      case O_WRAP: return ob_wrap(v, f->W, f->S);
+      case O_SAT: return v > hi ? hi : (v < lo ? lo : v);
+      case O_SAT_ZERO: return (v > hi || v < lo) ? 0 : v;
+      case O_SAT_SYM: { w128 slo = f->S ? -hi : 0; return v > hi ? hi : (v < slo ? slo : v); }
+    }
+  }
+  return v;
+}
+
+/* acc (format fa) += p, where p has Fp fraction bits: exact sum at max(F) then assign. */
+static w128 ob_macc(w128 acc, const ob_fmt *fa, w128 p, int Fp) {
+  int Fa = F_of(fa);
+  int rF = Fa > Fp ? Fa : Fp;
+  w128 s = (acc << (rF - Fa)) + (p << (rF - Fp));
+  return ob_convert(s, rF, fa);
+}
+
+/* ------------------------------------------------------------------ FIR */
+typedef struct {
+  ob_fmt in, coeff, acc, out;
+  int n, ftype;
+  w128 *reg;        /* IN_TYPE reg[N_TAPS]         ac_fir_load_coeffs.h:127 */
+  w128 *reg_trans;  /* ACC_TYPE reg_trans[N_TAPS]  ac_fir_load_coeffs.h:128 */
+  w128 *h;          /* COEFF_TYPE coeffs[N_TAPS]   ac_fir_load_coeffs.h:306 */
+  long wptr;        /* ac_fir_load_coeffs.h:129 */
+} ob_fir;
+
+ob_fir *ob_fir_create(const ob_fmt *in, const ob_fmt *coeff, const ob_fmt *acc, const ob_fmt *out, int n_taps, int ftype) {
+  ob_fir *f = (ob_fir *)calloc(1, sizeof(ob_fir));
+  f->in = *in; f->coeff = *coeff; f->acc = *acc; f->out = *out;
+  f->n = n_taps; f->ftype = ftype;
+  /* constructors zero the delay lines: ac_fir_load_coeffs.h:134-139 */
+  f->reg = (w128 *)calloc(n_taps, sizeof(w128));
+  f->reg_trans = (w128 *)calloc(n_taps, sizeof(w128));
+  f->h = (w128 *)calloc(n_taps, sizeof(w128));
+  f->wptr = 0;
+  return f;
+}
+void ob_fir_destroy(ob_fir *f) { if (f) { free(f->reg); free(f->reg_trans); free(f->h); free(f); } }
+
+/* load phase of ac_fir_load_coeffs::run (ac_fir_load_coeffs.h:324-331), the ctor pointer of
+ * ac_fir_const_coeffs (ac_fir_const_coeffs.h:314) and the array argument of
+ * ac_fir_prog_coeffs::run (ac_fir_prog_coeffs.h:277): N_TAPS raw coefficients. */
+void ob_fir_load(ob_fir *f, const int64_t *c) {
+  for (int i = 0; i < f->n; i++) f->h[i] = ob_wrap((w128)c[i], f->coeff.W, f->coeff.S);
+}
+
+/* firShiftReg: ac_fir_load_coeffs.h:145-151 */
+static void fir_shift(ob_fir *f, w128 din) {
+  for (int i = f->n - 1; i >= 0; i--) f->reg[i] = (i == 0) ? din : f->reg[i - 1];
+}
+/* firCircularBuffWrite / Read: ac_fir_load_coeffs.h:157-174 */
+static void fir_cb_write(ob_fir *f, w128 din) {
+  f->reg[f->wptr] = din;
+  if (f->wptr == f->n - 1) f->wptr = 0; else f->wptr++;
+}
+static w128 fir_cb_read(ob_fir *f, long idx) {
+  long rptr = f->wptr - 1 - idx;
+  if (rptr < 0) rptr += f->n;
+  return f->reg[rptr];
+}
+
+static w128 fir_one(ob_fir *f, w128 x) {
+  const int N = f->n;
+  const int Fin = F_of(&f->in), Fc = F_of(&f->coeff), Fa = F_of(&f->acc);
+  w128 acc = 0;
+  switch (f->ftype) {
+    case FT_SHIFT_REG:  /* fir*ShiftReg: ac_fir_load_coeffs.h:180-188 */
+      fir_shift(f, x);
+      for (int i = N - 1; i >= 0; i--) acc = ob_macc(acc, &f->acc, f->reg[i] * f->h[i], Fin + Fc);
+      break;
+    case FT_ROTATE_SHIFT: {  /* fir*RotateShift: ac_fir_load_coeffs.h:194-208 */
+      w128 t;
+      for (int i = N; i >= 0; i--) {
+        if (i == N) t = x;
+        else { t = f->reg[N - 1]; acc = ob_macc(acc, &f->acc, f->reg[N - 1] * f->h[i], Fin + Fc); }
+        fir_shift(f, t);
+      }
+      break;
+    }
+    case FT_C_BUFF:  /* fir*CircularBuff: ac_fir_load_coeffs.h:214-224 */
+      for (int i = 0; i <= N - 1; i++) {
+        if (i == 0) fir_cb_write(f, x);
+        acc = ob_macc(acc, &f->acc, fir_cb_read(f, i) * f->h[i], Fin + Fc);
+      }
+      break;
+    case FT_FOLD_EVEN:  /* fir*SymmetricEvenTaps: ac_fir_load_coeffs.h:231-239 (pre-add exact) */
+      fir_shift(f, x);
+      for (int i = N / 2 - 1; i >= 0; i--) acc = ob_macc(acc, &f->acc, f->h[i] * (f->reg[i] + f->reg[N - 1 - i]), Fin + Fc);
+      break;
+    case FT_FOLD_ODD:  /* fir*SymmetricOddTaps: ac_fir_load_coeffs.h:246-259 (`fold` is ACC_TYPE) */
+      fir_shift(f, x);
+      for (int i = 0; i < (N - 1) / 2 + 1; i++) {
+        w128 fold;
+        if (i == (N - 1) / 2) fold = ob_convert(f->reg[i], Fin, &f->acc);
+        else fold = ob_convert(f->reg[i] + f->reg[N - 1 - i], Fin, &f->acc);
+        acc = ob_macc(acc, &f->acc, f->h[i] * fold, Fc + Fa);
+      }
+      break;
+    case FT_TRANSPOSED: {  /* fir*Transposed: ac_fir_load_coeffs.h:265-278 */
+      for (int i = N - 1; i >= 0; i--) {
+        w128 temp = (i == 0) ? 0 : f->reg_trans[i - 1];
+        f->reg_trans[i] = ob_macc(temp, &f->acc, x * f->h[N - 1 - i], Fin + Fc);
+      }
+      acc = f->reg_trans[N - 1];
+      break;
+    }
+    default: return 0;
+  }
+  return ob_convert(acc, Fa, &f->out);  /* data_out = acc: ac_fir_load_coeffs.h:187 */
+}
+
+/* sample loop of run(): ac_fir_load_coeffs.h:335-364 / ac_fir_const_coeffs.h:325-354 /
+ * ac_fir_prog_coeffs.h:281-302 called once per sample. n inputs -> n outputs. */
+long ob_fir_run(ob_fir *f, const int64_t *in, long n, int64_t *out) {
+  if (f->ftype < 0 || f->ftype > FT_TRANSPOSED) return -1;
+  for (long k = 0; k < n; k++) out[k] = (int64_t)fir_one(f, ob_wrap((w128)in[k], f->in.W, f->in.S));
+  return n;
+}
+
+/* ------------------------------------------------------------------ CIC */
+typedef struct {
+  ob_fmt in, out, it;   /* it = lossless INT_TYPE */
+  int R, M, N, intr;
+  w128 *intg;           /* intg_reg[N]           ac_cic_full_core.h:74 */
+  w128 *comb;           /* comb_dly_ln[N][M]     ac_cic_full_core.h:219 */
+  unsigned rate_cnt, rate_cnt1, cnt;  /* 8-bit counters, ac_cic_full_core.h:72-73,91 */
+  int dvalid;
+  /* inf: samples handed from the low-rate to the high-rate half of intr run() */
+  w128 *inf; long inf_head, inf_len, inf_cap;
+} ob_cic;
+
+static int log2_ceil_u(unsigned long long n) { int k = 0; while ((1ULL << k) < n) k++; return k; }
+
+/* find_inter_type_cic_dec (ac_cic_dec_full.h:116-137) / _intr (ac_cic_intr_full.h:107-127) */
+int ob_cic_int_width(int intr, const ob_fmt *in, int R, int M, int N) {
+  unsigned long long g = 1;
+  for (int i = 0; i < (intr ? N - 1 : N); i++) g *= (unsigned long long)R;
+  for (int i = 0; i < N; i++) g *= (unsigned long long)M;
+  return log2_ceil_u(g) + in->W + (in->S ? 0 : 1);
+}
+
+ob_cic *ob_cic_create(int intr, const ob_fmt *in, const ob_fmt *out, int R, int M, int N) {
+  ob_cic *c = (ob_cic *)calloc(1, sizeof(ob_cic));
+  c->in = *in; c->out = *out; c->R = R; c->M = M; c->N = N; c->intr = intr;
+  c->it.W = ob_cic_int_width(intr, in, R, M, N);
+  c->it.I = c->it.W - F_of(in);
+  c->it.S = 1; c->it.Q = Q_TRN; c->it.O = O_WRAP;
+  c->intg = (w128 *)calloc(N, sizeof(w128));
+  c->comb = (w128 *)calloc((size_t)N * M, sizeof(w128));
+  /* ac_cic_full_core_intg ctor, ac_cic_full_core.h:94-102 (both classes pass value=true) */
+  c->rate_cnt = 0; c->dvalid = 1; c->cnt = 0; c->rate_cnt1 = (unsigned)(R - 1) & 0xFFu;
+  return c;
+}
+void ob_cic_destroy(ob_cic *c) { if (c) { free(c->intg); free(c->comb); free(c->inf); free(c); } }
+
+/* intStage: ac_cic_full_core.h:80-87 */
+static w128 cic_int_stage(ob_cic *c, w128 x) {
+  const int Fi = F_of(&c->it);
+  for (int i = c->N - 1; i > 0; i--) c->intg[i] = ob_convert(c->intg[i] + c->intg[i - 1], Fi, &c->it);
+  c->intg[0] = ob_convert(x + c->intg[0], Fi, &c->it);
+  return c->intg[c->N - 1];
+}
+/* comb + diffStage: ac_cic_full_core.h:228-255 */
+static w128 cic_comb(ob_cic *c, w128 x) {
+  const int Fi = F_of(&c->it);
+  w128 v = x;
+  for (int k = 0; k < c->N; k++) {
+    w128 *d = c->comb + (size_t)k * c->M;
+    w128 o = ob_convert(v - d[c->M - 1], Fi, &c->it);
+    for (int i = c->M - 1; i > 0; i--) d[i] = d[i - 1];
+    d[0] = v;
+    v = o;
+  }
+  return v;
+}
+
+static void inf_push(ob_cic *c, w128 v) {
+  if (c->inf_head + c->inf_len == c->inf_cap) {
+    if (c->inf_head > 0) { memmove(c->inf, c->inf + c->inf_head, (size_t)c->inf_len * sizeof(w128)); c->inf_head = 0; }
+    else { c->inf_cap = c->inf_cap ? 2 * c->inf_cap : 1024; c->inf = (w128 *)realloc(c->inf, (size_t)c->inf_cap * sizeof(w128)); }
+  }
+  c->inf[c->inf_head + c->inf_len++] = v;
+}
+
+/* run(): ac_cic_dec_full.h:163-222 (decIntg -> inf -> decDiff) or
+ *        ac_cic_intr_full.h:150-215 (intrDiff -> inf -> intrIntg). Returns outputs written. */
+long ob_cic_run(ob_cic *c, const int64_t *in, long n, int64_t *out) {
+  const int Fi = F_of(&c->it);
+  long k = 0;
+  if (!c->intr) {
+    for (long j = 0; j < n; j++) {
+      /* decIntgCore: ac_cic_full_core.h:110-135 */
+      w128 x = ob_convert(ob_wrap((w128)in[j], c->in.W, c->in.S), F_of(&c->in), &c->it);
+      int valid = (c->rate_cnt == 0);
+      w128 y = cic_int_stage(c, x);
+      c->dvalid = valid;
+      c->rate_cnt = (c->rate_cnt + 1) & 0xFFu;
+      if (c->rate_cnt > (unsigned)(c->R - 1)) c->rate_cnt = 0;
+      /* decIntg writes inf when dvalid (ac_cic_dec_full.h:196-198); decDiff drains it (:213-221) */
+      if (c->dvalid) out[k++] = (int64_t)ob_convert(cic_comb(c, y), Fi, &c->out);
+    }
+    return k;
+  }
+  /* intrDiff: ac_cic_intr_full.h:173-185 */
+  for (long j = 0; j < n; j++) {
+    w128 x = ob_convert(ob_wrap((w128)in[j], c->in.W, c->in.S), F_of(&c->in), &c->it);
+    inf_push(c, cic_comb(c, x));
+  }
+  /* intrIntg: ac_cic_intr_full.h:195-215; data_in_t is a local re-initialised to 0 per call (:196) */
+  w128 data_in_t = 0;
+  while (c->inf_len > 0) {
+    if (c->dvalid) { data_in_t = c->inf[c->inf_head++]; c->inf_len--; }
+    /* intrIntgCore: ac_cic_full_core.h:143-160 */
+    w128 feed;
+    if (c->rate_cnt1 == ((unsigned)(c->R - 1) & 0xFFu)) { feed = data_in_t; c->rate_cnt1 = 0; c->dvalid = 0; }
+    else if (c->rate_cnt1 == ((unsigned)(c->R - 2) & 0xFFu)) { feed = 0; c->rate_cnt1 = (c->rate_cnt1 + 1) & 0xFFu; c->dvalid = 1; }
+    else { feed = 0; c->rate_cnt1 = (c->rate_cnt1 + 1) & 0xFFu; c->dvalid = 0; }
+    w128 y = cic_int_stage(c, feed);
+    if (c->cnt < (unsigned)(c->N - 1)) c->cnt = (c->cnt + 1) & 0xFFu;
+    else out[k++] = (int64_t)ob_convert(y, Fi, &c->out);
+  }
+  if (c->inf_len == 0) c->inf_head = 0;
+  return k;
+}

@@ -1,0 +1,93 @@
+"""oracle/ref_configs.py -- TEST INFRASTRUCTURE.
+
+The reference classes are C++ templates, so every (formats, taps, R/M/N) combination the
+parity tests want from the *real* reference has to be instantiated at compile time.  This
+table is the single source of truth for those instantiations: `gen_ref_cfgs.py` turns it
+into the X-macro include files compiled into oracle/_ref/libacdsp_ref.so, and
+oracle/refdrv.py uses it to look a configuration up by value.
+
+fmt tuples are ac_fixed<W, I, S, Q, O> with Q/O given by name.
+"""
+import math
+
+TRN, RND = "AC_TRN", "AC_RND"
+WRAP = "AC_WRAP"
+
+
+def fmt(W, I, S=True, Q=TRN, O=WRAP):
+    return (W, I, bool(S), Q, O)
+
+
+# (name, in, coeff, acc, out, taps-list)
+FIR_FORMATS = [
+    # BASELINE.json configs 1/2/4: <16,1> x <16,1> -> <40,8>
+    ("q15_acc40", fmt(16, 1), fmt(16, 1), fmt(40, 8), fmt(40, 8), [1, 2, 3, 16, 27, 64, 256, 1024]),
+    # reference bench formats (tests/rtest_ac_fir_{const,load,prog}_coeffs.cpp)
+    ("bench_const", fmt(16, 8), fmt(32, 16), fmt(64, 32), fmt(64, 32), [29]),
+    ("bench_load", fmt(32, 16), fmt(32, 16), fmt(64, 32), fmt(64, 32), [27, 8]),
+    ("bench_prog", fmt(28, 6), fmt(23, 7), fmt(64, 32), fmt(64, 32), [27, 12]),
+    # per-tap truncation (F_acc < F_in + F_c), narrow output: exercises floor + wrap everywhere
+    ("q15_trunc", fmt(16, 1), fmt(16, 1), fmt(24, 4), fmt(16, 1), [5, 16, 63]),
+    # rounding accumulator / output
+    ("q15_rnd", fmt(16, 1), fmt(16, 1), fmt(24, 4, True, RND), fmt(16, 1, True, RND), [16, 31]),
+    # unsigned input, signed coefficients
+    ("u12", fmt(12, 0, False), fmt(14, 2), fmt(30, 6), fmt(20, 4), [9, 32]),
+    # BASELINE.json config 5 second stage: <20,5> x <16,1> -> <40,8>, 63 taps
+    ("cic_post", fmt(20, 5), fmt(16, 1), fmt(40, 8), fmt(40, 8), [63]),
+    # accumulator too narrow for the fold pre-add (wrap inside FOLD_ODD's `fold`)
+    ("narrow_acc", fmt(16, 1), fmt(16, 1), fmt(18, 1), fmt(18, 1), [7, 10]),
+]
+
+
+def log2_ceil(n):
+    return 0 if n <= 1 else (n - 1).bit_length()
+
+
+def cic_int_width(mode, W, S, R, M, N):
+    """Lossless internal width: ac_cic_dec_full.h:132 / ac_cic_intr_full.h:122."""
+    g = (R ** N) * (M ** N) if mode == "dec" else (R ** (N - 1)) * (M ** N)
+    return log2_ceil(g) + W + (0 if S else 1)
+
+
+def _cic_list():
+    out = []
+    for mode in ("dec", "intr"):
+        # sweep with <16,1> input and the lossless output type
+        for R in (2, 3, 4, 7, 8, 16):
+            for M in (1, 2):
+                for N in (1, 2, 3, 4, 5):
+                    W, I = 16, 1
+                    ow = cic_int_width(mode, W, True, R, M, N)
+                    if ow > 64:
+                        continue
+                    out.append((mode, R, M, N, fmt(W, I), fmt(ow, ow - (W - I))))
+        # narrowed outputs (INT_TYPE -> OUT_TYPE conversion with truncation and wrap)
+        out.append((mode, 8, 1, 4, fmt(16, 1), fmt(16, 1)))
+        out.append((mode, 4, 2, 3, fmt(16, 1), fmt(12, 4, True, RND)))
+        # unsigned input
+        out.append((mode, 5, 1, 3, fmt(10, 2, False), fmt(24, 12)))
+    # the two golden-vector configurations (tests/ac_cic_{dec,intr}_full_param.h:34-47)
+    out.append(("dec", 7, 2, 4, fmt(32, 16), fmt(48, 32)))
+    out.append(("intr", 7, 2, 5, fmt(32, 16), fmt(49, 33)))
+    # wide state (> 32 bits) with 16-bit input
+    out.append(("dec", 16, 2, 5, fmt(16, 1), fmt(41, 26)))
+    out.append(("dec", 32, 1, 6, fmt(16, 1), fmt(46, 31)))
+    out.append(("intr", 32, 1, 6, fmt(16, 1), fmt(41, 26)))
+    seen, uniq = set(), []
+    for c in out:
+        if c not in seen:
+            seen.add(c)
+            uniq.append(c)
+    return uniq
+
+
+CIC_CONFIGS = _cic_list()
+
+
+def fir_configs():
+    """Flat list of (id, name, in, coeff, acc, out, taps)."""
+    res = []
+    for name, fi, fc, fa, fo, taps in FIR_FORMATS:
+        for t in taps:
+            res.append((len(res), name, fi, fc, fa, fo, t))
+    return res

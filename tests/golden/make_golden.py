@@ -1,0 +1,144 @@
+"""tests/golden/make_golden.py -- regenerate the committed fixtures in tests/golden/.
+
+Run in the dev container (needs /root/reference and oracle/_ref/libacdsp_ref.so):
+    python tests/golden/make_golden.py
+
+Fixtures (all raw two's-complement integers, int64):
+  cic_dec_golden.npz / cic_intr_golden.npz
+      the reference's own MATLAB-generated bit-exact vectors
+      (tests/ac_cic_{dec,intr}_full_{input,ref}.txt, values are exact multiples of 2^-16),
+      converted to raw integers, with the bench's framing applied
+      (rtest_ac_cic_dec_full.cpp:78-85 prepends one 0; rtest_ac_cic_intr_full.cpp:88-99 uses
+      the first 1000 inputs and skips the first N=5 reference values).
+  fir_bench_{const,load,prog}.npz
+      the reference FIR benches' stimulus (two-tone, rtest_ac_fir_const_coeffs.cpp:126-151),
+      coefficient files, the MATLAB double reference, and the output of the UNMODIFIED
+      reference class (Oracle A) on that stimulus, plus the SQNR it obtains.
+  ref_outputs.npz
+      outputs of the UNMODIFIED reference classes (Oracle A) on seeded random inputs for every
+      configuration in oracle/ref_configs.py x ftype (FIR) and every CIC configuration, fed in
+      several run() calls.  The GPU box has no /root/reference; these pin the CUDA path to the
+      real reference there.
+"""
+import math
+import os
+import sys
+from fractions import Fraction
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from oracle import ref_configs as rc  # noqa: E402
+
+REF = os.environ.get("AC_DSP_REF", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+SEED = 20260101
+
+
+def read_exact(path, F):
+    """Decimal text -> raw integers value*2^F, checked to be exact."""
+    vals = []
+    for tok in open(path).read().replace(",", " ").split():
+        fr = Fraction(tok) * (1 << F)
+        assert fr.denominator == 1, (path, tok)
+        vals.append(int(fr))
+    return np.array(vals, dtype=np.int64)
+
+
+def read_doubles(path):
+    return np.array([float(t) for t in open(path).read().replace(",", " ").split()], dtype=np.float64)
+
+
+def bench_stimulus(fin, n=1024):
+    """rtest_ac_fir_const_coeffs.cpp:126-151: two tones, normalised to the type maximum, AC_TRN."""
+    W, I, S, _, _ = O.normfmt(fin)
+    F = W - I
+    tmax = ((1 << (W - 1)) - 1) / float(1 << F)
+    pi = 3.14159265358979323846
+    tones = [math.sin(2 * pi * 25 * i / 500.0) + math.sin(2 * pi * 150 * i / 500.0) for i in range(n)]
+    amax = max(abs(t) for t in tones)
+    raw = [math.floor(((t / amax) * tmax) * float(1 << F)) for t in tones]
+    return np.array(raw, dtype=np.int64)
+
+
+def sqnr(out_raw, F, ref):
+    d = out_raw.astype(np.float64) / float(1 << F)
+    return 10 * math.log10(np.sum(ref * ref) / np.sum((d - ref) ** 2))
+
+
+def main():
+    t = REF + "/tests/"
+    # ---- CIC goldens
+    din = read_exact(t + "ac_cic_dec_full_input.txt", 16)
+    dref = read_exact(t + "ac_cic_dec_full_ref.txt", 16)
+    din = np.concatenate([[0], din]).astype(np.int64)
+    a = O.CicA("dec", (32, 16), (48, 32), 7, 2, 4)
+    got = a.run(din)
+    assert np.array_equal(got[: dref.size], dref), "reference class does not reproduce its own golden vector"
+    np.savez_compressed(OUT + "/cic_dec_golden.npz", x=din, ref=dref, R=7, M=2, N=4, fin=[32, 16, 1], fout=[48, 32, 1])
+    iin = read_exact(t + "ac_cic_intr_full_input.txt", 16)[:1000]
+    iref = read_exact(t + "ac_cic_intr_full_ref.txt", 16)[5:]
+    a = O.CicA("intr", (32, 16), (49, 33), 7, 2, 5)
+    got = a.run(iin)
+    assert got.size == 6990 and np.array_equal(got, iref[: got.size])
+    np.savez_compressed(OUT + "/cic_intr_golden.npz", x=iin, ref=iref[: got.size], R=7, M=2, N=5, fin=[32, 16, 1], fout=[49, 33, 1])
+    print("cic goldens:", din.size, "->", dref.size, ";", iin.size, "->", got.size)
+
+    # ---- FIR benches
+    benches = {
+        "const": ("bench_const", 29, "ac_fir_const_coeffs", 84.2385),
+        "load": ("bench_load", 27, "ac_fir_load_coeffs", 89.5576),
+        "prog": ("bench_prog", 27, "ac_fir_prog_coeffs", 89.5576),
+    }
+    fmts = {name: (fi, fc, fa, fo) for name, fi, fc, fa, fo, _ in rc.FIR_FORMATS}
+    for cls, (fname, taps, stem, want) in benches.items():
+        fi, fc, fa, fo = fmts[fname]
+        Fc = fc[0] - fc[1]
+        cd = read_doubles(t + stem + "_cfg.txt")
+        assert cd.size == taps
+        craw = np.array([math.floor(c * (1 << Fc)) for c in cd], dtype=np.int64)
+        x = bench_stimulus(fi)
+        ref = read_doubles(t + stem + "_ref.txt")
+        f = O.FirA(cls, fi, fc, fa, fo, taps, "FOLD_ODD")
+        f.load(craw)
+        y = f.run(x)
+        s = sqnr(y, fo[0] - fo[1], ref[: y.size])
+        print(f"fir bench {cls}: SQNR {s:.4f} dB (reference bench prints {want})")
+        assert abs(s - want) < 5e-4
+        np.savez_compressed(OUT + f"/fir_bench_{cls}.npz", x=x, coeffs=craw, y=y, ref_double=ref, sqnr=s,
+                            fin=fi[:3], fcoeff=fc[:3], facc=fa[:3], fout=fo[:3], taps=taps)
+
+    # ---- reference outputs on seeded random inputs
+    rng = np.random.default_rng(SEED)
+    store = {}
+    for cid, name, fi, fc, fa, fo, taps in rc.fir_configs():
+        n = 3 * taps + 40 if taps >= 256 else 320
+        x = O.rand_raw(rng, fi, n)
+        c = O.rand_raw(rng, fc, taps)
+        csym = c.copy()
+        csym[taps - (taps // 2):] = c[: taps // 2][::-1]          # symmetric set for the FOLD types
+        store[f"fir{cid}_x"] = x
+        store[f"fir{cid}_c"] = c
+        store[f"fir{cid}_csym"] = csym
+        for ft in O.FTYPES[:6]:
+            cls = O.FIR_CLASSES[(cid + O.FTYPES.index(ft)) % 3]
+            f = O.FirA(cls, fi, fc, fa, fo, taps, ft)
+            f.load(csym if ft.startswith("FOLD") else c)
+            y = np.concatenate([f.run(x[:5]), f.run(x[5:6]), f.run(x[6:])])
+            store[f"fir{cid}_{ft}_y"] = y
+    for cid, (mode, R, M, N, fi, fo) in enumerate(rc.CIC_CONFIGS):
+        n = 260 if mode == "dec" else 90
+        x = O.rand_raw(rng, fi, n)
+        f = O.CicA(mode, fi, fo, R, M, N)
+        parts = [f.run(x[:1]), f.run(x[1:10]), f.run(x[10:13]), f.run(x[13:])]
+        store[f"cic{cid}_x"] = x
+        store[f"cic{cid}_y"] = np.concatenate(parts)
+        store[f"cic{cid}_counts"] = np.array([p.size for p in parts], dtype=np.int64)
+    np.savez_compressed(OUT + "/ref_outputs.npz", **store)
+    print("ref_outputs:", len(store), "arrays,", os.path.getsize(OUT + "/ref_outputs.npz") // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
