@@ -1,0 +1,158 @@
+/* b200dsp.h -- C-ABI of the B200-native fixed-point streaming-filter engine.
+ *
+ * This is the drop-in boundary for the FIR / CIC hot path of hlslibs/ac_dsp.  The reference has
+ * no FFI layer: its boundary is five C++ class templates whose run() drains ac_channel FIFOs
+ * (citations relative to the reference's include/ac_dsp/):
+ *
+ *   ac_fir_const_coeffs<IN,OUT,COEFF,ACC,N_TAPS,ftype>::run(in, out)             ac_fir_const_coeffs.h:309-355
+ *   ac_fir_load_coeffs <IN,OUT,COEFF,ACC,N_TAPS,ftype>::run(in, coeffs, out, ld)  ac_fir_load_coeffs.h:300-365
+ *   ac_fir_prog_coeffs <IN,OUT,COEFF,ACC,N_TAPS,ftype>::run(in, out, coeffs[])    ac_fir_prog_coeffs.h:261-303
+ *   ac_cic_dec_full    <IN,OUT,R,M,N>::run(in, out)                              ac_cic_dec_full.h:147-222
+ *   ac_cic_intr_full   <IN,OUT,R,M,N>::run(in, out)                              ac_cic_intr_full.h:137-215
+ *
+ * Here one opaque handle stands for one such object (times n_channels independent copies); the
+ * template parameters become a run-time descriptor, ac_fixed<W,I,S,Q,O> values cross the boundary as
+ * raw two's-complement integers, and run() takes plain arrays instead of channels.  The header
+ * facade in include/b200dsp/ re-creates the five class templates on top of these entry points.
+ *
+ * Raw sample containers: the smallest of int16_t / int32_t / int64_t that holds W bits
+ * (b2d_container_bytes), value sign- (S=1) or zero- (S=0) extended, little endian.
+ *
+ * Everything computes on the GPU (sm_100a).  There is no CPU fallback: a configuration the CUDA
+ * kernels cannot reproduce bit-exactly is rejected with B2D_EUNSUPPORTED at create time.
+ * No function throws; every function returns a b2d_status (0 = ok, negative = error).
+ * A handle is single-caller (like the reference object); distinct handles are independent.
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2D_OK = 0,
+  B2D_EUNSUPPORTED = -1, /* valid reference configuration the engine does not implement            */
+  B2D_EINVAL = -2,       /* malformed argument (null pointer, zero taps, W out of range ...)       */
+  B2D_ECUDA = -3,        /* CUDA runtime error (b2d_last_error() has the text)                     */
+  B2D_ENCCL = -4,        /* NCCL error or NCCL library not loadable                                */
+  B2D_ENOMEM = -5,
+  B2D_ESTATE = -6        /* call sequence error: run() before coefficients were loaded, ...        */
+} b2d_status;
+
+/* ac_q_mode / ac_o_mode in the AC Datatypes order. */
+typedef enum { B2D_TRN = 0, B2D_RND, B2D_TRN_ZERO, B2D_RND_ZERO, B2D_RND_INF, B2D_RND_MIN_INF, B2D_RND_CONV, B2D_RND_CONV_ODD } b2d_qmode;
+typedef enum { B2D_WRAP = 0, B2D_SAT, B2D_SAT_ZERO, B2D_SAT_SYM } b2d_omode;
+
+/* ac_fixed<W, I, S, Q, O>.  Supported: inputs/coefficients W <= 32; accumulator W <= 64 with
+ * Q in {TRN, RND} and O = WRAP (these make the per-tap `acc += a*b` re-quantisation
+ * order-independent, which is what lets taps and outputs run in parallel); outputs W <= 64 with any
+ * Q / O. */
+typedef struct { int32_t W, I, S, Q, O; } b2d_fmt;
+
+/* FTYPE enum of the reference (ac_fir_const_coeffs.h:96). The three hot classes dispatch the first
+ * six; with an _ANTI value their run() leaves the output unwritten, so the engine rejects those. */
+typedef enum {
+  B2D_SHIFT_REG = 0, B2D_ROTATE_SHIFT, B2D_C_BUFF, B2D_FOLD_EVEN, B2D_FOLD_ODD, B2D_TRANSPOSED,
+  B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI
+} b2d_ftype;
+
+typedef enum { B2D_FIR_CONST = 0, B2D_FIR_LOAD = 1, B2D_FIR_PROG = 2 } b2d_fir_kind;
+typedef enum { B2D_CIC_DEC = 0, B2D_CIC_INTR = 1 } b2d_cic_mode;
+
+/* Multi-channel sample layout of the in/out arrays of one run() call with n samples per channel:
+ * PLANAR: channel c at [c*n, (c+1)*n);  INTERLEAVED: sample i of channel c at [i*n_channels + c]
+ * (16-bit IQ = 2 interleaved channels sharing one coefficient set). */
+typedef enum { B2D_PLANAR = 0, B2D_INTERLEAVED = 1 } b2d_layout;
+
+typedef struct {
+  b2d_fmt in, coeff, acc, out;  /* IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE                           */
+  uint32_t n_taps;              /* N_TAPS >= 1                                                      */
+  int32_t ftype;                /* b2d_ftype                                                        */
+  int32_t kind;                 /* b2d_fir_kind: which reference class's load protocol is mirrored  */
+  uint32_t n_channels;          /* independent filter instances sharing this descriptor (>= 1)      */
+  int32_t layout;               /* b2d_layout                                                       */
+  int32_t device;               /* CUDA device ordinal, -1 = current device                         */
+} b2d_fir_desc;
+
+typedef struct {
+  b2d_fmt in, out;              /* IN_TYPE, OUT_TYPE; the lossless INT_TYPE is derived internally   */
+  uint32_t R, M, N;             /* rate change 2..256, differential delay >= 1, stages 1..255       */
+  int32_t mode;                 /* b2d_cic_mode                                                     */
+  uint32_t n_channels;
+  int32_t layout;
+  int32_t device;
+} b2d_cic_desc;
+
+typedef struct b2d_fir b2d_fir;
+typedef struct b2d_cic b2d_cic;
+typedef struct b2d_comm b2d_comm;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char *b2d_version(void);
+const char *b2d_strerror(int status);
+const char *b2d_last_error(void);                 /* thread-local detail text of the last failure   */
+int b2d_container_bytes(int32_t W);               /* 2, 4 or 8                                      */
+int b2d_device_count(void);                       /* number of visible CUDA devices (0 if none)     */
+
+/* ---- FIR: ac_fir_const_coeffs / ac_fir_load_coeffs / ac_fir_prog_coeffs -------------------- */
+/* Class instantiation + constructor: zeroed delay line (ac_fir_load_coeffs.h:134-139). */
+int b2d_fir_create(b2d_fir **h, const b2d_fir_desc *desc);
+int b2d_fir_destroy(b2d_fir *h);
+/* Coefficients, n == n_taps raw values in the coefficient container, HOST memory.
+ *   CONST: the constructor's pointer (ac_fir_const_coeffs.h:314) -- allowed once.
+ *   LOAD : the ld=true phase of run() (ac_fir_load_coeffs.h:324-331).
+ *   PROG : the array argument of run() (ac_fir_prog_coeffs.h:277); may change between run() calls,
+ *          the delay line is kept.
+ * channel = -1 loads every channel.  With a communicator attached (b2d_fir_set_comm) the values of
+ * rank `root` are broadcast to all ranks with one ncclBroadcast; other ranks may pass NULL. */
+int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel);
+int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root);
+/* run() sample loop: n samples per channel in, n per channel out (*n_out = n).
+ * _run takes HOST buffers (copies in, computes, copies out, synchronous); _run_dev takes DEVICE
+ * buffers and is asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). */
+int b2d_fir_run(b2d_fir *h, const void *in, size_t n, void *out, size_t *n_out);
+int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_fir_reset(b2d_fir *h);                    /* back to the constructed state, coefficients kept */
+/* Checkpoint: the delay line etc. as an opaque blob (size via _state_bytes). */
+int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes);
+int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes);
+int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
+/* Name of the kernel family chosen for this descriptor ("fir_q15x2", "fir_generic", ...). */
+const char *b2d_fir_path(b2d_fir *h);
+
+/* ---- CIC: ac_cic_dec_full / ac_cic_intr_full ---------------------------------------------- */
+int b2d_cic_create(b2d_cic **h, const b2d_cic_desc *desc);
+int b2d_cic_destroy(b2d_cic *h);
+/* Lossless internal width of find_inter_type_cic_dec / _intr (ac_cic_dec_full.h:132, ac_cic_intr_full.h:122). */
+int b2d_cic_int_width(const b2d_cic_desc *desc, int32_t *outW);
+/* Upper bound on outputs per channel produced by a run() of n inputs per channel. */
+size_t b2d_cic_max_out(b2d_cic *h, size_t n);
+/* run(): DEC emits the samples at global input indices 0, R, 2R, ... ; INTR emits, after K inputs in
+ * total, max(0, (K-1)R + 1 - (N-1)) outputs in total (the last input of a call yields one output until
+ * more data arrives -- the reference's stream-edge rule).  *n_out = outputs per channel of this call;
+ * PLANAR outputs use a channel stride of *n_out. */
+int b2d_cic_run(b2d_cic *h, const void *in, size_t n, void *out, size_t *n_out);
+int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_cic_reset(b2d_cic *h);
+int b2d_cic_state_bytes(b2d_cic *h, size_t *bytes);
+int b2d_cic_get_state(b2d_cic *h, void *blob, size_t bytes);
+int b2d_cic_set_state(b2d_cic *h, const void *blob, size_t bytes);
+const char *b2d_cic_path(b2d_cic *h);
+
+/* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
+#define B2D_UNIQUE_ID_BYTES 128
+/* Channel c of n_channels lives on rank c % world (contiguous block alternative: see DESIGN.md). */
+int b2d_shard_count(uint32_t n_channels, int32_t rank, int32_t world, uint32_t *n_local);
+int b2d_comm_unique_id(void *id128);                                 /* rank 0: ncclGetUniqueId     */
+int b2d_comm_create(b2d_comm **c, const void *id128, int32_t rank, int32_t world, int32_t device);
+int b2d_comm_destroy(b2d_comm *c);
+int b2d_comm_barrier(b2d_comm *c);                                   /* 1-element all-reduce + sync */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DSP_H */
