@@ -1,0 +1,52 @@
+"""Build recipe of libb200dsp.so: explicit nvcc for sm_100a, in-tree output (ac_dsp_b200/lib/).
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.  There is no fallback:
+if the library is missing and cannot be built, importing the engine fails.
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libb200dsp.so")
+SOURCES = ["runtime.cu", "fir_generic.cu", "fir_q15.cu", "cic_generic.cu", "cic_fast.cu", "nccl_dl.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200dsp.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into ac_dsp_b200/lib/libb200dsp.so (no-op when up to date)."""
+    if not force and not stale():
+        return LIB
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libb200dsp.so")
+    os.makedirs(LIBDIR, exist_ok=True)
+    tmp = LIB + ".tmp"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

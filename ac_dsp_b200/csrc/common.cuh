@@ -68,6 +68,14 @@ __host__ __device__ __forceinline__ int64_t tap_term(i128 p, int s, int Q) {
   return (int64_t)((u128)p << (-s));
 }
 
+// Full `acc += p` of an ACC_TYPE accumulator (any Q / O): exact sum at max(F), then assignment.
+__host__ __device__ __forceinline__ int64_t macc(int64_t acc, const Fmt &fa, i128 p, int Fp) {
+  const int Fa = fa.F();
+  const int rF = Fa > Fp ? Fa : Fp;
+  const i128 s = (i128)((u128)(i128)acc << (rF - Fa)) + (i128)((u128)p << (rF - Fp));
+  return convert(s, rF, fa);
+}
+
 __host__ __device__ __forceinline__ int container_bytes(int W) { return W <= 16 ? 2 : (W <= 32 ? 4 : 8); }
 
 // Raw load/store in the 2/4/8-byte container of a format.

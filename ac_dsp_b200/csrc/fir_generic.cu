@@ -1,0 +1,132 @@
+// fir_generic.cu -- the any-format FIR path: one thread per output sample, taps visited in the
+// reference's own order with the full ac_fixed `acc += a*b` re-quantisation at every tap, so every
+// quantisation / overflow mode of ACC_TYPE and OUT_TYPE is reproduced (not only the order-independent
+// AC_TRN / AC_RND + AC_WRAP ones the fast paths rely on).
+//
+// Tap order per architecture (reference include/ac_dsp/ac_fir_load_coeffs.h; const / prog are
+// line-for-line analogues):
+//   SHIFT_REG     :180-188  i = N-1..0   acc += reg[i]*h[i]                 (oldest sample first)
+//   ROTATE_SHIFT  :194-208  same order (the rotate only moves data)
+//   C_BUFF        :214-224  i = 0..N-1   acc += read(i)*h[i]                (newest sample first)
+//   FOLD_EVEN     :231-239  i = N/2-1..0 acc += h[i]*(reg[i]+reg[N-1-i])    (pre-add exact)
+//   FOLD_ODD      :246-259  i = 0..(N-1)/2, fold = ACC_TYPE(reg[i]+reg[N-1-i]) (centre: reg[i]), acc += h[i]*fold
+//   TRANSPOSED    :265-278  y[n] = q(..q(q(x[n-N+1]h[N-1]) + x[n-N+2]h[N-2]).. + x[n]h[0])  (oldest first)
+// reg[k] is the sample k steps back; before the first sample of the stream it is 0 (:134-139).
+#include "kernels.h"
+
+namespace b2d {
+
+struct FirGenArgs {
+  Fmt in, coeff, acc, out;
+  int N, ftype;
+  uint32_t C;
+  int interleaved, in_bytes, out_bytes;
+  const void *x;
+  void *y;
+  size_t n;
+  const void *tail;
+  const int64_t *h;
+};
+
+__device__ __forceinline__ int64_t fir_gen_sample(const FirGenArgs &a, uint32_t c, size_t i, int k) {
+  const int T = a.N - 1;
+  if ((size_t)k <= i) return load_raw(a.x, elem_index(i - k, c, a.n, a.C, a.interleaved), a.in_bytes, a.in.S);
+  return load_raw(a.tail, (size_t)c * T + (size_t)(T - (k - (int64_t)i)), a.in_bytes, a.in.S);
+}
+
+__global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
+  const size_t total = a.n * a.C;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = a.interleaved ? (uint32_t)(t % a.C) : (uint32_t)(t / a.n);
+    const size_t i = a.interleaved ? t / a.C : t % a.n;
+    const int64_t *h = a.h + (size_t)c * a.N;
+    const int N = a.N;
+    const int Fin = a.in.F(), Fc = a.coeff.F(), Fa = a.acc.F();
+    int64_t acc = 0;
+    switch (a.ftype) {
+      case B2D_SHIFT_REG:
+      case B2D_ROTATE_SHIFT:
+      case B2D_TRANSPOSED:
+        for (int k = N - 1; k >= 0; k--) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        break;
+      case B2D_C_BUFF:
+        for (int k = 0; k < N; k++) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        break;
+      case B2D_FOLD_EVEN:
+        for (int k = N / 2 - 1; k >= 0; k--) {
+          const i128 pre = (i128)fir_gen_sample(a, c, i, k) + (i128)fir_gen_sample(a, c, i, N - 1 - k);
+          acc = macc(acc, a.acc, (i128)h[k] * pre, Fin + Fc);
+        }
+        break;
+      case B2D_FOLD_ODD:
+        for (int k = 0; k < (N - 1) / 2 + 1; k++) {
+          i128 pre = (i128)fir_gen_sample(a, c, i, k);
+          if (k != (N - 1) / 2) pre += (i128)fir_gen_sample(a, c, i, N - 1 - k);
+          const int64_t fold = convert(pre, Fin, a.acc);
+          acc = macc(acc, a.acc, (i128)h[k] * (i128)fold, Fc + Fa);
+        }
+        break;
+      default: break;
+    }
+    store_raw(a.y, elem_index(i, c, a.n, a.C, a.interleaved), a.out_bytes, convert((i128)acc, Fa, a.out));
+  }
+}
+
+cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st) {
+  if (p.n == 0) return cudaSuccess;
+  FirGenArgs a;
+  a.in = p.fin; a.coeff = p.fcoeff; a.acc = p.facc; a.out = p.fout;
+  a.N = p.n_taps; a.ftype = p.ftype; a.C = p.C; a.interleaved = p.interleaved;
+  a.in_bytes = container_bytes(p.fin.W); a.out_bytes = container_bytes(p.fout.W);
+  a.x = p.in; a.y = p.out; a.n = p.n; a.tail = p.tail; a.h = p.coeff64;
+  const size_t total = p.n * p.C;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  fir_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ---- history carry -----------------------------------------------------------------------
+struct TailArgs {
+  const void *in, *tail;
+  void *tail_next;
+  size_t n;
+  int T, bytes;
+  uint32_t C;
+  int interleaved;
+};
+
+__global__ void tail_kernel(TailArgs a) {
+  const size_t total = (size_t)a.T * a.C;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = (uint32_t)(t / a.T);
+    const size_t j = t % a.T;
+    // position j of the last T elements of (tail ++ in)
+    const size_t pos = a.n + j;
+    int64_t v;
+    if (pos < (size_t)a.T) v = load_raw(a.tail, (size_t)c * a.T + pos, a.bytes, 1);
+    else v = load_raw(a.in, elem_index(pos - a.T, c, a.n, a.C, a.interleaved), a.bytes, 1);
+    store_raw(a.tail_next, (size_t)c * a.T + j, a.bytes, v);
+  }
+}
+
+static cudaError_t launch_tail(const void *in, const void *tail, void *tail_next, size_t n, int T, int bytes, uint32_t C,
+                               int interleaved, cudaStream_t st) {
+  if (T <= 0) return cudaSuccess;
+  TailArgs a{in, tail, tail_next, n, T, bytes, C, interleaved};
+  const size_t total = (size_t)T * C;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  tail_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fir_tail(const FirLaunch &p, cudaStream_t st) {
+  return launch_tail(p.in, p.tail, p.tail_next, p.n, p.n_taps - 1, container_bytes(p.fin.W), p.C, p.interleaved, st);
+}
+
+cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st) {
+  return launch_tail(p.in, p.tail, p.tail_next, p.n, p.H, container_bytes(p.fin.W), p.C, p.interleaved, st);
+}
+
+}  // namespace b2d

@@ -1,0 +1,55 @@
+// kernels.h -- launch entry points of the CUDA kernels (host runtime <-> kernel translation units).
+#pragma once
+#include "common.cuh"
+
+namespace b2d {
+
+// One run() of a FIR handle on device-resident buffers.
+struct FirLaunch {
+  Fmt fin, fcoeff, facc, fout;
+  int n_taps, ftype;
+  uint32_t C;            // channels
+  int interleaved;       // layout of in / out
+  const void *in;        // n samples per channel, input container
+  void *out;             // n samples per channel, output container
+  size_t n;
+  const void *tail;      // [C][n_taps-1] previous samples, input container, planar, oldest first
+  void *tail_next;       // same shape: history after this call
+  const int64_t *coeff64;   // [C][n_taps] raw coefficients (generic path)
+  const uint32_t *coeff_pk; // [C][pk_words] byte-plane packed, reversed coefficients (q15 path), or null
+  int pk_words;
+};
+
+// generic path: every format / ftype / Q / O, reference tap order, 128-bit intermediates.
+cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st);
+// q15 path: W_in, W_c <= 16 in int16 containers, exact left-shift accumulate, DP2A byte planes.
+bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
+void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
+int fir_q15_pk_words(int n_taps, int ftype);
+cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st);
+// history carry: tail_next = last (n_taps-1) samples of (tail ++ in).
+cudaError_t launch_fir_tail(const FirLaunch &p, cudaStream_t st);
+
+struct CicLaunch {
+  Fmt fin, fout;
+  int intW;              // lossless internal width (find_inter_type_cic_*)
+  int R, M, N, intr;
+  uint32_t C;
+  int interleaved;
+  const void *in;        // n inputs per channel
+  void *out;             // n_out outputs per channel (planar stride n_out)
+  size_t n, n_out;
+  unsigned long long n_seen;   // inputs consumed per channel before this call
+  unsigned long long out_first; // global index of the first output of this call
+  const void *tail;      // [C][H] previous inputs, planar, oldest first
+  void *tail_next;
+  int H;                 // history length kept (inputs)
+};
+
+int cic_history_len(int intr, int R, int M, int N);
+cudaError_t launch_cic_generic(const CicLaunch &p, cudaStream_t st);
+bool cic_fast_supported(const CicLaunch &p);
+cudaError_t launch_cic_fast(const CicLaunch &p, cudaStream_t st);
+cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st);
+
+}  // namespace b2d

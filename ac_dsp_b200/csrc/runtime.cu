@@ -1,0 +1,716 @@
+// runtime.cu -- host runtime behind the C-ABI of include/b200dsp.h: handles, descriptor validation,
+// kernel-family dispatch, history carry between run() calls, the pipelined host-buffer path and the
+// NCCL coefficient broadcast.  No CPU compute path exists: every run() ends in a CUDA kernel launch.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "nccl_dl.h"
+
+using namespace b2d;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int status, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+#define CU(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) return fail(B2D_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char *b2d_version(void) { return "b200dsp 0.1 (sm_100a)"; }
+extern "C" const char *b2d_last_error(void) { return g_err; }
+extern "C" const char *b2d_strerror(int s) {
+  switch (s) {
+    case B2D_OK: return "ok";
+    case B2D_EUNSUPPORTED: return "configuration not supported by the CUDA engine";
+    case B2D_EINVAL: return "invalid argument";
+    case B2D_ECUDA: return "CUDA error";
+    case B2D_ENCCL: return "NCCL error";
+    case B2D_ENOMEM: return "out of memory";
+    case B2D_ESTATE: return "call sequence error";
+    default: return "unknown status";
+  }
+}
+extern "C" int b2d_container_bytes(int32_t W) { return (W < 1 || W > 64) ? 0 : container_bytes(W); }
+extern "C" int b2d_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int b2d_host_alloc(void **p, size_t bytes) {
+  if (!p) return fail(B2D_EINVAL, "null pointer");
+  CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+  return B2D_OK;
+}
+extern "C" int b2d_host_free(void *p) {
+  if (p) CU(cudaFreeHost(p));
+  return B2D_OK;
+}
+
+static Fmt to_fmt(const b2d_fmt &f) { return Fmt{f.W, f.I, f.S ? 1 : 0, f.Q, f.O}; }
+static int check_fmt(const b2d_fmt &f, int maxW, const char *what) {
+  if (f.W < 1 || f.W > 64) return fail(B2D_EINVAL, "%s: width %d outside 1..64", what, f.W);
+  if (f.W > maxW) return fail(B2D_EUNSUPPORTED, "%s: width %d > %d", what, f.W, maxW);
+  if (f.I < -64 || f.I > 128) return fail(B2D_EUNSUPPORTED, "%s: integer width %d outside -64..128", what, f.I);
+  if (f.Q < B2D_TRN || f.Q > B2D_RND_CONV_ODD) return fail(B2D_EINVAL, "%s: bad quantisation mode %d", what, f.Q);
+  if (f.O < B2D_WRAP || f.O > B2D_SAT_SYM) return fail(B2D_EINVAL, "%s: bad overflow mode %d", what, f.O);
+  return B2D_OK;
+}
+static int use_device(int dev) {
+  int cur = -1;
+  CU(cudaGetDevice(&cur));
+  if (cur != dev) CU(cudaSetDevice(dev));
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------ host pipeline
+// run() on HOST buffers: the stream is cut into chunks; chunk i+1 is copied in while chunk i computes
+// and chunk i-1 is copied out (three streams, three device slots).  Each chunk is an ordinary run_dev()
+// call, so the result is the reference's own "several run() calls" behaviour by construction.
+struct Pipe {
+  static const int S = 3;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[S] = {}, e_k[S] = {}, e_out[S] = {};
+  void *d_in[S] = {}, *d_out[S] = {};
+  size_t cap_in = 0, cap_out = 0;
+  bool ready = false;
+  int init() {
+    if (ready) return B2D_OK;
+    CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < S; i++) {
+      CU(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming));
+    }
+    ready = true;
+    return B2D_OK;
+  }
+  int ensure(size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > cap_in) {
+      for (int i = 0; i < S; i++) { if (d_in[i]) cudaFree(d_in[i]); d_in[i] = nullptr; }
+      cap_in = 0;
+      for (int i = 0; i < S; i++) if (cudaMalloc(&d_in[i], in_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", in_bytes); }
+      cap_in = in_bytes;
+    }
+    if (out_bytes > cap_out) {
+      for (int i = 0; i < S; i++) { if (d_out[i]) cudaFree(d_out[i]); d_out[i] = nullptr; }
+      cap_out = 0;
+      for (int i = 0; i < S; i++) if (cudaMalloc(&d_out[i], out_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", out_bytes); }
+      cap_out = out_bytes;
+    }
+    return B2D_OK;
+  }
+  void destroy() {
+    for (int i = 0; i < S; i++) {
+      if (d_in[i]) cudaFree(d_in[i]);
+      if (d_out[i]) cudaFree(d_out[i]);
+      if (e_in[i]) cudaEventDestroy(e_in[i]);
+      if (e_k[i]) cudaEventDestroy(e_k[i]);
+      if (e_out[i]) cudaEventDestroy(e_out[i]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_k) cudaStreamDestroy(s_k);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+};
+
+// copy `len` samples per channel starting at time `off` between a full buffer (n_full per channel) and a
+// compact chunk buffer (len per channel)
+static cudaError_t copy_chunk(void *dst, const void *src, bool to_device, int bytes, uint32_t C, int interleaved,
+                              size_t n_full, size_t off, size_t len, cudaStream_t st) {
+  if (len == 0) return cudaSuccess;
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (interleaved || C == 1) {
+    const size_t o = off * C * bytes, sz = len * C * bytes;
+    return to_device ? cudaMemcpyAsync(dst, (const char *)src + o, sz, kind, st) : cudaMemcpyAsync((char *)dst + o, src, sz, kind, st);
+  }
+  if (to_device) return cudaMemcpy2DAsync(dst, len * bytes, (const char *)src + off * bytes, n_full * bytes, len * bytes, C, kind, st);
+  return cudaMemcpy2DAsync((char *)dst + off * bytes, n_full * bytes, src, len * bytes, len * bytes, C, kind, st);
+}
+
+// ----------------------------------------------------------------------------------------------- comm
+struct b2d_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  void *d_buf = nullptr;
+  size_t cap = 0;
+};
+
+static int nccl_fail(const NcclApi *api, int rc, const char *what) {
+  return fail(B2D_ENCCL, "%s: %s", what, api->GetErrorString(rc));
+}
+
+extern "C" int b2d_shard_count(uint32_t n_channels, int32_t rank, int32_t world, uint32_t *n_local) {
+  if (!n_local || world < 1 || rank < 0 || rank >= world) return fail(B2D_EINVAL, "bad rank/world");
+  *n_local = n_channels / world + ((uint32_t)rank < n_channels % world ? 1u : 0u);  // channel c -> rank c % world
+  return B2D_OK;
+}
+extern "C" int b2d_comm_unique_id(void *id128) {
+  if (!id128) return fail(B2D_EINVAL, "null id");
+  const char *why = "";
+  const NcclApi *api = nccl_api(&why);
+  if (!api) return fail(B2D_ENCCL, "%s", why);
+  ncclUniqueId id;
+  int rc = api->GetUniqueId(&id);
+  if (rc != ncclSuccess) return nccl_fail(api, rc, "ncclGetUniqueId");
+  memcpy(id128, &id, sizeof(id));
+  return B2D_OK;
+}
+extern "C" int b2d_comm_create(b2d_comm **c, const void *id128, int32_t rank, int32_t world, int32_t device) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B2D_EINVAL, "bad arguments");
+  const char *why = "";
+  const NcclApi *api = nccl_api(&why);
+  if (!api) return fail(B2D_ENCCL, "%s", why);
+  if (device < 0) CU(cudaGetDevice(&device));
+  int st = use_device(device);
+  if (st) return st;
+  b2d_comm *k = new (std::nothrow) b2d_comm();
+  if (!k) return fail(B2D_ENOMEM, "comm");
+  k->rank = rank; k->world = world; k->device = device;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  int rc = api->CommInitRank(&k->comm, world, id, rank);
+  if (rc != ncclSuccess) { delete k; return nccl_fail(api, rc, "ncclCommInitRank"); }
+  cudaError_t e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { api->CommDestroy(k->comm); delete k; return fail(B2D_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  *c = k;
+  return B2D_OK;
+}
+extern "C" int b2d_comm_destroy(b2d_comm *c) {
+  if (!c) return B2D_OK;
+  const NcclApi *api = nccl_api(nullptr);
+  use_device(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (api && c->comm) api->CommDestroy(c->comm);
+  if (c->d_buf) cudaFree(c->d_buf);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return B2D_OK;
+}
+static int comm_buf(b2d_comm *c, size_t bytes) {
+  if (bytes <= c->cap) return B2D_OK;
+  if (c->d_buf) cudaFree(c->d_buf);
+  c->d_buf = nullptr; c->cap = 0;
+  CU(cudaMalloc(&c->d_buf, bytes));
+  c->cap = bytes;
+  return B2D_OK;
+}
+extern "C" int b2d_comm_barrier(b2d_comm *c) {
+  if (!c) return fail(B2D_EINVAL, "null comm");
+  const NcclApi *api = nccl_api(nullptr);
+  int st = use_device(c->device);
+  if (st) return st;
+  if ((st = comm_buf(c, 8))) return st;
+  CU(cudaMemsetAsync(c->d_buf, 0, 8, c->stream));
+  int rc = api->AllReduce(c->d_buf, c->d_buf, 1, ncclInt32, ncclSum, c->comm, c->stream);
+  if (rc != ncclSuccess) return nccl_fail(api, rc, "ncclAllReduce");
+  CU(cudaStreamSynchronize(c->stream));
+  return B2D_OK;
+}
+// values[0..n) of rank `root` -> every rank (int64 payload), synchronous.
+static int comm_bcast_i64(b2d_comm *c, int64_t *values, size_t n, int root) {
+  const NcclApi *api = nccl_api(nullptr);
+  int st = use_device(c->device);
+  if (st) return st;
+  if ((st = comm_buf(c, n * 8))) return st;
+  if (c->rank == root) CU(cudaMemcpyAsync(c->d_buf, values, n * 8, cudaMemcpyHostToDevice, c->stream));
+  int rc = api->Broadcast(c->d_buf, c->d_buf, n, ncclInt64, root, c->comm, c->stream);
+  if (rc != ncclSuccess) return nccl_fail(api, rc, "ncclBroadcast");
+  CU(cudaMemcpyAsync(values, c->d_buf, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ FIR
+enum { PATH_GENERIC = 0, PATH_Q15 = 1 };
+
+struct b2d_fir {
+  b2d_fir_desc d;
+  Fmt fin, fc, fa, fo;
+  int device = 0, T = 0, in_bytes = 2, out_bytes = 2, c_bytes = 2;
+  int path = PATH_GENERIC;
+  std::vector<int64_t> h_coeff;   // [C][N] raw, wrapped to COEFF_TYPE
+  std::vector<char> ch_loaded;    // per channel
+  int64_t *d_coeff64 = nullptr;
+  uint32_t *d_coeff_pk = nullptr;
+  int pk_words = 0;
+  void *d_tail[2] = {nullptr, nullptr};
+  int cur = 0;
+  b2d_comm *comm = nullptr;
+  int root = 0;
+  Pipe pipe;
+};
+
+static bool all_loaded(const b2d_fir *h) {
+  for (char c : h->ch_loaded) if (!c) return false;
+  return true;
+}
+
+extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
+  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
+  *out = nullptr;
+  int st;
+  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
+  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
+  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
+  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
+  if (desc->n_taps < 1 || desc->n_taps > (1u << 20)) return fail(B2D_EINVAL, "n_taps %u outside 1..2^20", desc->n_taps);
+  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
+  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
+  if (desc->kind < B2D_FIR_CONST || desc->kind > B2D_FIR_PROG) return fail(B2D_EINVAL, "bad kind");
+  if (desc->ftype == B2D_FOLD_EVEN_ANTI || desc->ftype == B2D_FOLD_ODD_ANTI)
+    return fail(B2D_EUNSUPPORTED, "the reference FIR classes do not dispatch the _ANTI architectures (output left unwritten)");
+  if (desc->ftype < B2D_SHIFT_REG || desc->ftype > B2D_FOLD_ODD_ANTI) return fail(B2D_EINVAL, "bad ftype");
+  Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
+  {  // bit budget of the 128-bit generic evaluation
+    const int Fp = desc->ftype == B2D_FOLD_ODD ? fc.F() + fa.F() : fin.F() + fc.F();
+    const int Wp = desc->ftype == B2D_FOLD_ODD ? fc.W + fa.W : fin.W + fc.W + 2;
+    const int rF = std::max(Fp, fa.F());
+    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + std::max(0, fo.F() - fa.F()) > 125 ||
+        (desc->ftype == B2D_FOLD_ODD && fin.W + 1 + std::max(0, fa.F() - fin.F()) > 125))
+      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
+  }
+  int dev = desc->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if ((st = use_device(dev))) return st;
+  b2d_fir *h = new (std::nothrow) b2d_fir();
+  if (!h) return fail(B2D_ENOMEM, "handle");
+  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
+  h->T = (int)desc->n_taps - 1;
+  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
+  const uint32_t C = desc->n_channels;
+  const size_t N = desc->n_taps;
+  h->h_coeff.assign(C * N, 0);
+  h->ch_loaded.assign(C, 0);
+  h->path = fir_q15_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q15 : PATH_GENERIC;
+  const char *force = getenv("B2D_FORCE_GENERIC");
+  if (force && *force == '1') h->path = PATH_GENERIC;
+  cudaError_t e = cudaMalloc(&h->d_coeff64, C * N * sizeof(int64_t));
+  const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaMalloc(&h->d_tail[i], tail_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
+  }
+  if (e == cudaSuccess && h->path == PATH_Q15) {
+    h->pk_words = fir_q15_pk_words((int)N, desc->ftype);
+    e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    b2d_fir_destroy(h);
+    return fail(e == cudaErrorMemoryAllocation ? B2D_ENOMEM : B2D_ECUDA, "b2d_fir_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_destroy(b2d_fir *h) {
+  if (!h) return B2D_OK;
+  use_device(h->device);
+  cudaDeviceSynchronize();
+  h->pipe.destroy();
+  if (h->d_coeff64) cudaFree(h->d_coeff64);
+  if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
+  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
+  delete h;
+  return B2D_OK;
+}
+
+extern "C" const char *b2d_fir_path(b2d_fir *h) { return !h ? "" : (h->path == PATH_Q15 ? "fir_q15" : "fir_generic"); }
+
+extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  if (comm && (root < 0 || root >= comm->world)) return fail(B2D_EINVAL, "root %d outside the communicator", root);
+  h->comm = comm; h->root = root;
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  const size_t N = h->d.n_taps;
+  const uint32_t C = h->d.n_channels;
+  if (n != N) return fail(B2D_EINVAL, "expected %zu coefficients, got %zu", N, n);
+  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
+  const bool have_local = !h->comm || h->comm->rank == h->root;
+  if (have_local && !coeff_raw) return fail(B2D_EINVAL, "null coefficient pointer");
+  if (h->d.kind == B2D_FIR_CONST) {  // ac_fir_const_coeffs: the pointer is bound once, at construction
+    for (uint32_t c = 0; c < C; c++)
+      if ((channel < 0 || (uint32_t)channel == c) && h->ch_loaded[c])
+        return fail(B2D_ESTATE, "constant-coefficient filter: coefficients are fixed at construction");
+  }
+  int st = use_device(h->device);
+  if (st) return st;
+  std::vector<int64_t> v(N, 0);
+  if (have_local) {
+    for (size_t i = 0; i < N; i++) {
+      int64_t r;
+      if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
+      else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
+      else r = ((const int64_t *)coeff_raw)[i];
+      v[i] = wrap_bits(r, h->fc.W, h->fc.S);
+    }
+  }
+  if (h->comm && (st = comm_bcast_i64(h->comm, v.data(), N, h->root))) return st;
+  // the coefficient set may be swapped between run() calls while earlier launches are still in flight
+  CU(cudaDeviceSynchronize());
+  for (uint32_t c = 0; c < C; c++) {
+    if (channel >= 0 && (uint32_t)channel != c) continue;
+    std::copy(v.begin(), v.end(), h->h_coeff.begin() + c * N);
+    h->ch_loaded[c] = 1;
+    CU(cudaMemcpy(h->d_coeff64 + c * N, v.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (h->path == PATH_Q15) {
+      std::vector<uint32_t> pk(h->pk_words, 0);
+      fir_q15_pack(h->fc, v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
+      CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+  }
+  return B2D_OK;
+}
+
+static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  FirLaunch p;
+  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
+  p.n_taps = (int)h->d.n_taps; p.ftype = h->d.ftype; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
+  p.in = d_in; p.out = d_out; p.n = n;
+  p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1];
+  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words;
+  CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : launch_fir_generic(p, st));
+  CU(launch_fir_tail(p, st));
+  h->cur ^= 1;
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  if (!h || (n && (!d_in || !d_out))) return fail(B2D_EINVAL, "null argument");
+  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
+  int st = use_device(h->device);
+  if (st) return st;
+  if ((st = fir_launch(h, d_in, n, d_out, (cudaStream_t)cuda_stream))) return st;
+  if (n_out) *n_out = n;
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_run(b2d_fir *h, const void *in, size_t n, void *out, size_t *n_out) {
+  if (!h || (n && (!in || !out))) return fail(B2D_EINVAL, "null argument");
+  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
+  if (n_out) *n_out = n;
+  if (n == 0) return B2D_OK;
+  int st = use_device(h->device);
+  if (st) return st;
+  Pipe &P = h->pipe;
+  if ((st = P.init())) return st;
+  const uint32_t C = h->d.n_channels;
+  const int il = h->d.layout == B2D_INTERLEAVED;
+  const size_t per = (size_t)C * (h->in_bytes + h->out_bytes);
+  size_t L = std::max<size_t>((size_t)(96u << 20) / per, 4096);  // ~96 MiB of traffic per chunk
+  L = std::min(L, n);
+  if ((st = P.ensure(L * C * h->in_bytes, L * C * h->out_bytes))) return st;
+  size_t i = 0;
+  for (size_t off = 0; off < n; off += L, i++) {
+    const int s = (int)(i % Pipe::S);
+    const size_t len = std::min(L, n - off);
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
+    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
+    CU(cudaEventRecord(P.e_in[s], P.s_in));
+    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
+    if ((st = fir_launch(h, P.d_in[s], len, P.d_out[s], P.s_k))) return st;
+    CU(cudaEventRecord(P.e_k[s], P.s_k));
+    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
+    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, il, n, off, len, P.s_out));
+    CU(cudaEventRecord(P.e_out[s], P.s_out));
+  }
+  CU(cudaStreamSynchronize(P.s_out));
+  CU(cudaStreamSynchronize(P.s_k));
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_reset(b2d_fir *h) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
+  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
+  return B2D_OK;
+}
+
+struct StateHdr { uint32_t magic, version; uint64_t n_seen; uint32_t hist, channels, bytes, pad; };
+static const uint32_t kFirMagic = 0x46324442u, kCicMagic = 0x43324442u;
+
+extern "C" int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  *bytes = sizeof(StateHdr) + (size_t)h->T * h->d.n_channels * h->in_bytes;
+  return B2D_OK;
+}
+extern "C" int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes) {
+  size_t need = 0;
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  b2d_fir_state_bytes(h, &need);
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  StateHdr hd{kFirMagic, 1, 0, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0};
+  memcpy(blob, &hd, sizeof(hd));
+  if (need > sizeof(hd)) CU(cudaMemcpy((char *)blob + sizeof(hd), h->d_tail[h->cur], need - sizeof(hd), cudaMemcpyDeviceToHost));
+  return B2D_OK;
+}
+extern "C" int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes) {
+  size_t need = 0;
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  b2d_fir_state_bytes(h, &need);
+  StateHdr hd;
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kFirMagic || hd.hist != (uint32_t)h->T || hd.channels != h->d.n_channels || hd.bytes != (uint32_t)h->in_bytes)
+    return fail(B2D_EINVAL, "state blob does not belong to this filter configuration");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  if (need > sizeof(hd)) CU(cudaMemcpy(h->d_tail[h->cur], (const char *)blob + sizeof(hd), need - sizeof(hd), cudaMemcpyHostToDevice));
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CIC
+static int log2_ceil_u128(unsigned __int128 v) {
+  int k = 0;
+  while ((((unsigned __int128)1) << k) < v) k++;
+  return k;
+}
+
+// find_inter_type_cic_dec (ac_cic_dec_full.h:116-137): outW = log2_ceil(R^N * M^N) + W + !S
+// find_inter_type_cic_intr (ac_cic_intr_full.h:107-127): outW = log2_ceil(R^(N-1) * M^N) + W + !S
+static int cic_int_width(const b2d_cic_desc *d, int *outW) {
+  unsigned __int128 g = 1;
+  const unsigned __int128 lim = ((unsigned __int128)1) << 100;
+  const uint32_t nr = d->mode == B2D_CIC_INTR ? d->N - 1 : d->N;
+  for (uint32_t i = 0; i < nr; i++) { g *= d->R; if (g > lim) return -1; }
+  for (uint32_t i = 0; i < d->N; i++) { g *= d->M; if (g > lim) return -1; }
+  *outW = log2_ceil_u128(g) + d->in.W + (d->in.S ? 0 : 1);
+  return 0;
+}
+
+static int cic_check(const b2d_cic_desc *d, int *outW) {
+  int st;
+  if (!d) return fail(B2D_EINVAL, "null descriptor");
+  if ((st = check_fmt(d->in, 32, "IN_TYPE"))) return st;
+  if ((st = check_fmt(d->out, 64, "OUT_TYPE"))) return st;
+  if (d->mode != B2D_CIC_DEC && d->mode != B2D_CIC_INTR) return fail(B2D_EINVAL, "bad mode");
+  // rate counters of the reference are 8 bits wide (ac_cic_full_core.h:72-73,91); R = 1 never re-reads in the interpolator
+  if (d->R < 2 || d->R > 256) return fail(B2D_EINVAL, "R = %u outside 2..256", d->R);
+  if (d->M < 1 || d->N < 1 || d->N > 255) return fail(B2D_EINVAL, "M = %u, N = %u invalid", d->M, d->N);
+  if (d->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
+  if (d->layout != B2D_PLANAR && d->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
+  if (cic_int_width(d, outW) || *outW > 64) return fail(B2D_EUNSUPPORTED, "lossless internal width exceeds 64 bits");
+  if (d->N > 16 || (uint64_t)d->N * d->M > 64) return fail(B2D_EUNSUPPORTED, "N > 16 or N*M > 64");
+  return B2D_OK;
+}
+
+struct b2d_cic {
+  b2d_cic_desc d;
+  Fmt fin, fo;
+  int device = 0, intW = 0, H = 0, in_bytes = 2, out_bytes = 4;
+  int fast = 0;
+  unsigned long long n_seen = 0;
+  void *d_tail[2] = {nullptr, nullptr};
+  int cur = 0;
+  Pipe pipe;
+};
+
+extern "C" int b2d_cic_int_width(const b2d_cic_desc *desc, int32_t *outW) {
+  if (!outW) return fail(B2D_EINVAL, "null argument");
+  int w = 0;
+  int st = cic_check(desc, &w);
+  if (st) return st;
+  *outW = w;
+  return B2D_OK;
+}
+
+static unsigned long long cic_emitted(const b2d_cic *h, unsigned long long K) {
+  const long long R = h->d.R, N = h->d.N;
+  if (h->d.mode == B2D_CIC_DEC) return (K + R - 1) / R;  // inputs 0, R, 2R, ... are forwarded
+  if (K == 0) return 0;
+  const long long e = ((long long)K - 1) * R + 1 - (N - 1);  // integrator steps so far minus the N-1 dropped
+  return e > 0 ? (unsigned long long)e : 0;
+}
+
+extern "C" int b2d_cic_create(b2d_cic **out, const b2d_cic_desc *desc) {
+  if (!out) return fail(B2D_EINVAL, "null argument");
+  *out = nullptr;
+  int w = 0;
+  int st = cic_check(desc, &w);
+  if (st) return st;
+  int dev = desc->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if ((st = use_device(dev))) return st;
+  b2d_cic *h = new (std::nothrow) b2d_cic();
+  if (!h) return fail(B2D_ENOMEM, "handle");
+  h->d = *desc; h->fin = to_fmt(desc->in); h->fo = to_fmt(desc->out); h->device = dev; h->intW = w;
+  h->in_bytes = container_bytes(desc->in.W); h->out_bytes = container_bytes(desc->out.W);
+  h->H = cic_history_len(desc->mode == B2D_CIC_INTR, desc->R, desc->M, desc->N);
+  const size_t tail_bytes = (size_t)h->H * desc->n_channels * h->in_bytes;
+  for (int i = 0; i < 2; i++) {
+    cudaError_t e = cudaMalloc(&h->d_tail[i], tail_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      b2d_cic_destroy(h);
+      return fail(B2D_ECUDA, "b2d_cic_create: %s", cudaGetErrorString(e));
+    }
+  }
+  CicLaunch p{};
+  p.fin = h->fin; p.fout = h->fo; p.intW = w; p.R = desc->R; p.M = desc->M; p.N = desc->N;
+  p.intr = desc->mode == B2D_CIC_INTR; p.C = desc->n_channels; p.interleaved = desc->layout == B2D_INTERLEAVED;
+  h->fast = cic_fast_supported(p) ? 1 : 0;
+  const char *force = getenv("B2D_FORCE_GENERIC");
+  if (force && *force == '1') h->fast = 0;
+  *out = h;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cic_destroy(b2d_cic *h) {
+  if (!h) return B2D_OK;
+  use_device(h->device);
+  cudaDeviceSynchronize();
+  h->pipe.destroy();
+  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
+  delete h;
+  return B2D_OK;
+}
+
+extern "C" const char *b2d_cic_path(b2d_cic *h) { return !h ? "" : (h->fast ? "cic_fast" : "cic_generic"); }
+
+extern "C" size_t b2d_cic_max_out(b2d_cic *h, size_t n) {
+  if (!h) return 0;
+  return h->d.mode == B2D_CIC_DEC ? n / h->d.R + 1 : n * h->d.R;
+}
+
+static int cic_launch(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  CicLaunch p;
+  p.fin = h->fin; p.fout = h->fo; p.intW = h->intW; p.R = h->d.R; p.M = h->d.M; p.N = h->d.N;
+  p.intr = h->d.mode == B2D_CIC_INTR; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
+  p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
+  p.n_seen = h->n_seen; p.out_first = cic_emitted(h, h->n_seen);
+  p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1]; p.H = h->H;
+  CU(h->fast ? launch_cic_fast(p, st) : launch_cic_generic(p, st));
+  CU(launch_cic_tail(p, st));
+  h->cur ^= 1;
+  h->n_seen += n;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
+  const size_t no = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
+  if (no && !d_out) return fail(B2D_EINVAL, "null output");
+  int st = use_device(h->device);
+  if (st) return st;
+  if ((st = cic_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
+  if (n_out) *n_out = no;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cic_run(b2d_cic *h, const void *in, size_t n, void *out, size_t *n_out) {
+  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
+  const size_t no_total = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
+  if (no_total && !out) return fail(B2D_EINVAL, "null output");
+  if (n_out) *n_out = no_total;
+  if (n == 0) return B2D_OK;
+  int st = use_device(h->device);
+  if (st) return st;
+  Pipe &P = h->pipe;
+  if ((st = P.init())) return st;
+  const uint32_t C = h->d.n_channels;
+  const int il = h->d.layout == B2D_INTERLEAVED;
+  const bool dec = h->d.mode == B2D_CIC_DEC;
+  const double out_per_in = dec ? 1.0 / h->d.R : (double)h->d.R;
+  const double per = C * (h->in_bytes + h->out_bytes * out_per_in);
+  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
+  L = std::min(L, n);
+  const size_t Lout = dec ? L / h->d.R + 1 : L * h->d.R;
+  if ((st = P.ensure(L * C * h->in_bytes, Lout * C * h->out_bytes))) return st;
+  size_t i = 0, off_out = 0;
+  for (size_t off = 0; off < n; off += L, i++) {
+    const int s = (int)(i % Pipe::S);
+    const size_t len = std::min(L, n - off);
+    const size_t no = (size_t)(cic_emitted(h, h->n_seen + len) - cic_emitted(h, h->n_seen));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
+    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
+    CU(cudaEventRecord(P.e_in[s], P.s_in));
+    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
+    if ((st = cic_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
+    CU(cudaEventRecord(P.e_k[s], P.s_k));
+    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
+    // outputs are PLANAR with a channel stride of the whole call's output count
+    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
+    CU(cudaEventRecord(P.e_out[s], P.s_out));
+    off_out += no;
+  }
+  CU(cudaStreamSynchronize(P.s_out));
+  CU(cudaStreamSynchronize(P.s_k));
+  return B2D_OK;
+}
+
+extern "C" int b2d_cic_reset(b2d_cic *h) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, (size_t)h->H * h->d.n_channels * h->in_bytes));
+  h->n_seen = 0;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cic_state_bytes(b2d_cic *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  *bytes = sizeof(StateHdr) + (size_t)h->H * h->d.n_channels * h->in_bytes;
+  return B2D_OK;
+}
+extern "C" int b2d_cic_get_state(b2d_cic *h, void *blob, size_t bytes) {
+  size_t need = 0;
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  b2d_cic_state_bytes(h, &need);
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  StateHdr hd{kCicMagic, 1, h->n_seen, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, 0};
+  memcpy(blob, &hd, sizeof(hd));
+  CU(cudaMemcpy((char *)blob + sizeof(hd), h->d_tail[h->cur], need - sizeof(hd), cudaMemcpyDeviceToHost));
+  return B2D_OK;
+}
+extern "C" int b2d_cic_set_state(b2d_cic *h, const void *blob, size_t bytes) {
+  size_t need = 0;
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  b2d_cic_state_bytes(h, &need);
+  StateHdr hd;
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kCicMagic || hd.hist != (uint32_t)h->H || hd.channels != h->d.n_channels || hd.bytes != (uint32_t)h->in_bytes)
+    return fail(B2D_EINVAL, "state blob does not belong to this filter configuration");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->d_tail[h->cur], (const char *)blob + sizeof(hd), need - sizeof(hd), cudaMemcpyHostToDevice));
+  h->n_seen = hd.n_seen;
+  return B2D_OK;
+}

@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference's five hot-path class templates, on top of the C-ABI.
+
+Same names, template parameters (as constructor arguments) and run()/load call surface as
+  ac_fir_const_coeffs / ac_fir_load_coeffs / ac_fir_prog_coeffs   (reference include/ac_dsp/ac_fir_*_coeffs.h)
+  ac_cic_dec_full / ac_cic_intr_full                               (reference include/ac_dsp/ac_cic_*_full.h)
+`ac_channel<T>` FIFOs become arrays of RAW two's-complement integers: numpy arrays (host path, copies inside
+the call) or torch CUDA tensors (device path, asynchronous on torch's current stream).  All arithmetic runs in
+the CUDA library; this module only marshals.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_NP_DT = {2: np.int16, 4: np.int32, 8: np.int64}
+
+
+def ac_fixed(W, I, S=True, Q="AC_TRN", O="AC_WRAP"):
+    """ac_fixed<W, I, S, Q, O> type descriptor."""
+    return (int(W), int(I), bool(S), Q, O)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _container_dtype(fmt):
+    return _NP_DT[L.load().b2d_container_bytes(fmt.W)]
+
+
+class _Block:
+    """Shared marshaling: channel layout, numpy / torch dispatch."""
+
+    def _setup_io(self, fin, fout, n_channels, layout):
+        self._C = int(n_channels)
+        self._layout = L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR
+        self._in_dt = _container_dtype(fin)
+        self._out_dt = _container_dtype(fout)
+
+    def _n_per_channel(self, shape):
+        if self._C == 1:
+            if len(shape) != 1:
+                raise ValueError("single-channel blocks take 1-D arrays")
+            return shape[0]
+        want = "(n, C)" if self._layout == L.INTERLEAVED else "(C, n)"
+        if len(shape) != 2 or shape[1 if self._layout == L.INTERLEAVED else 0] != self._C:
+            raise ValueError(f"expected shape {want} with C = {self._C}, got {tuple(shape)}")
+        return shape[0 if self._layout == L.INTERLEAVED else 1]
+
+    def _out_shape(self, n_out, rate_changing):
+        if self._C == 1:
+            return (n_out,)
+        if self._layout == L.INTERLEAVED and not rate_changing:
+            return (n_out, self._C)
+        return (self._C, n_out)  # CIC outputs are planar (b200dsp.h: b2d_cic_run)
+
+    def _run(self, x, fn_host, fn_dev, max_out, rate_changing, out=None):
+        lib = L.load()
+        n_out = C.c_size_t(0)
+        if _is_torch(x):
+            import torch
+            if not x.is_cuda:
+                raise ValueError("torch inputs must live on the GPU (use numpy arrays for the host path)")
+            tdt = {np.int16: torch.int16, np.int32: torch.int32, np.int64: torch.int64}
+            if x.dtype != tdt[self._in_dt]:
+                raise TypeError(f"input dtype must be {tdt[self._in_dt]}")
+            x = x.contiguous()
+            n = self._n_per_channel(tuple(x.shape))
+            cap = max_out(n)
+            if out is not None:
+                if not out.is_cuda or out.dtype != tdt[self._out_dt] or out.numel() < self._C * cap or not out.is_contiguous():
+                    raise ValueError("out= must be a contiguous CUDA tensor of the output container dtype and capacity")
+                y = out.reshape(-1)[: self._C * cap].reshape(self._out_shape(cap, rate_changing))
+            else:
+                y = torch.empty(self._out_shape(cap, rate_changing), dtype=tdt[self._out_dt], device=x.device)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            L.check(fn_dev(self._h, x.data_ptr(), n, y.data_ptr(), C.byref(n_out), stream))
+            if n_out.value != cap:  # planar stride is the true output count
+                y = y.reshape(-1)[: self._C * n_out.value].reshape(self._out_shape(n_out.value, rate_changing))
+            return y
+        x = np.ascontiguousarray(np.asarray(x).astype(self._in_dt, copy=False))
+        n = self._n_per_channel(x.shape)
+        cap = max_out(n)
+        y = np.empty(self._C * max(cap, 1), dtype=self._out_dt)
+        L.check(fn_host(self._h, x.ctypes.data, n, y.ctypes.data, C.byref(n_out)))
+        return y[: self._C * n_out.value].reshape(self._out_shape(n_out.value, rate_changing)).copy()
+
+
+class _Fir(_Block):
+    _kind = "load"
+
+    def __init__(self, IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype="SHIFT_REG", n_channels=1,
+                 layout="planar", device=-1, comm=None, root=0):
+        lib = L.load()
+        self._h = None
+        self.N_TAPS = int(N_TAPS)
+        ft = L.FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        d = L.B2dFirDesc(L.make_fmt(IN_TYPE), L.make_fmt(COEFF_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE),
+                         self.N_TAPS, ft, L.FIR_KINDS.index(self._kind), int(n_channels),
+                         L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR, int(device))
+        h = C.c_void_p()
+        L.check(lib.b2d_fir_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self._coeff_dt = _container_dtype(d.coeff)
+        self._setup_io(d.fin, d.out, n_channels, layout)
+        if comm is not None:
+            L.check(lib.b2d_fir_set_comm(self._h, comm._c, int(root)))
+
+    @property
+    def path(self):
+        """Kernel family serving this configuration ('fir_q15' or 'fir_generic')."""
+        return L.load().b2d_fir_path(self._h).decode()
+
+    def _load(self, coeffs, channel=-1):
+        lib = L.load()
+        if coeffs is None:  # non-root rank of a broadcast
+            L.check(lib.b2d_fir_load(self._h, None, self.N_TAPS, int(channel)))
+            return
+        c = np.ascontiguousarray(np.asarray(coeffs).astype(self._coeff_dt, copy=False))
+        L.check(lib.b2d_fir_load(self._h, c.ctypes.data, c.size, int(channel)))
+
+    def _process(self, data_in, out=None):
+        lib = L.load()
+        return self._run(data_in, lib.b2d_fir_run, lib.b2d_fir_run_dev, lambda n: n, False, out)
+
+    def reset(self):
+        L.check(L.load().b2d_fir_reset(self._h))
+
+    def get_state(self):
+        lib = L.load()
+        n = C.c_size_t(0)
+        L.check(lib.b2d_fir_state_bytes(self._h, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        L.check(lib.b2d_fir_get_state(self._h, buf.ctypes.data, buf.size))
+        return buf
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        L.check(L.load().b2d_fir_set_state(self._h, blob.ctypes.data, blob.size))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_fir_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ac_fir_const_coeffs(_Fir):
+    """ac_fir_const_coeffs<IN,OUT,COEFF,ACC,N_TAPS,ftype>(const COEFF *coeffs); run(in, out)
+    (reference ac_fir_const_coeffs.h:309-355).  The coefficient array is bound at construction."""
+    _kind = "const"
+
+    def __init__(self, IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype, coeffs, **kw):
+        super().__init__(IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype, **kw)
+        self._load(coeffs)
+
+    def run(self, data_in, out=None):
+        return self._process(data_in, out)
+
+
+class ac_fir_load_coeffs(_Fir):
+    """ac_fir_load_coeffs<...>::run(data_in, coeffs_ch, data_out, ld)  (reference ac_fir_load_coeffs.h:300-365).
+    One `ld` token is consumed per call; coefficients are taken only if ld is true AND N_TAPS values are queued,
+    otherwise the token is silently dropped (:324-331)."""
+    _kind = "load"
+
+    def run(self, data_in=None, coeffs_ch=None, ld=None, channel=-1, out=None):
+        if ld is not None and bool(ld) and coeffs_ch is not None and len(coeffs_ch) >= self.N_TAPS:
+            self._load(np.asarray(coeffs_ch)[: self.N_TAPS], channel)
+        if data_in is None or len(data_in) == 0:
+            return np.empty(0, dtype=self._out_dt)
+        return self._process(data_in, out)
+
+    def load(self, coeffs, channel=-1):
+        """Convenience: run() with ld=true and N_TAPS coefficients queued (multi-GPU: `coeffs` may be None off-root)."""
+        self._load(coeffs, channel)
+
+
+class ac_fir_prog_coeffs(_Fir):
+    """ac_fir_prog_coeffs<...>::run(data_in, data_out, coeffs[N_TAPS])  (reference ac_fir_prog_coeffs.h:261-303).
+    The reference consumes one sample per call; here a call consumes the whole array, which is the same as calling
+    the reference once per sample with the same coefficient array.  The delay line survives a coefficient change."""
+    _kind = "prog"
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._last = None
+
+    def run(self, data_in, coeffs=None, channel=-1, out=None):
+        if coeffs is not None:
+            key = np.asarray(coeffs).tobytes()
+            if key != self._last or channel >= 0:
+                self._load(coeffs, channel)
+                self._last = key if channel < 0 else None
+        return self._process(data_in, out)
+
+    def load(self, coeffs, channel=-1):
+        self._load(coeffs, channel)
+        self._last = None
+
+
+class _Cic(_Block):
+    _mode = 0
+
+    def __init__(self, IN_TYPE, OUT_TYPE, R, M, N, n_channels=1, layout="planar", device=-1):
+        lib = L.load()
+        self._h = None
+        d = L.B2dCicDesc(L.make_fmt(IN_TYPE), L.make_fmt(OUT_TYPE), int(R), int(M), int(N), self._mode, int(n_channels),
+                         L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR, int(device))
+        w = C.c_int32(0)
+        L.check(lib.b2d_cic_int_width(C.byref(d), C.byref(w)))
+        self.int_width = w.value
+        h = C.c_void_p()
+        L.check(lib.b2d_cic_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self.R, self.M, self.N = int(R), int(M), int(N)
+        self._setup_io(d.fin, d.out, n_channels, layout)
+
+    @property
+    def path(self):
+        return L.load().b2d_cic_path(self._h).decode()
+
+    def run(self, data_in, out=None):
+        lib = L.load()
+        return self._run(data_in, lib.b2d_cic_run, lib.b2d_cic_run_dev, lambda n: lib.b2d_cic_max_out(self._h, n), True, out)
+
+    def reset(self):
+        L.check(L.load().b2d_cic_reset(self._h))
+
+    def get_state(self):
+        lib = L.load()
+        n = C.c_size_t(0)
+        L.check(lib.b2d_cic_state_bytes(self._h, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        L.check(lib.b2d_cic_get_state(self._h, buf.ctypes.data, buf.size))
+        return buf
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        L.check(L.load().b2d_cic_set_state(self._h, blob.ctypes.data, blob.size))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_cic_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ac_cic_dec_full(_Cic):
+    """ac_cic_dec_full<IN, OUT, R, M, N>::run(data_in, data_out)  (reference ac_cic_dec_full.h:147-222)."""
+    _mode = 0
+
+
+class ac_cic_intr_full(_Cic):
+    """ac_cic_intr_full<IN, OUT, R, M, N>::run(data_in, data_out)  (reference ac_cic_intr_full.h:137-215)."""
+    _mode = 1
+
+
+class Comm:
+    """NCCL communicator of the C-ABI (one rank per GPU); only used for the coefficient broadcast at load()."""
+
+    def __init__(self, unique_id, rank, world, device=-1):
+        lib = L.load()
+        self._c = C.c_void_p()
+        idb = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        L.check(lib.b2d_comm_create(C.byref(self._c), idb, int(rank), int(world), int(device)))
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        L.check(L.load().b2d_comm_unique_id(buf))
+        return bytes(buf)
+
+    def barrier(self):
+        L.check(L.load().b2d_comm_barrier(self._c))
+
+    def close(self):
+        if getattr(self, "_c", None):
+            L.load().b2d_comm_destroy(self._c)
+            self._c = None
+
+
+def shard_channels(n_channels, rank, world):
+    """Channel c lives on rank c % world (b2d_shard_count): the local channel ids of `rank`."""
+    n = C.c_uint32(0)
+    L.check(L.load().b2d_shard_count(int(n_channels), int(rank), int(world), C.byref(n)))
+    ids = list(range(rank, n_channels, world))
+    assert len(ids) == n.value
+    return ids

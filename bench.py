@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on the B200 engine, with the reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir256|fir1024|cic_dec|cic_intr] [--impl reference]
+
+A step is one run() of the hot path over one batch of synthetic 16-bit samples already resident in HBM
+(default workload: BASELINE.json configs[1], the 256-tap ac_fixed<16,1> -> <40,8> FIR over 2^30 interleaved IQ
+samples per GPU).  Rank 0 prints ONE JSON line.  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` is the same metric through the C-ABI host-buffer call (b2d_*_run on pinned host memory, copies
+inside the timed region); `roofline` is the dominant kernel's algorithmic HBM bytes / its event-timed duration
+against MEASURED_PEAKS.json; `cpu_baseline` is the reference's own C++ templates (oracle/_ref, built in the dev
+container from /root/reference over the clean-room ac_types shim) on this box's host cores over a bounded sample.
+`--impl reference` prints that CPU run as its own line.  The oracle is only ever the thing timed as the
+CPU baseline here -- never part of the GPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q15, ACC40 = (16, 1), (40, 8)
+SEED = 20260101
+
+# name -> description of one step per GPU.  bytes_per_unit: SURVEY.md 8(d) algorithmic bytes per counted sample.
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "fir256": dict(kind="fir", taps=256, channels=2, layout="interleaved", n=1 << 30, unit_is_iq=True,
+                   bytes_per_unit=20.0, macs_per_unit=512,
+                   name="ac_fir_load_coeffs 256-tap ac_fixed<16,1,true> x <16,1,true> -> <40,8,true>, interleaved 16-bit IQ, 2^30 IQ samples per GPU"),
+    # BASELINE.json configs[3], per-GPU share: 8 real channels x 2^27 samples, 1024 taps
+    "fir1024": dict(kind="fir", taps=1024, channels=8, layout="planar", n=1 << 27, unit_is_iq=False,
+                    bytes_per_unit=10.0, macs_per_unit=1024,
+                    name="ac_fir_prog_coeffs 1024-tap <16,1> -> <40,8>, 8 real channels x 2^27 samples per GPU"),
+    # BASELINE.json configs[2]
+    "cic_dec": dict(kind="cic", mode="dec", R=8, M=1, N=4, out=(28, 13), channels=2, layout="interleaved", n=1 << 30,
+                    unit_is_iq=True, bytes_per_unit=5.0, macs_per_unit=0,
+                    name="ac_cic_dec_full R=8 M=1 N=4 ac_fixed<16,1,true> -> <28,13,true>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
+    # BASELINE.json configs[4] first stage
+    "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
+                     unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
+                     name="ac_cic_intr_full R=4 M=1 N=3 <16,1> -> <20,5>, 1 real channel x 2^28 inputs per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        out, _ = self.p.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference(wl, seconds_target=12.0, threads=None):
+    """The reference's own run() for this workload on the host cores: one filter instance per thread (an instance is
+    inherently sequential; instances are independent, the same decomposition as the GPU's channel sharding)."""
+    from oracle import oracle as O
+    O.build()
+    threads = threads or len(os.sched_getaffinity(0))
+    kind = "reference" if O.have_ref() else "port"
+    rng = np.random.default_rng(SEED)
+    if wl["kind"] == "fir":
+        taps = wl["taps"]
+        h = O.rand_raw(rng, Q15, taps)
+
+        def make():
+            f = (O.FirA("load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG") if kind == "reference"
+                 else O.FirB(Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG"))
+            f.load(h)
+            return f
+        per_thread = int(seconds_target * 0.5e6 * 256 / taps)       # ~0.5 M real samples/s/core at 256 taps
+    else:
+        def make():
+            cls = O.CicA if kind == "reference" else O.CicB
+            return cls(wl["mode"], Q15, wl["out"], wl["R"], wl["M"], wl["N"])
+        per_thread = min(1 << 23, int(seconds_target * (20e6 if wl["mode"] == "dec" else 4e6)))   # bounded: 16 B per queued sample
+    per_thread = max(1 << 12, per_thread)
+    threads = min(threads, 64)
+    objs = [make() for _ in range(threads)]
+    xs = [O.rand_raw(rng, Q15, per_thread) for _ in range(threads)]
+    for o in objs:
+        o.run(xs[0][:2048])                                          # warm caches / page in
+
+    secs = [0.0] * threads
+
+    def work(i):
+        t = time.perf_counter()
+        objs[i].run(xs[i])
+        # the reference arm times run() alone (channels pre-filled, drained afterwards): BASELINE.md section 3
+        secs[i] = objs[i].last_run_seconds() if kind == "reference" else time.perf_counter() - t
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    rate_real = sum(per_thread / s for s in secs)            # instances run concurrently: rates add
+    rate = rate_real / 2 if wl["unit_is_iq"] else rate_real
+    dt = max(secs)
+    return {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "seconds": dt,
+            "sample": f"{threads} independent filter instances (one per host thread) x {per_thread} real samples each, "
+                      f"{'reference C++ templates over the ac_types shim (oracle/_ref)' if kind == 'reference' else 'oracle_b.c integer restatement'}"}
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference(wl, seconds_target=2.0)
+        if i >= args.warmup:
+            vals.append(last)
+    tot_s = sum(v["seconds"] for v in vals)
+    v = float(np.mean([v["value"] for v in vals]))
+    line = {"impl": "reference", "metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
+            "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16 samples, exact integer accumulate (ac_fixed)", "data": "synthetic",
+            "config": {"workload": wl["name"], "note": "CPU reference arm: bounded sample per step, host cores only"},
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="fir256", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=None, help="override samples per channel per step (power of two)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.log2n:
+        wl["n"] = 1 << args.log2n
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import ac_dsp_b200 as E
+    from ac_dsp_b200 import build as _b
+    if rank == 0:
+        _b.build()
+    if world > 1:
+        dist.barrier()
+    E.load()
+
+    # ---- coefficient set: rank 0 owns it, one ncclBroadcast at load() (the only collective on this path)
+    comm = None
+    if world > 1:
+        ids = [E.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = E.Comm(ids[0], rank, world, local)
+    rng = np.random.default_rng(SEED)
+    C, n, il = wl["channels"], wl["n"], wl["layout"] == "interleaved"
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    shape = (n, C) if il else ((C, n) if C > 1 else (n,))
+    x = torch.randint(-32768, 32768, shape, dtype=torch.int16, device="cuda", generator=gen)
+    if wl["kind"] == "fir":
+        h = rng.integers(-32768, 32767, size=wl["taps"], endpoint=True).astype(np.int16)
+        f = E.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG", n_channels=C, layout=wl["layout"],
+                                 device=local, comm=comm, root=0)
+        f.load(h if rank == 0 else None)
+        launches_per_step = 2          # fir_q15_kernel + history carry
+    else:
+        cls = E.ac_cic_dec_full if wl["mode"] == "dec" else E.ac_cic_intr_full
+        f = cls(Q15, wl["out"], wl["R"], wl["M"], wl["N"], n_channels=C, layout=wl["layout"], device=local)
+        launches_per_step = 2
+    path = f.path
+    units_per_step = n if wl["unit_is_iq"] else n * C   # IQ pairs, or real samples over all local channels
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    y = f.run(x)
+    ybuf = torch.empty(max(y.numel(), C * (n * wl.get("R", 1) if wl.get("mode") == "intr" else n)), dtype=y.dtype, device="cuda")
+    del y
+    for _ in range(args.warmup):
+        y = f.run(x, out=ybuf)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y = f.run(x, out=ybuf)   # inputs + outputs per step (>= 5 GiB) exceed the 126 MB L2 many times over
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    value = units_per_step * world / (ms_per_step * 1e-3) / 1e6
+    out_bytes = y.numel() * y.element_size()
+    in_bytes = x.numel() * x.element_size()
+    del y
+
+    # ---- end to end through the C-ABI host-buffer call (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n2 = min(n, 1 << 27 if wl["kind"] == "fir" else 1 << 28)
+        shape2 = (n2, C) if il else ((C, n2) if C > 1 else (n2,))
+        xh = torch.empty(shape2, dtype=torch.int16).pin_memory()
+        xh.copy_(x[:n2] if (il or C == 1) else x[:, :n2])
+        xn = xh.numpy()
+        lib = E.load()
+        import ctypes as ct
+        if wl["kind"] == "fir":
+            yh = torch.empty(n2 * C, dtype=torch.int64).pin_memory()
+            call = lambda: lib.b2d_fir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), None)
+        else:
+            cap = lib.b2d_cic_max_out(f._h, n2)
+            yh = torch.empty(cap * C, dtype=torch.int32).pin_memory()
+            call = lambda: lib.b2d_cic_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
+        no = ct.c_size_t(n2)
+        for _ in range(2):
+            assert call() == 0, lib.b2d_last_error()
+        sync_all()
+        t0 = time.perf_counter()
+        k2 = max(3, min(args.steps, 5))
+        for _ in range(k2):
+            assert call() == 0, lib.b2d_last_error()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        u2 = n2 if wl["unit_is_iq"] else n2 * C
+        e2e = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xh.numel() * 2),
+               "d2h_bytes_per_step": int(no.value * C * yh.element_size()), "steps": k2,
+               "api": "b2d_fir_run / b2d_cic_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
+               "samples_per_step": u2}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = wl["bytes_per_unit"] * units_per_step
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": path,
+                "algorithmic_bytes_per_launch": alg_bytes, "actual_io_bytes_per_launch": in_bytes + out_bytes}
+        if wl["macs_per_unit"]:
+            tmacs = wl["macs_per_unit"] * units_per_step / (ms_per_step * 1e-3) / 1e12
+            # IDP.2A issue ceiling measured by tools/ubench_pipes.cu: 64 lanes/clk/SM, 2 16b x 8b products per lane-op,
+            # 2 byte planes per 16 x 16 MAC -> 64 MAC/clk/SM
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            roof["int_pipe"] = {"achieved_tmac_s": tmacs, "ceiling_tmac_s": 148 * 64 * sm_mhz * 1e6 / 1e12,
+                                "frac": tmacs / (148 * 64 * sm_mhz * 1e6 / 1e12),
+                                "note": "CUDA-core IDP.2A issue ceiling at the sampled SM clock (tensor cores excluded by the north star)"}
+        line = {"metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
+                "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int16 samples, exact integer accumulate (s32 byte planes -> s64, ac_fixed<40,8>)" if wl["kind"] == "fir" else "int16 samples, u32 modular integrate/comb",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "samples_per_step_per_gpu": units_per_step, "kernel_path": path,
+                           "l2": "inputs per step exceed L2 (>= 0.5 GiB vs 126 MB); no flush needed",
+                           "parallelism": f"channels sharded over {world} GPU(s), one ncclBroadcast of the coefficient set at load()"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roof}
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference(wl)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    f.close()
+    if comm:
+        comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

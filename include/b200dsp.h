@@ -97,6 +97,10 @@ const char *b2d_strerror(int status);
 const char *b2d_last_error(void);                 /* thread-local detail text of the last failure   */
 int b2d_container_bytes(int32_t W);               /* 2, 4 or 8                                      */
 int b2d_device_count(void);                       /* number of visible CUDA devices (0 if none)     */
+/* Page-locked host buffers: run() on HOST memory overlaps its copies with compute only when the
+ * buffers are page-locked (these, or any cudaHostAlloc / cudaHostRegister / torch pinned memory). */
+int b2d_host_alloc(void **p, size_t bytes);
+int b2d_host_free(void *p);
 
 /* ---- FIR: ac_fir_const_coeffs / ac_fir_load_coeffs / ac_fir_prog_coeffs -------------------- */
 /* Class instantiation + constructor: zeroed delay line (ac_fir_load_coeffs.h:134-139). */

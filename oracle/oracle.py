@@ -105,6 +105,10 @@ def lib_a():
         L.acref_fir_run.restype = C.c_long
         L.acref_fir_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.acref_fir_destroy.argtypes = [C.c_void_p]
+        L.acref_fir_last_seconds.restype = C.c_double
+        L.acref_fir_last_seconds.argtypes = [C.c_void_p]
+        L.acref_cic_last_seconds.restype = C.c_double
+        L.acref_cic_last_seconds.argtypes = [C.c_void_p]
         for fn in (L.acref_cic_dec_create, L.acref_cic_intr_create):
             fn.restype = C.c_void_p
             fn.argtypes = [C.c_int]
@@ -217,6 +221,10 @@ class FirA:
             raise RuntimeError("coefficients not set")
         return out[:n]
 
+    def last_run_seconds(self):
+        """Seconds spent inside the reference's run() during the last run() (channel fill / drain excluded)."""
+        return self.L.acref_fir_last_seconds(self.h)
+
     def __del__(self):
         if getattr(self, "h", None):
             self.L.acref_fir_destroy(self.h)
@@ -239,6 +247,9 @@ class CicA:
         out = np.empty(max(cap, 1), dtype=np.int64)
         n = self.L.acref_cic_run(self.h, _p(x), x.size, _p(out))
         return out[:n].copy()
+
+    def last_run_seconds(self):
+        return self.L.acref_cic_last_seconds(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):

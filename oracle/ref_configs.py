@@ -36,6 +36,9 @@ FIR_FORMATS = [
     ("cic_post", fmt(20, 5), fmt(16, 1), fmt(40, 8), fmt(40, 8), [63]),
     # accumulator too narrow for the fold pre-add (wrap inside FOLD_ODD's `fold`)
     ("narrow_acc", fmt(16, 1), fmt(16, 1), fmt(18, 1), fmt(18, 1), [7, 10]),
+    # order-dependent accumulators: saturation / sign-dependent rounding (the reference's tap order matters)
+    ("q15_sat", fmt(16, 1), fmt(16, 1), fmt(24, 4, True, TRN, "AC_SAT"), fmt(16, 1, True, "AC_RND_CONV", "AC_SAT_SYM"), [9, 16]),
+    ("q15_tz", fmt(16, 1), fmt(16, 1), fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), [10]),
 ]
 
 

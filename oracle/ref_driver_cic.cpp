@@ -22,6 +22,8 @@
 #define INC_FILE "_ref/cfgs_cic_intr.inc"
 #endif
 
+#include <chrono>
+
 #include "ref_driver_cic.h"
 
 namespace {
@@ -32,7 +34,9 @@ struct CicImpl : acref::CicBase {
   ac_channel<OUT> out_ch;
   long run(const long long *in, long n, long long *out) {
     for (long i = 0; i < n; i++) in_ch.write(ac_shim::from_raw<IN>(in[i]));
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     f.run(in_ch, out_ch);
+    run_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     long k = 0;
     while (out_ch.available(1)) out[k++] = ac_shim::to_raw(out_ch.read());
     return k;
@@ -55,5 +59,6 @@ extern "C" void *CREATE_FN(int cfg) {
 extern "C" long acref_cic_run(void *h, const long long *in, long n, long long *out) {
   return ((acref::CicBase *)h)->run(in, n, out);
 }
+extern "C" double acref_cic_last_seconds(void *h) { return ((acref::CicBase *)h)->run_seconds; }
 extern "C" void acref_cic_destroy(void *h) { delete (acref::CicBase *)h; }
 #endif

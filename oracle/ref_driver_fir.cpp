@@ -20,11 +20,17 @@
 #include <ac_dsp/ac_fir_load_coeffs.h>
 #include <ac_dsp/ac_fir_prog_coeffs.h>
 
+#include <chrono>
 #include <vector>
 
 namespace {
 
+typedef std::chrono::steady_clock Clock;
+static inline double secs(Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
 struct FirBase {
+  double run_seconds;  // time spent inside the reference's run() during the last acref_fir_run (channel fill / drain excluded)
+  FirBase() : run_seconds(0) {}
   virtual ~FirBase() {}
   virtual int load(const long long *c) = 0;
   virtual long run(const long long *in, long n, long long *out) = 0;
@@ -47,7 +53,9 @@ struct FirConst : FirBase {
   long run(const long long *in, long n, long long *out) {
     if (!f) return -1;
     for (long i = 0; i < n; i++) in_ch.write(ac_shim::from_raw<IN>(in[i]));
+    Clock::time_point t0 = Clock::now();
     f->run(in_ch, out_ch);
+    run_seconds = secs(t0, Clock::now());
     long k = 0;
     while (out_ch.available(1)) out[k++] = ac_shim::to_raw(out_ch.read());
     return k;
@@ -70,7 +78,9 @@ struct FirLoad : FirBase {
   long run(const long long *in, long n, long long *out) {
     for (long i = 0; i < n; i++) in_ch.write(ac_shim::from_raw<IN>(in[i]));
     ld.write(false);
+    Clock::time_point t0 = Clock::now();
     f.run(in_ch, c_ch, out_ch, ld);
+    run_seconds = secs(t0, Clock::now());
     long k = 0;
     while (out_ch.available(1)) out[k++] = ac_shim::to_raw(out_ch.read());
     return k;
@@ -89,11 +99,13 @@ struct FirProg : FirBase {
   }
   long run(const long long *in, long n, long long *out) {
     long k = 0;
+    Clock::time_point t0 = Clock::now();  // one run() per sample, as the reference bench does: the whole loop is the run
     for (long i = 0; i < n; i++) {
       in_ch.write(ac_shim::from_raw<IN>(in[i]));
       f.run(in_ch, out_ch, coeffs);
       while (out_ch.available(1)) out[k++] = ac_shim::to_raw(out_ch.read());
     }
+    run_seconds = secs(t0, Clock::now());
     return k;
   }
 };
@@ -138,6 +150,7 @@ void *acref_fir_create(int cfg, int cls, int ftype) {
 }
 int acref_fir_load(void *h, const long long *c) { return ((FirBase *)h)->load(c); }
 long acref_fir_run(void *h, const long long *in, long n, long long *out) { return ((FirBase *)h)->run(in, n, out); }
+double acref_fir_last_seconds(void *h) { return ((FirBase *)h)->run_seconds; }
 void acref_fir_destroy(void *h) { delete (FirBase *)h; }
 
 }  // extern "C"

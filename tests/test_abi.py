@@ -1,0 +1,106 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/b200dsp.h declares, and its host-side
+logic (descriptor validation, width calculators, sharding) behaves -- no compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "b200dsp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol(engine):
+    lib = engine.load()
+    names = declared_functions()
+    assert len(names) >= 34
+    for n in names:
+        assert hasattr(lib, n), f"libb200dsp.so does not export {n}"
+
+
+def test_container_bytes_and_strerror(engine):
+    lib = engine.load()
+    assert [lib.b2d_container_bytes(w) for w in (1, 16, 17, 32, 33, 64, 65, 0)] == [2, 2, 4, 4, 8, 8, 0, 0]
+    assert lib.b2d_strerror(0) == b"ok" and b"supported" in lib.b2d_strerror(-1)
+    assert b"sm_100a" in lib.b2d_version()
+
+
+def test_int_width_matches_reference_formulas(engine):
+    from ac_dsp_b200 import _lib as L
+    lib = engine.load()
+    cases = [(0, (16, 1), 8, 1, 4, 28), (0, (16, 1), 8, 2, 4, 32), (1, (16, 1), 4, 1, 3, 20),
+             (0, (32, 16), 7, 2, 4, 48), (1, (32, 16), 7, 2, 5, 49), (0, (10, 2, False), 5, 1, 3, 18)]
+    for mode, fin, R, M, N, want in cases:
+        d = L.B2dCicDesc(L.make_fmt(fin), L.make_fmt((want, 1)), R, M, N, mode, 1, 0, 0)
+        w = C.c_int32(0)
+        assert lib.b2d_cic_int_width(C.byref(d), C.byref(w)) == 0
+        assert w.value == want
+
+
+def test_descriptor_validation_without_gpu(engine):
+    """Rejections happen before any CUDA call, so they are observable on a CPU-only box."""
+    from ac_dsp_b200 import _lib as L
+    lib = engine.load()
+    q15, acc = L.make_fmt((16, 1)), L.make_fmt((40, 8))
+    h = C.c_void_p()
+
+    def fir(**kw):
+        base = dict(fin=q15, coeff=q15, acc=acc, out=acc, n_taps=16, ftype=0, kind=1, n_channels=1, layout=0, device=0)
+        base.update(kw)
+        return lib.b2d_fir_create(C.byref(h), C.byref(L.B2dFirDesc(*[base[k] for k, _ in L.B2dFirDesc._fields_])))
+
+    assert fir(ftype=6) == L.EUNSUPPORTED and fir(ftype=7) == L.EUNSUPPORTED   # _ANTI: reference leaves output unwritten
+    assert b"_ANTI" in lib.b2d_last_error()
+    assert fir(n_taps=0) == L.EINVAL
+    assert fir(n_channels=0) == L.EINVAL
+    assert fir(fin=L.make_fmt((40, 8))) == L.EUNSUPPORTED                      # inputs wider than 32 bits
+    assert fir(acc=L.make_fmt((65, 8))) == L.EINVAL
+    assert fir(ftype=9) == L.EINVAL
+
+    def cic(**kw):
+        base = dict(fin=q15, out=L.make_fmt((28, 13)), R=8, M=1, N=4, mode=0, n_channels=1, layout=0, device=0)
+        base.update(kw)
+        return lib.b2d_cic_create(C.byref(h), C.byref(L.B2dCicDesc(*[base[k] for k, _ in L.B2dCicDesc._fields_])))
+
+    assert cic(R=1) == L.EINVAL and cic(R=257) == L.EINVAL                     # 8-bit rate counters; R = 1 never re-reads
+    assert cic(N=0) == L.EINVAL and cic(M=0) == L.EINVAL
+    assert cic(R=256, N=8) == L.EUNSUPPORTED                                   # lossless width 80 > 64
+    assert lib.b2d_device_count() >= 0
+
+
+def test_shard_count(engine):
+    lib = engine.load()
+    n = C.c_uint32(0)
+    for C_, world in ((64, 8), (8, 8), (10, 4), (3, 8), (1, 1)):
+        tot = 0
+        for r in range(world):
+            assert lib.b2d_shard_count(C_, r, world, C.byref(n)) == 0
+            assert n.value == len(range(r, C_, world))
+            tot += n.value
+        assert tot == C_
+    assert lib.b2d_shard_count(8, 8, 8, C.byref(n)) != 0
+
+
+def test_no_cpu_fallback_without_gpu(engine):
+    """On a box without a GPU the engine must fail loudly rather than compute on the host."""
+    if engine.load().b2d_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(engine.B2dError) as e:
+        engine.ac_fir_load_coeffs((16, 1), (40, 8), (16, 1), (40, 8), 16)
+    assert e.value.status == -3
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = "import sys; import ac_dsp_b200; assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _d, files in os.walk(os.path.join(ROOT, "ac_dsp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("the CPU oracle", ""), f

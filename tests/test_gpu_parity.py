@@ -1,0 +1,386 @@
+"""GPU suite (-m gpu): the CUDA engine, called through its C-ABI, against
+  * the outputs of the UNMODIFIED reference classes (tests/golden/ref_outputs.npz, the two CIC golden vectors,
+    the three FIR bench vectors) -- bit-exact, and
+  * the CPU oracle (oracle/oracle_b.c) on seeded random inputs -- bit-exact,
+  * size-independent properties at BASELINE.json's full sizes (random windows re-derived by the oracle).
+Nothing here reads /root/reference.
+"""
+import math
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import ref_configs as rc
+
+pytestmark = pytest.mark.gpu
+
+Q15, ACC40 = (16, 1), (40, 8)
+KINDS = ["const", "load", "prog"]
+
+
+def make_fir(E, kind, fi, fc, fa, fo, taps, ft, coeffs, **kw):
+    if kind == "const":
+        return E.ac_fir_const_coeffs(fi, fo, fc, fa, taps, ft, coeffs, **kw)
+    if kind == "load":
+        f = E.ac_fir_load_coeffs(fi, fo, fc, fa, taps, ft, **kw)
+        f.run(None, coeffs, True)
+        return f
+    f = E.ac_fir_prog_coeffs(fi, fo, fc, fa, taps, ft, **kw)
+    f.load(coeffs)
+    return f
+
+
+@pytest.fixture(params=["auto", "generic"])
+def path(request, monkeypatch):
+    """Every golden case runs through the kernel family the engine would pick AND through the generic kernels."""
+    if request.param == "generic":
+        monkeypatch.setenv("B2D_FORCE_GENERIC", "1")
+    else:
+        monkeypatch.delenv("B2D_FORCE_GENERIC", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("cfg", rc.fir_configs(), ids=lambda c: f"{c[1]}-{c[6]}")
+def test_fir_vs_reference_outputs(engine, ref_outputs, cfg, path):
+    cid, _name, fi, fc, fa, fo, taps = cfg
+    x = ref_outputs[f"fir{cid}_x"]
+    for k, ft in enumerate(engine.FTYPES[:6]):
+        c = ref_outputs[f"fir{cid}_csym" if ft.startswith("FOLD") else f"fir{cid}_c"]
+        f = make_fir(engine, KINDS[(cid + k) % 3], fi, fc, fa, fo, taps, ft, c)
+        if path == "generic":
+            assert f.path == "fir_generic"
+        y = np.concatenate([f.run(x[:5]), f.run(x[5:6]), f.run(x[6:])]).astype(np.int64)
+        assert np.array_equal(y, ref_outputs[f"fir{cid}_{ft}_y"]), (cfg, ft, f.path)
+
+
+def test_q15_path_is_taken_for_the_baseline_formats(engine):
+    h = np.ones(256, dtype=np.int16)
+    for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "TRANSPOSED", "FOLD_EVEN", "FOLD_ODD"):
+        assert make_fir(engine, "load", Q15, Q15, ACC40, ACC40, 256, ft, h).path == "fir_q15"
+    assert make_fir(engine, "load", (20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", h[:63]).path == "fir_generic"
+    assert make_fir(engine, "load", Q15, Q15, (24, 4), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"  # per-tap truncation
+
+
+def test_cic_vs_reference_outputs(engine, ref_outputs, path):
+    for cid, (mode, R, M, N, fi, fo) in enumerate(rc.CIC_CONFIGS):
+        x = ref_outputs[f"cic{cid}_x"]
+        cls = engine.ac_cic_dec_full if mode == "dec" else engine.ac_cic_intr_full
+        f = cls(fi, fo, R, M, N)
+        parts = [f.run(x[:1]), f.run(x[1:10]), f.run(x[10:13]), f.run(x[13:])]
+        assert [p.size for p in parts] == list(ref_outputs[f"cic{cid}_counts"]), (mode, R, M, N)
+        assert np.array_equal(np.concatenate(parts).astype(np.int64), ref_outputs[f"cic{cid}_y"]), (mode, R, M, N, f.path)
+
+
+def test_cic_golden_vectors(engine, path):
+    g = golden("cic_dec_golden.npz")
+    y = engine.ac_cic_dec_full((32, 16), (48, 32), 7, 2, 4).run(g["x"])
+    assert y.size == 1430 and np.array_equal(y[:1429], g["ref"])
+    g = golden("cic_intr_golden.npz")
+    y = engine.ac_cic_intr_full((32, 16), (49, 33), 7, 2, 5).run(g["x"])
+    assert y.size == 6990 and np.array_equal(y, g["ref"])
+
+
+@pytest.mark.parametrize("cls", KINDS)
+def test_fir_reference_benches(engine, cls, path):
+    g = golden(f"fir_bench_{cls}.npz")
+    fi, fc, fa, fo = (tuple(int(v) for v in g[k]) for k in ("fin", "fcoeff", "facc", "fout"))
+    f = make_fir(engine, cls, fi, fc, fa, fo, int(g["taps"]), "FOLD_ODD", g["coeffs"])
+    if cls == "prog":   # the bench calls run() once per sample (rtest_ac_fir_prog_coeffs.cpp:109-113)
+        y = np.concatenate([f.run(g["x"][i:i + 1], g["coeffs"]) for i in range(64)] + [f.run(g["x"][64:], g["coeffs"])])
+    else:
+        y = f.run(g["x"])
+    assert np.array_equal(y.astype(np.int64), g["y"])
+    ref = g["ref_double"][: y.size]
+    sqnr = 10 * math.log10(np.sum(ref * ref) / np.sum((y / float(1 << (fo[0] - fo[1])) - ref) ** 2))
+    assert abs(sqnr - float(g["sqnr"])) < 1e-9 and sqnr >= 60.0
+
+
+# ------------------------------------------------------------------------ oracle-differential, FIR
+def oracle_fir(O, fi, fc, fa, fo, taps, ft, coeffs, x):
+    f = O.FirB(fi, fc, fa, fo, taps, ft)
+    f.load(coeffs)
+    return f.run(x)
+
+
+@pytest.mark.parametrize("taps,n", [(1, 100), (2, 1000), (16, 4096), (16, 1 << 20), (27, 5000), (63, 9999), (255, 8192),
+                                    (256, 4095), (256, 70001), (1024, 20000), (2048, 9000)])
+def test_fir_q15_random(engine, oracle, taps, n):
+    rng = np.random.default_rng(taps * 7919 + n)
+    x = oracle.rand_raw(rng, Q15, n)
+    h = oracle.rand_raw(rng, Q15, taps)
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h)
+    assert f.path == "fir_q15"
+    y = f.run(x.astype(np.int16))
+    assert np.array_equal(y.astype(np.int64), oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, x))
+
+
+@pytest.mark.parametrize("kind", ["min", "max", "alt"])
+def test_fir_q15_extremes_and_wrap(engine, oracle, kind):
+    """all-(-1.0) x all-(-1.0) over 256 taps reaches 2^40 and wraps to 0 in <40,8> (DERIVED KAT)."""
+    rng = np.random.default_rng(3)
+    for taps in (256, 1024):
+        x = oracle.rand_raw(rng, Q15, 3000, kind)
+        h = oracle.rand_raw(rng, Q15, taps, "min" if kind != "max" else "max")
+        y = make_fir(engine, "const", Q15, Q15, ACC40, ACC40, taps, "C_BUFF", h).run(x)
+        want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "C_BUFF", h, x)
+        assert np.array_equal(y.astype(np.int64), want)
+        if kind == "min" and taps == 256:
+            assert y[255] == 0 and y[254] == (255 << 32) - (1 << 40)
+
+
+def test_fir_q15_iq_interleaved_and_planar(engine, oracle):
+    rng = np.random.default_rng(11)
+    n, taps = 40000 + 3, 256
+    x = rng.integers(-32768, 32767, size=(n, 2), endpoint=True).astype(np.int16)
+    h = oracle.rand_raw(rng, Q15, taps)
+    want = [oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, x[:, c]) for c in range(2)]
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, n_channels=2, layout="interleaved")
+    y = f.run(x)
+    assert y.shape == (n, 2) and y.dtype == np.int64
+    for c in range(2):
+        assert np.array_equal(y[:, c], want[c])
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, n_channels=2, layout="planar")
+    y = f.run(np.ascontiguousarray(x.T))
+    for c in range(2):
+        assert np.array_equal(y[c], want[c])
+
+
+def test_fir_per_channel_coefficients_and_layouts(engine, oracle):
+    """cfg 4 shape (scaled down): independent channels, a coefficient set per channel, 1024 taps."""
+    rng = np.random.default_rng(12)
+    C, n, taps = 5, 6001, 1024
+    x = rng.integers(-32768, 32767, size=(C, n), endpoint=True).astype(np.int16)
+    hs = [oracle.rand_raw(rng, Q15, taps) for _ in range(C)]
+    want = [oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", hs[c], x[c]) for c in range(C)]
+    for layout in ("planar", "interleaved"):
+        f = engine.ac_fir_prog_coeffs(Q15, ACC40, Q15, ACC40, taps, "SHIFT_REG", n_channels=C, layout=layout)
+        for c in range(C):
+            f.load(hs[c], channel=c)
+        xin = x if layout == "planar" else np.ascontiguousarray(x.T)
+        y = f.run(xin)
+        y = y if layout == "planar" else y.T
+        for c in range(C):
+            assert np.array_equal(y[c], want[c]), (layout, c)
+
+
+@pytest.mark.parametrize("ft", ["SHIFT_REG", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"])
+def test_fir_chunk_split_invariance(engine, oracle, ft):
+    """One run() vs arbitrary splits (1-sample calls, chunks < N_TAPS): the delay line is carried exactly."""
+    rng = np.random.default_rng(13)
+    taps, n = 63, 3000
+    x = oracle.rand_raw(rng, Q15, n)
+    h = oracle.rand_raw(rng, Q15, taps)
+    want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, ft, h, x)
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, ft, h)
+    cuts = [0, 1, 2, 10, 11, 70, 71, 500, 1999, n]
+    y = np.concatenate([f.run(x[a:b].astype(np.int16)) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(y.astype(np.int64), want)
+    f.reset()
+    assert np.array_equal(f.run(x.astype(np.int16)).astype(np.int64), want)
+
+
+def test_fir_prog_coefficient_change_keeps_delay_line(engine, oracle):
+    rng = np.random.default_rng(14)
+    taps = 16
+    x = oracle.rand_raw(rng, Q15, 400)
+    h1, h2 = oracle.rand_raw(rng, Q15, taps), oracle.rand_raw(rng, Q15, taps)
+    ob = oracle.FirB(Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG")
+    ob.load(h1)
+    w1 = ob.run(x[:150])
+    ob.load(h2)
+    w2 = ob.run(x[150:])
+    f = engine.ac_fir_prog_coeffs(Q15, ACC40, Q15, ACC40, taps, "SHIFT_REG")
+    y = np.concatenate([f.run(x[:150].astype(np.int16), h1), f.run(x[150:].astype(np.int16), h2)])
+    assert np.array_equal(y.astype(np.int64), np.concatenate([w1, w2]))
+
+
+@pytest.mark.parametrize("fmts", [
+    ((16, 1), (16, 1), (24, 4), (16, 1)),                                   # per-tap truncation, narrow output
+    ((16, 1), (16, 1), (24, 4, True, "AC_RND"), (16, 1, True, "AC_RND")),    # rounding
+    ((16, 1), (16, 1), (24, 4, True, "AC_TRN", "AC_SAT"), (16, 1, True, "AC_RND_CONV", "AC_SAT_SYM")),  # order-dependent
+    ((16, 1), (16, 1), (30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), (12, 1, True, "AC_RND_INF", "AC_SAT")),
+    ((12, 0, False), (14, 2), (30, 6), (20, 4)),                             # unsigned input
+    ((32, 16), (32, 16), (64, 32), (64, 32)),                                # bench_load formats
+    ((28, 6), (23, 7), (64, 32), (64, 32)),                                  # bench_prog formats
+    ((16, 1), (16, 1), (40, 8), (18, 2, True, "AC_RND", "AC_SAT")),          # q15 path with a converting epilogue
+    ((16, 0, False), (16, 0, False), (48, 16, False), (48, 16, False)),      # unsigned q15 path
+    ((16, 1), (12, 4, False), (36, 9), (36, 9)),                             # signed x unsigned coefficients
+])
+def test_fir_formats_random(engine, oracle, fmts):
+    """Every ftype, including saturating / convergent-rounding accumulators (reference tap order matters there)."""
+    fi, fc, fa, fo = fmts
+    rng = np.random.default_rng(zlib.crc32(str(fmts).encode()))
+    for taps in (7, 10, 33):
+        x = oracle.rand_raw(rng, fi, 700)
+        h = oracle.rand_raw(rng, fc, taps)
+        h[taps - taps // 2:] = h[: taps // 2][::-1]
+        for ft in engine.FTYPES[:6]:
+            want = oracle_fir(oracle, fi, fc, fa, fo, taps, ft, h, x)
+            f = make_fir(engine, "load", fi, fc, fa, fo, taps, ft, h)
+            y = np.concatenate([f.run(x[:100]), f.run(x[100:])])
+            assert np.array_equal(y.astype(np.int64), want), (fmts, taps, ft, f.path)
+
+
+def test_fir_device_path_and_state(engine, oracle):
+    import torch
+    rng = np.random.default_rng(15)
+    taps, n = 256, 50000
+    x = oracle.rand_raw(rng, Q15, n)
+    h = oracle.rand_raw(rng, Q15, taps)
+    want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, x)
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h)
+    xd = torch.from_numpy(x.astype(np.int16)).cuda()
+    y1 = f.run(xd[:20000])
+    blob = f.get_state()
+    y2 = f.run(xd[20000:])
+    torch.cuda.synchronize()
+    assert np.array_equal(torch.cat([y1, y2]).cpu().numpy(), want)
+    g = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h)
+    g.set_state(blob)                       # checkpoint / resume
+    assert np.array_equal(g.run(xd[20000:]).cpu().numpy(), want[20000:])
+
+
+def test_fir_call_sequence_errors(engine):
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 16)
+    with pytest.raises(engine.B2dError) as e:
+        f.run(np.zeros(10, dtype=np.int16))
+    assert e.value.status == -6             # run() before coefficients
+    f.run(None, np.ones(8), True)           # under-filled coefficient channel: token silently dropped (load:328)
+    with pytest.raises(engine.B2dError):
+        f.run(np.zeros(10, dtype=np.int16))
+    c = engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 16, "SHIFT_REG", np.ones(16))
+    with pytest.raises(engine.B2dError):
+        c._load(np.ones(16))                # constant coefficients are bound once
+    assert c.run(np.zeros(0, dtype=np.int16)).size == 0
+
+
+# ------------------------------------------------------------------------ oracle-differential, CIC
+CIC_CASES = [("dec", 8, 1, 4, Q15, (28, 13)), ("dec", 8, 2, 4, Q15, (32, 17)), ("dec", 7, 2, 4, (32, 16), (48, 32)),
+             ("dec", 2, 1, 1, Q15, (17, 2)), ("dec", 16, 1, 5, Q15, (36, 21)), ("dec", 256, 1, 2, Q15, (32, 17)),
+             ("dec", 8, 1, 4, Q15, (16, 1)), ("dec", 5, 1, 3, (10, 2, False), (24, 12)),
+             ("intr", 4, 1, 3, Q15, (20, 5)), ("intr", 7, 2, 5, (32, 16), (49, 33)), ("intr", 2, 1, 5, Q15, (20, 5)),
+             ("intr", 8, 2, 4, Q15, (29, 14)), ("intr", 16, 1, 1, Q15, (16, 1)), ("intr", 4, 2, 3, Q15, (12, 4, True, "AC_RND"))]
+
+
+@pytest.mark.parametrize("case", CIC_CASES, ids=lambda c: f"{c[0]}-R{c[1]}M{c[2]}N{c[3]}-{c[4][0]}")
+def test_cic_random_and_chunked(engine, oracle, case, path):
+    mode, R, M, N, fi, fo = case
+    rng = np.random.default_rng(R * 100 + M * 10 + N)
+    n = 50000 if mode == "dec" else 9000
+    x = oracle.rand_raw(rng, fi, n)
+    want = oracle.CicB(mode, fi, fo, R, M, N).run(x)
+    cls = engine.ac_cic_dec_full if mode == "dec" else engine.ac_cic_intr_full
+    f = cls(fi, fo, R, M, N)
+    y = f.run(x)
+    assert np.array_equal(y.astype(np.int64), want), f.path
+    f.reset()
+    cuts = [0, 1, 2, 3, 9, 10, 10 + R, 11 + R, 500, 501, 7777, n]
+    parts = [f.run(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts).astype(np.int64), want)
+
+
+def test_cic_multichannel_layouts_and_state(engine, oracle):
+    rng = np.random.default_rng(21)
+    C, n = 3, 30001
+    x = rng.integers(-32768, 32767, size=(C, n), endpoint=True).astype(np.int16)
+    for mode, R, M, N, fo in (("dec", 8, 1, 4, (28, 13)), ("intr", 4, 1, 3, (20, 5))):
+        cls = engine.ac_cic_dec_full if mode == "dec" else engine.ac_cic_intr_full
+        want = [oracle.CicB(mode, Q15, fo, R, M, N).run(x[c]) for c in range(C)]
+        for layout in ("planar", "interleaved"):
+            f = cls(Q15, fo, R, M, N, n_channels=C, layout=layout)
+            xin = x if layout == "planar" else np.ascontiguousarray(x.T)
+            half = (n // 2) | 1
+            a = f.run(xin[:, :half] if layout == "planar" else xin[:half])
+            blob = f.get_state()
+            b = f.run(xin[:, half:] if layout == "planar" else xin[half:])
+            for c in range(C):
+                assert np.array_equal(np.concatenate([a[c], b[c]]).astype(np.int64), want[c]), (mode, layout, c)
+            g = cls(Q15, fo, R, M, N, n_channels=C, layout=layout)
+            g.set_state(blob)
+            b2 = g.run(xin[:, half:] if layout == "planar" else xin[half:])
+            assert np.array_equal(b2, b)
+
+
+def test_cic_device_path(engine, oracle):
+    import torch
+    rng = np.random.default_rng(22)
+    x = rng.integers(-32768, 32767, size=(1 << 20, 2), endpoint=True).astype(np.int16)
+    f = engine.ac_cic_dec_full(Q15, (28, 13), 8, 1, 4, n_channels=2, layout="interleaved")
+    y = f.run(torch.from_numpy(x).cuda()).cpu().numpy()
+    for c in range(2):
+        assert np.array_equal(y[c].astype(np.int64), oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(x[:, c]))
+
+
+# ------------------------------------------------------------------------ full-size properties
+def test_full_size_fir_windows(engine, oracle):
+    """BASELINE config 2 at full size (2^30 IQ samples, 256 taps): an output depends on a 256-sample window only,
+    so random windows of the device result are re-derived by the oracle from the same inputs."""
+    import torch
+    n = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(20260101)
+    x = torch.randint(-32768, 32768, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    rng = np.random.default_rng(20260101)
+    h = oracle.rand_raw(rng, Q15, 256)
+    f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, n_channels=2, layout="interleaved")
+    y = f.run(x)
+    torch.cuda.synchronize()
+    assert y.shape == (n, 2)
+    starts = [0, 1, 4096 - 300, n - 2000] + [int(v) for v in rng.integers(300, n - 3000, size=24)]
+    for s in starts:
+        lo = max(0, s - 255)
+        xs = x[lo:s + 1500].cpu().numpy()
+        ys = y[s:s + 1500].cpu().numpy()
+        for c in range(2):
+            want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, xs[:, c])
+            assert np.array_equal(ys[:, c], want[s - lo:]), (s, c)
+    del y
+    # linearity in the coefficients at full size: filter(h1 + h2) == filter(h1) + filter(h2) (mod 2^40), checksummed
+    h1 = oracle.rand_raw(rng, (15, 1), 256)
+    h2 = oracle.rand_raw(rng, (15, 1), 256)
+    sums = []
+    for hh in (h1, h2, h1 + h2):
+        f.run(None, hh, True)
+        f.reset()
+        sums.append(int(f.run(x).sum().item()))
+    assert (sums[0] + sums[1] - sums[2]) % (1 << 40) == 0
+
+
+def test_full_size_cic_windows(engine, oracle):
+    """BASELINE config 3 at full size (2^30 IQ inputs, R=8, N=4): windows re-derived by the oracle + DC-gain checksum."""
+    import torch
+    n = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(20260102)
+    x = torch.randint(-32768, 32768, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    f = engine.ac_cic_dec_full(Q15, (28, 13), 8, 1, 4, n_channels=2, layout="interleaved")
+    y = f.run(x)
+    torch.cuda.synchronize()
+    assert y.shape == (2, n // 8)
+    rng = np.random.default_rng(5)
+    for m in [0, 1, 5, n // 8 - 700] + [int(v) for v in rng.integers(10, n // 8 - 1000, size=24)]:
+        m0 = max(0, m - 8)                      # N*M low-rate samples of run-in make the restarted oracle exact
+        xs = x[m0 * 8:(m + 600) * 8].cpu().numpy()
+        for c in range(2):
+            want = oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(xs[:, c])
+            assert np.array_equal(y[c, m:m + 600].cpu().numpy().astype(np.int64), want[m - m0:]), (m, c)
+    # sum of all outputs == boxcar^4 gain-weighted input sum (mod 2^28) is awkward at the stream end; use DC instead
+    f.reset()
+    ydc = f.run(torch.full((1 << 24, 2), 3, dtype=torch.int16, device="cuda"))
+    assert int(ydc[0, -1]) == 3 * 8 ** 4 and int(ydc[1, 1000]) == 3 * 8 ** 4
+
+
+def test_comm_single_rank_broadcast(engine, oracle):
+    """The NCCL coefficient broadcast with a world of one (the multi-rank path is exercised by bench.py --gpus N)."""
+    uid = engine.Comm.unique_id()
+    comm = engine.Comm(uid, 0, 1)
+    comm.barrier()
+    rng = np.random.default_rng(31)
+    h = oracle.rand_raw(rng, Q15, 64)
+    x = oracle.rand_raw(rng, Q15, 5000)
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 64, "SHIFT_REG", comm=comm, root=0)
+    f.load(h)
+    assert np.array_equal(f.run(x.astype(np.int16)).astype(np.int64), oracle_fir(oracle, Q15, Q15, ACC40, ACC40, 64, "SHIFT_REG", h, x))
+    f.close()
+    comm.close()
