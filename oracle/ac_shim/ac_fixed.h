@@ -125,6 +125,17 @@ public:
   long double to_long_double() const { return std::ldexp((long double)v, -F); }
   int to_int() const { return (int)(F >= 0 ? (v >> F) : (v << -F)); }
 
+  // bit slices of the raw value (WS <= 64): read as ac_int<WS,S>, write from any ac_int
+  template <int WS>
+  ac_int<WS, S> slc(int lsb) const { return ac_int<WS, S>((long long)(v >> lsb)); }
+  template <int W2, bool S2>
+  ac_fixed &set_slc(int lsb, const ac_int<W2, S2> &s) {
+    const unsigned __int128 m = (W2 >= 128 ? ~(unsigned __int128)0 : ((((unsigned __int128)1) << W2) - 1)) << lsb;
+    const unsigned __int128 u = (((unsigned __int128)v) & ~m) | ((((unsigned __int128)(ac_shim::wide_t)s.v) << lsb) & m);
+    v = ac_shim::wrap_bits((ac_shim::wide_t)u, W, S);
+    return *this;
+  }
+
   // --- arithmetic (result types follow the AC Datatypes width rules) ---
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   ac_fixed<W + W2, I + I2, S || S2> operator*(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {

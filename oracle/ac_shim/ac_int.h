@@ -33,12 +33,14 @@ public:
   ac_int &operator+=(long long x) { set(v + x); return *this; }
   ac_int &operator-=(long long x) { set(v - x); return *this; }
   int to_int() const { return (int)v; }
+  long long to_int64() const { return v; }
+  unsigned long long to_uint64() const { return (unsigned long long)v; }
 
 private:
   void set(long long x) {
     if (W <= 0) { v = 0; return; }
     if (W >= 64) { v = x; return; }
-    unsigned long long m = (1ULL << W) - 1ULL;
+    unsigned long long m = (1ULL << (W >= 64 ? 0 : W)) - 1ULL;
     unsigned long long u = ((unsigned long long)x) & m;
     if (S && ((u >> (W > 0 ? W - 1 : 0)) & 1ULL)) u |= ~m;
     v = (long long)u;

@@ -1,0 +1,178 @@
+// tests/cpp/facade_bench.cpp -- drives the B200 engine through the header facade (include/b200dsp/ac_dsp/*.h) the way
+// the reference's own benches drive the reference classes (tests/rtest_ac_*.cpp of hlslibs/ac_dsp): ac_fixed values
+// queued on ac_channel FIFOs, run(), outputs drained from the output channel.  The configurations are those benches'
+// (formats, taps, ftype, R/M/N) plus the BASELINE.json ones; stimulus and expected outputs come from the committed
+// fixtures in tests/golden/ (raw integers as text, written and compared by tests/test_facade.py).
+//
+//   facade_bench <case> <in.txt> <coef.txt|-> <out.txt> [chunk]
+//
+// `chunk` > 0 feeds the input in several run() calls of that many samples (state must carry across calls).
+#include <ac_fixed.h>
+#include <ac_channel.h>
+#include <ac_dsp/ac_fir_const_coeffs.h>
+#include <ac_dsp/ac_fir_load_coeffs.h>
+#include <ac_dsp/ac_fir_prog_coeffs.h>
+#include <ac_dsp/ac_cic_dec_full.h>
+#include <ac_dsp/ac_cic_intr_full.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+static std::vector<long long> read_ints(const char *path) {
+  std::vector<long long> v;
+  std::ifstream f(path);
+  long long x;
+  while (f >> x) v.push_back(x);
+  return v;
+}
+
+template <class T>
+static T from_raw(long long r) { return b200dsp::fixed_traits<T>::from_raw(r); }
+template <class T>
+static long long to_raw(const T &t) { return b200dsp::fixed_traits<T>::to_raw(t); }
+
+template <class T>
+static void drain_to(ac_channel<T> &ch, std::vector<long long> &out) {
+  while (ch.available(1)) out.push_back(to_raw(ch.read()));
+}
+
+// the wrapper idiom of the reference's constant-coefficient bench: the taps are a member of the DERIVED class
+template <class IN, class OUT, class COEFF, class ACC, unsigned N, FTYPE ft>
+class const_wrapper : public ac_fir_const_coeffs<IN, OUT, COEFF, ACC, N, ft> {
+public:
+  COEFF coeffs[N];
+  explicit const_wrapper(const std::vector<long long> &c) : ac_fir_const_coeffs<IN, OUT, COEFF, ACC, N, ft>(coeffs) {
+    for (unsigned i = 0; i < N; i++) coeffs[i] = from_raw<COEFF>(c[i]);
+  }
+};
+
+template <class IN, class OUT, class COEFF, class ACC, unsigned N, FTYPE ft>
+static int run_const(const std::vector<long long> &x, const std::vector<long long> &c, size_t chunk, std::vector<long long> &y) {
+  if (c.size() != N) return 2;
+  const_wrapper<IN, OUT, COEFF, ACC, N, ft> filter(c);
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  for (size_t i = 0; i < x.size(); i++) {
+    in.write(from_raw<IN>(x[i]));
+    if (chunk && (i + 1) % chunk == 0) filter.run(in, out);
+  }
+  filter.run(in, out);
+  drain_to(out, y);
+  return 0;
+}
+
+template <class IN, class OUT, class COEFF, class ACC, unsigned N, FTYPE ft>
+static int run_load(const std::vector<long long> &x, const std::vector<long long> &c, size_t chunk, std::vector<long long> &y) {
+  if (c.size() != N) return 2;
+  ac_fir_load_coeffs<IN, OUT, COEFF, ACC, N, ft> filter;
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  ac_channel<COEFF> coeffs_ch;
+  ac_channel<bool> ld;
+  // an under-filled load request must be dropped silently (reference ac_fir_load_coeffs.h:328)
+  coeffs_ch.write(from_raw<COEFF>(c[0]));
+  ld.write(true);
+  filter.run(in, coeffs_ch, out, ld);
+  if (coeffs_ch.debug_size() != 1) return 3;
+  for (unsigned i = 1; i < N; i++) coeffs_ch.write(from_raw<COEFF>(c[i]));
+  ld.write(true);
+  filter.run(in, coeffs_ch, out, ld);   // load phase, no samples queued
+  ld.write(false);
+  for (size_t i = 0; i < x.size(); i++) {
+    in.write(from_raw<IN>(x[i]));
+    if (chunk && (i + 1) % chunk == 0) filter.run(in, coeffs_ch, out, ld);
+  }
+  filter.run(in, coeffs_ch, out, ld);
+  drain_to(out, y);
+  return 0;
+}
+
+template <class IN, class OUT, class COEFF, class ACC, int N, FTYPE ft>
+static int run_prog(const std::vector<long long> &x, const std::vector<long long> &c, size_t chunk, std::vector<long long> &y) {
+  if ((int)c.size() != N) return 2;
+  ac_fir_prog_coeffs<IN, OUT, COEFF, ACC, N, ft> filter;
+  COEFF coeffs[N];
+  for (int i = 0; i < N; i++) coeffs[i] = from_raw<COEFF>(c[i]);
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  if (chunk) {  // the reference bench's pattern: one queued sample, one run() (rtest_ac_fir_prog_coeffs.cpp:109-113)
+    for (size_t i = 0; i < x.size(); i++) {
+      in.write(from_raw<IN>(x[i]));
+      filter.run(in, out, coeffs);
+      if (out.debug_size() != i + 1) return 3;
+    }
+  } else {
+    for (size_t i = 0; i < x.size(); i++) in.write(from_raw<IN>(x[i]));
+    filter.run(in, out, coeffs);                 // consumes exactly one sample
+    if (out.debug_size() != (x.empty() ? 0u : 1u)) return 3;
+    filter.run_block(in, out, coeffs);           // extension: the rest in one go
+  }
+  drain_to(out, y);
+  return 0;
+}
+
+template <class FILTER, class IN, class OUT>
+static int run_cic(const std::vector<long long> &x, size_t chunk, std::vector<long long> &y) {
+  FILTER filter;
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  for (size_t i = 0; i < x.size(); i++) {
+    in.write(from_raw<IN>(x[i]));
+    if (chunk && (i + 1) % chunk == 0) filter.run(in, out);
+  }
+  filter.run(in, out);
+  drain_to(out, y);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 5) {
+    std::fprintf(stderr, "usage: %s <case> <in.txt> <coef.txt|-> <out.txt> [chunk]\n", argv[0]);
+    return 64;
+  }
+  const std::string name = argv[1];
+  const std::vector<long long> x = read_ints(argv[2]);
+  const std::vector<long long> c = std::strcmp(argv[3], "-") ? read_ints(argv[3]) : std::vector<long long>();
+  const size_t chunk = argc > 5 ? (size_t)std::atoll(argv[5]) : 0;
+  std::vector<long long> y;
+  int rc = 64;
+  try {
+    // ---- the reference benches' configurations (tests/rtest_ac_fir_*_coeffs.cpp, tests/ac_cic_*_full_param.h)
+    typedef ac_fixed<64, 32, true, AC_TRN, AC_WRAP> acc64;
+    if (name == "bench_const")
+      rc = run_const<ac_fixed<16, 8, true, AC_TRN, AC_WRAP>, acc64, ac_fixed<32, 16, true, AC_TRN, AC_WRAP>, acc64, 29, FOLD_ODD>(x, c, chunk, y);
+    else if (name == "bench_load")
+      rc = run_load<ac_fixed<32, 16, true, AC_TRN, AC_WRAP>, acc64, ac_fixed<32, 16, true, AC_TRN, AC_WRAP>, acc64, 27, FOLD_ODD>(x, c, chunk, y);
+    else if (name == "bench_prog")
+      rc = run_prog<ac_fixed<28, 6, true, AC_TRN, AC_WRAP>, acc64, ac_fixed<23, 7, true, AC_TRN, AC_WRAP>, acc64, 27, FOLD_ODD>(x, c, chunk, y);
+    else if (name == "bench_cic_dec")
+      rc = run_cic<ac_cic_dec_full<ac_fixed<32, 16, true>, ac_fixed<48, 32, true>, 7, 2, 4>, ac_fixed<32, 16, true>, ac_fixed<48, 32, true> >(x, chunk, y);
+    else if (name == "bench_cic_intr")
+      rc = run_cic<ac_cic_intr_full<ac_fixed<32, 16, true>, ac_fixed<49, 33, true>, 7, 2, 5>, ac_fixed<32, 16, true>, ac_fixed<49, 33, true> >(x, chunk, y);
+    // ---- BASELINE.json configurations
+    else if (name == "q15_const16")
+      rc = run_const<ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 16, SHIFT_REG>(x, c, chunk, y);
+    else if (name == "q15_load256")
+      rc = run_load<ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 256, SHIFT_REG>(x, c, chunk, y);
+    else if (name == "q15_prog1024")
+      rc = run_prog<ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 1024, TRANSPOSED>(x, c, chunk, y);
+    else if (name == "q15_cic_dec")
+      rc = run_cic<ac_cic_dec_full<ac_fixed<16, 1, true>, ac_fixed<28, 13, true>, 8, 1, 4>, ac_fixed<16, 1, true>, ac_fixed<28, 13, true> >(x, chunk, y);
+    else if (name == "q15_cic_intr")
+      rc = run_cic<ac_cic_intr_full<ac_fixed<16, 1, true>, ac_fixed<20, 5, true>, 4, 1, 3>, ac_fixed<16, 1, true>, ac_fixed<20, 5, true> >(x, chunk, y);
+    else
+      std::fprintf(stderr, "unknown case %s\n", name.c_str());
+  } catch (const b200dsp::engine_error &e) {
+    std::fprintf(stderr, "engine_error %d: %s\n", e.status(), e.what());
+    return 70;
+  }
+  if (rc) return rc;
+  std::ofstream o(argv[4]);
+  for (size_t i = 0; i < y.size(); i++) o << y[i] << "\n";
+  return 0;
+}

@@ -1,0 +1,114 @@
+"""The C++ header facade (include/b200dsp/ac_dsp/*.h): the reference's class templates re-created on the C-ABI.
+
+tests/cpp/facade_bench.cpp drives the facade the way the reference's rtest_*.cpp benches drive the reference
+classes (ac_fixed values on ac_channel FIFOs); this file builds it, feeds it the committed fixtures and compares
+bit-for-bit.  CPU part: it compiles (and, where the reference tree is present, the reference's UNMODIFIED benches
+compile against the facade too) and fails loudly without a GPU.  GPU part: parity.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+LIBDIR = os.path.join(ROOT, "ac_dsp_b200", "lib")
+REF = os.environ.get("AC_DSP_REF", "/root/reference")
+CXXFLAGS = ["-std=c++11", "-O1", "-Wall", "-Werror", f"-I{ROOT}/include/b200dsp", f"-I{ROOT}/oracle/ac_shim"]
+LDFLAGS = [f"-L{LIBDIR}", "-lb200dsp", f"-Wl,-rpath,{LIBDIR}"]
+
+
+@pytest.fixture(scope="module")
+def bench_exe(engine, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("facade") / "facade_bench")
+    subprocess.check_call(["g++"] + CXXFLAGS + [os.path.join(ROOT, "tests", "cpp", "facade_bench.cpp")] + LDFLAGS + ["-o", exe])
+    return exe
+
+
+def run_case(exe, tmp_path, case, x, coeffs=None, chunk=0):
+    fin, fco, fout = (str(tmp_path / n) for n in ("in.txt", "coef.txt", "out.txt"))
+    np.savetxt(fin, np.asarray(x, dtype=np.int64), fmt="%d")
+    if coeffs is not None:
+        np.savetxt(fco, np.asarray(coeffs, dtype=np.int64), fmt="%d")
+    p = subprocess.run([exe, case, fin, fco if coeffs is not None else "-", fout, str(chunk)], capture_output=True, text=True)
+    return p, (np.loadtxt(fout, dtype=np.int64, ndmin=1) if p.returncode == 0 else None)
+
+
+def test_facade_compiles_and_fails_loudly_without_gpu(engine, bench_exe, tmp_path):
+    if engine.load().b2d_device_count() > 0:
+        pytest.skip("GPU present: covered by the parity tests")
+    p, y = run_case(bench_exe, tmp_path, "q15_cic_dec", np.arange(64))
+    assert p.returncode == 70 and "engine_error" in p.stderr, (p.returncode, p.stderr)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "tests", "rtest_ac_fir_load_coeffs.cpp")),
+                    reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["ac_fir_const_coeffs", "ac_fir_load_coeffs", "ac_fir_prog_coeffs", "ac_cic_dec_full", "ac_cic_intr_full"])
+def test_unmodified_reference_benches_compile_against_the_facade(engine, name, tmp_path):
+    """Drop-in at the source level: the reference's own bench, untouched, with the facade directory in front of the
+    reference's include path (its <ac_dsp/...> includes then resolve to the facade)."""
+    obj = str(tmp_path / (name + ".o"))
+    cmd = ["g++", "-std=c++11", "-O0", f"-I{ROOT}/include/b200dsp", f"-I{ROOT}/oracle/ac_shim", f"-I{REF}/include",
+           f"-I{REF}/tests", "-c", os.path.join(REF, "tests", f"rtest_{name}.cpp"), "-o", obj, "-H"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    used = [l for l in p.stderr.splitlines() if l.startswith(".") and f"ac_dsp/{name}.h" in l]
+    assert used and all("include/b200dsp/ac_dsp" in l for l in used), used
+    # and it links against the engine
+    subprocess.check_call(["g++", obj] + LDFLAGS + ["-o", str(tmp_path / name)])
+
+
+FIR_BENCHES = {"bench_const": "fir_bench_const.npz", "bench_load": "fir_bench_load.npz", "bench_prog": "fir_bench_prog.npz"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(FIR_BENCHES))
+@pytest.mark.parametrize("chunk", [0, 100])
+def test_facade_fir_reference_benches(bench_exe, tmp_path, case, chunk):
+    """Stimulus / taps of the reference's FIR benches; expected = the UNMODIFIED reference class's outputs (fixture)."""
+    g = np.load(os.path.join(GOLDEN, FIR_BENCHES[case]))
+    p, y = run_case(bench_exe, tmp_path, case, g["x"], g["coeffs"], chunk)
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(y, g["y"])
+    # the bench's own pass criterion: SQNR against the MATLAB double reference >= 60 dB, and equal to the reference's
+    F = int(g["fout"][0] - g["fout"][1])
+    ref = g["ref_double"]
+    if case == "bench_const":   # rtest_ac_fir_const_coeffs.cpp:174 casts the reference through OUT_TYPE
+        ref = np.floor(ref * 2.0 ** F) / 2.0 ** F
+    d = y.astype(np.float64) / 2.0 ** F
+    sqnr = 10 * np.log10(np.sum(ref ** 2) / np.sum((d - ref) ** 2))
+    assert sqnr >= 60 and abs(sqnr - float(g["sqnr"])) < 1e-6, (sqnr, float(g["sqnr"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,fx", [("bench_cic_dec", "cic_dec_golden.npz"), ("bench_cic_intr", "cic_intr_golden.npz")])
+@pytest.mark.parametrize("chunk", [0, 333])
+def test_facade_cic_golden_vectors(bench_exe, tmp_path, case, fx, chunk):
+    """The reference's MATLAB bit-exact CIC vectors through the facade classes."""
+    g = np.load(os.path.join(GOLDEN, fx))
+    p, y = run_case(bench_exe, tmp_path, case, g["x"], None, chunk)
+    assert p.returncode == 0, p.stderr
+    n = len(g["ref"])
+    assert len(y) >= n and np.array_equal(y[:n], g["ref"])
+
+
+@pytest.mark.gpu
+def test_facade_baseline_configs(bench_exe, tmp_path, oracle):
+    rng = np.random.default_rng(77)
+    q15, acc40 = (16, 1), (40, 8)
+    for case, taps, ft, n, chunk in [("q15_const16", 16, "SHIFT_REG", 3000, 0), ("q15_load256", 256, "SHIFT_REG", 5000, 777),
+                                     ("q15_prog1024", 1024, "TRANSPOSED", 40, 1), ("q15_prog1024", 1024, "TRANSPOSED", 3000, 0)]:
+        x = oracle.rand_raw(rng, q15, n)
+        h = oracle.rand_raw(rng, q15, taps)
+        p, y = run_case(bench_exe, tmp_path, case, x, h, chunk)
+        assert p.returncode == 0, (case, p.stderr)
+        ob = oracle.FirB(q15, q15, acc40, acc40, taps, ft)
+        ob.load(h)
+        assert np.array_equal(y, ob.run(x)), case
+    x = oracle.rand_raw(rng, q15, 4001)
+    for case, mode, fout, R, M, N in [("q15_cic_dec", "dec", (28, 13), 8, 1, 4), ("q15_cic_intr", "intr", (20, 5), 4, 1, 3)]:
+        for chunk in (0, 13):
+            p, y = run_case(bench_exe, tmp_path, case, x, None, chunk)
+            assert p.returncode == 0, (case, p.stderr)
+            assert np.array_equal(y, oracle.CicB(mode, q15, fout, R, M, N).run(x)), (case, chunk)
