@@ -236,6 +236,7 @@ static bool dec_case_exists(int R, int N, int M) {
 bool cic_fast_supported(const CicLaunch &p) {
   if (p.intr) return false;
   if (p.fin.W > 16 || p.intW > 32) return false;
+  if (!p.fin.S && p.fin.W == 16) return false;   // samples are sign-extended from their int16 container
   if (p.interleaved && p.C != 2 && p.C != 1) return false;
   return dec_case_exists(p.R, p.N, p.M);
 }

@@ -50,6 +50,8 @@ int cic_history_len(int intr, int R, int M, int N);
 cudaError_t launch_cic_generic(const CicLaunch &p, cudaStream_t st);
 bool cic_fast_supported(const CicLaunch &p);
 cudaError_t launch_cic_fast(const CicLaunch &p, cudaStream_t st);
+bool cic_intr_fast_supported(const CicLaunch &p);
+cudaError_t launch_cic_intr_fast(const CicLaunch &p, cudaStream_t st);
 cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st);
 
 }  // namespace b2d

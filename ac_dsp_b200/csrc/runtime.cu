@@ -578,7 +578,7 @@ extern "C" int b2d_cic_create(b2d_cic **out, const b2d_cic_desc *desc) {
   CicLaunch p{};
   p.fin = h->fin; p.fout = h->fo; p.intW = w; p.R = desc->R; p.M = desc->M; p.N = desc->N;
   p.intr = desc->mode == B2D_CIC_INTR; p.C = desc->n_channels; p.interleaved = desc->layout == B2D_INTERLEAVED;
-  h->fast = cic_fast_supported(p) ? 1 : 0;
+  h->fast = cic_fast_supported(p) ? 1 : (cic_intr_fast_supported(p) ? 2 : 0);
   const char *force = getenv("B2D_FORCE_GENERIC");
   if (force && *force == '1') h->fast = 0;
   *out = h;
@@ -595,7 +595,7 @@ extern "C" int b2d_cic_destroy(b2d_cic *h) {
   return B2D_OK;
 }
 
-extern "C" const char *b2d_cic_path(b2d_cic *h) { return !h ? "" : (h->fast ? "cic_fast" : "cic_generic"); }
+extern "C" const char *b2d_cic_path(b2d_cic *h) { return !h ? "" : (h->fast == 1 ? "cic_fast" : (h->fast == 2 ? "cic_intr_fast" : "cic_generic")); }
 
 extern "C" size_t b2d_cic_max_out(b2d_cic *h, size_t n) {
   if (!h) return 0;
@@ -610,7 +610,7 @@ static int cic_launch(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_
   p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
   p.n_seen = h->n_seen; p.out_first = cic_emitted(h, h->n_seen);
   p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1]; p.H = h->H;
-  CU(h->fast ? launch_cic_fast(p, st) : launch_cic_generic(p, st));
+  CU(h->fast == 1 ? launch_cic_fast(p, st) : (h->fast == 2 ? launch_cic_intr_fast(p, st) : launch_cic_generic(p, st)));
   CU(launch_cic_tail(p, st));
   h->cur ^= 1;
   h->n_seen += n;

@@ -150,7 +150,7 @@ def run_reference(args, wl):
         return
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference(wl, seconds_target=2.0)
+        last = cpu_reference(wl, seconds_target=args.ref_seconds)
         if i >= args.warmup:
             vals.append(last)
     tot_s = sum(v["seconds"] for v in vals)
@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=None, help="override samples per channel per step (power of two)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU seconds per step (bounded sample)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.log2n:
@@ -202,11 +203,8 @@ def main():
     E.load()
 
     # ---- coefficient set: rank 0 owns it, one ncclBroadcast at load() (the only collective on this path)
-    comm = None
-    if world > 1:
-        ids = [E.Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm = E.Comm(ids[0], rank, world, local)
+    from ac_dsp_b200 import parallel as P
+    comm = P.make_comm(rank, world, local)
     rng = np.random.default_rng(SEED)
     C, n, il = wl["channels"], wl["n"], wl["layout"] == "interleaved"
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
@@ -297,8 +295,15 @@ def main():
         peak, peak_src = peaks()
         alg_bytes = wl["bytes_per_unit"] * units_per_step
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            t = json.load(open(tp)).get(args.workload)
+            if t:   # measured DRAM bytes per unit (one ncu --set full capture) scaled to this launch's units
+                traffic = t["dram_bytes_per_unit"] * units_per_step
+                traffic_src = f"{t['source']}: {t['dram_bytes']} B measured at {t['capture_units']} units/launch, scaled"
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": path,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": path,
                 "algorithmic_bytes_per_launch": alg_bytes, "actual_io_bytes_per_launch": in_bytes + out_bytes}
         if wl["macs_per_unit"]:
             tmacs = wl["macs_per_unit"] * units_per_step / (ms_per_step * 1e-3) / 1e12

@@ -314,6 +314,25 @@ def test_cic_device_path(engine, oracle):
         assert np.array_equal(y[c].astype(np.int64), oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(x[:, c]))
 
 
+def test_cic_intr_fast_path_device(engine, oracle):
+    """BASELINE config 5 first stage on the polyphase kernel: device path, several calls (the call boundary falls
+    inside an input period, so the second call's tiles start mid-period), tiles > 1, DC gain."""
+    import torch
+    rng = np.random.default_rng(23)
+    n = 300001
+    x = rng.integers(-32768, 32767, size=n, endpoint=True).astype(np.int16)
+    f = engine.ac_cic_intr_full(Q15, (20, 5), 4, 1, 3)
+    assert f.path == "cic_intr_fast"
+    xd = torch.from_numpy(x).cuda()
+    cuts = [0, 1, 100003, 100004, n]
+    parts = [f.run(xd[a:b]).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
+    want = oracle.CicB("intr", Q15, (20, 5), 4, 1, 3).run(x)
+    assert np.array_equal(np.concatenate(parts).astype(np.int64), want)
+    f.reset()
+    ydc = f.run(torch.full((5000,), 7, dtype=torch.int16, device="cuda"))
+    assert int(ydc[-1]) == 7 * 4 ** 2          # DC gain of the interpolator: (R*M)^N / R
+
+
 # ------------------------------------------------------------------------ full-size properties
 def test_full_size_fir_windows(engine, oracle):
     """BASELINE config 2 at full size (2^30 IQ samples, 256 taps): an output depends on a 256-sample window only,
