@@ -14,6 +14,8 @@
 // output is generally not the first phase of an input period (the reference's stream-edge rule leaves a period
 // half-emitted between run() calls), so the periods are computed into a shared-memory staging row in their natural
 // alignment and copied out with a word offset, fully coalesced 128-bit stores either way.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b2d {
@@ -76,7 +78,6 @@ __global__ void __launch_bounds__(kIntrThreads) cic_intr_fast_kernel(CicIntrArgs
   const uint32_t c = blockIdx.y;
   const int16_t *xc = a.interleaved ? a.x + c : a.x + (size_t)c * a.n;
   const size_t xstride = a.interleaved ? a.C : 1;
-  const int sh = 32 - a.intW;
 
   // inputs k0-(T-1) .. k0+TI of a tile, NL per thread, fetched one tile ahead so that their latency hides behind the
   // arithmetic and the stores of the current tile (history for k < n_seen, zero past the end of the call)
@@ -151,17 +152,118 @@ __global__ void __launch_bounds__(kIntrThreads) cic_intr_fast_kernel(CicIntrArgs
           else if (sub == 2) w = make_uint4(lo.z, lo.w, hi.x, hi.y);
           else w = make_uint4(lo.w, hi.x, hi.y, hi.z);
         }
-        int4 o;
-        o.x = (int)(w.x << sh) >> sh; o.y = (int)(w.y << sh) >> sh;
-        o.z = (int)(w.z << sh) >> sh; o.w = (int)(w.w << sh) >> sh;
-        *(int4 *)(yo + 4 * g) = o;
+        *(uint4 *)(yo + 4 * g) = w;   // exact in 32 bits (lossless intW <= 32): already sign-extended
       }
-      for (int j = 4 * groups + threadIdx.x; j < cnt; j += kIntrThreads) yo[j] = (int)(ys[off + j] << sh) >> sh;
+      for (int j = 4 * groups + threadIdx.x; j < cnt; j += kIntrThreads) yo[j] = (int32_t)ys[off + j];
     } else {
       for (int j = threadIdx.x; j < cnt; j += kIntrThreads) cic_intr_store_converted(a, c, (size_t)(j0 + j), ys[off + j]);
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------ R = 4, no staging
+// BASELINE config 5 geometry.  One thread = one 16-byte group of 4 consecutive outputs of THIS call's array, i.e.
+// phases A..A+3 of one or two input periods, A = out_first mod 4 being uniform over the launch (template parameter).
+// A warp walks U x 32 consecutive groups; the T (+1) input samples a thread needs are its own one plus those of its
+// left neighbours, taken with warp shuffles from the current and the previous iteration's registers -- no shared
+// memory, one 2-byte load and one 128-bit store per group.  Outputs are exact in 32 bits (the lossless width of
+// find_inter_type_cic_intr is <= 32), so no sign-extension pass is needed.
+constexpr int kDirThreads = 256;
+constexpr int kDirU = 8;            // groups per thread
+
+template <int N, int M, int A>
+__global__ void __launch_bounds__(kDirThreads) cic_intr4_direct_kernel(CicIntrArgs a) {
+  constexpr int R = 4;
+  typedef IntrTaps<R, N, M> Taps;
+  constexpr Taps taps = make_intr_taps<R, N, M>();
+  constexpr int T = Taps::T;
+  constexpr int D = A ? 1 : 0;                 // the group reaches into the next period
+  constexpr int NX = T + D;                    // samples per group: x[kl], x[kl-1], .., x[kl-NX+1]
+  static_assert(NX <= 32, "window exceeds a warp");
+  const uint32_t c = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int16_t *xc = a.interleaved ? a.x + c : a.x + (size_t)c * a.n;
+  const size_t xstride = a.interleaved ? a.C : 1;
+  const int16_t *tl = a.tail + (size_t)c * a.H;
+  int32_t *yc = (int32_t *)a.y + (size_t)c * a.n_out;
+  const long long ngroups = (long long)(a.n_out / 4);
+  const long long kfirst0 = a.out_first / 4;   // period of output group 0
+
+  auto load_x = [&](long long k) -> uint32_t {   // sample with global index k; history / zero outside this call
+    const long long li = k - a.n_seen;
+    int v = 0;
+    if (li >= 0) { if ((size_t)li < a.n) v = xc[(size_t)li * xstride]; }
+    else if (li >= -(long long)a.H) v = tl[a.H + li];
+    return (uint32_t)v;
+  };
+
+  const long long warps_total = (long long)gridDim.x * (kDirThreads / 32);
+  const long long warp_id = (long long)blockIdx.x * (kDirThreads / 32) + (threadIdx.x >> 5);
+  for (long long g0 = warp_id * (32 * kDirU); g0 < ngroups; g0 += warps_total * (32 * kDirU)) {
+    const long long kl0 = kfirst0 + g0 + D;                       // sample index of lane 0, iteration 0
+    // unchecked loads when the whole chunk (with its left halo) lies inside this call's input
+    const bool interior = kl0 - 32 >= a.n_seen && (size_t)(kl0 + 32 * kDirU - a.n_seen) <= a.n;
+    const int16_t *xp = xc + (size_t)(kl0 - a.n_seen) * xstride;  // only dereferenced when interior
+    uint32_t prev = interior ? (uint32_t)(int)xp[((long long)lane - 32) * (long long)xstride] : load_x(kl0 - 32 + lane);
+    uint32_t cur[kDirU];
+#pragma unroll
+    for (int u = 0; u < kDirU; u++)
+      cur[u] = interior ? (uint32_t)(int)xp[(size_t)(32 * u + lane) * xstride] : load_x(kl0 + 32 * u + lane);
+#pragma unroll
+    for (int u = 0; u < kDirU; u++) {
+      uint32_t xv[NX];
+      xv[0] = cur[u];
+#pragma unroll
+      for (int m = 1; m < NX; m++) {
+        // x[k - m] sits m lanes to the left: in this iteration's registers, or (for the first m lanes) in the last m
+        // lanes of the previous iteration's
+        const uint32_t send = lane >= 32 - m ? prev : cur[u];
+        xv[m] = __shfl_sync(0xffffffffu, send, (lane - m) & 31);
+      }
+      prev = cur[u];
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int ph = (A + i) % 4;
+        const int d = D - (A + i) / 4;           // samples between this output's period and x[kl]
+        uint32_t acc = 0;
+#pragma unroll
+        for (int m = 0; m < T; m++)
+          if (taps.v[ph + R * m] != 0) acc += taps.v[ph + R * m] * xv[d + m];
+        o[i] = acc;
+      }
+      const long long g = g0 + 32 * u + lane;
+      if (g < ngroups) *(uint4 *)(yc + 4 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  // the last n_out % 4 outputs of the call (one thread each)
+  const int rem = (int)(a.n_out & 3);
+  if (blockIdx.x == 0 && (int)threadIdx.x < rem) {
+    const long long j = ngroups * 4 + threadIdx.x, o = a.out_first + j, k = o / 4;
+    const int ph = (int)(o - 4 * k);
+    uint32_t acc = 0;
+    for (int m = 0; m < T; m++) acc += taps.v[ph + R * m] * load_x(k - m);
+    yc[j] = (int32_t)acc;
+  }
+}
+
+template <int N, int M>
+static cudaError_t launch_intr4_direct(const CicIntrArgs &a, cudaStream_t st) {
+  const long long ngroups = (long long)(a.n_out / 4);
+  const long long per_cta = (long long)kDirThreads * kDirU;
+  long long gx = (ngroups + per_cta - 1) / per_cta;
+  if (gx < 1) gx = 1;
+  const long long cap = (148LL * 16 + a.C - 1) / a.C;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, a.C);
+  switch ((int)(a.out_first & 3)) {
+    case 0: cic_intr4_direct_kernel<N, M, 0><<<grid, kDirThreads, 0, st>>>(a); break;
+    case 1: cic_intr4_direct_kernel<N, M, 1><<<grid, kDirThreads, 0, st>>>(a); break;
+    case 2: cic_intr4_direct_kernel<N, M, 2><<<grid, kDirThreads, 0, st>>>(a); break;
+    default: cic_intr4_direct_kernel<N, M, 3><<<grid, kDirThreads, 0, st>>>(a); break;
+  }
+  return cudaGetLastError();
 }
 
 template <int R, int N, int M>
@@ -196,6 +298,13 @@ cudaError_t launch_cic_intr_fast(const CicLaunch &p, cudaStream_t st) {
   a.intW = p.intW; a.in = p.fin; a.out = p.fout; a.out_bytes = container_bytes(p.fout.W);
   a.ident = (p.fout.F() == p.fin.F() && p.fout.W == p.intW && p.fout.S == 1) ? 1 : 0;
   a.ntiles = 0;
+  const bool direct_ok = p.R == 4 && a.ident && a.out_bytes == 4 && (a.n_out % 4 == 0 || a.C == 1) && ((uintptr_t)a.y & 15) == 0 &&
+                         !(getenv("B2D_CIC_INTR_STAGED") && *getenv("B2D_CIC_INTR_STAGED") == '1');
+  if (direct_ok) {
+    if (p.N == 3 && p.M == 1) return launch_intr4_direct<3, 1>(a, st);
+    if (p.N == 4 && p.M == 1) return launch_intr4_direct<4, 1>(a, st);
+    if (p.N == 3 && p.M == 2) return launch_intr4_direct<3, 2>(a, st);
+  }
 #define X(r, n, m) if (p.R == r && p.N == n && p.M == m) return launch_intr<r, n, m>(a, st);
   B2D_CIC_INTR_CASES(X)
 #undef X

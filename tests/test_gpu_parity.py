@@ -314,23 +314,33 @@ def test_cic_device_path(engine, oracle):
         assert np.array_equal(y[c].astype(np.int64), oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(x[:, c]))
 
 
-def test_cic_intr_fast_path_device(engine, oracle):
-    """BASELINE config 5 first stage on the polyphase kernel: device path, several calls (the call boundary falls
-    inside an input period, so the second call's tiles start mid-period), tiles > 1, DC gain."""
+@pytest.mark.parametrize("staged", ["0", "1"])
+@pytest.mark.parametrize("N,M,fo", [(3, 1, (20, 5)), (4, 1, (22, 7)), (3, 2, (23, 8))])
+def test_cic_intr_fast_path_device(engine, oracle, staged, N, M, fo, monkeypatch):
+    """BASELINE config 5 first stage (R = 4) on the polyphase kernels -- the shuffle-window kernel (all four output
+    alignments A = out_first mod 4 occur across the calls below) and the shared-memory staged one: device path, call
+    boundaries inside an input period, chunks smaller than a warp window, DC gain."""
     import torch
-    rng = np.random.default_rng(23)
+    monkeypatch.setenv("B2D_CIC_INTR_STAGED", staged)
+    rng = np.random.default_rng(23 + N + M)
     n = 300001
     x = rng.integers(-32768, 32767, size=n, endpoint=True).astype(np.int16)
-    f = engine.ac_cic_intr_full(Q15, (20, 5), 4, 1, 3)
+    f = engine.ac_cic_intr_full(Q15, fo, 4, M, N)
     assert f.path == "cic_intr_fast"
     xd = torch.from_numpy(x).cuda()
-    cuts = [0, 1, 100003, 100004, n]
+    cuts = [0, 1, 2, 3, 5, 40, 100003, 100004, 100010, 250000, n]
     parts = [f.run(xd[a:b]).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
-    want = oracle.CicB("intr", Q15, (20, 5), 4, 1, 3).run(x)
-    assert np.array_equal(np.concatenate(parts).astype(np.int64), want)
+    want = oracle.CicB("intr", Q15, fo, 4, M, N).run(x)
+    got = np.concatenate(parts).astype(np.int64)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    for kind in ("min", "max", "alt"):          # extremes: the lossless width is exactly filled
+        f.reset()
+        xe = oracle.rand_raw(rng, Q15, 4097, kind).astype(np.int16)
+        assert np.array_equal(f.run(torch.from_numpy(xe).cuda()).cpu().numpy().astype(np.int64),
+                              oracle.CicB("intr", Q15, fo, 4, M, N).run(xe)), kind
     f.reset()
     ydc = f.run(torch.full((5000,), 7, dtype=torch.int16, device="cuda"))
-    assert int(ydc[-1]) == 7 * 4 ** 2          # DC gain of the interpolator: (R*M)^N / R
+    assert int(ydc[-1]) == 7 * (4 * M) ** N // 4          # DC gain of the interpolator: (R*M)^N / R
 
 
 # ------------------------------------------------------------------------ full-size properties
