@@ -18,6 +18,7 @@ struct FirLaunch {
   const int64_t *coeff64;   // [C][n_taps] raw coefficients (generic path)
   const uint32_t *coeff_pk; // [C][pk_words] byte-plane packed, reversed coefficients (q15 path), or null
   int pk_words;
+  const int32_t *coeff32;   // [C][fir_wide_words] taps of the wide path (fir_wide_pack), or null
 };
 
 // generic path: every format / ftype / Q / O, reference tap order, 128-bit intermediates.
@@ -27,6 +28,12 @@ bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fm
 void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
 int fir_q15_pk_words(int n_taps, int ftype);
 cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st);
+// wide path: operands <= 32 bits, wrapping 64-bit accumulator with Q in {TRN, RND}; IMAD.WIDE per tap.
+bool fir_wide_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
+int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, int ftype);
+int fir_wide_words(int n_taps);
+void fir_wide_pack(const int64_t *c, int n_taps, int ftype, int mode, int32_t *out, int words);
+cudaError_t launch_fir_wide(const FirLaunch &p, cudaStream_t st);
 // history carry: tail_next = last (n_taps-1) samples of (tail ++ in).
 cudaError_t launch_fir_tail(const FirLaunch &p, cudaStream_t st);
 

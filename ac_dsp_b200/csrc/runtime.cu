@@ -237,7 +237,7 @@ static int comm_bcast_i64(b2d_comm *c, int64_t *values, size_t n, int root) {
 }
 
 // ------------------------------------------------------------------------------------------------ FIR
-enum { PATH_GENERIC = 0, PATH_Q15 = 1 };
+enum { PATH_GENERIC = 0, PATH_Q15 = 1, PATH_WIDE = 2 };
 
 struct b2d_fir {
   b2d_fir_desc d;
@@ -249,6 +249,8 @@ struct b2d_fir {
   int64_t *d_coeff64 = nullptr;
   uint32_t *d_coeff_pk = nullptr;
   int pk_words = 0;
+  int32_t *d_coeff32 = nullptr;
+  int wide_words = 0, wide_mode = 0;
   void *d_tail[2] = {nullptr, nullptr};
   int cur = 0;
   b2d_comm *comm = nullptr;
@@ -297,9 +299,11 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
   const size_t N = desc->n_taps;
   h->h_coeff.assign(C * N, 0);
   h->ch_loaded.assign(C, 0);
-  h->path = fir_q15_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q15 : PATH_GENERIC;
+  h->path = fir_q15_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q15
+            : (fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_WIDE : PATH_GENERIC);
   const char *force = getenv("B2D_FORCE_GENERIC");
   if (force && *force == '1') h->path = PATH_GENERIC;
+  if (force && *force == '2' && fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype)) h->path = PATH_WIDE;
   cudaError_t e = cudaMalloc(&h->d_coeff64, C * N * sizeof(int64_t));
   const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
@@ -309,6 +313,11 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
   if (e == cudaSuccess && h->path == PATH_Q15) {
     h->pk_words = fir_q15_pk_words((int)N, desc->ftype);
     e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
+  }
+  if (e == cudaSuccess && h->path == PATH_WIDE) {
+    h->wide_words = fir_wide_words((int)N);
+    h->wide_mode = fir_wide_mode(fin, fc, fa, (int)N, desc->ftype);
+    e = cudaMalloc(&h->d_coeff32, (size_t)C * h->wide_words * sizeof(int32_t));
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -326,12 +335,13 @@ extern "C" int b2d_fir_destroy(b2d_fir *h) {
   h->pipe.destroy();
   if (h->d_coeff64) cudaFree(h->d_coeff64);
   if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
+  if (h->d_coeff32) cudaFree(h->d_coeff32);
   for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
   delete h;
   return B2D_OK;
 }
 
-extern "C" const char *b2d_fir_path(b2d_fir *h) { return !h ? "" : (h->path == PATH_Q15 ? "fir_q15" : "fir_generic"); }
+extern "C" const char *b2d_fir_path(b2d_fir *h) { return !h ? "" : (h->path == PATH_Q15 ? "fir_q15" : (h->path == PATH_WIDE ? "fir_wide" : "fir_generic")); }
 
 extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
   if (!h) return fail(B2D_EINVAL, "null handle");
@@ -378,6 +388,11 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
       fir_q15_pack(h->fc, v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
       CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    if (h->path == PATH_WIDE) {
+      std::vector<int32_t> w(h->wide_words, 0);
+      fir_wide_pack(v.data(), (int)N, h->d.ftype, h->wide_mode, w.data(), h->wide_words);
+      CU(cudaMemcpy(h->d_coeff32 + (size_t)c * h->wide_words, w.data(), h->wide_words * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
   }
   return B2D_OK;
 }
@@ -389,8 +404,8 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   p.n_taps = (int)h->d.n_taps; p.ftype = h->d.ftype; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
   p.in = d_in; p.out = d_out; p.n = n;
   p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1];
-  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words;
-  CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : launch_fir_generic(p, st));
+  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
+  CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : (h->path == PATH_WIDE ? launch_fir_wide(p, st) : launch_fir_generic(p, st)));
   CU(launch_fir_tail(p, st));
   h->cur ^= 1;
   return B2D_OK;

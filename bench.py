@@ -26,6 +26,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: libraries that print banners on fd 1 (NCCL's version line) are sent to stderr
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 Q15, ACC40 = (16, 1), (40, 8)
 SEED = 20260101
 
@@ -43,6 +51,10 @@ WORKLOADS = {
     "cic_dec": dict(kind="cic", mode="dec", R=8, M=1, N=4, out=(28, 13), channels=2, layout="interleaved", n=1 << 30,
                     unit_is_iq=True, bytes_per_unit=5.0, macs_per_unit=0,
                     name="ac_cic_dec_full R=8 M=1 N=4 ac_fixed<16,1,true> -> <28,13,true>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
+    # BASELINE.json configs[4] second stage, unfused: the wide (IMAD.WIDE) path on the interpolator's <20,5> output
+    "fir63": dict(kind="fir", taps=63, channels=1, layout="planar", n=1 << 28, unit_is_iq=False, infmt=(20, 5),
+                  bytes_per_unit=12.0, macs_per_unit=63,
+                  name="ac_fir_const_coeffs 63-tap <20,5> x <16,1> -> <40,8>, 1 real channel x 2^28 samples per GPU (int32 in, int64 out)"),
     # BASELINE.json configs[4] first stage
     "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
                      unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
@@ -107,8 +119,9 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
         h = O.rand_raw(rng, Q15, taps)
 
         def make():
-            f = (O.FirA("load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG") if kind == "reference"
-                 else O.FirB(Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG"))
+            fi = wl.get("infmt", Q15)
+            f = (O.FirA("load", fi, Q15, ACC40, ACC40, taps, "SHIFT_REG") if kind == "reference"
+                 else O.FirB(fi, Q15, ACC40, ACC40, taps, "SHIFT_REG"))
             f.load(h)
             return f
         per_thread = int(seconds_target * 0.5e6 * 256 / taps)       # ~0.5 M real samples/s/core at 256 taps
@@ -120,7 +133,7 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
     per_thread = max(1 << 12, per_thread)
     threads = min(threads, 64)
     objs = [make() for _ in range(threads)]
-    xs = [O.rand_raw(rng, Q15, per_thread) for _ in range(threads)]
+    xs = [O.rand_raw(rng, wl.get("infmt", Q15), per_thread) for _ in range(threads)]
     for o in objs:
         o.run(xs[0][:2048])                                          # warm caches / page in
 
@@ -162,7 +175,7 @@ def run_reference(args, wl):
             "config": {"workload": wl["name"], "note": "CPU reference arm: bounded sample per step, host cores only"},
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -209,10 +222,12 @@ def main():
     C, n, il = wl["channels"], wl["n"], wl["layout"] == "interleaved"
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
     shape = (n, C) if il else ((C, n) if C > 1 else (n,))
-    x = torch.randint(-32768, 32768, shape, dtype=torch.int16, device="cuda", generator=gen)
+    infmt = wl.get("infmt", Q15)
+    lim = 1 << (infmt[0] - 1)
+    x = torch.randint(-lim, lim, shape, dtype=torch.int16 if infmt[0] <= 16 else torch.int32, device="cuda", generator=gen)
     if wl["kind"] == "fir":
         h = rng.integers(-32768, 32767, size=wl["taps"], endpoint=True).astype(np.int16)
-        f = E.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG", n_channels=C, layout=wl["layout"],
+        f = E.ac_fir_load_coeffs(infmt, ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG", n_channels=C, layout=wl["layout"],
                                  device=local, comm=comm, root=0)
         f.load(h if rank == 0 else None)
         launches_per_step = 2          # fir_q15_kernel + history carry
@@ -259,7 +274,7 @@ def main():
     if not args.no_e2e:
         n2 = min(n, 1 << 27 if wl["kind"] == "fir" else 1 << 28)
         shape2 = (n2, C) if il else ((C, n2) if C > 1 else (n2,))
-        xh = torch.empty(shape2, dtype=torch.int16).pin_memory()
+        xh = torch.empty(shape2, dtype=x.dtype).pin_memory()
         xh.copy_(x[:n2] if (il or C == 1) else x[:, :n2])
         xn = xh.numpy()
         lib = E.load()
@@ -286,7 +301,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         u2 = n2 if wl["unit_is_iq"] else n2 * C
-        e2e = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xh.numel() * 2),
+        e2e = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
                "d2h_bytes_per_step": int(no.value * C * yh.element_size()), "steps": k2,
                "api": "b2d_fir_run / b2d_cic_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
                "samples_per_step": u2}
@@ -305,7 +320,7 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": path,
                 "algorithmic_bytes_per_launch": alg_bytes, "actual_io_bytes_per_launch": in_bytes + out_bytes}
-        if wl["macs_per_unit"]:
+        if wl["macs_per_unit"] and path == "fir_q15":
             tmacs = wl["macs_per_unit"] * units_per_step / (ms_per_step * 1e-3) / 1e12
             # IDP.2A issue ceiling measured by tools/ubench_pipes.cu: 64 lanes/clk/SM, 2 16b x 8b products per lane-op,
             # 2 byte planes per 16 x 16 MAC -> 64 MAC/clk/SM
@@ -325,7 +340,7 @@ def main():
         if world == 1 and not args.no_cpu:
             cb = cpu_reference(wl)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     f.close()
     if comm:
         comm.close()

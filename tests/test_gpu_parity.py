@@ -33,11 +33,14 @@ def make_fir(E, kind, fi, fc, fa, fo, taps, ft, coeffs, **kw):
     return f
 
 
-@pytest.fixture(params=["auto", "generic"])
+@pytest.fixture(params=["auto", "generic", "wide"])
 def path(request, monkeypatch):
-    """Every golden case runs through the kernel family the engine would pick AND through the generic kernels."""
+    """Every golden case runs through the kernel family the engine would pick, through the generic kernels, and with
+    the 16-bit DP2A path disabled (so the IMAD.WIDE path also sees the 16-bit formats)."""
     if request.param == "generic":
         monkeypatch.setenv("B2D_FORCE_GENERIC", "1")
+    elif request.param == "wide":
+        monkeypatch.setenv("B2D_FORCE_GENERIC", "2")
     else:
         monkeypatch.delenv("B2D_FORCE_GENERIC", raising=False)
     return request.param
