@@ -72,6 +72,11 @@ def load():
         "b2d_cic_reset": (C.c_int, [vp]), "b2d_cic_state_bytes": (C.c_int, [vp, psz]),
         "b2d_cic_get_state": (C.c_int, [vp, vp, sz]), "b2d_cic_set_state": (C.c_int, [vp, vp, sz]),
         "b2d_cic_path": (C.c_char_p, [vp]),
+        "b2d_cicfir_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dCicDesc), C.POINTER(B2dFirDesc)]),
+        "b2d_cicfir_destroy": (C.c_int, [vp]), "b2d_cicfir_load": (C.c_int, [vp, vp, sz, i32]),
+        "b2d_cicfir_max_out": (sz, [vp, sz]), "b2d_cicfir_run": (C.c_int, [vp, vp, sz, vp, psz]),
+        "b2d_cicfir_run_dev": (C.c_int, [vp, vp, sz, vp, psz, vp]), "b2d_cicfir_reset": (C.c_int, [vp]),
+        "b2d_cicfir_path": (C.c_char_p, [vp]),
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),

@@ -61,4 +61,24 @@ bool cic_intr_fast_supported(const CicLaunch &p);
 cudaError_t launch_cic_intr_fast(const CicLaunch &p, cudaStream_t st);
 cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st);
 
+// Interpolating polyphase FIR on 16-bit samples (fused CIC interpolator + FIR cascade): upfir_q15.cu
+struct UpLaunch {
+  Fmt facc, fout;
+  int R, taps_total, planes, lsh;
+  uint32_t C;
+  int interleaved;
+  const void *in;        // n inputs per channel (int16 container)
+  void *out;             // n_out outputs per channel, planar stride n_out
+  size_t n, n_out;
+  unsigned long long n_seen, out_first;
+  const void *tail;      // [C][H] previous inputs
+  int H;
+  const uint32_t *cw;    // [C][upfir_q15_words] packed composite taps
+};
+bool upfir_q15_geometry(int R, int taps_total, int max_abs_bits);
+int upfir_q15_planes(int max_abs_bits);
+int upfir_q15_words(int R, int taps_total, int planes);
+void upfir_q15_pack(const int64_t *c, int taps_total, int R, int planes, uint32_t *out);
+cudaError_t launch_upfir_q15(const UpLaunch &p, cudaStream_t st);
+
 }  // namespace b2d

@@ -729,3 +729,263 @@ extern "C" int b2d_cic_set_state(b2d_cic *h, const void *blob, size_t bytes) {
   h->n_seen = hd.n_seen;
   return B2D_OK;
 }
+
+// -------------------------------------------------------------------------------------------- cascade
+// ac_cic_intr_full -> ac_fir_* as one handle: fused polyphase kernel when exact, else the two kernels back to back.
+struct b2d_cicfir {
+  b2d_cic_desc cd;
+  b2d_fir_desc fd;
+  int device = 0, fused = 0;
+  // fused
+  Fmt fa, fo;
+  int R = 0, taps_total = 0, planes = 3, words = 0, H = 0, lsh = 0, in_bytes = 2, out_bytes = 8;
+  std::vector<int64_t> hcic;
+  std::vector<char> ch_loaded;
+  uint32_t *d_cw = nullptr;
+  void *d_tail[2] = {nullptr, nullptr};
+  int cur = 0;
+  unsigned long long n_seen = 0;
+  // two-stage
+  b2d_cic *cic = nullptr;
+  b2d_fir *fir = nullptr;
+  void *d_mid = nullptr;
+  size_t mid_cap = 0;
+  Pipe pipe;
+};
+
+static unsigned long long intr_emitted(unsigned long long K, long long R, long long N) {
+  if (K == 0) return 0;
+  const long long e = ((long long)K - 1) * R + 1 - (N - 1);
+  return e > 0 ? (unsigned long long)e : 0;
+}
+
+// Can the pair be evaluated as one exact integer FIR on the 16-bit input?  (see upfir_q15.cu)
+static bool cicfir_fusable(const b2d_cic_desc &cd, const b2d_fir_desc &fd, int intW, int *lsh, int *taps_total, int *planes) {
+  const Fmt in = to_fmt(cd.in), mid = to_fmt(cd.out), fc = to_fmt(fd.coeff), fa = to_fmt(fd.acc);
+  if (in.W > 16 || (!in.S && in.W == 16)) return false;
+  if (!(mid.S && mid.F() == in.F() && mid.W >= intW)) return false;          // the lossless INT_TYPE passes unchanged
+  if (fa.O != B2D_WRAP || (fa.Q != B2D_TRN && fa.Q != B2D_RND)) return false;
+  const int s = mid.F() + fc.F() - fa.F();
+  if (s > 0 || -s > 40 || -s >= fa.W) return false;
+  switch (fd.ftype) {
+    case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: break;
+    case B2D_FOLD_ODD:
+      if (!(fa.F() >= mid.F() && mid.W + 1 + (fa.F() - mid.F()) <= fa.W)) return false;
+      break;
+    default: return false;
+  }
+  // composite tap magnitude: |c| <= 2^(Wc-1) * (R*M)^N
+  unsigned __int128 g = 1;
+  for (uint32_t i = 0; i < cd.N; i++) { g *= (unsigned __int128)cd.R * cd.M; if (g > ((unsigned __int128)1 << 40)) return false; }
+  const int bits = fc.W + (fc.S ? 0 : 1) + log2_ceil_u128(g);
+  const int total = (int)fd.n_taps + (int)cd.N * ((int)cd.R * (int)cd.M - 1);
+  if (!upfir_q15_geometry((int)cd.R, total, bits)) return false;
+  *lsh = -s; *taps_total = total; *planes = upfir_q15_planes(bits);
+  return true;
+}
+
+extern "C" int b2d_cicfir_destroy(b2d_cicfir *h) {
+  if (!h) return B2D_OK;
+  use_device(h->device);
+  cudaDeviceSynchronize();
+  h->pipe.destroy();
+  if (h->cic) b2d_cic_destroy(h->cic);
+  if (h->fir) b2d_fir_destroy(h->fir);
+  if (h->d_mid) cudaFree(h->d_mid);
+  if (h->d_cw) cudaFree(h->d_cw);
+  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
+  delete h;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cicfir_create(b2d_cicfir **out, const b2d_cic_desc *cd, const b2d_fir_desc *fd) {
+  if (!out || !cd || !fd) return fail(B2D_EINVAL, "null argument");
+  *out = nullptr;
+  int intW = 0;
+  int st = cic_check(cd, &intW);
+  if (st) return st;
+  if (cd->mode != B2D_CIC_INTR) return fail(B2D_EINVAL, "the cascade takes an interpolator (B2D_CIC_INTR) first stage");
+  if (fd->in.W != cd->out.W || fd->in.I != cd->out.I || (fd->in.S != 0) != (cd->out.S != 0))
+    return fail(B2D_EINVAL, "fir->in must be the interpolator's OUT_TYPE");
+  if (fd->n_channels != cd->n_channels) return fail(B2D_EINVAL, "both stages must have the same n_channels");
+  int dev = cd->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if ((st = use_device(dev))) return st;
+  b2d_cicfir *h = new (std::nothrow) b2d_cicfir();
+  if (!h) return fail(B2D_ENOMEM, "handle");
+  h->cd = *cd; h->fd = *fd; h->device = dev;
+  h->cd.device = dev; h->fd.device = dev; h->fd.layout = B2D_PLANAR;
+  h->fa = to_fmt(fd->acc); h->fo = to_fmt(fd->out);
+  h->out_bytes = container_bytes(fd->out.W);
+  h->R = (int)cd->R;
+  const uint32_t C = cd->n_channels;
+  h->ch_loaded.assign(C, 0);
+  const char *force = getenv("B2D_CICFIR_TWO_STAGE");
+  h->fused = cicfir_fusable(*cd, *fd, intW, &h->lsh, &h->taps_total, &h->planes) && !(force && *force == '1');
+  // the FIR descriptor is validated by creating the second-stage object in either mode (it also serves reset/load checks)
+  if ((st = b2d_fir_create(&h->fir, &h->fd))) { b2d_cicfir_destroy(h); return st; }
+  if (h->fused) {
+    // boxcar(R*M)^N, ac_cic_intr_full.h:150-215 as one FIR (cic_intr_fast.cu)
+    h->hcic.assign(1, 1);
+    for (uint32_t s = 0; s < cd->N; s++) {
+      std::vector<int64_t> nx(h->hcic.size() + cd->R * cd->M - 1, 0);
+      for (size_t i = 0; i < h->hcic.size(); i++)
+        for (uint32_t j = 0; j < cd->R * cd->M; j++) nx[i + j] += h->hcic[i];
+      h->hcic.swap(nx);
+    }
+    h->words = upfir_q15_words(h->R, h->taps_total, h->planes);
+    h->H = (h->taps_total + h->R - 1) / h->R + 2;
+    cudaError_t e = cudaMalloc(&h->d_cw, (size_t)C * h->words * sizeof(uint32_t));
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+      e = cudaMalloc(&h->d_tail[i], (size_t)h->H * C * 2);
+      if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, (size_t)h->H * C * 2);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); b2d_cicfir_destroy(h); return fail(B2D_ECUDA, "b2d_cicfir_create: %s", cudaGetErrorString(e)); }
+  } else {
+    if ((st = b2d_cic_create(&h->cic, &h->cd))) { b2d_cicfir_destroy(h); return st; }
+  }
+  *out = h;
+  return B2D_OK;
+}
+
+extern "C" const char *b2d_cicfir_path(b2d_cicfir *h) { return !h ? "" : (h->fused ? "cicfir_fused" : "cicfir_two_stage"); }
+extern "C" size_t b2d_cicfir_max_out(b2d_cicfir *h, size_t n) { return h ? n * h->cd.R : 0; }
+
+extern "C" int b2d_cicfir_load(b2d_cicfir *h, const void *coeff_raw, size_t n, int32_t channel) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = b2d_fir_load(h->fir, coeff_raw, n, channel);     // validation, wrapping to COEFF_TYPE, const-kind rule
+  if (st || !h->fused) return st;
+  const size_t N = h->fd.n_taps;
+  const uint32_t C = h->cd.n_channels;
+  for (uint32_t c = 0; c < C; c++) {
+    if (channel >= 0 && (uint32_t)channel != c) continue;
+    const int64_t *g = h->fir->h_coeff.data() + c * N;
+    std::vector<int64_t> eff(g, g + N);
+    if (h->fd.ftype == B2D_FOLD_EVEN) {
+      std::fill(eff.begin(), eff.end(), 0);
+      for (size_t i = 0; i < N / 2; i++) { eff[i] = g[i]; eff[N - 1 - i] = g[i]; }
+    } else if (h->fd.ftype == B2D_FOLD_ODD) {
+      std::fill(eff.begin(), eff.end(), 0);
+      for (size_t i = 0; i < (N - 1) / 2 + 1; i++) { eff[i] = g[i]; if (i != (N - 1) / 2) eff[N - 1 - i] = g[i]; }
+    }
+    std::vector<int64_t> comp((size_t)h->taps_total, 0);
+    for (size_t i = 0; i < h->hcic.size(); i++)
+      for (size_t j = 0; j < N; j++) comp[i + j] += h->hcic[i] * eff[j];
+    std::vector<uint32_t> pk((size_t)h->words, 0);
+    upfir_q15_pack(comp.data(), h->taps_total, h->R, h->planes, pk.data());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->d_cw + (size_t)c * h->words, pk.data(), (size_t)h->words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->ch_loaded[c] = 1;
+  }
+  return B2D_OK;
+}
+
+static size_t cicfir_count(const b2d_cicfir *h, size_t n) {
+  const unsigned long long seen = h->fused ? h->n_seen : h->cic->n_seen;
+  return (size_t)(intr_emitted(seen + n, h->cd.R, h->cd.N) - intr_emitted(seen, h->cd.R, h->cd.N));
+}
+
+static int cicfir_launch(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  if (h->fused) {
+    UpLaunch p;
+    p.facc = h->fa; p.fout = h->fo; p.R = h->R; p.taps_total = h->taps_total; p.planes = h->planes; p.lsh = h->lsh;
+    p.C = h->cd.n_channels; p.interleaved = h->cd.layout == B2D_INTERLEAVED;
+    p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
+    p.n_seen = h->n_seen; p.out_first = intr_emitted(h->n_seen, h->cd.R, h->cd.N);
+    p.tail = h->d_tail[h->cur]; p.H = h->H; p.cw = h->d_cw;
+    CU(launch_upfir_q15(p, st));
+    CicLaunch t{};
+    t.fin = to_fmt(h->cd.in); t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;
+    t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1]; t.H = h->H;
+    CU(launch_cic_tail(t, st));
+    h->cur ^= 1;
+    h->n_seen += n;
+    return B2D_OK;
+  }
+  const uint32_t C = h->cd.n_channels;
+  const size_t mid_bytes = (size_t)container_bytes(h->cd.out.W) * C * std::max<size_t>(n_out, 1);
+  if (mid_bytes > h->mid_cap) {
+    if (h->d_mid) cudaFree(h->d_mid);
+    h->d_mid = nullptr; h->mid_cap = 0;
+    if (cudaMalloc(&h->d_mid, mid_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", mid_bytes); }
+    h->mid_cap = mid_bytes;
+  }
+  size_t n_mid = 0, n_fir = 0;
+  int s = b2d_cic_run_dev(h->cic, d_in, n, h->d_mid, &n_mid, st);
+  if (s) return s;
+  if (n_mid != n_out) return fail(B2D_ESTATE, "cascade count mismatch");
+  return b2d_fir_run_dev(h->fir, h->d_mid, n_mid, d_out, &n_fir, st);
+}
+
+static int cicfir_ready(b2d_cicfir *h) {
+  if (h->fused) { for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded"); }
+  else if (!all_loaded(h->fir)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
+  return B2D_OK;
+}
+
+extern "C" int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
+  int st = cicfir_ready(h);
+  if (st) return st;
+  const size_t no = cicfir_count(h, n);
+  if (no && !d_out) return fail(B2D_EINVAL, "null output");
+  if ((st = use_device(h->device))) return st;
+  if ((st = cicfir_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
+  if (n_out) *n_out = no;
+  return B2D_OK;
+}
+
+extern "C" int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n_out) {
+  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
+  int st = cicfir_ready(h);
+  if (st) return st;
+  const size_t no_total = cicfir_count(h, n);
+  if (no_total && !out) return fail(B2D_EINVAL, "null output");
+  if (n_out) *n_out = no_total;
+  if (n == 0) return B2D_OK;
+  if ((st = use_device(h->device))) return st;
+  Pipe &P = h->pipe;
+  if ((st = P.init())) return st;
+  const uint32_t C = h->cd.n_channels;
+  const int il = h->cd.layout == B2D_INTERLEAVED;
+  const int in_bytes = container_bytes(h->cd.in.W);
+  const double per = C * (in_bytes + (double)h->out_bytes * h->cd.R);
+  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
+  L = std::min(L, n);
+  if ((st = P.ensure(L * C * in_bytes, L * h->cd.R * C * h->out_bytes))) return st;
+  size_t i = 0, off_out = 0;
+  for (size_t off = 0; off < n; off += L, i++) {
+    const int s = (int)(i % Pipe::S);
+    const size_t len = std::min(L, n - off);
+    const size_t no = cicfir_count(h, len);
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
+    CU(copy_chunk(P.d_in[s], in, true, in_bytes, C, il, n, off, len, P.s_in));
+    CU(cudaEventRecord(P.e_in[s], P.s_in));
+    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
+    if ((st = cicfir_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
+    CU(cudaEventRecord(P.e_k[s], P.s_k));
+    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
+    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
+    CU(cudaEventRecord(P.e_out[s], P.s_out));
+    off_out += no;
+  }
+  CU(cudaStreamSynchronize(P.s_out));
+  CU(cudaStreamSynchronize(P.s_k));
+  return B2D_OK;
+}
+
+extern "C" int b2d_cicfir_reset(b2d_cicfir *h) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  if (h->fused) {
+    for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, (size_t)h->H * h->cd.n_channels * 2));
+    h->n_seen = 0;
+    return B2D_OK;
+  }
+  if ((st = b2d_cic_reset(h->cic))) return st;
+  return b2d_fir_reset(h->fir);
+}

@@ -267,6 +267,57 @@ class ac_cic_intr_full(_Cic):
     _mode = 1
 
 
+class cic_intr_fir_cascade(_Block):
+    """ac_cic_intr_full<IN, MID, R, M, N> feeding ac_fir_*<MID, OUT, COEFF, ACC, N_TAPS, ftype> as ONE object
+    (BASELINE config 5): run(data_in) == fir.run(cic.run(data_in)) of the two reference objects, bit for bit, with the
+    same stream-edge behaviour.  When no stage drops bits the engine fuses both into a single polyphase kernel on the
+    16-bit input (path 'cicfir_fused'); otherwise the two kernels run back to back on the device."""
+
+    def __init__(self, IN_TYPE, MID_TYPE, R, M, N, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype="SHIFT_REG", coeffs=None,
+                 n_channels=1, layout="planar", device=-1):
+        lib = L.load()
+        self._h = None
+        self.N_TAPS = int(N_TAPS)
+        lay = L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR
+        ft = L.FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        cd = L.B2dCicDesc(L.make_fmt(IN_TYPE), L.make_fmt(MID_TYPE), int(R), int(M), int(N), 1, int(n_channels), lay, int(device))
+        fd = L.B2dFirDesc(L.make_fmt(MID_TYPE), L.make_fmt(COEFF_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE),
+                          self.N_TAPS, ft, 1, int(n_channels), L.PLANAR, int(device))
+        h = C.c_void_p()
+        L.check(lib.b2d_cicfir_create(C.byref(h), C.byref(cd), C.byref(fd)))
+        self._h = h
+        self._coeff_dt = _container_dtype(fd.coeff)
+        self._setup_io(cd.fin, fd.out, n_channels, layout)
+        if coeffs is not None:
+            self.load(coeffs)
+
+    @property
+    def path(self):
+        return L.load().b2d_cicfir_path(self._h).decode()
+
+    def load(self, coeffs, channel=-1):
+        c = np.ascontiguousarray(np.asarray(coeffs).astype(self._coeff_dt, copy=False))
+        L.check(L.load().b2d_cicfir_load(self._h, c.ctypes.data, c.size, int(channel)))
+
+    def run(self, data_in, out=None):
+        lib = L.load()
+        return self._run(data_in, lib.b2d_cicfir_run, lib.b2d_cicfir_run_dev, lambda n: lib.b2d_cicfir_max_out(self._h, n), True, out)
+
+    def reset(self):
+        L.check(L.load().b2d_cicfir_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_cicfir_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Comm:
     """NCCL communicator of the C-ABI (one rank per GPU); only used for the coefficient broadcast at load()."""
 

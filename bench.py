@@ -55,6 +55,10 @@ WORKLOADS = {
     "fir63": dict(kind="fir", taps=63, channels=1, layout="planar", n=1 << 28, unit_is_iq=False, infmt=(20, 5),
                   bytes_per_unit=12.0, macs_per_unit=63,
                   name="ac_fir_const_coeffs 63-tap <20,5> x <16,1> -> <40,8>, 1 real channel x 2^28 samples per GPU (int32 in, int64 out)"),
+    # BASELINE.json configs[4], per-GPU share (1 real channel): interpolator + 63-tap FIR as one fused polyphase kernel
+    "cicfir": dict(kind="cicfir", R=4, M=1, N=3, mid=(20, 5), taps=63, channels=1, layout="planar", n=1 << 26,
+                   unit_is_iq=False, bytes_per_unit=34.0, macs_per_unit=4 * 18 * 1.5,
+                   name="ac_cic_intr_full R=4 M=1 N=3 <16,1> -> <20,5> + 63-tap FIR <20,5> x <16,1> -> <40,8>, fused, 1 real channel x 2^26 inputs per GPU"),
     # BASELINE.json configs[4] first stage
     "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
                      unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
@@ -125,6 +129,29 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
             f.load(h)
             return f
         per_thread = int(seconds_target * 0.5e6 * 256 / taps)       # ~0.5 M real samples/s/core at 256 taps
+    elif wl["kind"] == "cicfir":
+        taps = wl["taps"]
+        h = O.rand_raw(rng, Q15, taps)
+
+        class Chain:   # cic.run(in, mid); fir.run(mid, out) -- the two reference objects joined by a channel
+            def __init__(self):
+                self.cic = (O.CicA if kind == "reference" else O.CicB)("intr", Q15, wl["mid"], wl["R"], wl["M"], wl["N"])
+                self.fir = (O.FirA("load", wl["mid"], Q15, ACC40, ACC40, taps, "SHIFT_REG") if kind == "reference"
+                            else O.FirB(wl["mid"], Q15, ACC40, ACC40, taps, "SHIFT_REG"))
+                self.fir.load(h)
+                self.secs = 0.0
+
+            def run(self, x):
+                mid = self.cic.run(x)
+                y = self.fir.run(mid)
+                if kind == "reference":
+                    self.secs = self.cic.last_run_seconds() + self.fir.last_run_seconds()
+                return y
+
+            def last_run_seconds(self):
+                return self.secs
+        make = Chain
+        per_thread = int(seconds_target * 2e6 * 63 / taps / wl["R"])
     else:
         def make():
             cls = O.CicA if kind == "reference" else O.CicB
@@ -231,6 +258,11 @@ def main():
                                  device=local, comm=comm, root=0)
         f.load(h if rank == 0 else None)
         launches_per_step = 2          # fir_q15_kernel + history carry
+    elif wl["kind"] == "cicfir":
+        h = rng.integers(-32768, 32767, size=wl["taps"], endpoint=True).astype(np.int16)
+        f = E.cic_intr_fir_cascade(Q15, wl["mid"], wl["R"], wl["M"], wl["N"], ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG",
+                                   coeffs=h, n_channels=C, layout=wl["layout"], device=local)
+        launches_per_step = 2
     else:
         cls = E.ac_cic_dec_full if wl["mode"] == "dec" else E.ac_cic_intr_full
         f = cls(Q15, wl["out"], wl["R"], wl["M"], wl["N"], n_channels=C, layout=wl["layout"], device=local)
@@ -245,7 +277,8 @@ def main():
             torch.cuda.synchronize()
 
     y = f.run(x)
-    ybuf = torch.empty(max(y.numel(), C * (n * wl.get("R", 1) if wl.get("mode") == "intr" else n)), dtype=y.dtype, device="cuda")
+    up = wl.get("R", 1) if (wl.get("mode") == "intr" or wl["kind"] == "cicfir") else 1
+    ybuf = torch.empty(max(y.numel(), C * n * up), dtype=y.dtype, device="cuda")
     del y
     for _ in range(args.warmup):
         y = f.run(x, out=ybuf)
@@ -282,6 +315,9 @@ def main():
         if wl["kind"] == "fir":
             yh = torch.empty(n2 * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_fir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), None)
+        elif wl["kind"] == "cicfir":
+            yh = torch.empty(lib.b2d_cicfir_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
+            call = lambda: lib.b2d_cicfir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
         else:
             cap = lib.b2d_cic_max_out(f._h, n2)
             yh = torch.empty(cap * C, dtype=torch.int32).pin_memory()

@@ -147,6 +147,25 @@ int b2d_cic_get_state(b2d_cic *h, void *blob, size_t bytes);
 int b2d_cic_set_state(b2d_cic *h, const void *blob, size_t bytes);
 const char *b2d_cic_path(b2d_cic *h);
 
+/* ---- cascade: ac_cic_intr_full -> ac_fir_* as ONE object ------------------------------------ */
+/* BASELINE config 5 (CIC interpolator followed by a FIR).  In the reference these are two objects joined by an
+ * ac_channel:  cic.run(in, mid); fir.run(mid, out);  (ac_cic_intr_full.h:150-153, ac_fir_const_coeffs.h:321-355).
+ * A b2d_cicfir handle stands for that pair and produces bit-identical results; `cic` must be an INTR descriptor,
+ * fir->in must equal cic->out, both must have the same n_channels.  Input layout = cic->layout, outputs are PLANAR
+ * with a channel stride of *n_out (like b2d_cic_run).  When neither stage drops bits (the lossless CIC type is
+ * passed on unchanged and the FIR accumulator is an exact-shift AC_WRAP one) both stages run as a single polyphase
+ * kernel on the original 16-bit samples and the intermediate stream never reaches HBM (b2d_cicfir_path:
+ * "cicfir_fused"); otherwise the two kernels run back to back through a device buffer ("cicfir_two_stage"). */
+typedef struct b2d_cicfir b2d_cicfir;
+int b2d_cicfir_create(b2d_cicfir **h, const b2d_cic_desc *cic, const b2d_fir_desc *fir);
+int b2d_cicfir_destroy(b2d_cicfir *h);
+int b2d_cicfir_load(b2d_cicfir *h, const void *coeff_raw, size_t n, int32_t channel);   /* the FIR's taps, as b2d_fir_load */
+size_t b2d_cicfir_max_out(b2d_cicfir *h, size_t n);
+int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n_out);
+int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_cicfir_reset(b2d_cicfir *h);
+const char *b2d_cicfir_path(b2d_cicfir *h);
+
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128
 /* Channel c of n_channels lives on rank c % world (contiguous block alternative: see DESIGN.md). */

@@ -63,8 +63,11 @@ def test_q15_path_is_taken_for_the_baseline_formats(engine):
     h = np.ones(256, dtype=np.int16)
     for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "TRANSPOSED", "FOLD_EVEN", "FOLD_ODD"):
         assert make_fir(engine, "load", Q15, Q15, ACC40, ACC40, 256, ft, h).path == "fir_q15"
-    assert make_fir(engine, "load", (20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", h[:63]).path == "fir_generic"
-    assert make_fir(engine, "load", Q15, Q15, (24, 4), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"  # per-tap truncation
+    assert make_fir(engine, "load", (20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", h[:63]).path == "fir_wide"
+    # order-dependent accumulators (saturation, sign-dependent rounding) only exist on the generic kernel
+    assert make_fir(engine, "load", Q15, Q15, (24, 4, True, "AC_TRN", "AC_SAT"), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"
+    assert make_fir(engine, "load", Q15, Q15, (24, 4, True, "AC_TRN_ZERO"), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"
+    assert make_fir(engine, "load", Q15, Q15, (24, 4), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_wide"  # per-tap truncation
 
 
 def test_cic_vs_reference_outputs(engine, ref_outputs, path):
@@ -416,3 +419,77 @@ def test_comm_single_rank_broadcast(engine, oracle):
     assert np.array_equal(f.run(x.astype(np.int16)).astype(np.int64), oracle_fir(oracle, Q15, Q15, ACC40, ACC40, 64, "SHIFT_REG", h, x))
     f.close()
     comm.close()
+
+
+# ------------------------------------------------------------------------ cascade: CIC interpolator -> FIR (config 5)
+def oracle_cascade(oracle, fin, fmid, R, M, N, fc, fa, fo, taps, ft, h, chunks):
+    cic = oracle.CicB("intr", fin, fmid, R, M, N)
+    fir = oracle.FirB(fmid, fc, fa, fo, taps, ft)
+    fir.load(h)
+    return np.concatenate([fir.run(cic.run(x)) for x in chunks])
+
+
+CASCADES = [  # (R, M, N, MID, taps, ftype, coeff fmt, expected path)
+    (4, 1, 3, (20, 5), 63, "SHIFT_REG", Q15, "cicfir_fused"),          # BASELINE config 5
+    (4, 1, 3, (20, 5), 63, "FOLD_ODD", Q15, "cicfir_fused"),
+    (4, 1, 3, (20, 5), 16, "FOLD_EVEN", Q15, "cicfir_fused"),
+    (4, 1, 3, (20, 5), 1, "SHIFT_REG", Q15, "cicfir_fused"),
+    (4, 1, 3, (24, 9), 30, "TRANSPOSED", (12, 1), "cicfir_fused"),     # wider MID than the lossless type, 2 byte planes?
+    (4, 1, 3, (20, 5), 21, "SHIFT_REG", (8, 1), "cicfir_fused"),          # composite taps fit 16 bits: two byte planes
+    (2, 1, 4, (19, 4), 33, "C_BUFF", Q15, "cicfir_fused"),
+    (2, 2, 3, (21, 6), 8, "SHIFT_REG", (10, 2, False), "cicfir_fused"),
+    (8, 1, 2, (19, 4), 40, "ROTATE_SHIFT", Q15, "cicfir_fused"),
+    (8, 1, 4, (25, 10), 63, "SHIFT_REG", Q15, "cicfir_two_stage"),     # composite taps exceed 24 bits
+    (4, 1, 3, (18, 3), 63, "SHIFT_REG", Q15, "cicfir_two_stage"),      # MID narrower than lossless: the CIC output wraps
+    (3, 1, 3, (20, 5), 20, "SHIFT_REG", Q15, "cicfir_two_stage"),      # R not in {2, 4, 8}
+]
+
+
+@pytest.mark.parametrize("case", CASCADES, ids=lambda c: f"R{c[0]}M{c[1]}N{c[2]}-{c[4]}{c[5]}-{c[7]}")
+@pytest.mark.parametrize("two_stage", ["0", "1"])
+def test_cic_fir_cascade(engine, oracle, case, two_stage, monkeypatch):
+    """One object for ac_cic_intr_full -> ac_fir_*: identical to the two oracle objects in sequence, whole stream and
+    chunked (call boundaries inside an input period), through the fused polyphase kernel and through the two-stage path."""
+    R, M, N, mid, taps, ft, fc, want_path = case
+    monkeypatch.setenv("B2D_CICFIR_TWO_STAGE", two_stage)
+    rng = np.random.default_rng(R * 1000 + N * 100 + taps)
+    n = 20011
+    x = oracle.rand_raw(rng, Q15, n)
+    h = oracle.rand_raw(rng, fc, taps)
+    if ft in ("FOLD_EVEN", "FOLD_ODD"):
+        h = np.concatenate([h[: (taps + 1) // 2], h[: taps // 2][::-1]])
+    f = engine.cic_intr_fir_cascade(Q15, mid, R, M, N, ACC40, fc, ACC40, taps, ft, coeffs=h)
+    assert f.path == (want_path if two_stage == "0" else "cicfir_two_stage")
+    want = oracle_cascade(oracle, Q15, mid, R, M, N, fc, ACC40, ACC40, taps, ft, h, [x])
+    y = f.run(x)
+    assert y.shape == want.shape and np.array_equal(y.astype(np.int64), want), f.path
+    f.reset()
+    cuts = [0, 1, 2, 3, 7, 8, 1000, 1001, 9999, n]
+    parts = [f.run(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts).astype(np.int64), want)
+
+
+def test_cic_fir_cascade_channels_device_and_extremes(engine, oracle):
+    import torch
+    rng = np.random.default_rng(99)
+    C, n = 3, 70001
+    h = oracle.rand_raw(rng, Q15, 63)
+    x = rng.integers(-32768, 32767, size=(C, n), endpoint=True).astype(np.int16)
+    want = [oracle_cascade(oracle, Q15, (20, 5), 4, 1, 3, Q15, ACC40, ACC40, 63, "SHIFT_REG", h, [x[c]]) for c in range(C)]
+    for layout in ("planar", "interleaved"):
+        f = engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT_REG", coeffs=h, n_channels=C, layout=layout)
+        assert f.path == "cicfir_fused"
+        xin = torch.from_numpy(x if layout == "planar" else np.ascontiguousarray(x.T)).cuda()
+        half = 33333
+        a = f.run(xin[:, :half] if layout == "planar" else xin[:half]).cpu().numpy()
+        b = f.run(xin[:, half:] if layout == "planar" else xin[half:]).cpu().numpy()
+        for c in range(C):
+            assert np.array_equal(np.concatenate([a[c], b[c]]), want[c]), (layout, c)
+    # extremes: all-min samples x all-min taps exercise the accumulator wrap and every byte plane's sign handling
+    for kx, kh in (("min", "min"), ("max", "min"), ("alt", "max")):
+        xe, he = oracle.rand_raw(rng, Q15, 5000, kx), oracle.rand_raw(rng, Q15, 63, kh)
+        f = engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT_REG", coeffs=he)
+        assert np.array_equal(f.run(xe).astype(np.int64),
+                              oracle_cascade(oracle, Q15, (20, 5), 4, 1, 3, Q15, ACC40, ACC40, 63, "SHIFT_REG", he, [xe])), (kx, kh)
+    with pytest.raises(engine.B2dError):
+        engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, coeffs=None).run(np.zeros(8, dtype=np.int16))
