@@ -198,7 +198,7 @@ def run_reference(args, wl):
     line = {"impl": "reference", "metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
             "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16 samples, exact integer accumulate (ac_fixed)", "data": "synthetic",
+            "dtype": "ac_fixed (exact integer)", "data": "synthetic",
             "config": {"workload": wl["name"], "note": "CPU reference arm: bounded sample per step, host cores only"},
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -367,7 +367,8 @@ def main():
         line = {"metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
                 "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16 samples, exact integer accumulate (s32 byte planes -> s64, ac_fixed<40,8>)" if wl["kind"] == "fir" else "int16 samples, u32 modular integrate/comb",
+                "dtype": {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+                          "cic": "s16 -> u32 (modular integrate / comb)"}[wl["kind"]],
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "samples_per_step_per_gpu": units_per_step, "kernel_path": path,
                            "l2": "inputs per step exceed L2 (>= 0.5 GiB vs 126 MB); no flush needed",
