@@ -10,7 +10,7 @@ from . import build as _build
 Q_MODES = ["AC_TRN", "AC_RND", "AC_TRN_ZERO", "AC_RND_ZERO", "AC_RND_INF", "AC_RND_MIN_INF", "AC_RND_CONV", "AC_RND_CONV_ODD"]
 O_MODES = ["AC_WRAP", "AC_SAT", "AC_SAT_ZERO", "AC_SAT_SYM"]
 FTYPES = ["SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED", "FOLD_EVEN_ANTI", "FOLD_ODD_ANTI"]
-FIR_KINDS = ["const", "load", "prog"]
+FIR_KINDS = ["const", "load", "prog", "reg_share"]
 PLANAR, INTERLEAVED = 0, 1
 
 OK, EUNSUPPORTED, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6
@@ -66,6 +66,8 @@ def load():
         "b2d_fir_reset": (C.c_int, [vp]), "b2d_fir_state_bytes": (C.c_int, [vp, psz]),
         "b2d_fir_get_state": (C.c_int, [vp, vp, sz]), "b2d_fir_set_state": (C.c_int, [vp, vp, sz]),
         "b2d_fir_path": (C.c_char_p, [vp]),
+        "b2d_fir_load_blocked": (C.c_int, [vp, vp, sz, u32, u32, u32, i32]), "b2d_fir_delay_line_out": (C.c_int, [vp, vp]),
+        "b2d_fir_run_window": (C.c_int, [vp, vp, vp]),
         "b2d_cic_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dCicDesc)]), "b2d_cic_destroy": (C.c_int, [vp]),
         "b2d_cic_int_width": (C.c_int, [C.POINTER(B2dCicDesc), C.POINTER(i32)]), "b2d_cic_max_out": (sz, [vp, sz]),
         "b2d_cic_run": (C.c_int, [vp, vp, sz, vp, psz]), "b2d_cic_run_dev": (C.c_int, [vp, vp, sz, vp, psz, vp]),

@@ -18,7 +18,7 @@ namespace b2d {
 
 struct FirGenArgs {
   Fmt in, coeff, acc, out;
-  int N, ftype;
+  int N, ftype, ascending;
   uint32_t C;
   int interleaved, in_bytes, out_bytes;
   const void *x;
@@ -43,25 +43,38 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
     const int N = a.N;
     const int Fin = a.in.F(), Fc = a.coeff.F(), Fa = a.acc.F();
     int64_t acc = 0;
+    // _ANTI: pre-subtract instead of pre-add (ac_fir_reg_share.h:151-165,186-205)
+    const int anti = a.ftype == B2D_FOLD_EVEN_ANTI || a.ftype == B2D_FOLD_ODD_ANTI;
     switch (a.ftype) {
       case B2D_SHIFT_REG:
       case B2D_ROTATE_SHIFT:
       case B2D_TRANSPOSED:
-        for (int k = N - 1; k >= 0; k--) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        if (a.ascending) {
+          for (int k = 0; k < N; k++) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        } else {
+          for (int k = N - 1; k >= 0; k--) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        }
         break;
       case B2D_C_BUFF:
         for (int k = 0; k < N; k++) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
         break;
       case B2D_FOLD_EVEN:
-        for (int k = N / 2 - 1; k >= 0; k--) {
-          const i128 pre = (i128)fir_gen_sample(a, c, i, k) + (i128)fir_gen_sample(a, c, i, N - 1 - k);
+      case B2D_FOLD_EVEN_ANTI:
+        for (int q = 0; q < N / 2; q++) {
+          const int k = a.ascending ? q : N / 2 - 1 - q;
+          const i128 xb = (i128)fir_gen_sample(a, c, i, N - 1 - k);
+          const i128 pre = (i128)fir_gen_sample(a, c, i, k) + (anti ? -xb : xb);
           acc = macc(acc, a.acc, (i128)h[k] * pre, Fin + Fc);
         }
         break;
       case B2D_FOLD_ODD:
+      case B2D_FOLD_ODD_ANTI:
         for (int k = 0; k < (N - 1) / 2 + 1; k++) {
           i128 pre = (i128)fir_gen_sample(a, c, i, k);
-          if (k != (N - 1) / 2) pre += (i128)fir_gen_sample(a, c, i, N - 1 - k);
+          if (k != (N - 1) / 2) {
+            const i128 xb = (i128)fir_gen_sample(a, c, i, N - 1 - k);
+            pre += anti ? -xb : xb;
+          }
           const int64_t fold = convert(pre, Fin, a.acc);
           acc = macc(acc, a.acc, (i128)h[k] * (i128)fold, Fc + Fa);
         }
@@ -76,7 +89,7 @@ cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st) {
   if (p.n == 0) return cudaSuccess;
   FirGenArgs a;
   a.in = p.fin; a.coeff = p.fcoeff; a.acc = p.facc; a.out = p.fout;
-  a.N = p.n_taps; a.ftype = p.ftype; a.C = p.C; a.interleaved = p.interleaved;
+  a.N = p.n_taps; a.ftype = p.ftype; a.ascending = p.ascending; a.C = p.C; a.interleaved = p.interleaved;
   a.in_bytes = container_bytes(p.fin.W); a.out_bytes = container_bytes(p.fout.W);
   a.x = p.in; a.y = p.out; a.n = p.n; a.tail = p.tail; a.h = p.coeff64;
   const size_t total = p.n * p.C;
@@ -123,6 +136,32 @@ static cudaError_t launch_tail(const void *in, const void *tail, void *tail_next
 
 cudaError_t launch_fir_tail(const FirLaunch &p, cudaStream_t st) {
   return launch_tail(p.in, p.tail, p.tail_next, p.n, p.n_taps - 1, container_bytes(p.fin.W), p.C, p.interleaved, st);
+}
+
+// reg[N_TAPS-1] of ac_fir_reg_share after this call's n samples: element n-1 of (tail ++ in), converted to OUT_TYPE
+struct DelayOutArgs {
+  const void *in, *tail;
+  int64_t *dl;
+  size_t n;
+  int T, bytes, in_signed, Fin;
+  uint32_t C;
+  int interleaved;
+  Fmt out;
+};
+__global__ void fir_delay_out_kernel(DelayOutArgs a) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C || a.n == 0) return;
+  const size_t pos = a.n - 1;
+  int64_t v;
+  if (pos < (size_t)a.T) v = load_raw(a.tail, (size_t)c * a.T + pos, a.bytes, a.in_signed);
+  else v = load_raw(a.in, elem_index(pos - a.T, c, a.n, a.C, a.interleaved), a.bytes, a.in_signed);
+  a.dl[c] = convert((i128)v, a.Fin, a.out);
+}
+cudaError_t launch_fir_delay_out(const FirLaunch &p, int64_t *dl, cudaStream_t st) {
+  if (p.n == 0) return cudaSuccess;
+  DelayOutArgs a{p.in, p.tail, dl, p.n, p.n_taps - 1, container_bytes(p.fin.W), p.fin.S, p.fin.F(), p.C, p.interleaved, p.fout};
+  fir_delay_out_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st) {

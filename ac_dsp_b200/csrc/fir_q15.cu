@@ -265,6 +265,11 @@ bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fm
   if (n_taps > kMaxTapsQ15) return false;
   switch (ftype) {
     case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: return true;
+    case B2D_FOLD_EVEN_ANTI:   // mirrored taps are negated: they must still fit the signed 16-bit byte planes
+      return coeff.W + (coeff.S ? 0 : 1) <= 15;
+    case B2D_FOLD_ODD_ANTI:
+      if (coeff.W + (coeff.S ? 0 : 1) > 15) return false;
+      // fall through
     case B2D_FOLD_ODD:
       // `fold` is ACC_TYPE (ac_fir_load_coeffs.h:248-255): exact only if the pre-add neither truncates nor wraps there
       return acc.F() >= in.F() && in.W + 1 + (in.S ? 0 : 1) + (acc.F() - in.F()) <= acc.W;
@@ -283,12 +288,13 @@ void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uin
   (void)coeff;
   const int N = n_taps;
   std::vector<int64_t> eff(N, 0);
-  if (ftype == B2D_FOLD_EVEN) {          // ac_fir_load_coeffs.h:231-239: taps i and N-1-i share h[i], i < N/2
-    for (int i = 0; i < N / 2; i++) { eff[i] = c[i]; eff[N - 1 - i] = c[i]; }
-  } else if (ftype == B2D_FOLD_ODD) {    // :246-259: i <= (N-1)/2, the last one unpaired
+  const int64_t sg = (ftype == B2D_FOLD_EVEN_ANTI || ftype == B2D_FOLD_ODD_ANTI) ? -1 : 1;   // ac_fir_reg_share.h:151-165,186-205
+  if (ftype == B2D_FOLD_EVEN || ftype == B2D_FOLD_EVEN_ANTI) {   // ac_fir_load_coeffs.h:231-239: taps i and N-1-i share h[i], i < N/2
+    for (int i = 0; i < N / 2; i++) { eff[i] = c[i]; eff[N - 1 - i] = sg * c[i]; }
+  } else if (ftype == B2D_FOLD_ODD || ftype == B2D_FOLD_ODD_ANTI) {   // :246-259: i <= (N-1)/2, the last one unpaired
     for (int i = 0; i < (N - 1) / 2 + 1; i++) {
       eff[i] = c[i];
-      if (i != (N - 1) / 2) eff[N - 1 - i] = c[i];
+      if (i != (N - 1) / 2) eff[N - 1 - i] = sg * c[i];
     }
   } else {
     for (int i = 0; i < N; i++) eff[i] = c[i];

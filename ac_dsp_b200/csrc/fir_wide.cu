@@ -38,6 +38,7 @@ struct WideArgs {
   int s;                  // F_in + F_c - F_acc
   long long rnd;          // 2^(s-1) for an AC_RND accumulator with s > 0
   int npairs, centre;     // MODE 2: taps i < npairs are paired with N-1-i; tap `centre` (or -1) is unpaired
+  int pair_sign;          // MODE 2: +1 pre-add, -1 pre-subtract (the _ANTI architectures)
   Fmt acc, out;
   int fastout;
 };
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kWideThreads) fir_wide_kernel(WideArgs a) {
       const long long h = cs[i];
 #pragma unroll
       for (int j = 0; j < kWideT; j++) {
-        const long long pre = (long long)xs[B + j - i] + (long long)xs[B + j - T + i];
+        const long long pre = (long long)xs[B + j - i] + (long long)(a.pair_sign * (long long)xs[B + j - T + i]);
         acc[j] += (h * pre + a.rnd) >> a.s;
       }
     }
@@ -144,9 +145,10 @@ int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, i
   if (n_taps > kWideMaxTaps) return -1;
   const int s = in.F() + coeff.F() - acc.F();
   if (s < -63 || s > 61) return -1;
-  const bool fold = ftype == B2D_FOLD_EVEN || ftype == B2D_FOLD_ODD;
-  if (ftype == B2D_FOLD_ODD && !fold_odd_exact(in, acc)) return -1;
-  if (s <= 0) return 0;
+  const bool anti = ftype == B2D_FOLD_EVEN_ANTI || ftype == B2D_FOLD_ODD_ANTI;
+  const bool fold = ftype == B2D_FOLD_EVEN || ftype == B2D_FOLD_ODD || anti;
+  if ((ftype == B2D_FOLD_ODD || ftype == B2D_FOLD_ODD_ANTI) && !fold_odd_exact(in, acc)) return -1;
+  if (s <= 0) return (anti && coeff.W + (coeff.S ? 0 : 1) > 31) ? -1 : 0;   // the mirrored taps are negated
   if (!fold) return 1;
   if (in.W + (in.S ? 0 : 1) > 31) return -1;     // |h * (xa + xb)| must stay below 2^62
   return 2;
@@ -155,7 +157,8 @@ int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, i
 bool fir_wide_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype) {
   (void)out;
   switch (ftype) {
-    case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: case B2D_FOLD_ODD: break;
+    case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: case B2D_FOLD_ODD:
+    case B2D_FOLD_EVEN_ANTI: case B2D_FOLD_ODD_ANTI: break;
     default: return false;
   }
   return fir_wide_mode(in, coeff, acc, n_taps, ftype) >= 0;
@@ -167,14 +170,15 @@ int fir_wide_words(int n_taps) { return (n_taps + 7) & ~7; }
 void fir_wide_pack(const int64_t *c, int n_taps, int ftype, int mode, int32_t *out, int words) {
   const int N = n_taps;
   std::vector<int64_t> eff(c, c + N);
-  if (mode == 0 && ftype == B2D_FOLD_EVEN) {        // ac_fir_load_coeffs.h:231-239: taps i and N-1-i share h[i], i < N/2
+  const int64_t sg = (ftype == B2D_FOLD_EVEN_ANTI || ftype == B2D_FOLD_ODD_ANTI) ? -1 : 1;   // ac_fir_reg_share.h:151-165,186-205
+  if (mode == 0 && (ftype == B2D_FOLD_EVEN || ftype == B2D_FOLD_EVEN_ANTI)) {   // ac_fir_load_coeffs.h:231-239: taps i and N-1-i share h[i], i < N/2
     for (int i = 0; i < N; i++) eff[i] = 0;
-    for (int i = 0; i < N / 2; i++) { eff[i] = c[i]; eff[N - 1 - i] = c[i]; }
-  } else if (mode == 0 && ftype == B2D_FOLD_ODD) {  // :246-259: i <= (N-1)/2, the last one unpaired
+    for (int i = 0; i < N / 2; i++) { eff[i] = c[i]; eff[N - 1 - i] = sg * c[i]; }
+  } else if (mode == 0 && (ftype == B2D_FOLD_ODD || ftype == B2D_FOLD_ODD_ANTI)) {   // :246-259: i <= (N-1)/2, the last one unpaired
     for (int i = 0; i < N; i++) eff[i] = 0;
     for (int i = 0; i < (N - 1) / 2 + 1; i++) {
       eff[i] = c[i];
-      if (i != (N - 1) / 2) eff[N - 1 - i] = c[i];
+      if (i != (N - 1) / 2) eff[N - 1 - i] = sg * c[i];
     }
   }
   for (int i = 0; i < words; i++) out[i] = i < N ? (int32_t)eff[i] : 0;
@@ -191,8 +195,10 @@ cudaError_t launch_fir_wide(const FirLaunch &p, cudaStream_t st) {
   a.s = p.fin.F() + p.fcoeff.F() - p.facc.F();
   a.rnd = (a.s > 0 && p.facc.Q == B2D_RND) ? (1LL << (a.s - 1)) : 0;
   // FOLD_EVEN: i < N/2 paired, nothing else is read (:231-239).  FOLD_ODD: i < (N-1)/2 paired, i = (N-1)/2 unpaired (:246-259)
-  a.npairs = p.ftype == B2D_FOLD_ODD ? (p.n_taps - 1) / 2 : p.n_taps / 2;
-  a.centre = p.ftype == B2D_FOLD_ODD ? (p.n_taps - 1) / 2 : -1;
+  const bool odd = p.ftype == B2D_FOLD_ODD || p.ftype == B2D_FOLD_ODD_ANTI;
+  a.npairs = odd ? (p.n_taps - 1) / 2 : p.n_taps / 2;
+  a.centre = odd ? (p.n_taps - 1) / 2 : -1;
+  a.pair_sign = (p.ftype == B2D_FOLD_EVEN_ANTI || p.ftype == B2D_FOLD_ODD_ANTI) ? -1 : 1;
   a.acc = p.facc; a.out = p.fout;
   a.fastout = (p.fout.W == p.facc.W && p.fout.I == p.facc.I && p.fout.S == p.facc.S && a.out_bytes == 8) ? 1 : 0;
   const int Tpad = (a.Npad + 3) & ~3;

@@ -8,6 +8,7 @@ namespace b2d {
 struct FirLaunch {
   Fmt fin, fcoeff, facc, fout;
   int n_taps, ftype;
+  int ascending;         // ac_fir_reg_share walks the taps upwards (matters for order-dependent accumulators only)
   uint32_t C;            // channels
   int interleaved;       // layout of in / out
   const void *in;        // n samples per channel, input container
@@ -36,6 +37,8 @@ void fir_wide_pack(const int64_t *c, int n_taps, int ftype, int mode, int32_t *o
 cudaError_t launch_fir_wide(const FirLaunch &p, cudaStream_t st);
 // history carry: tail_next = last (n_taps-1) samples of (tail ++ in).
 cudaError_t launch_fir_tail(const FirLaunch &p, cudaStream_t st);
+// ac_firProgCoeffs_delay_line: dl[c] = OUT_TYPE(sample N_TAPS-1 steps back) after this call (before the tail swap)
+cudaError_t launch_fir_delay_out(const FirLaunch &p, int64_t *dl, cudaStream_t st);
 
 struct CicLaunch {
   Fmt fin, fout;

@@ -255,6 +255,8 @@ struct b2d_fir {
   int cur = 0;
   b2d_comm *comm = nullptr;
   int root = 0;
+  int64_t *d_dl = nullptr;        // REG_SHARE: OUT_TYPE(reg[N_TAPS-1]) per channel
+  void *d_win = nullptr;          // run_window scratch: [C][N_TAPS-1] tail, [C] newest samples, [C] outputs, [C][N_TAPS-1] dummy tail
   Pipe pipe;
 };
 
@@ -274,10 +276,13 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
   if (desc->n_taps < 1 || desc->n_taps > (1u << 20)) return fail(B2D_EINVAL, "n_taps %u outside 1..2^20", desc->n_taps);
   if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
   if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
-  if (desc->kind < B2D_FIR_CONST || desc->kind > B2D_FIR_PROG) return fail(B2D_EINVAL, "bad kind");
-  if (desc->ftype == B2D_FOLD_EVEN_ANTI || desc->ftype == B2D_FOLD_ODD_ANTI)
-    return fail(B2D_EUNSUPPORTED, "the reference FIR classes do not dispatch the _ANTI architectures (output left unwritten)");
+  if (desc->kind < B2D_FIR_CONST || desc->kind > B2D_FIR_REG_SHARE) return fail(B2D_EINVAL, "bad kind");
   if (desc->ftype < B2D_SHIFT_REG || desc->ftype > B2D_FOLD_ODD_ANTI) return fail(B2D_EINVAL, "bad ftype");
+  const bool anti_ft = desc->ftype == B2D_FOLD_EVEN_ANTI || desc->ftype == B2D_FOLD_ODD_ANTI;
+  if (desc->kind != B2D_FIR_REG_SHARE && anti_ft)
+    return fail(B2D_EUNSUPPORTED, "the const / load / prog FIR classes do not dispatch the _ANTI architectures (output left unwritten)");
+  if (desc->kind == B2D_FIR_REG_SHARE && (desc->ftype == B2D_ROTATE_SHIFT || desc->ftype == B2D_C_BUFF || desc->ftype == B2D_TRANSPOSED))
+    return fail(B2D_EUNSUPPORTED, "ac_fir_reg_share does not dispatch this architecture (output left unwritten)");
   Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
   {  // bit budget of the 128-bit generic evaluation
     const int Fp = desc->ftype == B2D_FOLD_ODD ? fc.F() + fa.F() : fin.F() + fc.F();
@@ -314,6 +319,10 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
     h->pk_words = fir_q15_pk_words((int)N, desc->ftype);
     e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
   }
+  if (e == cudaSuccess && desc->kind == B2D_FIR_REG_SHARE) {
+    e = cudaMalloc(&h->d_dl, C * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemset(h->d_dl, 0, C * sizeof(int64_t));
+  }
   if (e == cudaSuccess && h->path == PATH_WIDE) {
     h->wide_words = fir_wide_words((int)N);
     h->wide_mode = fir_wide_mode(fin, fc, fa, (int)N, desc->ftype);
@@ -336,6 +345,8 @@ extern "C" int b2d_fir_destroy(b2d_fir *h) {
   if (h->d_coeff64) cudaFree(h->d_coeff64);
   if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
   if (h->d_coeff32) cudaFree(h->d_coeff32);
+  if (h->d_dl) cudaFree(h->d_dl);
+  if (h->d_win) cudaFree(h->d_win);
   for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
   delete h;
   return B2D_OK;
@@ -402,10 +413,12 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   FirLaunch p;
   p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
   p.n_taps = (int)h->d.n_taps; p.ftype = h->d.ftype; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
+  p.ascending = h->d.kind == B2D_FIR_REG_SHARE;
   p.in = d_in; p.out = d_out; p.n = n;
   p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1];
   p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
   CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : (h->path == PATH_WIDE ? launch_fir_wide(p, st) : launch_fir_generic(p, st)));
+  if (h->d_dl) CU(launch_fir_delay_out(p, h->d_dl, st));
   CU(launch_fir_tail(p, st));
   h->cur ^= 1;
   return B2D_OK;
@@ -463,6 +476,70 @@ extern "C" int b2d_fir_reset(b2d_fir *h) {
   CU(cudaDeviceSynchronize());
   const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
   for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
+  if (h->d_dl) CU(cudaMemset(h->d_dl, 0, h->d.n_channels * sizeof(int64_t)));
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_load_blocked(b2d_fir *h, const void *ram, size_t n_ram, uint32_t mww, uint32_t bs, uint32_t bo, int32_t channel) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  if (bs < 1 || mww < 1) return fail(B2D_EINVAL, "mem_word_width and blk_sz must be >= 1");
+  const size_t N = h->d.n_taps;
+  const int ft = h->d.ftype;
+  const size_t used = (ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI) ? N / 2 : ((ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI) ? (N - 1) / 2 + 1 : N);
+  if (used % bs) return fail(B2D_EUNSUPPORTED, "tap loop length %zu is not a multiple of blk_sz %u (the reference reads its delay line out of range)", used, bs);
+  const size_t need = used ? (used / bs - 1) * (size_t)mww + bo + bs : 0;
+  const bool have_local = !h->comm || h->comm->rank == h->root;
+  if (have_local && (!ram || n_ram < need)) return fail(B2D_EINVAL, "coefficient RAM needs %zu words, got %zu", need, n_ram);
+  std::vector<unsigned char> taps(N * (size_t)h->c_bytes, 0);
+  if (have_local)
+    for (size_t t = 0; t < used; t++)
+      memcpy(&taps[t * h->c_bytes], (const char *)ram + ((t / bs) * (size_t)mww + bo + t % bs) * h->c_bytes, h->c_bytes);
+  return b2d_fir_load(h, have_local ? taps.data() : nullptr, N, channel);
+}
+
+extern "C" int b2d_fir_delay_line_out(b2d_fir *h, void *out_raw) {
+  if (!h || !out_raw) return fail(B2D_EINVAL, "null argument");
+  if (!h->d_dl) return fail(B2D_ESTATE, "delay-line output exists for B2D_FIR_REG_SHARE handles only");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  std::vector<int64_t> v(h->d.n_channels);
+  CU(cudaMemcpy(v.data(), h->d_dl, v.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < v.size(); c++) {
+    if (h->out_bytes == 2) ((int16_t *)out_raw)[c] = (int16_t)v[c];
+    else if (h->out_bytes == 4) ((int32_t *)out_raw)[c] = (int32_t)v[c];
+    else ((int64_t *)out_raw)[c] = v[c];
+  }
+  return B2D_OK;
+}
+
+extern "C" int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw) {
+  if (!h || !window || !out_raw) return fail(B2D_EINVAL, "null argument");
+  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
+  int st = use_device(h->device);
+  if (st) return st;
+  const uint32_t C = h->d.n_channels;
+  const size_t N = h->d.n_taps, T = N - 1, ib = h->in_bytes, ob = h->out_bytes;
+  const size_t tail_b = (std::max<size_t>(T * C * ib, 16) + 15) & ~(size_t)15, in_b = (C * ib + 15) & ~(size_t)15, out_b = (C * ob + 15) & ~(size_t)15;
+  if (!h->d_win) CU(cudaMalloc(&h->d_win, 2 * tail_b + in_b + out_b));
+  // reg order (newest first) -> planar tail, oldest first, + the newest sample as the one-sample input
+  std::vector<unsigned char> host(tail_b + in_b, 0);
+  for (uint32_t c = 0; c < C; c++) {
+    const unsigned char *w = (const unsigned char *)window + (size_t)c * N * ib;
+    for (size_t j = 0; j < T; j++) memcpy(&host[(c * T + j) * ib], w + (T - j) * ib, ib);   // tail[j] = reg[T - j]
+    memcpy(&host[tail_b + c * ib], w, ib);
+  }
+  char *base = (char *)h->d_win;
+  CU(cudaMemcpy(base, host.data(), host.size(), cudaMemcpyHostToDevice));
+  FirLaunch p;
+  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
+  p.n_taps = (int)N; p.ftype = h->d.ftype; p.C = C; p.interleaved = 1;   // one sample per channel: [1][C]
+  p.ascending = h->d.kind == B2D_FIR_REG_SHARE;
+  p.in = base + tail_b; p.out = base + tail_b + in_b; p.n = 1;
+  p.tail = base; p.tail_next = base + tail_b + in_b + out_b;
+  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
+  CU(h->path == PATH_Q15 ? launch_fir_q15(p, nullptr) : (h->path == PATH_WIDE ? launch_fir_wide(p, nullptr) : launch_fir_generic(p, nullptr)));
+  CU(cudaMemcpy(out_raw, p.out, C * ob, cudaMemcpyDeviceToHost));
   return B2D_OK;
 }
 

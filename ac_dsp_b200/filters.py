@@ -205,6 +205,46 @@ class ac_fir_prog_coeffs(_Fir):
         self._last = None
 
 
+class ac_fir_reg_share(_Fir):
+    """ac_fir_reg_share<N_TAPS, IN, OUT, COEFF, ACC, MEM_WORD_WIDTH, BLK_SZ, BLK_OFFSET, ftype>
+    (reference ac_fir_reg_share.h:257-303): SHIFT_REG / FOLD_EVEN / FOLD_ODD and the two
+    anti-symmetric folds, taps read from a blocked coefficient RAM.  The reference's run() is scalar on a caller-owned
+    delay line; run(samples, coeffs_ram) here is that call repeated over the array with the object's own (initially
+    zero) delay line, delay_line() is ac_firProgCoeffs_delay_line, run_window() the scalar form on an explicit line."""
+    _kind = "reg_share"
+
+    def __init__(self, N_TAPS, IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, MEM_WORD_WIDTH=1, BLK_SZ=1, BLK_OFFSET=0,
+                 ftype="SHIFT_REG", **kw):
+        super().__init__(IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype, **kw)
+        self._blk = (int(MEM_WORD_WIDTH), int(BLK_SZ), int(BLK_OFFSET))
+        self._last = None
+
+    def load(self, coeffs_ram, channel=-1):
+        c = np.ascontiguousarray(np.asarray(coeffs_ram).astype(self._coeff_dt, copy=False))
+        L.check(L.load().b2d_fir_load_blocked(self._h, c.ctypes.data, c.size, *self._blk, int(channel)))
+        self._last = c.tobytes() if channel < 0 else None
+
+    def run(self, data_in, coeffs_ram=None, out=None):
+        if coeffs_ram is not None:
+            c = np.ascontiguousarray(np.asarray(coeffs_ram).astype(self._coeff_dt, copy=False))
+            if c.tobytes() != self._last:
+                self.load(c)
+        return self._process(data_in, out)
+
+    def delay_line(self):
+        y = np.zeros(self._C, dtype=self._out_dt)
+        L.check(L.load().b2d_fir_delay_line_out(self._h, y.ctypes.data))
+        return y if self._C > 1 else y[0]
+
+    def run_window(self, reg):
+        w = np.ascontiguousarray(np.asarray(reg).astype(self._in_dt, copy=False))
+        if w.size != self._C * self.N_TAPS:
+            raise ValueError("window must hold n_channels * N_TAPS samples (reg[0] newest)")
+        y = np.zeros(self._C, dtype=self._out_dt)
+        L.check(L.load().b2d_fir_run_window(self._h, w.ctypes.data, y.ctypes.data))
+        return y if self._C > 1 else y[0]
+
+
 class _Cic(_Block):
     _mode = 0
 

@@ -60,7 +60,9 @@ typedef enum {
   B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI
 } b2d_ftype;
 
-typedef enum { B2D_FIR_CONST = 0, B2D_FIR_LOAD = 1, B2D_FIR_PROG = 2 } b2d_fir_kind;
+/* REG_SHARE = ac_fir_reg_share (ac_fir_reg_share.h:257-303): dispatches SHIFT_REG, FOLD_EVEN, FOLD_ODD and the two _ANTI
+ * (anti-symmetric, pre-SUBTRACT) architectures, walks the taps upwards, reads its taps from a blocked coefficient RAM. */
+typedef enum { B2D_FIR_CONST = 0, B2D_FIR_LOAD = 1, B2D_FIR_PROG = 2, B2D_FIR_REG_SHARE = 3 } b2d_fir_kind;
 typedef enum { B2D_CIC_DEC = 0, B2D_CIC_INTR = 1 } b2d_cic_mode;
 
 /* Multi-channel sample layout of the in/out arrays of one run() call with n samples per channel:
@@ -115,6 +117,20 @@ int b2d_fir_destroy(b2d_fir *h);
  * rank `root` are broadcast to all ranks with one ncclBroadcast; other ranks may pass NULL. */
 int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel);
 int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root);
+/* ac_fir_reg_share's coefficient addressing (ac_fir_reg_share.h:122-133): tap t of the architecture's tap loop reads
+ * ram[(t / blk_sz) * mem_word_width + blk_offset + t % blk_sz]; n_ram words of raw COEFF_TYPE values in HOST memory.
+ * The tap loop length (N_TAPS, N_TAPS/2 or (N_TAPS-1)/2+1 by ftype) must be a multiple of blk_sz -- otherwise the
+ * reference indexes its delay line out of range.  With mem_word_width = blk_sz = 1, blk_offset = 0 this is b2d_fir_load. */
+int b2d_fir_load_blocked(b2d_fir *h, const void *coeff_ram, size_t n_ram, uint32_t mem_word_width, uint32_t blk_sz,
+                         uint32_t blk_offset, int32_t channel);
+/* ac_firProgCoeffs_delay_line (ac_fir_reg_share.h:304-307): OUT_TYPE(reg[N_TAPS-1]) -- the sample leaving the delay line,
+ * one raw value per channel in the output container (REG_SHARE handles only). */
+int b2d_fir_delay_line_out(b2d_fir *h, void *out_raw);
+/* One output per channel from an explicit delay line: window[c * n_taps + i] = reg[i] of channel c (reg[0] newest), raw
+ * IN_TYPE values in HOST memory; out_raw[c] in the output container.  Does not read or change the handle's own delay
+ * line.  This is ac_fir_reg_share's calling convention -- the delay line belongs to the caller and run() is scalar
+ * (ac_fir_reg_share.h:262-303) -- and what its facade class uses; block processing goes through b2d_fir_run. */
+int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw);
 /* run() sample loop: n samples per channel in, n per channel out (*n_out = n).
  * _run takes HOST buffers (copies in, computes, copies out, synchronous); _run_dev takes DEVICE
  * buffers and is asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). */

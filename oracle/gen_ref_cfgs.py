@@ -17,6 +17,9 @@ def main(outdir):
     with open(os.path.join(outdir, "cfgs_fir.inc"), "w") as fh:
         for cid, name, fi, fc, fa, fo, t in rc.fir_configs():
             fh.write(f"X({cid}, {f(fi)}, {f(fc)}, {f(fa)}, {f(fo)}, {t})\n")
+    with open(os.path.join(outdir, "cfgs_rs.inc"), "w") as fh:
+        for cid, (N, fi, fo, fc, fa, mww, bs, bo, ft) in enumerate(rc.RS_CONFIGS):
+            fh.write(f"X({cid}, {N}, {f(fi)}, {f(fo)}, {f(fc)}, {f(fa)}, {mww}, {bs}, {bo}, {ft}, {rc.rs_ram_words(rc.RS_CONFIGS[cid])})\n")
     for mode in ("dec", "intr"):
         with open(os.path.join(outdir, f"cfgs_cic_{mode}.inc"), "w") as fh:
             for cid, c in enumerate(rc.CIC_CONFIGS):

@@ -87,6 +87,14 @@ def lib_b():
         L.ob_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.ob_cic_int_width.restype = C.c_int
         L.ob_cic_int_width.argtypes = [C.c_int, C.POINTER(ObFmt), C.c_int, C.c_int, C.c_int]
+        L.ob_rs_create.restype = C.c_void_p
+        L.ob_rs_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int] * 5
+        L.ob_rs_destroy.argtypes = [C.c_void_p]
+        L.ob_rs_ram_words.argtypes = [C.c_void_p]
+        L.ob_rs_run.restype = C.c_long
+        L.ob_rs_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64)]
+        L.ob_rs_delay_out.restype = C.c_int64
+        L.ob_rs_delay_out.argtypes = [C.c_void_p]
         _lib_b = L
     return _lib_b
 
@@ -115,6 +123,14 @@ def lib_a():
         L.acref_cic_run.restype = C.c_long
         L.acref_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.acref_cic_destroy.argtypes = [C.c_void_p]
+        L.acref_rs_create.restype = C.c_void_p
+        L.acref_rs_create.argtypes = [C.c_int]
+        L.acref_rs_run.restype = C.c_long
+        L.acref_rs_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.acref_rs_delay_out.restype = C.c_int64
+        L.acref_rs_delay_out.argtypes = [C.c_void_p]
+        L.acref_rs_ram_words.argtypes = [C.c_void_p]
+        L.acref_rs_destroy.argtypes = [C.c_void_p]
         _lib_a = L
     return _lib_a
 
@@ -254,6 +270,60 @@ class CicA:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.acref_cic_destroy(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------- ac_fir_reg_share (row N1)
+class RsB:
+    """Oracle B ac_fir_reg_share object: run(samples, coefficient RAM) = one reference run() per sample."""
+
+    def __init__(self, fin, fout, fcoeff, facc, n_taps, mww=1, blk_sz=1, blk_off=0, ftype="SHIFT_REG"):
+        self.L = lib_b()
+        ft = FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        a, b, c, d = _obfmt(fin), _obfmt(fcoeff), _obfmt(facc), _obfmt(fout)
+        self.h = self.L.ob_rs_create(C.byref(a), C.byref(b), C.byref(c), C.byref(d), int(n_taps), int(mww), int(blk_sz), int(blk_off), ft)
+        self.ram_words = self.L.ob_rs_ram_words(self.h)
+
+    def run(self, x, ram):
+        x, ram = _i64(x), _i64(ram)
+        out = np.empty(x.size, dtype=np.int64)
+        n = self.L.ob_rs_run(self.h, _p(x), x.size, _p(ram), ram.size, _p(out))
+        if n < 0:
+            raise ValueError("unsupported ftype / coefficient RAM too small")
+        return out[:n]
+
+    def delay_out(self):
+        return int(self.L.ob_rs_delay_out(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_rs_destroy(self.h)
+            self.h = None
+
+
+class RsA:
+    """The real reference ac_fir_reg_share for one compiled-in configuration (index into ref_configs.RS_CONFIGS)."""
+
+    def __init__(self, cfg_id):
+        self.L = lib_a()
+        self.h = self.L.acref_rs_create(int(cfg_id))
+        if not self.h:
+            raise KeyError("configuration not instantiated in oracle/_ref")
+        self.ram_words = self.L.acref_rs_ram_words(self.h)
+
+    def run(self, x, ram):
+        x, ram = _i64(x), _i64(ram)
+        assert ram.size >= self.ram_words
+        out = np.empty(x.size, dtype=np.int64)
+        n = self.L.acref_rs_run(self.h, _p(x), x.size, _p(ram), _p(out))
+        return out[:n]
+
+    def delay_out(self):
+        return int(self.L.acref_rs_delay_out(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_rs_destroy(self.h)
             self.h = None
 
 

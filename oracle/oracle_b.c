@@ -184,6 +184,86 @@ long ob_fir_run(ob_fir *f, const int64_t *in, long n, int64_t *out) {
   return n;
 }
 
+/* ------------------------------------------------------------------ ac_fir_reg_share */
+/* One object of include/ac_dsp/ac_fir_reg_share.h:257-303 with its delay line (reg[N_TAPS], zero-initialised here;
+ * caller-owned in the reference).  run() takes ONE sample and the coefficient RAM per call. */
+typedef struct {
+  ob_fmt in, coeff, acc, out;
+  int n, ftype, mww, blk_sz, blk_off;
+  w128 *reg;
+} ob_rs;
+
+ob_rs *ob_rs_create(const ob_fmt *in, const ob_fmt *coeff, const ob_fmt *acc, const ob_fmt *out, int n_taps, int mww, int blk_sz,
+                    int blk_off, int ftype) {
+  ob_rs *f = (ob_rs *)calloc(1, sizeof(ob_rs));
+  f->in = *in; f->coeff = *coeff; f->acc = *acc; f->out = *out;
+  f->n = n_taps; f->ftype = ftype; f->mww = mww; f->blk_sz = blk_sz; f->blk_off = blk_off;
+  f->reg = (w128 *)calloc(n_taps, sizeof(w128));
+  return f;
+}
+void ob_rs_destroy(ob_rs *f) { if (f) { free(f->reg); free(f); } }
+
+/* words of coefficient RAM the block loops touch */
+int ob_rs_ram_words(const ob_rs *f) {
+  int used = f->ftype == FT_SHIFT_REG ? f->n : ((f->ftype == FT_FOLD_EVEN || f->ftype == FT_FOLD_EVEN_ANTI) ? f->n / 2 : (f->n - 1) / 2 + 1);
+  int nblk = (used + f->blk_sz - 1) / f->blk_sz;
+  return (nblk - 1) * f->mww + f->blk_off + f->blk_sz;
+}
+
+static w128 rs_one(ob_rs *f, w128 x, const w128 *ram) {
+  const int N = f->n;
+  const int Fin = F_of(&f->in), Fc = F_of(&f->coeff), Fa = F_of(&f->acc);
+  w128 acc = 0;
+  int ram_addr = 0;
+  /* firShiftReg: ac_fir_reg_share.h:105-111 */
+  for (int i = N - 1; i >= 0; i--) f->reg[i] = (i == 0) ? x : f->reg[i - 1];
+  switch (f->ftype) {
+    case FT_SHIFT_REG:       /* firProgCoeffsShiftReg: :122-135, taps visited UPWARDS, blocked RAM addressing */
+      for (int i = 0; i < N; i += f->blk_sz, ram_addr += f->mww)
+        for (int bc = f->blk_off, index = 0; bc < f->blk_off + f->blk_sz; bc++, index++)
+          acc = ob_macc(acc, &f->acc, f->reg[i + index] * ram[ram_addr + bc], Fin + Fc);
+      break;
+    case FT_FOLD_EVEN:       /* ...SymmetricEvenTaps: :136-150 */
+    case FT_FOLD_EVEN_ANTI:  /* ...AntiSymmetricEvenTaps: :151-165 (pre-subtract, exact) */
+      for (int i = 0; i < N / 2; i += f->blk_sz, ram_addr += f->mww)
+        for (int bc = f->blk_off, index = 0; bc < f->blk_off + f->blk_sz; bc++, index++) {
+          w128 b = f->reg[N - 1 - i - index];
+          w128 pre = f->ftype == FT_FOLD_EVEN ? f->reg[i + index] + b : f->reg[i + index] - b;
+          acc = ob_macc(acc, &f->acc, pre * ram[ram_addr + bc], Fin + Fc);
+        }
+      break;
+    case FT_FOLD_ODD:        /* ...SymmetricOddTaps: :166-185 (`fold` is ACC_TYPE, centre tap passes through) */
+    case FT_FOLD_ODD_ANTI:   /* ...AntiSymmetricOddTaps: :186-205 */
+      for (int i = 0; i < (N - 1) / 2 + 1; i += f->blk_sz, ram_addr += f->mww)
+        for (int bc = f->blk_off, index = 0; bc < f->blk_off + f->blk_sz; bc++, index++) {
+          w128 fold;
+          if (i + index == (N - 1) / 2) fold = ob_convert(f->reg[i + index], Fin, &f->acc);
+          else {
+            w128 b = f->reg[N - 1 - i - index];
+            fold = ob_convert(f->ftype == FT_FOLD_ODD ? f->reg[i + index] + b : f->reg[i + index] - b, Fin, &f->acc);
+          }
+          acc = ob_macc(acc, &f->acc, ram[ram_addr + bc] * fold, Fc + Fa);
+        }
+      break;
+    default: return 0;       /* run() writes an unset core_out for the other FTYPE values (:277-303) */
+  }
+  return ob_convert(acc, Fa, &f->out);
+}
+
+/* n calls of run(data_in, coeffs, data_out) with the same coefficient RAM (raw values, n_ram words) */
+long ob_rs_run(ob_rs *f, const int64_t *in, long n, const int64_t *ram_raw, int n_ram, int64_t *out) {
+  if (!(f->ftype == FT_SHIFT_REG || f->ftype == FT_FOLD_EVEN || f->ftype == FT_FOLD_EVEN_ANTI || f->ftype == FT_FOLD_ODD ||
+        f->ftype == FT_FOLD_ODD_ANTI)) return -1;
+  if (n_ram < ob_rs_ram_words(f)) return -2;
+  w128 *ram = (w128 *)calloc(n_ram > 0 ? n_ram : 1, sizeof(w128));
+  for (int i = 0; i < n_ram; i++) ram[i] = ob_wrap((w128)ram_raw[i], f->coeff.W, f->coeff.S);
+  for (long k = 0; k < n; k++) out[k] = (int64_t)rs_one(f, ob_wrap((w128)in[k], f->in.W, f->in.S), ram);
+  free(ram);
+  return n;
+}
+/* ac_firProgCoeffs_delay_line: :304-307 -> OUT_TYPE(reg[N_TAPS-1]) */
+int64_t ob_rs_delay_out(ob_rs *f) { return (int64_t)ob_convert(f->reg[f->n - 1], F_of(&f->in), &f->out); }
+
 /* ------------------------------------------------------------------ CIC */
 typedef struct {
   ob_fmt in, out, it;   /* it = lossless INT_TYPE */

@@ -87,6 +87,44 @@ def _cic_list():
 CIC_CONFIGS = _cic_list()
 
 
+# ac_fir_reg_share instantiations:
+# (N_TAPS, in, out, coeff, acc, MEM_WORD_WIDTH, BLK_SZ, BLK_OFFSET, ftype)
+_Q15, _ACC40 = fmt(16, 1), fmt(40, 8)
+RS_CONFIGS = [
+    (16, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "SHIFT_REG"),
+    (16, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "FOLD_EVEN"),
+    (16, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "FOLD_EVEN_ANTI"),
+    (15, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "FOLD_ODD"),
+    (15, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "FOLD_ODD_ANTI"),
+    (64, _Q15, _ACC40, _Q15, _ACC40, 1, 1, 0, "FOLD_EVEN_ANTI"),
+    # blocked coefficient RAM: tap t reads ram[(t / BLK_SZ) * MEM_WORD_WIDTH + BLK_OFFSET + t % BLK_SZ]
+    (16, _Q15, _ACC40, _Q15, _ACC40, 4, 2, 1, "SHIFT_REG"),
+    (24, _Q15, _ACC40, _Q15, _ACC40, 8, 4, 4, "FOLD_EVEN_ANTI"),
+    # per-tap truncation + narrow output (the anti-symmetric pre-add is inside the truncated product)
+    (16, _Q15, fmt(16, 1), _Q15, fmt(24, 4), 1, 1, 0, "FOLD_EVEN_ANTI"),
+    (15, _Q15, fmt(16, 1), _Q15, fmt(24, 4), 1, 1, 0, "FOLD_ODD_ANTI"),
+    (16, _Q15, fmt(16, 1, True, RND), _Q15, fmt(24, 4, True, RND), 1, 1, 0, "FOLD_EVEN"),
+    # the reference prog bench's formats, anti-symmetric
+    (27, fmt(28, 6), fmt(64, 32), fmt(23, 7), fmt(64, 32), 1, 1, 0, "FOLD_ODD_ANTI"),
+    (12, fmt(32, 16), fmt(64, 32), fmt(32, 16), fmt(64, 32), 1, 1, 0, "FOLD_EVEN_ANTI"),
+    # unsigned samples: the difference of two unsigned values is signed
+    (9, fmt(12, 0, False), fmt(20, 4), fmt(14, 2), fmt(30, 6), 1, 1, 0, "FOLD_ODD_ANTI"),
+    # order-dependent accumulator: ac_fir_reg_share walks the taps upwards (ac_fir_reg_share.h:122-133)
+    (16, _Q15, fmt(16, 1, True, "AC_RND_CONV", "AC_SAT_SYM"), _Q15, fmt(24, 4, True, TRN, "AC_SAT"), 1, 1, 0, "SHIFT_REG"),
+    (10, _Q15, fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), _Q15, fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), 1, 1, 0, "FOLD_EVEN_ANTI"),
+    # accumulator too narrow for the pre-add (wrap inside FOLD_ODD_ANTI's `fold`)
+    (7, _Q15, fmt(18, 1), _Q15, fmt(18, 1), 1, 1, 0, "FOLD_ODD_ANTI"),
+]
+
+
+def rs_ram_words(cfg):
+    """Coefficient RAM words an instantiation reads (ac_fir_reg_share.h:122-133 and analogues)."""
+    N, _fi, _fo, _fc, _fa, mww, bs, bo, ft = cfg
+    used = N if ft == "SHIFT_REG" else (N // 2 if ft.startswith("FOLD_EVEN") else (N - 1) // 2 + 1)
+    nblk = (used + bs - 1) // bs
+    return (nblk - 1) * mww + bo + bs
+
+
 def fir_configs():
     """Flat list of (id, name, in, coeff, acc, out, taps)."""
     res = []

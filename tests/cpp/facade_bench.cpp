@@ -14,6 +14,7 @@
 #include <ac_dsp/ac_fir_prog_coeffs.h>
 #include <ac_dsp/ac_cic_dec_full.h>
 #include <ac_dsp/ac_cic_intr_full.h>
+#include <ac_dsp/ac_fir_reg_share.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -116,6 +117,28 @@ static int run_prog(const std::vector<long long> &x, const std::vector<long long
   return 0;
 }
 
+// ac_fir_reg_share: caller-owned delay line, scalar run(), coefficient RAM per call; out.txt = outputs followed by the
+// final ac_firProgCoeffs_delay_line value
+template <int N, class IN, class OUT, class COEFF, class ACC, int MWW, int BS, int BO, FTYPE ft>
+static int run_reg_share(const std::vector<long long> &x, const std::vector<long long> &ram, std::vector<long long> &y) {
+  IN reg[N];
+  for (int i = 0; i < N; i++) reg[i] = 0;
+  ac_fir_reg_share<N, IN, OUT, COEFF, ACC, MWW, BS, BO, ft> filter(reg);
+  std::vector<COEFF> coeffs(ram.size() < (size_t)N ? (size_t)N : ram.size());
+  for (size_t i = 0; i < ram.size(); i++) coeffs[i] = from_raw<COEFF>(ram[i]);
+  for (size_t k = 0; k < x.size(); k++) {
+    IN in = from_raw<IN>(x[k]);
+    OUT out;
+    filter.run(in, coeffs.data(), out);
+    y.push_back(to_raw(out));
+    if (to_raw(reg[0]) != x[k]) return 3;      // the caller's delay line is kept up to date
+  }
+  OUT dl;
+  filter.ac_firProgCoeffs_delay_line(dl);
+  y.push_back(to_raw(dl));
+  return 0;
+}
+
 template <class FILTER, class IN, class OUT>
 static int run_cic(const std::vector<long long> &x, size_t chunk, std::vector<long long> &y) {
   FILTER filter;
@@ -165,6 +188,15 @@ int main(int argc, char **argv) {
       rc = run_cic<ac_cic_dec_full<ac_fixed<16, 1, true>, ac_fixed<28, 13, true>, 8, 1, 4>, ac_fixed<16, 1, true>, ac_fixed<28, 13, true> >(x, chunk, y);
     else if (name == "q15_cic_intr")
       rc = run_cic<ac_cic_intr_full<ac_fixed<16, 1, true>, ac_fixed<20, 5, true>, 4, 1, 3>, ac_fixed<16, 1, true>, ac_fixed<20, 5, true> >(x, chunk, y);
+    // ---- ac_fir_reg_share (oracle/ref_configs.py RS_CONFIGS 2, 4, 7, 9)
+    else if (name == "rs2")
+      rc = run_reg_share<16, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 1, 1, 0, FOLD_EVEN_ANTI>(x, c, y);
+    else if (name == "rs4")
+      rc = run_reg_share<15, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 1, 1, 0, FOLD_ODD_ANTI>(x, c, y);
+    else if (name == "rs7")
+      rc = run_reg_share<24, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 8, 4, 4, FOLD_EVEN_ANTI>(x, c, y);
+    else if (name == "rs9")
+      rc = run_reg_share<15, ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<24, 4, true>, 1, 1, 0, FOLD_ODD_ANTI>(x, c, y);
     else
       std::fprintf(stderr, "unknown case %s\n", name.c_str());
   } catch (const b200dsp::engine_error &e) {

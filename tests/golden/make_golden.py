@@ -14,6 +14,10 @@ Fixtures (all raw two's-complement integers, int64):
       the reference FIR benches' stimulus (two-tone, rtest_ac_fir_const_coeffs.cpp:126-151),
       coefficient files, the MATLAB double reference, and the output of the UNMODIFIED
       reference class (Oracle A) on that stimulus, plus the SQNR it obtains.
+  rs_outputs.npz
+      outputs of the UNMODIFIED reference class ac_fir_reg_share (oracle/ref_driver_rs.cpp) for every configuration
+      in oracle/ref_configs.RS_CONFIGS: samples, coefficient RAM image, outputs of three run batches, final
+      ac_firProgCoeffs_delay_line value.
   ref_outputs.npz
       outputs of the UNMODIFIED reference classes (Oracle A) on seeded random inputs for every
       configuration in oracle/ref_configs.py x ftype (FIR) and every CIC configuration, fed in
@@ -136,6 +140,19 @@ def main():
         store[f"cic{cid}_x"] = x
         store[f"cic{cid}_y"] = np.concatenate(parts)
         store[f"cic{cid}_counts"] = np.array([p.size for p in parts], dtype=np.int64)
+    # ---- ac_fir_reg_share: the real reference class on seeded inputs, separate file
+    rs = {}
+    rng2 = np.random.default_rng(SEED + 1)
+    for cid, cfg in enumerate(rc.RS_CONFIGS):
+        N, fi, fo, fc, fa, mww, bs, bo, ft = cfg
+        f = O.RsA(cid)
+        x = O.rand_raw(rng2, fi, 4 * N + 50)
+        ram = O.rand_raw(rng2, fc, f.ram_words)
+        rs[f"rs{cid}_x"], rs[f"rs{cid}_ram"] = x, ram
+        rs[f"rs{cid}_y"] = np.concatenate([f.run(x[:7], ram), f.run(x[7:8], ram), f.run(x[8:], ram)])
+        rs[f"rs{cid}_dl"] = np.array([f.delay_out()], dtype=np.int64)
+    np.savez_compressed(OUT + "/rs_outputs.npz", **rs)
+    print("rs_outputs:", len(rs), "arrays")
     np.savez_compressed(OUT + "/ref_outputs.npz", **store)
     print("ref_outputs:", len(store), "arrays,", os.path.getsize(OUT + "/ref_outputs.npz") // 1024, "KiB")
 

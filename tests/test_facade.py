@@ -112,3 +112,18 @@ def test_facade_baseline_configs(bench_exe, tmp_path, oracle):
             p, y = run_case(bench_exe, tmp_path, case, x, None, chunk)
             assert p.returncode == 0, (case, p.stderr)
             assert np.array_equal(y, oracle.CicB(mode, q15, fout, R, M, N).run(x)), (case, chunk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", [2, 4, 7, 9])
+def test_facade_reg_share(bench_exe, tmp_path, cid):
+    """ac_fir_reg_share through its facade class (caller-owned delay line, scalar run(), blocked coefficient RAM)
+    against the committed outputs of the unmodified reference class."""
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    x = g[f"rs{cid}_x"][:60]
+    p, y = run_case(bench_exe, tmp_path, f"rs{cid}", x, g[f"rs{cid}_ram"])
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(y[:-1], g[f"rs{cid}_y"][:60])
+    from oracle import ref_configs as rc
+    N, fi, fo = rc.RS_CONFIGS[cid][:3]
+    assert y[-1] == int(x[60 - N]) << ((fo[0] - fo[1]) - (fi[0] - fi[1]))   # OUT_TYPE(reg[N_TAPS-1]): widening or equal formats here

@@ -493,3 +493,48 @@ def test_cic_fir_cascade_channels_device_and_extremes(engine, oracle):
                               oracle_cascade(oracle, Q15, (20, 5), 4, 1, 3, Q15, ACC40, ACC40, 63, "SHIFT_REG", he, [xe])), (kx, kh)
     with pytest.raises(engine.B2dError):
         engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, coeffs=None).run(np.zeros(8, dtype=np.int16))
+
+
+# ------------------------------------------------------------------------ ac_fir_reg_share
+@pytest.mark.parametrize("cid", range(len(rc.RS_CONFIGS)), ids=lambda i: f"rs{i}-{rc.RS_CONFIGS[i][8]}-{rc.RS_CONFIGS[i][0]}")
+def test_reg_share_vs_reference_outputs(engine, cid, path):
+    """The engine against the committed outputs of the UNMODIFIED reference class ac_fir_reg_share: block run(),
+    ac_firProgCoeffs_delay_line, and the scalar explicit-delay-line form the facade uses."""
+    g = golden("rs_outputs.npz")
+    N, fi, fo, fc, fa, mww, bs, bo, ft = rc.RS_CONFIGS[cid]
+    x, ram, want = g[f"rs{cid}_x"], g[f"rs{cid}_ram"], g[f"rs{cid}_y"]
+    f = engine.ac_fir_reg_share(N, fi, fo, fc, fa, mww, bs, bo, ft)
+    y = np.concatenate([f.run(x[:7], ram), f.run(x[7:8]), f.run(x[8:], ram)])
+    assert np.array_equal(y.astype(np.int64), want), f.path
+    assert int(f.delay_line()) == int(g[f"rs{cid}_dl"][0])
+    # scalar form: the caller owns the delay line (reg[0] newest); three positions inside the stream
+    for n in (0, 5, x.size - 1):
+        reg = np.zeros(N, dtype=np.int64)
+        hist = x[max(0, n - N + 1): n + 1][::-1]
+        reg[: hist.size] = hist
+        assert int(f.run_window(reg)) == int(want[n]), n
+
+
+def test_reg_share_random_and_errors(engine, oracle):
+    rng = np.random.default_rng(41)
+    for N, ft, fc in ((256, "FOLD_EVEN_ANTI", (15, 1)), (255, "FOLD_ODD_ANTI", (15, 1)), (256, "FOLD_EVEN_ANTI", Q15), (64, "SHIFT_REG", Q15)):
+        f = engine.ac_fir_reg_share(N, Q15, ACC40, fc, ACC40, 1, 1, 0, ft, n_channels=2, layout="interleaved")
+        assert f.path == ("fir_q15" if (fc != Q15 or ft == "SHIFT_REG") else "fir_wide"), f.path   # negated 16-bit taps need 17 bits
+        ob = [oracle.RsB(Q15, ACC40, fc, ACC40, N, 1, 1, 0, ft) for _ in range(2)]
+        ram = oracle.rand_raw(rng, fc, ob[0].ram_words)
+        x = rng.integers(-32768, 32767, size=(9000, 2), endpoint=True).astype(np.int16)
+        y = f.run(x, ram)
+        for c in range(2):
+            assert np.array_equal(y[:, c].astype(np.int64), ob[c].run(x[:, c], ram)), (N, ft, c)
+        dl = f.delay_line()
+        assert [int(v) for v in dl] == [ob[c].delay_out() for c in range(2)]
+    with pytest.raises(engine.B2dError):      # ac_fir_reg_share does not dispatch TRANSPOSED
+        engine.ac_fir_reg_share(16, Q15, ACC40, Q15, ACC40, 1, 1, 0, "TRANSPOSED")
+    with pytest.raises(engine.B2dError):      # ... and the const / load / prog classes do not dispatch _ANTI
+        engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 16, "FOLD_EVEN_ANTI")
+    f = engine.ac_fir_reg_share(16, Q15, ACC40, Q15, ACC40, 4, 3, 0, "SHIFT_REG")
+    with pytest.raises(engine.B2dError):      # 16 taps are not a whole number of 3-tap blocks
+        f.load(np.zeros(64))
+    f = engine.ac_fir_reg_share(16, Q15, ACC40, Q15, ACC40, 4, 2, 1, "SHIFT_REG")
+    with pytest.raises(engine.B2dError):      # RAM image too small
+        f.load(np.zeros(8))

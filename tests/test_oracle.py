@@ -119,3 +119,36 @@ def test_int_width(oracle):
     assert oracle.cic_int_width("intr", (16, 1), 4, 1, 3) == 20
     assert oracle.cic_int_width("dec", (32, 16), 7, 2, 4) == 48
     assert oracle.cic_int_width("intr", (32, 16), 7, 2, 5) == 49
+
+
+# ------------------------------------------------------------------------ ac_fir_reg_share
+@pytest.mark.parametrize("cid", range(len(rc.RS_CONFIGS)), ids=lambda i: f"rs{i}-{rc.RS_CONFIGS[i][8]}-{rc.RS_CONFIGS[i][0]}")
+def test_reg_share_restatement_vs_reference_outputs(oracle, cid):
+    """Oracle B against the committed outputs of the UNMODIFIED reference class (tests/golden/rs_outputs.npz)."""
+    g = golden("rs_outputs.npz")
+    N, fi, fo, fc, fa, mww, bs, bo, ft = rc.RS_CONFIGS[cid]
+    f = oracle.RsB(fi, fo, fc, fa, N, mww, bs, bo, ft)
+    assert f.ram_words == rc.rs_ram_words(rc.RS_CONFIGS[cid]) == g[f"rs{cid}_ram"].size
+    x, ram = g[f"rs{cid}_x"], g[f"rs{cid}_ram"]
+    y = np.concatenate([f.run(x[:7], ram), f.run(x[7:8], ram), f.run(x[8:], ram)])
+    assert np.array_equal(y, g[f"rs{cid}_y"])
+    assert f.delay_out() == int(g[f"rs{cid}_dl"][0])
+
+
+def test_reg_share_live_reference_equals_restatement(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no reference tree)")
+    rng = np.random.default_rng(3)
+    for cid, (N, fi, fo, fc, fa, mww, bs, bo, ft) in enumerate(rc.RS_CONFIGS):
+        a, b = oracle.RsA(cid), oracle.RsB(fi, fo, fc, fa, N, mww, bs, bo, ft)
+        for kind in ("uniform", "min", "max", "alt"):
+            x, ram = oracle.rand_raw(rng, fi, 3 * N + 5, kind), oracle.rand_raw(rng, fc, a.ram_words, "uniform" if kind == "alt" else kind)
+            assert np.array_equal(a.run(x, ram), b.run(x, ram)), (cid, kind)
+            assert a.delay_out() == b.delay_out()
+
+
+def test_reg_share_kat_antisymmetric_kills_dc(oracle):
+    """Derived from the semantics (not a reference test): an anti-symmetric fold of a constant input is zero."""
+    f = oracle.RsB((16, 1), (40, 8), (16, 1), (40, 8), 16, 1, 1, 0, "FOLD_EVEN_ANTI")
+    y = f.run(np.full(64, 1234), np.arange(1, 9) * 1000)
+    assert np.all(y[15:] == 0) and np.any(y[:15] != 0)
