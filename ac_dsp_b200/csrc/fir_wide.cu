@@ -17,12 +17,10 @@
 // per 64 MACs in modes 0 / 1).
 #include <vector>
 
-#include "kernels.h"
+#include "fir_wide.cuh"
 
 namespace b2d {
 
-constexpr int kWideThreads = 128;
-constexpr int kWideT = 8;
 constexpr int kWideTile = kWideThreads * kWideT;
 constexpr int kWideMaxTaps = 4096;
 
@@ -91,32 +89,7 @@ __global__ void __launch_bounds__(kWideThreads) fir_wide_kernel(WideArgs a) {
       for (int j = 0; j < kWideT; j++) acc[j] += (h * (long long)xs[B + j - a.centre] + a.rnd) >> a.s;
     }
   } else {
-    int win[kWideT];
-    {
-      const int4 w0 = *(const int4 *)(xs + B), w1 = *(const int4 *)(xs + B + 4);
-      win[0] = w0.x; win[1] = w0.y; win[2] = w0.z; win[3] = w0.w; win[4] = w1.x; win[5] = w1.y; win[6] = w1.z; win[7] = w1.w;
-    }
-    for (int i0 = 0; i0 < a.Npad; i0 += 8) {
-      int nw[8], h[8];
-      {
-        const int4 v0 = *(const int4 *)(xs + B - i0 - 8), v1 = *(const int4 *)(xs + B - i0 - 4);
-        nw[0] = v0.x; nw[1] = v0.y; nw[2] = v0.z; nw[3] = v0.w; nw[4] = v1.x; nw[5] = v1.y; nw[6] = v1.z; nw[7] = v1.w;
-        const int4 c0 = *(const int4 *)(cs + i0), c1 = *(const int4 *)(cs + i0 + 4);
-        h[0] = c0.x; h[1] = c0.y; h[2] = c0.z; h[3] = c0.w; h[4] = c1.x; h[5] = c1.y; h[6] = c1.z; h[7] = c1.w;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; t++) {
-#pragma unroll
-        for (int j = 0; j < kWideT; j++) {
-          const int xv = (j - t >= 0) ? win[(j - t) & 7] : nw[(8 + j - t) & 7];   // x[n0 + j - i0 - t]
-          const long long p = (long long)xv * (long long)h[t];
-          if (MODE == 0) acc[j] += p;
-          else acc[j] += (p + a.rnd) >> a.s;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kWideT; j++) win[j] = nw[j];
-    }
+    wide_mac_block<MODE>(xs, B, cs, a.Npad, a.s, a.rnd, acc);
   }
 
 #pragma unroll

@@ -64,6 +64,25 @@ bool cic_intr_fast_supported(const CicLaunch &p);
 cudaError_t launch_cic_intr_fast(const CicLaunch &p, cudaStream_t st);
 cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st);
 
+// Polyphase decimating FIR (ac_poly_dec): fir_dec.cu
+struct DecLaunch {
+  Fmt fin, fcoeff, facc, fout;
+  int nt, df, wide;      // taps per phase, decimation factor, 1 = IMAD.WIDE kernel / 0 = generic kernel
+  uint32_t C;
+  int interleaved;
+  const void *in;        // n inputs per channel
+  void *out;             // n_out outputs per channel, planar stride n_out
+  size_t n, n_out;
+  unsigned long long n_seen;
+  const void *tail;      // [C][nt*df - 1] previous samples
+  const int64_t *coeff64;   // [C][nt*df] raw taps in the reference's phase order
+  const int32_t *coeff32;   // [C][df][polydec_words(nt)] or null
+};
+int polydec_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int ntaps, int df);
+int polydec_words(int ntaps);
+void polydec_pack(const int64_t *c, int ntaps, int df, int32_t *out);
+cudaError_t launch_polydec(const DecLaunch &p, cudaStream_t st);
+
 // Interpolating polyphase FIR on 16-bit samples (fused CIC interpolator + FIR cascade): upfir_q15.cu
 struct UpLaunch {
   Fmt facc, fout;

@@ -1066,3 +1066,192 @@ extern "C" int b2d_cicfir_reset(b2d_cicfir *h) {
   if ((st = b2d_cic_reset(h->cic))) return st;
   return b2d_fir_reset(h->fir);
 }
+
+// -------------------------------------------------------------------------------------------- ac_poly_dec
+struct b2d_polydec {
+  b2d_polydec_desc d;
+  Fmt fin, fc, fa, fo;
+  int device = 0, in_bytes = 2, out_bytes = 8, c_bytes = 2, wide = 0, T = 0;
+  std::vector<char> ch_loaded;
+  int64_t *d_coeff64 = nullptr;
+  int32_t *d_coeff32 = nullptr;
+  void *d_tail[2] = {nullptr, nullptr};
+  int cur = 0;
+  unsigned long long n_seen = 0;
+  Pipe pipe;
+};
+
+extern "C" int b2d_polydec_destroy(b2d_polydec *h) {
+  if (!h) return B2D_OK;
+  use_device(h->device);
+  cudaDeviceSynchronize();
+  h->pipe.destroy();
+  if (h->d_coeff64) cudaFree(h->d_coeff64);
+  if (h->d_coeff32) cudaFree(h->d_coeff32);
+  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
+  delete h;
+  return B2D_OK;
+}
+
+extern "C" int b2d_polydec_create(b2d_polydec **out, const b2d_polydec_desc *desc) {
+  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
+  *out = nullptr;
+  int st;
+  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
+  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
+  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
+  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
+  if (desc->n_taps < 1 || desc->df < 1 || (uint64_t)desc->n_taps * desc->df > (1u << 20)) return fail(B2D_EINVAL, "NTAPS = %u, DF = %u invalid", desc->n_taps, desc->df);
+  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
+  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
+  const Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
+  {  // bit budget of the 128-bit generic evaluation (as for the FIR classes)
+    const int Fp = fin.F() + fc.F(), Wp = fin.W + fc.W + 2, rF = std::max(Fp, fa.F());
+    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + std::max(0, fo.F() - fa.F()) > 125)
+      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
+  }
+  int dev = desc->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if ((st = use_device(dev))) return st;
+  b2d_polydec *h = new (std::nothrow) b2d_polydec();
+  if (!h) return fail(B2D_ENOMEM, "handle");
+  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
+  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
+  const uint32_t C = desc->n_channels;
+  const size_t L = (size_t)desc->n_taps * desc->df;
+  h->T = (int)L - 1;
+  h->ch_loaded.assign(C, 0);
+  h->wide = polydec_wide_mode(fin, fc, fa, (int)desc->n_taps, (int)desc->df) >= 0;
+  const char *force = getenv("B2D_FORCE_GENERIC");
+  if (force && *force == '1') h->wide = 0;
+  cudaError_t e = cudaMalloc(&h->d_coeff64, C * L * sizeof(int64_t));
+  if (e == cudaSuccess && h->wide) e = cudaMalloc(&h->d_coeff32, (size_t)C * desc->df * polydec_words((int)desc->n_taps) * sizeof(int32_t));
+  const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaMalloc(&h->d_tail[i], tail_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); b2d_polydec_destroy(h); return fail(B2D_ECUDA, "b2d_polydec_create: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return B2D_OK;
+}
+
+extern "C" const char *b2d_polydec_path(b2d_polydec *h) { return !h ? "" : (h->wide ? "polydec_wide" : "polydec_generic"); }
+extern "C" size_t b2d_polydec_max_out(b2d_polydec *h, size_t n) { return h ? n / h->d.df + 1 : 0; }
+
+extern "C" int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t channel) {
+  if (!h || !coeff_raw) return fail(B2D_EINVAL, "null argument");
+  const size_t L = (size_t)h->d.n_taps * h->d.df;
+  const uint32_t C = h->d.n_channels;
+  if (n != L) return fail(B2D_EINVAL, "expected %zu coefficients (NTAPS * DF), got %zu", L, n);
+  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
+  int st = use_device(h->device);
+  if (st) return st;
+  std::vector<int64_t> v(L);
+  for (size_t i = 0; i < L; i++) {
+    int64_t r;
+    if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
+    else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
+    else r = ((const int64_t *)coeff_raw)[i];
+    v[i] = wrap_bits(r, h->fc.W, h->fc.S);
+  }
+  CU(cudaDeviceSynchronize());
+  const int words = polydec_words((int)h->d.n_taps);
+  std::vector<int32_t> pk;
+  if (h->wide) { pk.assign((size_t)h->d.df * words, 0); polydec_pack(v.data(), (int)h->d.n_taps, (int)h->d.df, pk.data()); }
+  for (uint32_t c = 0; c < C; c++) {
+    if (channel >= 0 && (uint32_t)channel != c) continue;
+    CU(cudaMemcpy(h->d_coeff64 + c * L, v.data(), L * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (h->wide) CU(cudaMemcpy(h->d_coeff32 + (size_t)c * pk.size(), pk.data(), pk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->ch_loaded[c] = 1;
+  }
+  return B2D_OK;
+}
+
+static size_t polydec_count(const b2d_polydec *h, size_t n) {
+  return (size_t)((h->n_seen + n) / h->d.df - h->n_seen / h->d.df);
+}
+
+static int polydec_launch(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  DecLaunch p;
+  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
+  p.nt = (int)h->d.n_taps; p.df = (int)h->d.df; p.wide = h->wide; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
+  p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out; p.n_seen = h->n_seen; p.tail = h->d_tail[h->cur];
+  p.coeff64 = h->d_coeff64; p.coeff32 = h->d_coeff32;
+  CU(launch_polydec(p, st));
+  FirLaunch t{};                    // history carry: the last NTAPS*DF - 1 samples, exactly as for an FIR of that length
+  t.fin = h->fin; t.n_taps = h->T + 1; t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;
+  t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1];
+  CU(launch_fir_tail(t, st));
+  h->cur ^= 1;
+  h->n_seen += n;
+  return B2D_OK;
+}
+
+static int polydec_ready(const b2d_polydec *h) {
+  for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
+  return B2D_OK;
+}
+
+extern "C" int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
+  int st = polydec_ready(h);
+  if (st) return st;
+  const size_t no = polydec_count(h, n);
+  if (no && !d_out) return fail(B2D_EINVAL, "null output");
+  if ((st = use_device(h->device))) return st;
+  if ((st = polydec_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
+  if (n_out) *n_out = no;
+  return B2D_OK;
+}
+
+extern "C" int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t *n_out) {
+  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
+  int st = polydec_ready(h);
+  if (st) return st;
+  const size_t no_total = polydec_count(h, n);
+  if (no_total && !out) return fail(B2D_EINVAL, "null output");
+  if (n_out) *n_out = no_total;
+  if (n == 0) return B2D_OK;
+  if ((st = use_device(h->device))) return st;
+  Pipe &P = h->pipe;
+  if ((st = P.init())) return st;
+  const uint32_t C = h->d.n_channels;
+  const int il = h->d.layout == B2D_INTERLEAVED;
+  const double per = C * (h->in_bytes + (double)h->out_bytes / h->d.df);
+  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
+  L = std::min(L, n);
+  if ((st = P.ensure(L * C * h->in_bytes, (L / h->d.df + 1) * C * h->out_bytes))) return st;
+  size_t i = 0, off_out = 0;
+  for (size_t off = 0; off < n; off += L, i++) {
+    const int s = (int)(i % Pipe::S);
+    const size_t len = std::min(L, n - off);
+    const size_t no = polydec_count(h, len);
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
+    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
+    CU(cudaEventRecord(P.e_in[s], P.s_in));
+    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
+    if ((st = polydec_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
+    CU(cudaEventRecord(P.e_k[s], P.s_k));
+    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
+    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
+    CU(cudaEventRecord(P.e_out[s], P.s_out));
+    off_out += no;
+  }
+  CU(cudaStreamSynchronize(P.s_out));
+  CU(cudaStreamSynchronize(P.s_k));
+  return B2D_OK;
+}
+
+extern "C" int b2d_polydec_reset(b2d_polydec *h) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
+  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
+  h->n_seen = 0;
+  return B2D_OK;
+}

@@ -358,6 +358,54 @@ class cic_intr_fir_cascade(_Block):
             pass
 
 
+class ac_poly_dec(_Block):
+    """ac_poly_dec<IN, COEFF, STR_COEFF, ACC, OUT, NTAPS, DF>::run(data_in, data_out, coeffs_st)
+    (reference ac_poly_dec.h:87-137): polyphase decimator, one output per DF inputs, coefficients
+    coeffs[NTAPS * DF] in phase order.  A call consumes whole groups of DF samples; the rest stays pending."""
+
+    def __init__(self, IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE, NTAPS, DF, coeffs=None, n_channels=1, layout="planar", device=-1):
+        lib = L.load()
+        self._h = None
+        self.NTAPS, self.DF = int(NTAPS), int(DF)
+        d = L.B2dPolydecDesc(L.make_fmt(IN_TYPE), L.make_fmt(COEFF_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE), self.NTAPS, self.DF,
+                             int(n_channels), L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR, int(device))
+        h = C.c_void_p()
+        L.check(lib.b2d_polydec_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self._coeff_dt = _container_dtype(d.coeff)
+        self._setup_io(d.fin, d.out, n_channels, layout)
+        if coeffs is not None:
+            self.load(coeffs)
+
+    @property
+    def path(self):
+        return L.load().b2d_polydec_path(self._h).decode()
+
+    def load(self, coeffs, channel=-1):
+        c = np.ascontiguousarray(np.asarray(coeffs).astype(self._coeff_dt, copy=False))
+        L.check(L.load().b2d_polydec_load(self._h, c.ctypes.data, c.size, int(channel)))
+
+    def run(self, data_in, coeffs_st=None, out=None):
+        if coeffs_st is not None:
+            self.load(coeffs_st)
+        lib = L.load()
+        return self._run(data_in, lib.b2d_polydec_run, lib.b2d_polydec_run_dev, lambda n: lib.b2d_polydec_max_out(self._h, n), True, out)
+
+    def reset(self):
+        L.check(L.load().b2d_polydec_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_polydec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Comm:
     """NCCL communicator of the C-ABI (one rank per GPU); only used for the coefficient broadcast at load()."""
 

@@ -59,6 +59,10 @@ WORKLOADS = {
     "cicfir": dict(kind="cicfir", R=4, M=1, N=3, mid=(20, 5), taps=63, channels=1, layout="planar", n=1 << 26,
                    unit_is_iq=False, bytes_per_unit=34.0, macs_per_unit=4 * 18 * 1.5,
                    name="ac_cic_intr_full R=4 M=1 N=3 <16,1> -> <20,5> + 63-tap FIR <20,5> x <16,1> -> <40,8>, fused, 1 real channel x 2^26 inputs per GPU"),
+    # the decimate-by-8 polyphase FIR that follows the R = 8 CIC decimator in a DDC chain
+    "polydec": dict(kind="polydec", taps=32, df=8, channels=2, layout="interleaved", n=1 << 30, unit_is_iq=True,
+                    bytes_per_unit=6.0, macs_per_unit=64,
+                    name="ac_poly_dec NTAPS=32 DF=8 (256 taps) <16,1> x <16,1> -> <40,8>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
     # BASELINE.json configs[4] first stage
     "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
                      unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
@@ -129,6 +133,16 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
             f.load(h)
             return f
         per_thread = int(seconds_target * 0.5e6 * 256 / taps)       # ~0.5 M real samples/s/core at 256 taps
+    elif wl["kind"] == "polydec":
+        cid = [i for i, c in enumerate(O.rc.PD_CONFIGS) if c[4] == wl["taps"] and c[5] == wl["df"] and c[0][0] == 16][0]
+        h = O.rand_raw(rng, Q15, wl["taps"] * wl["df"])
+
+        def make():
+            f = O.PdA(cid) if kind == "reference" else O.PdB(Q15, Q15, ACC40, ACC40, wl["taps"], wl["df"])
+            f.load(h)
+            f.last_run_seconds = lambda: None
+            return f
+        per_thread = int(seconds_target * 2e6)
     elif wl["kind"] == "cicfir":
         taps = wl["taps"]
         h = O.rand_raw(rng, Q15, taps)
@@ -170,7 +184,8 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
         t = time.perf_counter()
         objs[i].run(xs[i])
         # the reference arm times run() alone (channels pre-filled, drained afterwards): BASELINE.md section 3
-        secs[i] = objs[i].last_run_seconds() if kind == "reference" else time.perf_counter() - t
+        inner = objs[i].last_run_seconds() if kind == "reference" else None
+        secs[i] = inner if inner else time.perf_counter() - t
     ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     for t in ths:
         t.start()
@@ -258,6 +273,10 @@ def main():
                                  device=local, comm=comm, root=0)
         f.load(h if rank == 0 else None)
         launches_per_step = 2          # fir_q15_kernel + history carry
+    elif wl["kind"] == "polydec":
+        h = rng.integers(-32768, 32767, size=wl["taps"] * wl["df"], endpoint=True).astype(np.int16)
+        f = E.ac_poly_dec(Q15, Q15, ACC40, ACC40, wl["taps"], wl["df"], coeffs=h, n_channels=C, layout=wl["layout"], device=local)
+        launches_per_step = 2
     elif wl["kind"] == "cicfir":
         h = rng.integers(-32768, 32767, size=wl["taps"], endpoint=True).astype(np.int16)
         f = E.cic_intr_fir_cascade(Q15, wl["mid"], wl["R"], wl["M"], wl["N"], ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG",
@@ -315,6 +334,9 @@ def main():
         if wl["kind"] == "fir":
             yh = torch.empty(n2 * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_fir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), None)
+        elif wl["kind"] == "polydec":
+            yh = torch.empty(lib.b2d_polydec_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
+            call = lambda: lib.b2d_polydec_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
         elif wl["kind"] == "cicfir":
             yh = torch.empty(lib.b2d_cicfir_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_cicfir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
@@ -368,6 +390,7 @@ def main():
                 "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+                          "polydec": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
                           "cic": "s16 -> u32 (modular integrate / comb)"}[wl["kind"]],
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "samples_per_step_per_gpu": units_per_step, "kernel_path": path,

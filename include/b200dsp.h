@@ -182,6 +182,30 @@ int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, s
 int b2d_cicfir_reset(b2d_cicfir *h);
 const char *b2d_cicfir_path(b2d_cicfir *h);
 
+/* ---- polyphase decimator: ac_poly_dec ----------------------------------------------------------- */
+/* ac_poly_dec<IN, COEFF, STR_COEFF, ACC, OUT, NTAPS, DF>::run(data_in, data_out, coeffs_st)  (ac_poly_dec.h:87-137):
+ * one output per DF inputs, out[m] = sum_{r<DF} sum_{tp<NTAPS} coeffs[tp + NTAPS*r] * x[(m - tp)*DF + DF-1 - r], every
+ * `+=` re-quantised to ACC_TYPE.  Coefficients: n_taps*df raw values in the reference's phase order (the coeffs[] member
+ * of its coefficient struct).  A call consumes whole groups of DF samples; up to DF-1 trailing samples stay pending
+ * inside the handle (in the reference they stay queued on data_in).  Outputs are PLANAR with a channel stride of *n_out. */
+typedef struct {
+  b2d_fmt in, coeff, acc, out;  /* IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE                            */
+  uint32_t n_taps;              /* NTAPS: taps per phase (NTAPS * DF coefficients in all)             */
+  uint32_t df;                  /* DF: decimation factor >= 1                                         */
+  uint32_t n_channels;
+  int32_t layout;               /* layout of the input                                                */
+  int32_t device;
+} b2d_polydec_desc;
+typedef struct b2d_polydec b2d_polydec;
+int b2d_polydec_create(b2d_polydec **h, const b2d_polydec_desc *desc);
+int b2d_polydec_destroy(b2d_polydec *h);
+int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t channel);
+size_t b2d_polydec_max_out(b2d_polydec *h, size_t n);
+int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t *n_out);
+int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_polydec_reset(b2d_polydec *h);
+const char *b2d_polydec_path(b2d_polydec *h);
+
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128
 /* Channel c of n_channels lives on rank c % world (contiguous block alternative: see DESIGN.md). */

@@ -20,6 +20,9 @@ def main(outdir):
     with open(os.path.join(outdir, "cfgs_rs.inc"), "w") as fh:
         for cid, (N, fi, fo, fc, fa, mww, bs, bo, ft) in enumerate(rc.RS_CONFIGS):
             fh.write(f"X({cid}, {N}, {f(fi)}, {f(fo)}, {f(fc)}, {f(fa)}, {mww}, {bs}, {bo}, {ft}, {rc.rs_ram_words(rc.RS_CONFIGS[cid])})\n")
+    with open(os.path.join(outdir, "cfgs_pd.inc"), "w") as fh:
+        for cid, (fi, fc, fa, fo, nt, df) in enumerate(rc.PD_CONFIGS):
+            fh.write(f"X({cid}, {f(fi)}, {f(fc)}, {f(fa)}, {f(fo)}, {nt}, {df})\n")
     for mode in ("dec", "intr"):
         with open(os.path.join(outdir, f"cfgs_cic_{mode}.inc"), "w") as fh:
             for cid, c in enumerate(rc.CIC_CONFIGS):

@@ -87,6 +87,12 @@ def lib_b():
         L.ob_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.ob_cic_int_width.restype = C.c_int
         L.ob_cic_int_width.argtypes = [C.c_int, C.POINTER(ObFmt), C.c_int, C.c_int, C.c_int]
+        L.ob_pd_create.restype = C.c_void_p
+        L.ob_pd_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int, C.c_int]
+        L.ob_pd_destroy.argtypes = [C.c_void_p]
+        L.ob_pd_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.ob_pd_run.restype = C.c_long
+        L.ob_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.ob_rs_create.restype = C.c_void_p
         L.ob_rs_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int] * 5
         L.ob_rs_destroy.argtypes = [C.c_void_p]
@@ -123,6 +129,12 @@ def lib_a():
         L.acref_cic_run.restype = C.c_long
         L.acref_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.acref_cic_destroy.argtypes = [C.c_void_p]
+        L.acref_pd_create.restype = C.c_void_p
+        L.acref_pd_create.argtypes = [C.c_int]
+        L.acref_pd_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.acref_pd_run.restype = C.c_long
+        L.acref_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.acref_pd_destroy.argtypes = [C.c_void_p]
         L.acref_rs_create.restype = C.c_void_p
         L.acref_rs_create.argtypes = [C.c_int]
         L.acref_rs_run.restype = C.c_long
@@ -324,6 +336,61 @@ class RsA:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.acref_rs_destroy(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------- ac_poly_dec (row N2)
+class PdB:
+    """Oracle B ac_poly_dec: load(coeffs[NTAPS*DF], phase order) then run(samples) -> floor((pending + n) / DF) outputs."""
+
+    def __init__(self, fin, fcoeff, facc, fout, ntaps, df):
+        self.L = lib_b()
+        a, b, c, d = _obfmt(fin), _obfmt(fcoeff), _obfmt(facc), _obfmt(fout)
+        self.h = self.L.ob_pd_create(C.byref(a), C.byref(b), C.byref(c), C.byref(d), int(ntaps), int(df))
+        self.n_coeff, self.df = int(ntaps) * int(df), int(df)
+
+    def load(self, coeffs):
+        c = _i64(coeffs)
+        assert c.size == self.n_coeff
+        self.L.ob_pd_load(self.h, _p(c))
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size // self.df + 2, dtype=np.int64)
+        n = self.L.ob_pd_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_pd_destroy(self.h)
+            self.h = None
+
+
+class PdA:
+    """The real reference ac_poly_dec for one compiled-in configuration (index into ref_configs.PD_CONFIGS)."""
+
+    def __init__(self, cfg_id):
+        self.L = lib_a()
+        self.h = self.L.acref_pd_create(int(cfg_id))
+        if not self.h:
+            raise KeyError("configuration not instantiated in oracle/_ref")
+        _fi, _fc, _fa, _fo, nt, df = rc.PD_CONFIGS[cfg_id]
+        self.n_coeff, self.df = nt * df, df
+
+    def load(self, coeffs):
+        c = _i64(coeffs)
+        assert c.size == self.n_coeff
+        self.L.acref_pd_load(self.h, _p(c))
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size // self.df + 2, dtype=np.int64)
+        n = self.L.acref_pd_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_pd_destroy(self.h)
             self.h = None
 
 

@@ -264,6 +264,49 @@ long ob_rs_run(ob_rs *f, const int64_t *in, long n, const int64_t *ram_raw, int 
 /* ac_firProgCoeffs_delay_line: :304-307 -> OUT_TYPE(reg[N_TAPS-1]) */
 int64_t ob_rs_delay_out(ob_rs *f) { return (int64_t)ob_convert(f->reg[f->n - 1], F_of(&f->in), &f->out); }
 
+/* ------------------------------------------------------------------ ac_poly_dec */
+/* include/ac_dsp/ac_poly_dec.h:87-137: polyphase decimator.  taps[NTAPS*DF] shift register (zeroed, :95), DF partial
+ * accumulators acc1[] and the total acc, all ACC_TYPE; coefficients in phase order coeffs[tp + NTAPS*df]. */
+typedef struct {
+  ob_fmt in, coeff, acc, out;
+  int nt, df;
+  w128 *taps, *h;
+  w128 *pend; int npend;   /* samples of an incomplete group wait in data_in (`while (data_in.available(DF))`, :107) */
+} ob_pd;
+
+ob_pd *ob_pd_create(const ob_fmt *in, const ob_fmt *coeff, const ob_fmt *acc, const ob_fmt *out, int ntaps, int df) {
+  ob_pd *f = (ob_pd *)calloc(1, sizeof(ob_pd));
+  f->in = *in; f->coeff = *coeff; f->acc = *acc; f->out = *out; f->nt = ntaps; f->df = df;
+  f->taps = (w128 *)calloc((size_t)ntaps * df, sizeof(w128));
+  f->h = (w128 *)calloc((size_t)ntaps * df, sizeof(w128));
+  f->pend = (w128 *)calloc((size_t)df, sizeof(w128));
+  return f;
+}
+void ob_pd_destroy(ob_pd *f) { if (f) { free(f->taps); free(f->h); free(f->pend); free(f); } }
+/* coeffs_t = coeffs_st.read(): :101-106 */
+void ob_pd_load(ob_pd *f, const int64_t *c) {
+  for (int i = 0; i < f->nt * f->df; i++) f->h[i] = ob_wrap((w128)c[i], f->coeff.W, f->coeff.S);
+}
+long ob_pd_run(ob_pd *f, const int64_t *in, long n, int64_t *out) {
+  const int NT = f->nt, DF = f->df, L = NT * DF;
+  const int Fin = F_of(&f->in), Fc = F_of(&f->coeff), Fa = F_of(&f->acc);
+  long k = 0, nout = 0;
+  while (f->npend + (n - k) >= DF) {                    /* a whole group of DF samples is available */
+    w128 acc = 0;
+    for (int df = DF - 1; df >= 0; df--) {              /* :110-123 */
+      w128 x = f->npend > 0 ? f->pend[0] : ob_wrap((w128)in[k++], f->in.W, f->in.S);
+      if (f->npend > 0) { memmove(f->pend, f->pend + 1, (size_t)(f->npend - 1) * sizeof(w128)); f->npend--; }
+      for (int i = L - 1; i >= 0; i--) f->taps[i] = (i == 0) ? x : f->taps[i - 1];
+      w128 acc1 = 0;                                    /* acc1[df] is 0 on entry (:96,122) */
+      for (int tp = 0; tp < NT; tp++) acc1 = ob_macc(acc1, &f->acc, f->taps[tp * DF] * f->h[tp + NT * df], Fin + Fc);
+      acc = ob_macc(acc, &f->acc, acc1, Fa);            /* acc = acc + acc1[df] */
+    }
+    out[nout++] = (int64_t)ob_convert(acc, Fa, &f->out);  /* OUT_TYPE acc_t = acc: :124-126 */
+  }
+  while (k < n) f->pend[f->npend++] = ob_wrap((w128)in[k++], f->in.W, f->in.S);
+  return nout;
+}
+
 /* ------------------------------------------------------------------ CIC */
 typedef struct {
   ob_fmt in, out, it;   /* it = lossless INT_TYPE */

@@ -117,6 +117,24 @@ RS_CONFIGS = [
 ]
 
 
+# ac_poly_dec instantiations: (in, coeff, acc, out, NTAPS, DF)
+PD_CONFIGS = [
+    (_Q15, _Q15, _ACC40, _ACC40, 8, 2),
+    (_Q15, _Q15, _ACC40, _ACC40, 16, 4),
+    (_Q15, _Q15, _ACC40, _ACC40, 32, 8),        # 256 taps in all: the DDC partner of the R = 8 CIC decimator
+    (_Q15, _Q15, _ACC40, _ACC40, 5, 3),
+    (_Q15, _Q15, _ACC40, _ACC40, 1, 2),
+    (fmt(28, 13), _Q15, fmt(48, 16), fmt(48, 16), 12, 2),          # the CIC decimator's <28,13> output as input
+    (_Q15, _Q15, fmt(24, 4), fmt(16, 1), 16, 4),                  # per-tap truncation, narrow output
+    (_Q15, _Q15, fmt(24, 4, True, RND), fmt(16, 1, True, RND), 6, 5),
+    (fmt(12, 0, False), fmt(14, 2), fmt(30, 6), fmt(20, 4), 7, 3),  # unsigned samples
+    (fmt(32, 16), fmt(32, 16), fmt(64, 32), fmt(64, 32), 9, 4),
+    # order-dependent accumulators: taps upwards inside a phase, phases DF-1 .. 0 (ac_poly_dec.h:113-126)
+    (_Q15, _Q15, fmt(24, 4, True, TRN, "AC_SAT"), fmt(16, 1, True, "AC_RND_CONV", "AC_SAT_SYM"), 8, 4),
+    (_Q15, _Q15, fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), 5, 2),
+]
+
+
 def rs_ram_words(cfg):
     """Coefficient RAM words an instantiation reads (ac_fir_reg_share.h:122-133 and analogues)."""
     N, _fi, _fo, _fc, _fa, mww, bs, bo, ft = cfg

@@ -15,6 +15,7 @@
 #include <ac_dsp/ac_cic_dec_full.h>
 #include <ac_dsp/ac_cic_intr_full.h>
 #include <ac_dsp/ac_fir_reg_share.h>
+#include <ac_dsp/ac_poly_dec.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -139,6 +140,31 @@ static int run_reg_share(const std::vector<long long> &x, const std::vector<long
   return 0;
 }
 
+// ac_poly_dec: coefficients as one struct on a channel, whole groups of DF samples per run()
+template <class IN, class COEFF, class ACC, class OUT, int NT, int DF>
+static int run_poly_dec(const std::vector<long long> &x, const std::vector<long long> &c, size_t chunk, std::vector<long long> &y) {
+  struct Str { COEFF coeffs[NT * DF]; };
+  if ((int)c.size() != NT * DF) return 2;
+  ac_poly_dec<IN, COEFF, Str, ACC, OUT, NT, DF> filter;
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  ac_channel<Str> coeffs_st;
+  Str junk, good;
+  for (int i = 0; i < NT * DF; i++) { junk.coeffs[i] = from_raw<COEFF>(~c[i]); good.coeffs[i] = from_raw<COEFF>(c[i]); }
+  coeffs_st.write(junk);
+  coeffs_st.write(good);                      // the last struct queued wins
+  for (size_t i = 0; i < x.size(); i++) {
+    in.write(from_raw<IN>(x[i]));
+    if (chunk && (i + 1) % chunk == 0) {
+      filter.run(in, out, coeffs_st);
+      if (in.debug_size() >= (unsigned)DF) return 3;   // only an incomplete group may stay queued
+    }
+  }
+  filter.run(in, out, coeffs_st);
+  drain_to(out, y);
+  return 0;
+}
+
 template <class FILTER, class IN, class OUT>
 static int run_cic(const std::vector<long long> &x, size_t chunk, std::vector<long long> &y) {
   FILTER filter;
@@ -197,6 +223,11 @@ int main(int argc, char **argv) {
       rc = run_reg_share<24, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, 8, 4, 4, FOLD_EVEN_ANTI>(x, c, y);
     else if (name == "rs9")
       rc = run_reg_share<15, ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<24, 4, true>, 1, 1, 0, FOLD_ODD_ANTI>(x, c, y);
+    // ---- ac_poly_dec (oracle/ref_configs.py PD_CONFIGS 2, 6)
+    else if (name == "pd2")
+      rc = run_poly_dec<ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<40, 8, true>, 32, 8>(x, c, chunk, y);
+    else if (name == "pd6")
+      rc = run_poly_dec<ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<24, 4, true>, ac_fixed<16, 1, true>, 16, 4>(x, c, chunk, y);
     else
       std::fprintf(stderr, "unknown case %s\n", name.c_str());
   } catch (const b200dsp::engine_error &e) {

@@ -17,7 +17,8 @@ Fixtures (all raw two's-complement integers, int64):
   rs_outputs.npz
       outputs of the UNMODIFIED reference class ac_fir_reg_share (oracle/ref_driver_rs.cpp) for every configuration
       in oracle/ref_configs.RS_CONFIGS: samples, coefficient RAM image, outputs of three run batches, final
-      ac_firProgCoeffs_delay_line value.
+      ac_firProgCoeffs_delay_line value; and of the UNMODIFIED ac_poly_dec (oracle/ref_driver_pd.cpp) for every
+      configuration in PD_CONFIGS (samples, phase-ordered coefficients, outputs of three run batches).
   ref_outputs.npz
       outputs of the UNMODIFIED reference classes (Oracle A) on seeded random inputs for every
       configuration in oracle/ref_configs.py x ftype (FIR) and every CIC configuration, fed in
@@ -151,6 +152,13 @@ def main():
         rs[f"rs{cid}_x"], rs[f"rs{cid}_ram"] = x, ram
         rs[f"rs{cid}_y"] = np.concatenate([f.run(x[:7], ram), f.run(x[7:8], ram), f.run(x[8:], ram)])
         rs[f"rs{cid}_dl"] = np.array([f.delay_out()], dtype=np.int64)
+    for cid, (fi, fc, fa, fo, nt, df) in enumerate(rc.PD_CONFIGS):      # ac_poly_dec (row N2), same file
+        f = O.PdA(cid)
+        x = O.rand_raw(rng2, fi, 6 * nt * df + 37)
+        c = O.rand_raw(rng2, fc, nt * df)
+        f.load(c)
+        rs[f"pd{cid}_x"], rs[f"pd{cid}_c"] = x, c
+        rs[f"pd{cid}_y"] = np.concatenate([f.run(x[:1]), f.run(x[1:df + 2]), f.run(x[df + 2:])])
     np.savez_compressed(OUT + "/rs_outputs.npz", **rs)
     print("rs_outputs:", len(rs), "arrays")
     np.savez_compressed(OUT + "/ref_outputs.npz", **store)

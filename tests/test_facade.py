@@ -127,3 +127,15 @@ def test_facade_reg_share(bench_exe, tmp_path, cid):
     from oracle import ref_configs as rc
     N, fi, fo = rc.RS_CONFIGS[cid][:3]
     assert y[-1] == int(x[60 - N]) << ((fo[0] - fo[1]) - (fi[0] - fi[1]))   # OUT_TYPE(reg[N_TAPS-1]): widening or equal formats here
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", [2, 6])
+@pytest.mark.parametrize("chunk", [0, 13])
+def test_facade_poly_dec(bench_exe, tmp_path, cid, chunk):
+    """ac_poly_dec through its facade class (coefficient struct on a channel, groups of DF samples) against the
+    committed outputs of the unmodified reference class."""
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    p, y = run_case(bench_exe, tmp_path, f"pd{cid}", g[f"pd{cid}_x"], g[f"pd{cid}_c"], chunk)
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(y, g[f"pd{cid}_y"])

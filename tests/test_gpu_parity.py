@@ -538,3 +538,38 @@ def test_reg_share_random_and_errors(engine, oracle):
     f = engine.ac_fir_reg_share(16, Q15, ACC40, Q15, ACC40, 4, 2, 1, "SHIFT_REG")
     with pytest.raises(engine.B2dError):      # RAM image too small
         f.load(np.zeros(8))
+
+
+# ------------------------------------------------------------------------ ac_poly_dec
+@pytest.mark.parametrize("cid", range(len(rc.PD_CONFIGS)), ids=lambda i: f"pd{i}-NT{rc.PD_CONFIGS[i][4]}-DF{rc.PD_CONFIGS[i][5]}")
+def test_poly_dec_vs_reference_outputs(engine, cid, path):
+    """The engine against the committed outputs of the UNMODIFIED reference class ac_poly_dec (ragged calls: 1 sample,
+    DF+1 samples, the rest -- incomplete groups stay pending between calls)."""
+    g = golden("rs_outputs.npz")
+    fi, fc, fa, fo, nt, df = rc.PD_CONFIGS[cid]
+    x = g[f"pd{cid}_x"]
+    f = engine.ac_poly_dec(fi, fc, fa, fo, nt, df, coeffs=g[f"pd{cid}_c"])
+    y = np.concatenate([f.run(x[:1]), f.run(x[1:df + 2]), f.run(x[df + 2:])])
+    assert np.array_equal(y.astype(np.int64), g[f"pd{cid}_y"]), f.path
+
+
+def test_poly_dec_ddc_chain_channels_and_device(engine, oracle):
+    """The R = 8 CIC decimator's partner: 32 taps x 8 phases = 256-tap decimate-by-8 on 16-bit IQ, device path, big tiles."""
+    import torch
+    rng = np.random.default_rng(55)
+    nt, df, n = 32, 8, 400003
+    c = oracle.rand_raw(rng, Q15, nt * df)
+    x = rng.integers(-32768, 32767, size=(n, 2), endpoint=True).astype(np.int16)
+    f = engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df, coeffs=c, n_channels=2, layout="interleaved")
+    assert f.path == "polydec_wide"
+    xd = torch.from_numpy(x).cuda()
+    cuts = [0, 3, 200000, 200001, n]
+    parts = [f.run(xd[a:b]).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
+    for ch in range(2):
+        ob = oracle.PdB(Q15, Q15, ACC40, ACC40, nt, df)
+        ob.load(c)
+        assert np.array_equal(np.concatenate([p[ch] for p in parts]), ob.run(x[:, ch])), ch
+    with pytest.raises(engine.B2dError):
+        engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df).run(np.zeros(16, dtype=np.int16))     # no coefficients yet
+    with pytest.raises(engine.B2dError):
+        engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df, coeffs=np.zeros(nt))                  # needs NTAPS * DF values

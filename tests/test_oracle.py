@@ -152,3 +152,28 @@ def test_reg_share_kat_antisymmetric_kills_dc(oracle):
     f = oracle.RsB((16, 1), (40, 8), (16, 1), (40, 8), 16, 1, 1, 0, "FOLD_EVEN_ANTI")
     y = f.run(np.full(64, 1234), np.arange(1, 9) * 1000)
     assert np.all(y[15:] == 0) and np.any(y[:15] != 0)
+
+
+# ------------------------------------------------------------------------ ac_poly_dec
+@pytest.mark.parametrize("cid", range(len(rc.PD_CONFIGS)), ids=lambda i: f"pd{i}-NT{rc.PD_CONFIGS[i][4]}-DF{rc.PD_CONFIGS[i][5]}")
+def test_poly_dec_restatement_vs_reference_outputs(oracle, cid):
+    g = golden("rs_outputs.npz")
+    fi, fc, fa, fo, nt, df = rc.PD_CONFIGS[cid]
+    f = oracle.PdB(fi, fc, fa, fo, nt, df)
+    f.load(g[f"pd{cid}_c"])
+    x = g[f"pd{cid}_x"]
+    y = np.concatenate([f.run(x[:1]), f.run(x[1:df + 2]), f.run(x[df + 2:])])
+    assert y.size == x.size // df and np.array_equal(y, g[f"pd{cid}_y"])
+
+
+def test_poly_dec_live_reference_equals_restatement(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no reference tree)")
+    rng = np.random.default_rng(4)
+    for cid, (fi, fc, fa, fo, nt, df) in enumerate(rc.PD_CONFIGS):
+        a, b = oracle.PdA(cid), oracle.PdB(fi, fc, fa, fo, nt, df)
+        for kind in ("uniform", "min", "max", "alt"):
+            c = oracle.rand_raw(rng, fc, nt * df, "uniform" if kind == "alt" else kind)
+            a.load(c); b.load(c)
+            x = oracle.rand_raw(rng, fi, 5 * nt * df + 3, kind)
+            assert np.array_equal(a.run(x), b.run(x)), (cid, kind)
