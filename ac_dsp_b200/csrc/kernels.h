@@ -67,7 +67,7 @@ cudaError_t launch_cic_tail(const CicLaunch &p, cudaStream_t st);
 // Polyphase decimating FIR (ac_poly_dec): fir_dec.cu
 struct DecLaunch {
   Fmt fin, fcoeff, facc, fout;
-  int nt, df, wide;      // taps per phase, decimation factor, 1 = IMAD.WIDE kernel / 0 = generic kernel
+  int nt, df, wide;      // taps per phase, decimation factor, 2 = DP2A kernel / 1 = IMAD.WIDE kernel / 0 = generic kernel
   uint32_t C;
   int interleaved;
   const void *in;        // n inputs per channel
@@ -77,7 +77,11 @@ struct DecLaunch {
   const void *tail;      // [C][nt*df - 1] previous samples
   const int64_t *coeff64;   // [C][nt*df] raw taps in the reference's phase order
   const int32_t *coeff32;   // [C][df][polydec_words(nt)] or null
+  const uint32_t *coeff_pk; // [C][polydec_q15_words(nt, df)] or null
 };
+bool polydec_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, int ntaps, int df);
+int polydec_q15_words(int ntaps, int df);
+void polydec_q15_pack(const Fmt &coeff, const int64_t *c, int ntaps, int df, uint32_t *out);
 int polydec_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int ntaps, int df);
 int polydec_words(int ntaps);
 void polydec_pack(const int64_t *c, int ntaps, int df, int32_t *out);

@@ -1075,6 +1075,7 @@ struct b2d_polydec {
   std::vector<char> ch_loaded;
   int64_t *d_coeff64 = nullptr;
   int32_t *d_coeff32 = nullptr;
+  uint32_t *d_coeff_pk = nullptr;
   void *d_tail[2] = {nullptr, nullptr};
   int cur = 0;
   unsigned long long n_seen = 0;
@@ -1088,6 +1089,7 @@ extern "C" int b2d_polydec_destroy(b2d_polydec *h) {
   h->pipe.destroy();
   if (h->d_coeff64) cudaFree(h->d_coeff64);
   if (h->d_coeff32) cudaFree(h->d_coeff32);
+  if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
   for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
   delete h;
   return B2D_OK;
@@ -1123,9 +1125,11 @@ extern "C" int b2d_polydec_create(b2d_polydec **out, const b2d_polydec_desc *des
   h->ch_loaded.assign(C, 0);
   h->wide = polydec_wide_mode(fin, fc, fa, (int)desc->n_taps, (int)desc->df) >= 0;
   const char *force = getenv("B2D_FORCE_GENERIC");
+  if (h->wide && polydec_q15_supported(fin, fc, fa, (int)desc->n_taps, (int)desc->df) && !(force && *force == '2')) h->wide = 2;
   if (force && *force == '1') h->wide = 0;
   cudaError_t e = cudaMalloc(&h->d_coeff64, C * L * sizeof(int64_t));
-  if (e == cudaSuccess && h->wide) e = cudaMalloc(&h->d_coeff32, (size_t)C * desc->df * polydec_words((int)desc->n_taps) * sizeof(int32_t));
+  if (e == cudaSuccess && h->wide == 2) e = cudaMalloc(&h->d_coeff_pk, (size_t)C * polydec_q15_words((int)desc->n_taps, (int)desc->df) * sizeof(uint32_t));
+  if (e == cudaSuccess && h->wide == 1) e = cudaMalloc(&h->d_coeff32, (size_t)C * desc->df * polydec_words((int)desc->n_taps) * sizeof(int32_t));
   const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
     e = cudaMalloc(&h->d_tail[i], tail_bytes);
@@ -1136,7 +1140,7 @@ extern "C" int b2d_polydec_create(b2d_polydec **out, const b2d_polydec_desc *des
   return B2D_OK;
 }
 
-extern "C" const char *b2d_polydec_path(b2d_polydec *h) { return !h ? "" : (h->wide ? "polydec_wide" : "polydec_generic"); }
+extern "C" const char *b2d_polydec_path(b2d_polydec *h) { return !h ? "" : (h->wide == 2 ? "polydec_q15" : (h->wide ? "polydec_wide" : "polydec_generic")); }
 extern "C" size_t b2d_polydec_max_out(b2d_polydec *h, size_t n) { return h ? n / h->d.df + 1 : 0; }
 
 extern "C" int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t channel) {
@@ -1158,11 +1162,14 @@ extern "C" int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n,
   CU(cudaDeviceSynchronize());
   const int words = polydec_words((int)h->d.n_taps);
   std::vector<int32_t> pk;
-  if (h->wide) { pk.assign((size_t)h->d.df * words, 0); polydec_pack(v.data(), (int)h->d.n_taps, (int)h->d.df, pk.data()); }
+  std::vector<uint32_t> pq;
+  if (h->wide == 1) { pk.assign((size_t)h->d.df * words, 0); polydec_pack(v.data(), (int)h->d.n_taps, (int)h->d.df, pk.data()); }
+  if (h->wide == 2) { pq.assign((size_t)polydec_q15_words((int)h->d.n_taps, (int)h->d.df), 0); polydec_q15_pack(h->fc, v.data(), (int)h->d.n_taps, (int)h->d.df, pq.data()); }
   for (uint32_t c = 0; c < C; c++) {
     if (channel >= 0 && (uint32_t)channel != c) continue;
     CU(cudaMemcpy(h->d_coeff64 + c * L, v.data(), L * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (h->wide) CU(cudaMemcpy(h->d_coeff32 + (size_t)c * pk.size(), pk.data(), pk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->wide == 1) CU(cudaMemcpy(h->d_coeff32 + (size_t)c * pk.size(), pk.data(), pk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->wide == 2) CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * pq.size(), pq.data(), pq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     h->ch_loaded[c] = 1;
   }
   return B2D_OK;
@@ -1178,7 +1185,7 @@ static int polydec_launch(b2d_polydec *h, const void *d_in, size_t n, void *d_ou
   p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
   p.nt = (int)h->d.n_taps; p.df = (int)h->d.df; p.wide = h->wide; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
   p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out; p.n_seen = h->n_seen; p.tail = h->d_tail[h->cur];
-  p.coeff64 = h->d_coeff64; p.coeff32 = h->d_coeff32;
+  p.coeff64 = h->d_coeff64; p.coeff32 = h->d_coeff32; p.coeff_pk = h->d_coeff_pk;
   CU(launch_polydec(p, st));
   FirLaunch t{};                    // history carry: the last NTAPS*DF - 1 samples, exactly as for an FIR of that length
   t.fin = h->fin; t.n_taps = h->T + 1; t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;

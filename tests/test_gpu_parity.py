@@ -561,7 +561,7 @@ def test_poly_dec_ddc_chain_channels_and_device(engine, oracle):
     c = oracle.rand_raw(rng, Q15, nt * df)
     x = rng.integers(-32768, 32767, size=(n, 2), endpoint=True).astype(np.int16)
     f = engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df, coeffs=c, n_channels=2, layout="interleaved")
-    assert f.path == "polydec_wide"
+    assert f.path == "polydec_q15"
     xd = torch.from_numpy(x).cuda()
     cuts = [0, 3, 200000, 200001, n]
     parts = [f.run(xd[a:b]).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
@@ -569,6 +569,18 @@ def test_poly_dec_ddc_chain_channels_and_device(engine, oracle):
         ob = oracle.PdB(Q15, Q15, ACC40, ACC40, nt, df)
         ob.load(c)
         assert np.array_equal(np.concatenate([p[ch] for p in parts]), ob.run(x[:, ch])), ch
+    # planar channels, odd tap count (padded phases), three accumulator flushes (5 phases x 112 padded taps), extremes
+    nt2, df2 = 100, 5
+    for kind in ("uniform", "min", "alt"):
+        c2 = oracle.rand_raw(rng, Q15, nt2 * df2, "uniform" if kind == "alt" else kind)
+        x2 = np.stack([oracle.rand_raw(rng, Q15, 30007, kind) for _ in range(3)]).astype(np.int16)
+        f2 = engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt2, df2, coeffs=c2, n_channels=3)
+        assert f2.path == "polydec_q15"
+        y2 = f2.run(x2)
+        for ch in range(3):
+            ob = oracle.PdB(Q15, Q15, ACC40, ACC40, nt2, df2)
+            ob.load(c2)
+            assert np.array_equal(y2[ch], ob.run(x2[ch])), (kind, ch)
     with pytest.raises(engine.B2dError):
         engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df).run(np.zeros(16, dtype=np.int16))     # no coefficients yet
     with pytest.raises(engine.B2dError):
