@@ -310,14 +310,35 @@ def test_cic_multichannel_layouts_and_state(engine, oracle):
             assert np.array_equal(b2, b)
 
 
-def test_cic_device_path(engine, oracle):
+@pytest.mark.parametrize("recursive", ["0", "1"])
+def test_cic_device_path(engine, oracle, recursive, monkeypatch):
+    """BASELINE config 3 on the fast decimator, both evaluation forms: the non-recursive three-stage half-band cascade
+    (DP2A first stage) and the integrator / comb recursion with run-in; interleaved IQ and planar, ragged calls."""
     import torch
+    monkeypatch.setenv("B2D_CIC_RECURSIVE", recursive)
     rng = np.random.default_rng(22)
     x = rng.integers(-32768, 32767, size=(1 << 20, 2), endpoint=True).astype(np.int16)
+    want = [oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(x[:, c]) for c in range(2)]
     f = engine.ac_cic_dec_full(Q15, (28, 13), 8, 1, 4, n_channels=2, layout="interleaved")
+    assert f.path == "cic_fast"
     y = f.run(torch.from_numpy(x).cuda()).cpu().numpy()
     for c in range(2):
-        assert np.array_equal(y[c].astype(np.int64), oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(x[:, c]))
+        assert np.array_equal(y[c].astype(np.int64), want[c])
+    f.reset()
+    cuts = [0, 8, 4096 + 8, 300000, 300008, 1 << 20]           # multiples of R keep the calls on the fast kernel
+    xd = torch.from_numpy(x).cuda()
+    parts = [f.run(xd[a:b]).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
+    for c in range(2):
+        assert np.array_equal(np.concatenate([p[c] for p in parts]).astype(np.int64), want[c])
+    g = engine.ac_cic_dec_full(Q15, (28, 13), 8, 1, 4, n_channels=2, layout="planar")
+    yp = g.run(torch.from_numpy(np.ascontiguousarray(x.T)).cuda()).cpu().numpy()
+    for c in range(2):
+        assert np.array_equal(yp[c].astype(np.int64), want[c])
+    for kind in ("min", "max", "alt"):
+        xe = oracle.rand_raw(rng, Q15, 40000, kind).astype(np.int16)
+        h = engine.ac_cic_dec_full(Q15, (28, 13), 8, 1, 4)
+        assert np.array_equal(h.run(torch.from_numpy(xe).cuda()).cpu().numpy().astype(np.int64),
+                              oracle.CicB("dec", Q15, (28, 13), 8, 1, 4).run(xe)), kind
 
 
 @pytest.mark.parametrize("staged", ["0", "1"])
