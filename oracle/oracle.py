@@ -59,6 +59,9 @@ def build(force=False):
     ref_here = os.path.exists(os.environ.get("AC_DSP_REF", "/root/reference") + "/include/ac_dsp/ac_fir_load_coeffs.h")
     if ref_here and not os.path.exists(os.path.join(HERE, "_ref", "libacdsp_ref.so")):
         need = True
+    if ref_here and os.path.exists(os.path.join(HERE, "..", "ac_dsp_b200", "lib", "libb200dsp.so")) and \
+            not os.path.exists(os.path.join(HERE, "_ref", "facade_rtest_ac_cic_dec_full")):
+        need = True
     if need:
         subprocess.check_call(["make", "-s", "-C", HERE, "-j8"], stdout=subprocess.DEVNULL)
 

@@ -139,3 +139,63 @@ def test_facade_poly_dec(bench_exe, tmp_path, cid, chunk):
     p, y = run_case(bench_exe, tmp_path, f"pd{cid}", g[f"pd{cid}_x"], g[f"pd{cid}_c"], chunk)
     assert p.returncode == 0, p.stderr
     assert np.array_equal(y, g[f"pd{cid}_y"])
+
+
+# ------------------------------------------------------------------------ the reference's own benches, unmodified (row N3)
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _exact_decimal(raw, F):
+    """raw * 2^-F as an exact decimal string (what MATLAB's dlmwrite put into the reference's vector files)."""
+    import decimal
+    with decimal.localcontext() as ctx:
+        ctx.prec = 120
+        return format(decimal.Decimal(int(raw)) / (decimal.Decimal(2) ** F), "f")
+
+
+def _write_vectors(d, name):
+    """Regenerate the text vectors a reference bench opens in its working directory from the committed fixtures
+    (the reference tree itself does not travel to the GPU box)."""
+    if name.startswith("ac_fir"):
+        cls = name.split("_")[2]
+        g = np.load(os.path.join(GOLDEN, f"fir_bench_{cls}.npz"))
+        with open(os.path.join(d, f"{name}_ref.txt"), "w") as f:
+            f.write("\n".join(repr(float(v)) for v in g["ref_double"]) + "\n")
+        Fc = int(g["fcoeff"][0] - g["fcoeff"][1])
+        with open(os.path.join(d, f"{name}_cfg.txt"), "w") as f:      # whitespace-separated doubles (load / prog read it at run time)
+            f.write("\n".join(_exact_decimal(v, Fc) for v in g["coeffs"]) + "\n")
+        return float(g["sqnr"])
+    if name == "ac_cic_dec_full":
+        g = np.load(os.path.join(GOLDEN, "cic_dec_golden.npz"))
+        x, ref, skip = g["x"][1:], g["ref"], 0          # the bench prepends the leading zero itself (rtest_ac_cic_dec_full.cpp:78-85)
+    else:
+        g = np.load(os.path.join(GOLDEN, "cic_intr_golden.npz"))
+        x, ref, skip = g["x"], g["ref"], int(g["N"])    # the bench throws the first N reference values away (rtest_ac_cic_intr_full.cpp:99)
+    Fi, Fo = int(g["fin"][0] - g["fin"][1]), int(g["fout"][0] - g["fout"][1])
+    with open(os.path.join(d, f"{name}_input.txt"), "w") as f:
+        f.write("\n".join(_exact_decimal(v, Fi) for v in x) + "\n")
+    with open(os.path.join(d, f"{name}_ref.txt"), "w") as f:
+        f.write("\n".join(["0"] * skip + [_exact_decimal(v, Fo) for v in ref]) + "\n")
+    return None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ac_fir_const_coeffs", "ac_fir_load_coeffs", "ac_fir_prog_coeffs", "ac_cic_dec_full", "ac_cic_intr_full"])
+def test_unmodified_reference_bench_passes_on_the_engine(name, tmp_path):
+    """The reference's own rtest_<name>.cpp -- compiled UNMODIFIED in the dev container against the header facade and
+    linked with libb200dsp.so (oracle/Makefile: facade_rtest_*) -- runs on the GPU and reports what it reports for the
+    reference implementation: bit-exact CIC vectors, FIR SQNR 84.2385 / 89.5576 / 89.5576 dB."""
+    exe = os.path.join(REF_BIN, f"facade_rtest_{name}")
+    if not os.path.exists(exe):
+        pytest.skip("facade_rtest binaries are built where the reference tree is present (oracle/Makefile)")
+    want_sqnr = _write_vectors(str(tmp_path), name)
+    p = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-2000:]
+    assert "PASSED" in out and "FAILED" not in out, out[-2000:]
+    if want_sqnr is not None:
+        import re
+        m = re.search(r"SQNR = ([0-9.]+)dB", out)
+        assert m and abs(float(m.group(1)) - want_sqnr) < 1e-3, out[-500:]
+    else:
+        assert "Data mismatch" not in out
