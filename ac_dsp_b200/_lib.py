@@ -36,6 +36,10 @@ class B2dPolydecDesc(C.Structure):
                 ("n_channels", C.c_uint32), ("layout", C.c_int32), ("device", C.c_int32)]
 
 
+class B2dIntgdumpDesc(C.Structure):
+    _fields_ = [("fin", B2dFmt), ("acc", B2dFmt), ("out", B2dFmt), ("ns", C.c_uint32), ("chn", C.c_uint32), ("device", C.c_int32)]
+
+
 class B2dError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(msg)
@@ -88,6 +92,9 @@ def load():
         "b2d_polydec_load": (C.c_int, [vp, vp, sz, i32]), "b2d_polydec_max_out": (sz, [vp, sz]),
         "b2d_polydec_run": (C.c_int, [vp, vp, sz, vp, psz]), "b2d_polydec_run_dev": (C.c_int, [vp, vp, sz, vp, psz, vp]),
         "b2d_polydec_reset": (C.c_int, [vp]), "b2d_polydec_path": (C.c_char_p, [vp]),
+        "b2d_intgdump_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dIntgdumpDesc)]), "b2d_intgdump_destroy": (C.c_int, [vp]),
+        "b2d_intgdump_run": (C.c_int, [vp, vp, sz, vp, sz, vp, psz]), "b2d_intgdump_run_dev": (C.c_int, [vp, vp, sz, vp, sz, vp, psz, vp]),
+        "b2d_intgdump_reset": (C.c_int, [vp]),
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),

@@ -87,6 +87,22 @@ int polydec_words(int ntaps);
 void polydec_pack(const int64_t *c, int ntaps, int df, int32_t *out);
 cudaError_t launch_polydec(const DecLaunch &p, cudaStream_t st);
 
+// Integrate-and-dump (ac_intg_dump): intg_dump.cu
+struct IdLaunch {
+  Fmt fin, facc, fout;
+  int chn, force_thread;
+  const void *in;                    // samples of this call, interleaved over chn
+  void *out;                         // [nseg_out][chn]
+  const int64_t *carry;              // [chn] ACC raw on entry
+  int64_t *carry_next;               // [chn] ACC raw on exit
+  const unsigned long long *table;   // device: [nseg + 1] boundaries, or null when every dumping segment has n_reg samples
+  unsigned long long n_reg;
+  size_t nseg_out;
+  int has_tail;
+  unsigned long long tail_end;
+};
+cudaError_t launch_intgdump(const IdLaunch &p, cudaStream_t st);
+
 // Interpolating polyphase FIR on 16-bit samples (fused CIC interpolator + FIR cascade): upfir_q15.cu
 struct UpLaunch {
   Fmt facc, fout;

@@ -406,6 +406,51 @@ class ac_poly_dec(_Block):
             pass
 
 
+class ac_intg_dump:
+    """ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (reference ac_intg_dump.h:113-151,
+    SURVEY.md 8f row N4): run(samples interleaved over CHN, n_sample tokens) -> (dumping frames, CHN) sums."""
+
+    def __init__(self, IN_TYPE, ACC_TYPE, OUT_TYPE, NS, CHN, device=-1):
+        lib = L.load()
+        self._h = None
+        d = L.B2dIntgdumpDesc(L.make_fmt(IN_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE), int(NS), int(CHN), int(device))
+        h = C.c_void_p()
+        L.check(lib.b2d_intgdump_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self.NS, self.CHN = int(NS), int(CHN)
+        self._in_dt, self._out_dt = _container_dtype(d.fin), _container_dtype(d.out)
+
+    def run(self, data_in, n_sample):
+        lib = L.load()
+        ns = np.ascontiguousarray(np.asarray(n_sample), dtype=np.uint32)
+        n_out = C.c_size_t(0)
+        if _is_torch(data_in):
+            import torch
+            x = data_in.contiguous()
+            y = torch.empty((ns.size, self.CHN), dtype={np.int16: torch.int16, np.int32: torch.int32, np.int64: torch.int64}[self._out_dt], device=x.device)
+            L.check(lib.b2d_intgdump_run_dev(self._h, x.data_ptr(), x.numel(), ns.ctypes.data, ns.size, y.data_ptr(), C.byref(n_out),
+                                             torch.cuda.current_stream(x.device).cuda_stream))
+            return y[: n_out.value // self.CHN]
+        x = np.ascontiguousarray(np.asarray(data_in).astype(self._in_dt, copy=False)).reshape(-1)
+        y = np.empty((max(ns.size, 1), self.CHN), dtype=self._out_dt)
+        L.check(lib.b2d_intgdump_run(self._h, x.ctypes.data, x.size, ns.ctypes.data, ns.size, y.ctypes.data, C.byref(n_out)))
+        return y[: n_out.value // self.CHN].copy()
+
+    def reset(self):
+        L.check(L.load().b2d_intgdump_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_intgdump_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Comm:
     """NCCL communicator of the C-ABI (one rank per GPU); only used for the coefficient broadcast at load()."""
 

@@ -206,6 +206,25 @@ int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out,
 int b2d_polydec_reset(b2d_polydec *h);
 const char *b2d_polydec_path(b2d_polydec *h);
 
+/* ---- integrate and dump: ac_intg_dump ------------------------------------------------------------ */
+/* ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (ac_intg_dump.h:113-151).  One call =
+ * n_frames frames; frame f reads the token n_sample[f]: with 1 <= n_sample[f] <= NS it consumes n_sample[f] samples of each
+ * of the CHN interleaved channels and dumps CHN sums, otherwise it consumes NS samples per channel, dumps nothing and
+ * the running sums carry on into the next frame (and the next call).  n_in must be exactly what the frames consume --
+ * the reference would read past the end of its input channel otherwise.  out: CHN values per dumping frame, frame-major. */
+typedef struct {
+  b2d_fmt in, acc, out;   /* IN_TYPE, ACC_TYPE, OUT_TYPE                                                     */
+  uint32_t ns, chn;       /* NS: longest frame; CHN: interleaved channels                                    */
+  int32_t device;
+} b2d_intgdump_desc;
+typedef struct b2d_intgdump b2d_intgdump;
+int b2d_intgdump_create(b2d_intgdump **h, const b2d_intgdump_desc *desc);
+int b2d_intgdump_destroy(b2d_intgdump *h);
+int b2d_intgdump_run(b2d_intgdump *h, const void *in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *out, size_t *n_out);
+int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *d_out,
+                         size_t *n_out, void *cuda_stream);
+int b2d_intgdump_reset(b2d_intgdump *h);
+
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128
 /* Channel c of n_channels lives on rank c % world (contiguous block alternative: see DESIGN.md). */

@@ -23,6 +23,9 @@ def main(outdir):
     with open(os.path.join(outdir, "cfgs_pd.inc"), "w") as fh:
         for cid, (fi, fc, fa, fo, nt, df) in enumerate(rc.PD_CONFIGS):
             fh.write(f"X({cid}, {f(fi)}, {f(fc)}, {f(fa)}, {f(fo)}, {nt}, {df})\n")
+    with open(os.path.join(outdir, "cfgs_id.inc"), "w") as fh:
+        for cid, (fi, fa, fo, ns, chn) in enumerate(rc.ID_CONFIGS):
+            fh.write(f"X({cid}, {f(fi)}, {f(fa)}, {f(fo)}, {ns}, {chn})\n")
     for mode in ("dec", "intr"):
         with open(os.path.join(outdir, f"cfgs_cic_{mode}.inc"), "w") as fh:
             for cid, c in enumerate(rc.CIC_CONFIGS):

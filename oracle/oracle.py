@@ -96,6 +96,11 @@ def lib_b():
         L.ob_pd_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.ob_pd_run.restype = C.c_long
         L.ob_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.ob_id_create.restype = C.c_void_p
+        L.ob_id_create.argtypes = [C.POINTER(ObFmt)] * 3 + [C.c_int, C.c_int]
+        L.ob_id_destroy.argtypes = [C.c_void_p]
+        L.ob_id_run.restype = C.c_long
+        L.ob_id_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.ob_rs_create.restype = C.c_void_p
         L.ob_rs_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int] * 5
         L.ob_rs_destroy.argtypes = [C.c_void_p]
@@ -138,6 +143,11 @@ def lib_a():
         L.acref_pd_run.restype = C.c_long
         L.acref_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.acref_pd_destroy.argtypes = [C.c_void_p]
+        L.acref_id_create.restype = C.c_void_p
+        L.acref_id_create.argtypes = [C.c_int]
+        L.acref_id_run.restype = C.c_long
+        L.acref_id_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.acref_id_destroy.argtypes = [C.c_void_p]
         L.acref_rs_create.restype = C.c_void_p
         L.acref_rs_create.argtypes = [C.c_int]
         L.acref_rs_run.restype = C.c_long
@@ -394,6 +404,58 @@ class PdA:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.acref_pd_destroy(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------- ac_intg_dump (row N4)
+def id_frame_samples(n_sample, NS, CHN):
+    """Samples (all channels) a frame with token n_sample consumes: n_sample * CHN if it dumps, else NS * CHN."""
+    return (int(n_sample) if 1 <= int(n_sample) <= NS else NS) * CHN
+
+
+class IdB:
+    """Oracle B ac_intg_dump: run(samples interleaved over CHN, n_sample tokens) -> CHN outputs per dumping frame."""
+
+    def __init__(self, fin, facc, fout, NS, CHN):
+        self.L = lib_b()
+        a, b, c = _obfmt(fin), _obfmt(facc), _obfmt(fout)
+        self.h = self.L.ob_id_create(C.byref(a), C.byref(b), C.byref(c), int(NS), int(CHN))
+        self.NS, self.CHN = int(NS), int(CHN)
+
+    def run(self, x, n_sample):
+        x, ns = _i64(x), _i64(n_sample)
+        out = np.empty(ns.size * self.CHN + 1, dtype=np.int64)
+        n = self.L.ob_id_run(self.h, _p(x), x.size, _p(ns), ns.size, _p(out))
+        if n < 0:
+            raise ValueError("samples do not cover the frames exactly")
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_id_destroy(self.h)
+            self.h = None
+
+
+class IdA:
+    """The real reference ac_intg_dump for one compiled-in configuration (index into ref_configs.ID_CONFIGS)."""
+
+    def __init__(self, cfg_id):
+        self.L = lib_a()
+        self.h = self.L.acref_id_create(int(cfg_id))
+        if not self.h:
+            raise KeyError("configuration not instantiated in oracle/_ref")
+        _fi, _fa, _fo, self.NS, self.CHN = rc.ID_CONFIGS[cfg_id]
+
+    def run(self, x, n_sample):
+        x, ns = _i64(x), _i64(n_sample)
+        assert x.size == sum(id_frame_samples(v, self.NS, self.CHN) for v in ns), "the reference reads past the end of its channel otherwise"
+        out = np.empty(ns.size * self.CHN + 1, dtype=np.int64)
+        n = self.L.acref_id_run(self.h, _p(x), x.size, _p(ns), ns.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_id_destroy(self.h)
             self.h = None
 
 

@@ -307,6 +307,49 @@ long ob_pd_run(ob_pd *f, const int64_t *in, long n, int64_t *out) {
   return nout;
 }
 
+/* ------------------------------------------------------------------ ac_intg_dump */
+/* include/ac_dsp/ac_intg_dump.h:84-151: integrate-and-dump over CHN interleaved channels.  Per frame one n_sample token
+ * is read; samples j = 1 .. NS are added into temp[i] (ACC_TYPE, re-quantised at every add) and at j == n_sample the
+ * CHN sums are dumped and cleared.  A token outside 1 .. NS never matches: the frame eats NS * CHN samples, dumps
+ * nothing, and temp[] carries into the next frame (:133-147). */
+typedef struct {
+  ob_fmt in, acc, out;
+  int ns, chn;
+  w128 *temp;
+} ob_id;
+
+ob_id *ob_id_create(const ob_fmt *in, const ob_fmt *acc, const ob_fmt *out, int ns, int chn) {
+  ob_id *f = (ob_id *)calloc(1, sizeof(ob_id));
+  f->in = *in; f->acc = *acc; f->out = *out; f->ns = ns; f->chn = chn;
+  f->temp = (w128 *)calloc((size_t)chn, sizeof(w128));
+  return f;
+}
+void ob_id_destroy(ob_id *f) { if (f) { free(f->temp); free(f); } }
+
+/* returns the number of outputs, or -1 if the samples do not cover the frames exactly */
+long ob_id_run(ob_id *f, const int64_t *in, long n, const int64_t *nsamp, long nframes, int64_t *out) {
+  const int Fin = F_of(&f->in), Fa = F_of(&f->acc);
+  long k = 0, nout = 0;
+  for (long fr = 0; fr < nframes; fr++) {
+    const long long want = nsamp[fr];
+    int flag = 0;
+    for (int j = 1; j <= f->ns; j++) {                       /* ACC_LOOP :137 */
+      for (int i = 0; i < f->chn; i++) {                     /* CHN_LOOP :138 */
+        if (k >= n) return -1;
+        w128 x = ob_wrap((w128)in[k++], f->in.W, f->in.S);
+        f->temp[i] = ob_macc(f->temp[i], &f->acc, x, Fin);   /* temp[i] = temp[i] + data_in  :100 */
+        if ((long long)j == want) {                          /* :101-105 */
+          out[nout++] = (int64_t)ob_convert(f->temp[i], Fa, &f->out);
+          f->temp[i] = 0;
+          flag = 1;
+        }
+      }
+      if (flag) break;
+    }
+  }
+  return k == n ? nout : -1;
+}
+
 /* ------------------------------------------------------------------ CIC */
 typedef struct {
   ob_fmt in, out, it;   /* it = lossless INT_TYPE */

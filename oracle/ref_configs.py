@@ -135,6 +135,19 @@ PD_CONFIGS = [
 ]
 
 
+# ac_intg_dump instantiations: (in, acc, out, NS, CHN)
+ID_CONFIGS = [
+    (_Q15, fmt(32, 17), fmt(32, 17), 64, 4),
+    (_Q15, fmt(40, 25), fmt(40, 25), 1024, 2),
+    (fmt(32, 16), fmt(64, 32), fmt(64, 32), 1024, 4),               # the header's usage example (ac_intg_dump.h:46-51)
+    (_Q15, fmt(24, 12), fmt(16, 8), 16, 3),                          # F_acc < F_in: every add truncates
+    (_Q15, fmt(24, 12, True, RND), fmt(16, 8, True, RND), 16, 1),
+    (fmt(12, 0, False), fmt(20, 8, False), fmt(20, 8, False), 100, 5),
+    (_Q15, fmt(20, 5, True, TRN, "AC_SAT"), fmt(12, 2, True, "AC_RND_CONV", "AC_SAT_SYM"), 32, 2),   # order-dependent
+    (_Q15, fmt(18, 3), fmt(18, 3), 32, 8),                            # accumulator wraps
+]
+
+
 def rs_ram_words(cfg):
     """Coefficient RAM words an instantiation reads (ac_fir_reg_share.h:122-133 and analogues)."""
     N, _fi, _fo, _fc, _fa, mww, bs, bo, ft = cfg

@@ -16,6 +16,7 @@
 #include <ac_dsp/ac_cic_intr_full.h>
 #include <ac_dsp/ac_fir_reg_share.h>
 #include <ac_dsp/ac_poly_dec.h>
+#include <ac_dsp/ac_intg_dump.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -165,6 +166,28 @@ static int run_poly_dec(const std::vector<long long> &x, const std::vector<long 
   return 0;
 }
 
+// ac_intg_dump: samples interleaved over CHN channels, one n_sample token per frame (passed in place of the taps)
+template <class IN, class ACC, class OUT, int NS, int CHN>
+static int run_intg_dump(const std::vector<long long> &x, const std::vector<long long> &tokens, std::vector<long long> &y) {
+  typedef ac_int<16, false> N_TYPE;
+  ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN> filter;
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  ac_channel<N_TYPE> n_sample;
+  size_t k = 0;
+  for (size_t f = 0; f < tokens.size(); f++) {          // two frames per run() call: the sums carry across calls
+    const long long n = tokens[f];
+    const size_t take = (size_t)((n >= 1 && n <= NS) ? n : NS) * CHN;
+    n_sample.write(N_TYPE(n));
+    for (size_t i = 0; i < take; i++) in.write(from_raw<IN>(x[k++]));
+    if (f % 2 == 1) filter.run(in, out, n_sample);
+  }
+  filter.run(in, out, n_sample);
+  if (k != x.size()) return 3;
+  drain_to(out, y);
+  return 0;
+}
+
 template <class FILTER, class IN, class OUT>
 static int run_cic(const std::vector<long long> &x, size_t chunk, std::vector<long long> &y) {
   FILTER filter;
@@ -228,6 +251,11 @@ int main(int argc, char **argv) {
       rc = run_poly_dec<ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<40, 8, true>, 32, 8>(x, c, chunk, y);
     else if (name == "pd6")
       rc = run_poly_dec<ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<24, 4, true>, ac_fixed<16, 1, true>, 16, 4>(x, c, chunk, y);
+    // ---- ac_intg_dump (oracle/ref_configs.py ID_CONFIGS 0, 3)
+    else if (name == "id0")
+      rc = run_intg_dump<ac_fixed<16, 1, true>, ac_fixed<32, 17, true>, ac_fixed<32, 17, true>, 64, 4>(x, c, y);
+    else if (name == "id3")
+      rc = run_intg_dump<ac_fixed<16, 1, true>, ac_fixed<24, 12, true>, ac_fixed<16, 8, true>, 16, 3>(x, c, y);
     else
       std::fprintf(stderr, "unknown case %s\n", name.c_str());
   } catch (const b200dsp::engine_error &e) {

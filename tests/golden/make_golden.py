@@ -159,6 +159,18 @@ def main():
         f.load(c)
         rs[f"pd{cid}_x"], rs[f"pd{cid}_c"] = x, c
         rs[f"pd{cid}_y"] = np.concatenate([f.run(x[:1]), f.run(x[1:df + 2]), f.run(x[df + 2:])])
+    for cid, (fi, fa, fo, NS, CHN) in enumerate(rc.ID_CONFIGS):         # ac_intg_dump (row N4), same file
+        f = O.IdA(cid)
+        ys, xs, toks = [], [], []
+        for call in range(3):                                            # three run() calls: the sums carry across them
+            ns = rng2.integers(1, NS, size=6, endpoint=True)
+            ns[1], ns[4] = NS + 2, 0                                     # frames that do not dump
+            if call == 2:
+                ns[5] = NS + 1                                           # ... also at the very end of a call
+            x = O.rand_raw(rng2, fi, sum(O.id_frame_samples(v, NS, CHN) for v in ns))
+            ys.append(f.run(x, ns)); xs.append(x); toks.append(ns)
+        rs[f"id{cid}_x"], rs[f"id{cid}_ns"], rs[f"id{cid}_y"] = np.concatenate(xs), np.concatenate(toks), np.concatenate(ys)
+        rs[f"id{cid}_xlen"] = np.array([v.size for v in xs], dtype=np.int64)
     np.savez_compressed(OUT + "/rs_outputs.npz", **rs)
     print("rs_outputs:", len(rs), "arrays")
     np.savez_compressed(OUT + "/ref_outputs.npz", **store)

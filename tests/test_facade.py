@@ -199,3 +199,13 @@ def test_unmodified_reference_bench_passes_on_the_engine(name, tmp_path):
         assert m and abs(float(m.group(1)) - want_sqnr) < 1e-3, out[-500:]
     else:
         assert "Data mismatch" not in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", [0, 3])
+def test_facade_intg_dump(bench_exe, tmp_path, cid):
+    """ac_intg_dump through its facade class (token channel, frames split over several run() calls)."""
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    p, y = run_case(bench_exe, tmp_path, f"id{cid}", g[f"id{cid}_x"], g[f"id{cid}_ns"])
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(y, g[f"id{cid}_y"])

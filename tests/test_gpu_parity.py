@@ -606,3 +606,35 @@ def test_poly_dec_ddc_chain_channels_and_device(engine, oracle):
         engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df).run(np.zeros(16, dtype=np.int16))     # no coefficients yet
     with pytest.raises(engine.B2dError):
         engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, nt, df, coeffs=np.zeros(nt))                  # needs NTAPS * DF values
+
+
+# ------------------------------------------------------------------------ ac_intg_dump
+@pytest.mark.parametrize("cid", range(len(rc.ID_CONFIGS)), ids=lambda i: f"id{i}-NS{rc.ID_CONFIGS[i][3]}-CHN{rc.ID_CONFIGS[i][4]}")
+def test_intg_dump_vs_reference_outputs(engine, cid, path):
+    """The engine against the committed outputs of the UNMODIFIED reference class ac_intg_dump: three calls with
+    non-dumping frames in the middle and at the end, so the running sums carry across frames and across calls."""
+    g = golden("rs_outputs.npz")
+    fi, fa, fo, NS, CHN = rc.ID_CONFIGS[cid]
+    x, ns, xlen = g[f"id{cid}_x"], g[f"id{cid}_ns"], g[f"id{cid}_xlen"]
+    f = engine.ac_intg_dump(fi, fa, fo, NS, CHN)
+    ys, o = [], 0
+    for call in range(3):
+        ys.append(f.run(x[o:o + xlen[call]], ns[6 * call:6 * call + 6]).reshape(-1))
+        o += xlen[call]
+    assert np.array_equal(np.concatenate(ys).astype(np.int64), g[f"id{cid}_y"])
+
+
+def test_intg_dump_regular_frames_device(engine, oracle):
+    """Constant frame length (the streaming case): 4 channels x 64 samples per dump on the device path, and the
+    argument check that stands in for the reference reading past the end of its channel."""
+    import torch
+    rng = np.random.default_rng(66)
+    NS, CHN, n, frames = 1024, 4, 64, 20000
+    x = rng.integers(-32768, 32767, size=frames * n * CHN, endpoint=True).astype(np.int16)
+    f = engine.ac_intg_dump(Q15, (32, 17), (32, 17), NS, CHN)
+    y = f.run(torch.from_numpy(x).cuda(), np.full(frames, n)).cpu().numpy()
+    want = oracle.IdB(Q15, (32, 17), (32, 17), NS, CHN).run(x, np.full(frames, n)).reshape(frames, CHN)
+    assert np.array_equal(y.astype(np.int64), want)
+    assert np.array_equal(want, x.reshape(frames, n, CHN).astype(np.int64).sum(axis=1))     # F_acc == F_in: plain sums
+    with pytest.raises(engine.B2dError):
+        f.run(x[:-1], np.full(frames, n))

@@ -177,3 +177,21 @@ def test_poly_dec_live_reference_equals_restatement(oracle):
             a.load(c); b.load(c)
             x = oracle.rand_raw(rng, fi, 5 * nt * df + 3, kind)
             assert np.array_equal(a.run(x), b.run(x)), (cid, kind)
+
+
+# ------------------------------------------------------------------------ ac_intg_dump
+def _id_calls(g, cid):
+    x, ns, xlen = g[f"id{cid}_x"], g[f"id{cid}_ns"], g[f"id{cid}_xlen"]
+    o = 0
+    for call in range(3):
+        yield x[o:o + xlen[call]], ns[6 * call:6 * call + 6]
+        o += xlen[call]
+
+
+@pytest.mark.parametrize("cid", range(len(rc.ID_CONFIGS)), ids=lambda i: f"id{i}-NS{rc.ID_CONFIGS[i][3]}-CHN{rc.ID_CONFIGS[i][4]}")
+def test_intg_dump_restatement_vs_reference_outputs(oracle, cid):
+    g = golden("rs_outputs.npz")
+    fi, fa, fo, NS, CHN = rc.ID_CONFIGS[cid]
+    f = oracle.IdB(fi, fa, fo, NS, CHN)
+    y = np.concatenate([f.run(x, ns) for x, ns in _id_calls(g, cid)])
+    assert np.array_equal(y, g[f"id{cid}_y"])
