@@ -63,6 +63,10 @@ WORKLOADS = {
     "polydec": dict(kind="polydec", taps=32, df=8, channels=2, layout="interleaved", n=1 << 30, unit_is_iq=True,
                     bytes_per_unit=6.0, macs_per_unit=64,
                     name="ac_poly_dec NTAPS=32 DF=8 (256 taps) <16,1> x <16,1> -> <40,8>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
+    # integrate-and-dump, 4 interleaved channels, 64 samples per dump
+    "intgdump": dict(kind="intgdump", chn=4, nsamp=64, ns=1024, channels=1, layout="planar", n=1 << 30, unit_is_iq=False,
+                     bytes_per_unit=2.0 + 4.0 / 64, macs_per_unit=0,
+                     name="ac_intg_dump CHN=4, 64 samples per dump, <16,1> -> <32,17>, 2^30 samples per GPU"),
     # BASELINE.json configs[4] first stage
     "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
                      unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
@@ -133,6 +137,17 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
             f.load(h)
             return f
         per_thread = int(seconds_target * 0.5e6 * 256 / taps)       # ~0.5 M real samples/s/core at 256 taps
+    elif wl["kind"] == "intgdump":
+        class IdRun:
+            def __init__(self):
+                self.f = O.IdA(0) if kind == "reference" else O.IdB(Q15, (32, 17), (32, 17), 64, wl["chn"])
+            def run(self, x):
+                m = (len(x) // (wl["chn"] * wl["nsamp"])) * wl["chn"] * wl["nsamp"]
+                return self.f.run(x[:m], np.full(m // (wl["chn"] * wl["nsamp"]), wl["nsamp"]))
+            def last_run_seconds(self):
+                return None
+        make = IdRun
+        per_thread = int(seconds_target * 8e6)
     elif wl["kind"] == "polydec":
         cid = [i for i, c in enumerate(O.rc.PD_CONFIGS) if c[4] == wl["taps"] and c[5] == wl["df"] and c[0][0] == 16][0]
         h = O.rand_raw(rng, Q15, wl["taps"] * wl["df"])
@@ -273,6 +288,19 @@ def main():
                                  device=local, comm=comm, root=0)
         f.load(h if rank == 0 else None)
         launches_per_step = 2          # fir_q15_kernel + history carry
+    elif wl["kind"] == "intgdump":
+        class _Id:   # adapter: fixed token array, out= ignored (outputs are 1/64 of the input)
+            def __init__(self):
+                self.f = E.ac_intg_dump(Q15, (32, 17), (32, 17), wl["ns"], wl["chn"], device=local)
+                self._h = self.f._h
+                self.path = "intgdump_warp"
+                self.tok = np.full(n // (wl["chn"] * wl["nsamp"]), wl["nsamp"], dtype=np.uint32)
+            def run(self, x, out=None):
+                return self.f.run(x, self.tok)
+            def close(self):
+                self.f.close()
+        f = _Id()
+        launches_per_step = 1
     elif wl["kind"] == "polydec":
         h = rng.integers(-32768, 32767, size=wl["taps"] * wl["df"], endpoint=True).astype(np.int16)
         f = E.ac_poly_dec(Q15, Q15, ACC40, ACC40, wl["taps"], wl["df"], coeffs=h, n_channels=C, layout=wl["layout"], device=local)
@@ -334,6 +362,10 @@ def main():
         if wl["kind"] == "fir":
             yh = torch.empty(n2 * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_fir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), None)
+        elif wl["kind"] == "intgdump":
+            tok2 = np.full(n2 // (wl["chn"] * wl["nsamp"]), wl["nsamp"], dtype=np.uint32)
+            yh = torch.empty(tok2.size * wl["chn"], dtype=torch.int32).pin_memory()
+            call = lambda: lib.b2d_intgdump_run(f._h, xn.ctypes.data, n2, tok2.ctypes.data, tok2.size, yh.data_ptr(), ct.byref(no))
         elif wl["kind"] == "polydec":
             yh = torch.empty(lib.b2d_polydec_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_polydec_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
@@ -391,6 +423,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
                           "polydec": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+                          "intgdump": "s16 -> s64 (exact integer sum, ac_fixed<32,17> wrap)",
                           "cic": "s16 -> u32 (modular integrate / comb)"}[wl["kind"]],
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "samples_per_step_per_gpu": units_per_step, "kernel_path": path,
