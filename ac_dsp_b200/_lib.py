@@ -94,7 +94,7 @@ def load():
         "b2d_polydec_reset": (C.c_int, [vp]), "b2d_polydec_path": (C.c_char_p, [vp]),
         "b2d_intgdump_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dIntgdumpDesc)]), "b2d_intgdump_destroy": (C.c_int, [vp]),
         "b2d_intgdump_run": (C.c_int, [vp, vp, sz, vp, sz, vp, psz]), "b2d_intgdump_run_dev": (C.c_int, [vp, vp, sz, vp, sz, vp, psz, vp]),
-        "b2d_intgdump_reset": (C.c_int, [vp]),
+        "b2d_intgdump_reset": (C.c_int, [vp]), "b2d_intgdump_path": (C.c_char_p, [vp]),
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),

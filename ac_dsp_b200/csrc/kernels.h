@@ -102,6 +102,7 @@ struct IdLaunch {
   unsigned long long tail_end;
 };
 cudaError_t launch_intgdump(const IdLaunch &p, cudaStream_t st);
+const char *intgdump_path(const IdLaunch &p);
 
 // Interpolating polyphase FIR on 16-bit samples (fused CIC interpolator + FIR cascade): upfir_q15.cu
 struct UpLaunch {

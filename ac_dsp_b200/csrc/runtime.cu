@@ -1274,7 +1274,10 @@ struct b2d_intgdump {
   size_t table_cap = 0;
   void *d_in = nullptr, *d_out = nullptr;
   size_t cap_in = 0, cap_out = 0;
+  const char *path = "none";
 };
+
+extern "C" const char *b2d_intgdump_path(b2d_intgdump *h) { return h ? h->path : "none"; }
 
 extern "C" int b2d_intgdump_destroy(b2d_intgdump *h) {
   if (!h) return B2D_OK;
@@ -1328,13 +1331,24 @@ static int intgdump_plan(const b2d_intgdump *h, const uint32_t *n_sample, size_t
                          size_t *nseg_out, int *has_tail, bool *regular) {
   const unsigned long long NS = h->d.ns, CHN = h->d.chn;
   bounds.clear();
-  bounds.push_back(0);
   unsigned long long pos = 0;
-  *regular = n_frames > 0;
+  // equal dumping frames (the common case) need no boundary table: one vectorisable pass over the tokens
+  uint32_t diff = 0;
+  const uint32_t n0 = n_frames ? n_sample[0] : 0;
+  for (size_t f = 0; f < n_frames; f++) diff |= n_sample[f] ^ n0;
+  *regular = n_frames > 0 && diff == 0 && n0 >= 1 && n0 <= NS;
+  if (*regular) {
+    pos = (unsigned long long)n0 * n_frames;
+    if (pos * CHN != n_in) return fail(B2D_EINVAL, "the frames consume %llu samples, got %zu", pos * CHN, n_in);
+    *nseg_out = n_frames;
+    *has_tail = 0;
+    return B2D_OK;
+  }
+  bounds.push_back(0);
   for (size_t f = 0; f < n_frames; f++) {
     const unsigned long long n = n_sample[f];
-    if (n >= 1 && n <= NS) { pos += n; bounds.push_back(pos); if (n != n_sample[0]) *regular = false; }
-    else { pos += NS; *regular = false; }
+    if (n >= 1 && n <= NS) { pos += n; bounds.push_back(pos); }
+    else pos += NS;
   }
   if (pos * CHN != n_in) return fail(B2D_EINVAL, "the frames consume %llu samples, got %zu", pos * CHN, n_in);
   *nseg_out = bounds.size() - 1;
@@ -1376,6 +1390,7 @@ extern "C" int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_
   }
   // a call without a tail segment leaves temp[] cleared (the last dump zeroed it)
   if (!has_tail) CU(cudaMemsetAsync(h->d_carry[h->cur ^ 1], 0, h->d.chn * sizeof(int64_t), stream));
+  h->path = intgdump_path(p);
   CU(launch_intgdump(p, stream));
   h->cur ^= 1;
   return B2D_OK;

@@ -436,6 +436,10 @@ class ac_intg_dump:
         L.check(lib.b2d_intgdump_run(self._h, x.ctypes.data, x.size, ns.ctypes.data, ns.size, y.ctypes.data, C.byref(n_out)))
         return y[: n_out.value // self.CHN].copy()
 
+    @property
+    def path(self):
+        return L.load().b2d_intgdump_path(self._h).decode()
+
     def reset(self):
         L.check(L.load().b2d_intgdump_reset(self._h))
 

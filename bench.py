@@ -64,9 +64,9 @@ WORKLOADS = {
                     bytes_per_unit=6.0, macs_per_unit=64,
                     name="ac_poly_dec NTAPS=32 DF=8 (256 taps) <16,1> x <16,1> -> <40,8>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
     # integrate-and-dump, 4 interleaved channels, 64 samples per dump
-    "intgdump": dict(kind="intgdump", chn=4, nsamp=64, ns=1024, channels=1, layout="planar", n=1 << 30, unit_is_iq=False,
-                     bytes_per_unit=2.0 + 4.0 / 64, macs_per_unit=0,
-                     name="ac_intg_dump CHN=4, 64 samples per dump, <16,1> -> <32,17>, 2^30 samples per GPU"),
+    "intgdump": dict(kind="intgdump", chn=4, nsamp=256, ns=1024, channels=1, layout="planar", n=1 << 30, unit_is_iq=False,
+                     bytes_per_unit=2.0 + 4.0 / 256, macs_per_unit=0,
+                     name="ac_intg_dump CHN=4, 256 samples per dump, <16,1> -> <32,17>, 2^30 samples per GPU"),
     # BASELINE.json configs[4] first stage
     "cic_intr": dict(kind="cic", mode="intr", R=4, M=1, N=3, out=(20, 5), channels=1, layout="planar", n=1 << 28,
                      unit_is_iq=False, bytes_per_unit=18.0, macs_per_unit=0,
@@ -142,8 +142,11 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
             def __init__(self):
                 self.f = O.IdA(0) if kind == "reference" else O.IdB(Q15, (32, 17), (32, 17), 64, wl["chn"])
             def run(self, x):
-                m = (len(x) // (wl["chn"] * wl["nsamp"])) * wl["chn"] * wl["nsamp"]
-                return self.f.run(x[:m], np.full(m // (wl["chn"] * wl["nsamp"]), wl["nsamp"]))
+                # the compiled-in reference instantiation (ref_configs.ID_CONFIGS[0]) has NS = 64: the CPU arm dumps every
+                # 64 samples (same adds per sample, 4x the dumps of the GPU workload)
+                per = 64 if kind == "reference" else wl["nsamp"]
+                m = (len(x) // (wl["chn"] * per)) * wl["chn"] * per
+                return self.f.run(x[:m], np.full(m // (wl["chn"] * per), per))
             def last_run_seconds(self):
                 return None
         make = IdRun
@@ -293,10 +296,12 @@ def main():
             def __init__(self):
                 self.f = E.ac_intg_dump(Q15, (32, 17), (32, 17), wl["ns"], wl["chn"], device=local)
                 self._h = self.f._h
-                self.path = "intgdump_warp"
                 self.tok = np.full(n // (wl["chn"] * wl["nsamp"]), wl["nsamp"], dtype=np.uint32)
             def run(self, x, out=None):
                 return self.f.run(x, self.tok)
+            @property
+            def path(self):
+                return self.f.path
             def close(self):
                 self.f.close()
         f = _Id()
@@ -314,7 +319,6 @@ def main():
         cls = E.ac_cic_dec_full if wl["mode"] == "dec" else E.ac_cic_intr_full
         f = cls(Q15, wl["out"], wl["R"], wl["M"], wl["N"], n_channels=C, layout=wl["layout"], device=local)
         launches_per_step = 2
-    path = f.path
     units_per_step = n if wl["unit_is_iq"] else n * C   # IQ pairs, or real samples over all local channels
 
     def sync_all():
@@ -324,6 +328,7 @@ def main():
             torch.cuda.synchronize()
 
     y = f.run(x)
+    path = f.path
     up = wl.get("R", 1) if (wl.get("mode") == "intr" or wl["kind"] == "cicfir") else 1
     ybuf = torch.empty(max(y.numel(), C * n * up), dtype=y.dtype, device="cuda")
     del y

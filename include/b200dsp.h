@@ -224,6 +224,8 @@ int b2d_intgdump_run(b2d_intgdump *h, const void *in, size_t n_in, const uint32_
 int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *d_out,
                          size_t *n_out, void *cuda_stream);
 int b2d_intgdump_reset(b2d_intgdump *h);
+/* kernel family the last run took: "intgdump_vec" (128-bit loads, equal frames), "intgdump_warp", "intgdump_thread" */
+const char *b2d_intgdump_path(b2d_intgdump *h);
 
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128

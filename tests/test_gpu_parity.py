@@ -638,3 +638,39 @@ def test_intg_dump_regular_frames_device(engine, oracle):
     assert np.array_equal(want, x.reshape(frames, n, CHN).astype(np.int64).sum(axis=1))     # F_acc == F_in: plain sums
     with pytest.raises(engine.B2dError):
         f.run(x[:-1], np.full(frames, n))
+
+
+@pytest.mark.parametrize("CHN,n,fi,fa", [
+    (1, 8, Q15, (32, 17)), (1, 256, Q15, (32, 17)), (1, 1000, Q15, (32, 17)), (2, 4, Q15, (40, 25)), (2, 64, Q15, (40, 25)),
+    (2, 324, Q15, (32, 17)), (4, 8, Q15, (32, 17)), (4, 64, Q15, (32, 17)), (4, 1024, Q15, (18, 3)), (8, 8, Q15, (18, 3)),
+    (8, 32, Q15, (32, 17)), (8, 77, Q15, (32, 17)), (4, 64, Q15, (24, 12)), (2, 128, (16, 1, True), (24, 12, True, "AC_RND")),
+    (4, 16, (12, 0, False), (20, 8, False)), (1, 2048, (16, 4, False), (30, 18, False)), (4, 2, Q15, (32, 17)), (8, 1, Q15, (32, 17)),
+    (1, 24, Q15, (32, 17)), (4, 64 * 1024, Q15, (40, 25)),
+], ids=lambda v: str(v).replace(" ", ""))
+def test_intg_dump_vector_path_geometries(engine, oracle, CHN, n, fi, fa):
+    """Equal frames on the device path over the geometries of intgdump_vec_kernel (sub-warp groups, whole warps, long
+    segments, per-term truncation / rounding, unsigned samples) and the ones that must fall back; two calls so the
+    second starts from a cleared accumulator, then a ragged third call that leaves a carry behind."""
+    import torch
+    rng = np.random.default_rng(1000 * CHN + n)
+    NS = max(n, 16)
+    frames = max(3, min(3000, (1 << 21) // (n * CHN)))
+    W, S = fi[0], (fi[2] if len(fi) > 2 else True)
+    lo, hi = (-(1 << (W - 1)), (1 << (W - 1)) - 1) if S else (0, (1 << W) - 1)
+    f = engine.ac_intg_dump(fi, fa, fa, NS, CHN)
+    ob = oracle.IdB(fi, fa, fa, NS, CHN)
+    for call in range(2):
+        x = rng.integers(lo, hi, size=frames * n * CHN, endpoint=True).astype(np.int16 if S else np.uint16)
+        y = f.run(torch.from_numpy(x.view(np.int16)).cuda(), np.full(frames, n)).cpu().numpy()
+        assert np.array_equal(y.astype(np.int64), ob.run(x, np.full(frames, n)).reshape(frames, CHN)), (call, f.path)
+    L = n * CHN // 8
+    vec = (n * CHN) % 8 == 0 and (L > 32 or ((L & (L - 1)) == 0 and L >= CHN)) and (fi[0] - fi[1]) - (fa[0] - fa[1]) <= 15
+    assert f.path == ("intgdump_vec" if vec else ("intgdump_warp" if 32 % CHN == 0 else "intgdump_thread")), f.path
+    tok = np.array([n, NS + 5, n, 0], dtype=np.uint32)     # ragged: two frames that do not dump
+    m = (2 * n + 2 * NS) * CHN
+    x = rng.integers(lo, hi, size=m, endpoint=True).astype(np.int16 if S else np.uint16)
+    y = f.run(torch.from_numpy(x.view(np.int16)).cuda(), tok).cpu().numpy()
+    assert np.array_equal(y.astype(np.int64), ob.run(x, tok).reshape(-1, CHN))
+    x = rng.integers(lo, hi, size=frames * n * CHN, endpoint=True).astype(np.int16 if S else np.uint16)
+    y = f.run(torch.from_numpy(x.view(np.int16)).cuda(), np.full(frames, n)).cpu().numpy()     # picks the carry up
+    assert np.array_equal(y.astype(np.int64), ob.run(x, np.full(frames, n)).reshape(frames, CHN))
