@@ -36,6 +36,14 @@ class B2dPolydecDesc(C.Structure):
                 ("n_channels", C.c_uint32), ("layout", C.c_int32), ("device", C.c_int32)]
 
 
+class B2dPolyintrDesc(C.Structure):
+    _fields_ = [("fin", B2dFmt), ("coeff", B2dFmt), ("acc", B2dFmt), ("out", B2dFmt), ("n_taps", C.c_uint32), ("intr_factor", C.c_uint32),
+                ("ftype", C.c_int32), ("n_channels", C.c_uint32), ("layout", C.c_int32), ("device", C.c_int32)]
+
+
+PI_FTYPES = ["FOLD_EVEN", "FOLD_ODD", "FOLD_ANTI"]   # the polyphase enum of ac_poly_intr.h:95
+
+
 class B2dIntgdumpDesc(C.Structure):
     _fields_ = [("fin", B2dFmt), ("acc", B2dFmt), ("out", B2dFmt), ("ns", C.c_uint32), ("chn", C.c_uint32), ("device", C.c_int32)]
 
@@ -92,6 +100,10 @@ def load():
         "b2d_polydec_load": (C.c_int, [vp, vp, sz, i32]), "b2d_polydec_max_out": (sz, [vp, sz]),
         "b2d_polydec_run": (C.c_int, [vp, vp, sz, vp, psz]), "b2d_polydec_run_dev": (C.c_int, [vp, vp, sz, vp, psz, vp]),
         "b2d_polydec_reset": (C.c_int, [vp]), "b2d_polydec_path": (C.c_char_p, [vp]),
+        "b2d_polyintr_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dPolyintrDesc)]), "b2d_polyintr_destroy": (C.c_int, [vp]),
+        "b2d_polyintr_coeffsz": (sz, [vp]), "b2d_polyintr_load": (C.c_int, [vp, vp, sz, vp, vp, i32]), "b2d_polyintr_max_out": (sz, [vp, sz]),
+        "b2d_polyintr_run": (C.c_int, [vp, vp, sz, vp, psz]), "b2d_polyintr_run_dev": (C.c_int, [vp, vp, sz, vp, psz, vp]),
+        "b2d_polyintr_reset": (C.c_int, [vp]), "b2d_polyintr_path": (C.c_char_p, [vp]),
         "b2d_intgdump_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dIntgdumpDesc)]), "b2d_intgdump_destroy": (C.c_int, [vp]),
         "b2d_intgdump_run": (C.c_int, [vp, vp, sz, vp, sz, vp, psz]), "b2d_intgdump_run_dev": (C.c_int, [vp, vp, sz, vp, sz, vp, psz, vp]),
         "b2d_intgdump_reset": (C.c_int, [vp]), "b2d_intgdump_path": (C.c_char_p, [vp]),

@@ -87,6 +87,26 @@ int polydec_words(int ntaps);
 void polydec_pack(const int64_t *c, int ntaps, int df, int32_t *out);
 cudaError_t launch_polydec(const DecLaunch &p, cudaStream_t st);
 
+// Polyphase interpolating FIR (ac_poly_intr): fir_intr.cu
+struct PiLaunch {
+  Fmt fin, fcoeff, facc, fout;
+  int nt, ifac, ftype, csz, fast;   // taps per phase, interpolation factor, B2D_PI_*, coefficients per channel, 64-bit path
+  uint32_t C;
+  int interleaved;
+  const void *in;            // n inputs per channel
+  void *out;                 // n_rows * ifac outputs per channel, planar
+  size_t n, n_rows;
+  int row_shift;             // source step of output row r is r - row_shift
+  const void *tail;          // [C][H] previous inputs
+  int H;
+  const int64_t *coeff64;    // [C][csz]
+  const uint8_t *sign, *corr;   // [C][ifac]
+  const int64_t *carry;      // [C][ifac] accumulators of the step before this call
+  int64_t *carry_next;
+};
+bool polyintr_fast_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, int ftype);
+cudaError_t launch_polyintr(const PiLaunch &p, cudaStream_t st);
+
 // Integrate-and-dump (ac_intg_dump): intg_dump.cu
 struct IdLaunch {
   Fmt fin, facc, fout;

@@ -1263,6 +1263,265 @@ extern "C" int b2d_polydec_reset(b2d_polydec *h) {
   return B2D_OK;
 }
 
+// -------------------------------------------------------------------------------------------- ac_poly_intr
+struct b2d_polyintr {
+  b2d_polyintr_desc d;
+  Fmt fin, fc, fa, fo;
+  int device = 0, in_bytes = 2, out_bytes = 8, c_bytes = 2, csz = 0, H = 0;
+  int mode = 0;                      // 0 generic, 1 wide (64-bit modular), 2 q15 (upfir_lane DP2A kernel)
+  int lsh = 0, planes = 2, words = 0;
+  bool init = false;                 // folded forms: a step has been taken (ac_poly_intr.h:165)
+  std::vector<char> ch_loaded;
+  int64_t *d_coeff64 = nullptr;
+  uint32_t *d_cw = nullptr;
+  uint8_t *d_sign = nullptr, *d_corr = nullptr;
+  int64_t *d_carry[2] = {nullptr, nullptr};
+  void *d_tail[2] = {nullptr, nullptr};
+  int cur = 0, ccur = 0;
+  unsigned long long n_seen = 0;
+  Pipe pipe;
+};
+
+extern "C" int b2d_polyintr_destroy(b2d_polyintr *h) {
+  if (!h) return B2D_OK;
+  use_device(h->device);
+  cudaDeviceSynchronize();
+  h->pipe.destroy();
+  if (h->d_coeff64) cudaFree(h->d_coeff64);
+  if (h->d_cw) cudaFree(h->d_cw);
+  if (h->d_sign) cudaFree(h->d_sign);
+  if (h->d_corr) cudaFree(h->d_corr);
+  for (int i = 0; i < 2; i++) { if (h->d_tail[i]) cudaFree(h->d_tail[i]); if (h->d_carry[i]) cudaFree(h->d_carry[i]); }
+  delete h;
+  return B2D_OK;
+}
+
+static int polyintr_csz(uint32_t nt, uint32_t ifac, int ftype) {
+  return (int)(ifac * (ftype == B2D_PI_FOLD_EVEN ? nt / 2 : (ftype == B2D_PI_FOLD_ODD ? nt / 2 + 1 : nt)));
+}
+
+// FOLD_ANTI on 16-bit operands with an exact wrapping accumulator is the plain polyphase FIR of upfir_q15.cu
+static bool polyintr_q15_ok(const b2d_polyintr_desc &d, int *lsh) {
+  const Fmt in = to_fmt(d.in), fc = to_fmt(d.coeff), fa = to_fmt(d.acc);
+  if (d.ftype != B2D_PI_FOLD_ANTI) return false;
+  if (in.W > 16 || (!in.S && in.W == 16) || fc.W > 16 || (!fc.S && fc.W == 16)) return false;
+  if (fa.O != B2D_WRAP || (fa.Q != B2D_TRN && fa.Q != B2D_RND)) return false;
+  const int s = in.F() + fc.F() - fa.F();
+  if (s > 0 || -s > 40 || -s >= fa.W) return false;
+  if (!upfir_q15_geometry((int)d.intr_factor, (int)(d.n_taps * d.intr_factor), 16)) return false;
+  *lsh = -s;
+  return true;
+}
+
+extern "C" int b2d_polyintr_create(b2d_polyintr **out, const b2d_polyintr_desc *desc) {
+  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
+  *out = nullptr;
+  int st;
+  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
+  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
+  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
+  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
+  if (desc->n_taps < 1 || desc->n_taps > (1u << 16)) return fail(B2D_EINVAL, "NTAPS = %u outside 1..65536", desc->n_taps);
+  if (desc->intr_factor < 1 || desc->intr_factor > 255) return fail(B2D_EINVAL, "IF = %u outside 1..255", desc->intr_factor);
+  if (desc->ftype < B2D_PI_FOLD_EVEN || desc->ftype > B2D_PI_FOLD_ANTI) return fail(B2D_EINVAL, "bad ftype");
+  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
+  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
+  const Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
+  {  // bit budget of the 128-bit generic evaluation: the folded forms multiply COEFF_TYPE by an ACC_TYPE fold
+    const bool folded = desc->ftype != B2D_PI_FOLD_ANTI;
+    const int Fp = (folded ? fa.F() : fin.F()) + fc.F(), Wp = (folded ? fa.W : fin.W) + fc.W + 2, rF = std::max(Fp, fa.F());
+    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + 2 + std::max(0, fo.F() - fa.F()) > 125 ||
+        fin.W + 2 + std::max(0, fa.F() - fin.F()) > 125)
+      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
+  }
+  int dev = desc->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if ((st = use_device(dev))) return st;
+  b2d_polyintr *h = new (std::nothrow) b2d_polyintr();
+  if (!h) return fail(B2D_ENOMEM, "handle");
+  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
+  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
+  h->csz = polyintr_csz(desc->n_taps, desc->intr_factor, desc->ftype);
+  const uint32_t C = desc->n_channels, IF = desc->intr_factor;
+  h->H = (int)desc->n_taps + 2;
+  h->ch_loaded.assign(C, 0);
+  h->mode = polyintr_fast_supported(fin, fc, fa, desc->ftype) ? 1 : 0;
+  const char *force = getenv("B2D_FORCE_GENERIC");
+  if (h->mode && polyintr_q15_ok(*desc, &h->lsh) && !(force && *force == '2')) h->mode = 2;
+  if (force && *force == '1') h->mode = 0;
+  if (h->mode == 2) { h->planes = 2; h->words = upfir_q15_words((int)IF, (int)(desc->n_taps * IF), h->planes); }
+  cudaError_t e = cudaMalloc(&h->d_coeff64, (size_t)C * std::max(h->csz, 1) * sizeof(int64_t));
+  if (e == cudaSuccess && h->mode == 2) e = cudaMalloc(&h->d_cw, (size_t)C * h->words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_sign, (size_t)C * IF);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_corr, (size_t)C * IF);
+  const size_t tail_bytes = std::max<size_t>((size_t)h->H * C * h->in_bytes, 16);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaMalloc(&h->d_tail[i], tail_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_carry[i], (size_t)C * IF * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemset(h->d_carry[i], 0, (size_t)C * IF * sizeof(int64_t));
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); b2d_polyintr_destroy(h); return fail(B2D_ECUDA, "b2d_polyintr_create: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return B2D_OK;
+}
+
+extern "C" const char *b2d_polyintr_path(b2d_polyintr *h) { return !h ? "" : (h->mode == 2 ? "polyintr_q15" : (h->mode ? "polyintr_wide" : "polyintr_generic")); }
+extern "C" size_t b2d_polyintr_coeffsz(b2d_polyintr *h) { return h ? (size_t)h->csz : 0; }
+extern "C" size_t b2d_polyintr_max_out(b2d_polyintr *h, size_t n) { return h ? n * h->d.intr_factor : 0; }
+
+extern "C" int b2d_polyintr_load(b2d_polyintr *h, const void *coeff_raw, size_t n, const uint8_t *sign, const uint8_t *corr, int32_t channel) {
+  if (!h || (!coeff_raw && h->csz)) return fail(B2D_EINVAL, "null argument");
+  const uint32_t C = h->d.n_channels, IF = h->d.intr_factor;
+  const size_t L = (size_t)h->csz;
+  if (n != L) return fail(B2D_EINVAL, "expected %zu coefficients, got %zu", L, n);
+  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
+  std::vector<uint8_t> sg(IF, 1), cr(IF);
+  for (uint32_t j = 0; j < IF; j++) {
+    cr[j] = corr ? corr[j] : (uint8_t)j;
+    if (sign) sg[j] = sign[j] ? 1 : 0;
+    if (cr[j] >= IF) return fail(B2D_EINVAL, "corr[%u] = %u outside 0..IF-1 (the reference would index acc_a / acc_b out of range)", j, cr[j]);
+  }
+  int st = use_device(h->device);
+  if (st) return st;
+  std::vector<int64_t> v(std::max<size_t>(L, 1));
+  for (size_t i = 0; i < L; i++) {
+    int64_t r;
+    if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
+    else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
+    else r = ((const int64_t *)coeff_raw)[i];
+    v[i] = wrap_bits(r, h->fc.W, h->fc.S);
+  }
+  CU(cudaDeviceSynchronize());
+  std::vector<uint32_t> pk;
+  if (h->mode == 2) {      // composite taps of the polyphase form: c[ph + IF*m] = coeffs[m + NTAPS*ph]
+    const int NT = (int)h->d.n_taps;
+    std::vector<int64_t> comp((size_t)NT * IF);
+    for (uint32_t ph = 0; ph < IF; ph++)
+      for (int m = 0; m < NT; m++) comp[ph + (size_t)IF * m] = v[m + (size_t)NT * ph];
+    pk.assign((size_t)h->words, 0);
+    upfir_q15_pack(comp.data(), NT * (int)IF, (int)IF, h->planes, pk.data());
+  }
+  for (uint32_t c = 0; c < C; c++) {
+    if (channel >= 0 && (uint32_t)channel != c) continue;
+    if (L) CU(cudaMemcpy(h->d_coeff64 + c * L, v.data(), L * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (h->mode == 2) CU(cudaMemcpy(h->d_cw + (size_t)c * h->words, pk.data(), pk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_sign + (size_t)c * IF, sg.data(), IF, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_corr + (size_t)c * IF, cr.data(), IF, cudaMemcpyHostToDevice));
+    h->ch_loaded[c] = 1;
+  }
+  return B2D_OK;
+}
+
+static size_t polyintr_rows(const b2d_polyintr *h, size_t n) {
+  if (h->d.ftype == B2D_PI_FOLD_ANTI || h->init) return n;
+  return n ? n - 1 : 0;
+}
+
+static int polyintr_launch(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t n_rows, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  const uint32_t C = h->d.n_channels;
+  const bool il = h->d.layout == B2D_INTERLEAVED;
+  if (h->mode == 2) {
+    UpLaunch p;
+    p.facc = h->fa; p.fout = h->fo; p.R = (int)h->d.intr_factor; p.taps_total = (int)(h->d.n_taps * h->d.intr_factor);
+    p.planes = h->planes; p.lsh = h->lsh; p.C = C; p.interleaved = il;
+    p.in = d_in; p.out = d_out; p.n = n; p.n_out = n * h->d.intr_factor;
+    p.n_seen = h->n_seen; p.out_first = h->n_seen * h->d.intr_factor;
+    p.tail = h->d_tail[h->cur]; p.H = h->H; p.cw = h->d_cw;
+    CU(launch_upfir_q15(p, st));
+  } else {
+    PiLaunch p;
+    p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
+    p.nt = (int)h->d.n_taps; p.ifac = (int)h->d.intr_factor; p.ftype = h->d.ftype; p.csz = h->csz; p.fast = h->mode == 1;
+    p.C = C; p.interleaved = il; p.in = d_in; p.out = d_out; p.n = n; p.n_rows = n_rows;
+    p.row_shift = (h->d.ftype != B2D_PI_FOLD_ANTI && h->init) ? 1 : 0;
+    p.tail = h->d_tail[h->cur]; p.H = h->H; p.coeff64 = h->d_coeff64; p.sign = h->d_sign; p.corr = h->d_corr;
+    p.carry = h->d_carry[h->ccur]; p.carry_next = h->d_carry[h->ccur ^ 1];
+    CU(launch_polyintr(p, st));
+    if (h->d.ftype != B2D_PI_FOLD_ANTI) h->ccur ^= 1;
+  }
+  CicLaunch t{};
+  t.fin = h->fin; t.C = C; t.interleaved = il; t.in = d_in; t.n = n;
+  t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1]; t.H = h->H;
+  CU(launch_cic_tail(t, st));
+  h->cur ^= 1;
+  h->n_seen += n;
+  h->init = true;
+  return B2D_OK;
+}
+
+static int polyintr_ready(const b2d_polyintr *h) {
+  for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the control / coefficient structures of every channel were loaded");
+  return B2D_OK;
+}
+
+extern "C" int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
+  int st = polyintr_ready(h);
+  if (st) return st;
+  const size_t rows = polyintr_rows(h, n);
+  if (rows && !d_out) return fail(B2D_EINVAL, "null output");
+  if ((st = use_device(h->device))) return st;
+  if ((st = polyintr_launch(h, d_in, n, d_out, rows, (cudaStream_t)cuda_stream))) return st;
+  if (n_out) *n_out = rows * h->d.intr_factor;
+  return B2D_OK;
+}
+
+extern "C" int b2d_polyintr_run(b2d_polyintr *h, const void *in, size_t n, void *out, size_t *n_out) {
+  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
+  int st = polyintr_ready(h);
+  if (st) return st;
+  const uint32_t C = h->d.n_channels, IF = h->d.intr_factor;
+  const size_t rows_total = polyintr_rows(h, n), no_total = rows_total * IF;
+  if (no_total && !out) return fail(B2D_EINVAL, "null output");
+  if (n_out) *n_out = no_total;
+  if (n == 0) return B2D_OK;
+  if ((st = use_device(h->device))) return st;
+  Pipe &P = h->pipe;
+  if ((st = P.init())) return st;
+  const int il = h->d.layout == B2D_INTERLEAVED;
+  const double per = C * (h->in_bytes + (double)h->out_bytes * IF);
+  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
+  L = std::min(L, n);
+  if ((st = P.ensure(L * C * h->in_bytes, L * IF * C * h->out_bytes))) return st;
+  size_t i = 0, off_out = 0;
+  for (size_t off = 0; off < n; off += L, i++) {
+    const int s = (int)(i % Pipe::S);
+    const size_t len = std::min(L, n - off);
+    const size_t no = polyintr_rows(h, len) * IF;
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
+    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
+    CU(cudaEventRecord(P.e_in[s], P.s_in));
+    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
+    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
+    if ((st = polyintr_launch(h, P.d_in[s], len, P.d_out[s], no / IF, P.s_k))) return st;
+    CU(cudaEventRecord(P.e_k[s], P.s_k));
+    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
+    if (no) CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
+    CU(cudaEventRecord(P.e_out[s], P.s_out));
+    off_out += no;
+  }
+  CU(cudaStreamSynchronize(P.s_out));
+  CU(cudaStreamSynchronize(P.s_k));
+  return B2D_OK;
+}
+
+extern "C" int b2d_polyintr_reset(b2d_polyintr *h) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  CU(cudaDeviceSynchronize());
+  const size_t tail_bytes = std::max<size_t>((size_t)h->H * h->d.n_channels * h->in_bytes, 16);
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
+    CU(cudaMemset(h->d_carry[i], 0, (size_t)h->d.n_channels * h->d.intr_factor * sizeof(int64_t)));
+  }
+  h->n_seen = 0;
+  h->init = false;
+  return B2D_OK;
+}
+
 // -------------------------------------------------------------------------------------------- ac_intg_dump
 struct b2d_intgdump {
   b2d_intgdump_desc d;

@@ -406,6 +406,65 @@ class ac_poly_dec(_Block):
             pass
 
 
+class ac_poly_intr(_Block):
+    """ac_poly_intr<IN, COEFF, ACC, OUT, STR_CTRL, STR_COEFF, NTAPS, COEFFSZ, IF, ftype>::run(data_in, data_out, ctrl_st,
+    coeffs_st, read_ctrl_chan)  (reference ac_poly_intr.h:261-312): polyphase interpolator, IF
+    outputs per input.  ftype is "FOLD_EVEN" / "FOLD_ODD" (symmetric-pair structures: outputs one step late, sign[] and
+    corr[] from the control struct) or "FOLD_ANTI" (plain polyphase form).  load() is the read_ctrl = true call."""
+
+    def __init__(self, IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE, NTAPS, IF, ftype="FOLD_ANTI", coeffs=None, sign=None, corr=None,
+                 n_channels=1, layout="planar", device=-1):
+        lib = L.load()
+        self._h = None
+        self.NTAPS, self.IF = int(NTAPS), int(IF)
+        ft = L.PI_FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
+        d = L.B2dPolyintrDesc(L.make_fmt(IN_TYPE), L.make_fmt(COEFF_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE), self.NTAPS, self.IF, ft,
+                              int(n_channels), L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR, int(device))
+        h = C.c_void_p()
+        L.check(lib.b2d_polyintr_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self._coeff_dt = _container_dtype(d.coeff)
+        self._setup_io(d.fin, d.out, n_channels, layout)
+        if coeffs is not None:
+            self.load(coeffs, sign, corr)
+
+    @property
+    def path(self):
+        return L.load().b2d_polyintr_path(self._h).decode()
+
+    @property
+    def coeffsz(self):
+        return int(L.load().b2d_polyintr_coeffsz(self._h))
+
+    def load(self, coeffs, sign=None, corr=None, channel=-1):
+        c = np.ascontiguousarray(np.asarray(coeffs).astype(self._coeff_dt, copy=False))
+        sg = None if sign is None else np.ascontiguousarray(np.asarray(sign) != 0, dtype=np.uint8)
+        cr = None if corr is None else np.ascontiguousarray(np.asarray(corr), dtype=np.uint8)
+        for a in (sg, cr):
+            if a is not None and a.size != self.IF:
+                raise ValueError("sign / corr need IF entries")
+        L.check(L.load().b2d_polyintr_load(self._h, c.ctypes.data, c.size, None if sg is None else sg.ctypes.data,
+                                           None if cr is None else cr.ctypes.data, int(channel)))
+
+    def run(self, data_in, out=None):
+        lib = L.load()
+        return self._run(data_in, lib.b2d_polyintr_run, lib.b2d_polyintr_run_dev, lambda n: lib.b2d_polyintr_max_out(self._h, n), True, out)
+
+    def reset(self):
+        L.check(L.load().b2d_polyintr_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_polyintr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ac_intg_dump:
     """ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (reference ac_intg_dump.h:113-151,
     SURVEY.md 8f row N4): run(samples interleaved over CHN, n_sample tokens) -> (dumping frames, CHN) sums."""

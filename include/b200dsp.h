@@ -206,6 +206,41 @@ int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out,
 int b2d_polydec_reset(b2d_polydec *h);
 const char *b2d_polydec_path(b2d_polydec *h);
 
+/* ---- polyphase interpolating FIR: ac_poly_intr ---------------------------------------------------- */
+/* ac_poly_intr<IN, COEFF, ACC, OUT, STR_CTRL, STR_COEFF, NTAPS, COEFFSZ, IF, ftype>::run(data_in, data_out, ctrl_st,
+ * coeffs_st, read_ctrl_chan)  (ac_poly_intr.h:261-312).  A reference run() call consumes one read_ctrl token: true loads
+ * the control struct {bool sign[IF]; ac_int<8,false> corr[IF];} and the coefficient struct (b2d_polyintr_load), false
+ * consumes one sample and writes IF outputs (b2d_polyintr_run with n samples = n such calls).  NTAPS is the length of
+ * the low-rate delay line.  ftype is the enum of ac_poly_intr.h:95: the two folded architectures implement the
+ * symmetric-pair technique and emit the outputs of a step one step late (nothing for the very first sample, :160);
+ * FOLD_ANTI is the plain polyphase form and ignores sign / corr.  Coefficients per channel: IF * NTAPS/2 (FOLD_EVEN,
+ * index i + j*NTAPS/2), IF * (NTAPS/2 + 1) (FOLD_ODD, i + (NTAPS/2+1)*j), IF * NTAPS (FOLD_ANTI, i + NTAPS*j).
+ * Outputs: IF per step, phase-minor, planar over channels with stride *n_out. */
+typedef enum { B2D_PI_FOLD_EVEN = 0, B2D_PI_FOLD_ODD = 1, B2D_PI_FOLD_ANTI = 2 } b2d_polyintr_ftype;
+typedef struct {
+  b2d_fmt in, coeff, acc, out;  /* IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE                              */
+  uint32_t n_taps;              /* NTAPS                                                                */
+  uint32_t intr_factor;         /* IF, 1 .. 255 (corr is ac_int<8,false> in the reference's usage)      */
+  int32_t ftype;                /* b2d_polyintr_ftype                                                   */
+  uint32_t n_channels;
+  int32_t layout;               /* layout of the input                                                  */
+  int32_t device;
+} b2d_polyintr_desc;
+typedef struct b2d_polyintr b2d_polyintr;
+int b2d_polyintr_create(b2d_polyintr **h, const b2d_polyintr_desc *desc);
+int b2d_polyintr_destroy(b2d_polyintr *h);
+size_t b2d_polyintr_coeffsz(b2d_polyintr *h);
+/* coeff_raw: b2d_polyintr_coeffsz(h) raw coefficients; sign / corr: IF bytes each (NULL = all true / identity);
+ * channel -1 = all channels.  May be called between runs: the accumulators of the last step keep the values they were
+ * computed with, the new sign / corr apply to the outputs that follow (as in the reference). */
+int b2d_polyintr_load(b2d_polyintr *h, const void *coeff_raw, size_t n, const uint8_t *sign, const uint8_t *corr, int32_t channel);
+size_t b2d_polyintr_max_out(b2d_polyintr *h, size_t n);
+int b2d_polyintr_run(b2d_polyintr *h, const void *in, size_t n, void *out, size_t *n_out);
+int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_polyintr_reset(b2d_polyintr *h);
+/* "polyintr_q15" (DP2A polyphase kernel, FOLD_ANTI on 16-bit operands), "polyintr_wide" (64-bit modular), "polyintr_generic" */
+const char *b2d_polyintr_path(b2d_polyintr *h);
+
 /* ---- integrate and dump: ac_intg_dump ------------------------------------------------------------ */
 /* ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (ac_intg_dump.h:113-151).  One call =
  * n_frames frames; frame f reads the token n_sample[f]: with 1 <= n_sample[f] <= NS it consumes n_sample[f] samples of each

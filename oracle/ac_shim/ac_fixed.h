@@ -11,6 +11,7 @@
 //   * a*b  -> ac_fixed<W1+W2, I1+I2, S1||S2>               (exact)
 //   * a+b  -> I = max(I1+(S2&&!S1), I2+(S1&&!S2))+1, F = max(F1,F2), S = S1||S2 (exact)
 //   * a-b  -> same widths as a+b but always signed          (exact)
+//   * -a   -> ac_fixed<W+1, I+1, true> (exact);  a >> n / a << n keep the type of a (bit-pattern shift)
 //   * conversion/assignment: drop fraction bits with quantisation mode Q, then drop
 //     integer bits with overflow mode O.  a += b  ==  a = a + b.
 // Raw values live in an __int128, so every width the hot path can produce
@@ -172,6 +173,20 @@ public:
   ac_fixed &operator+=(const ac_fixed<W2, I2, S2, Q2, O2> &o) { *this = this->operator+(o); return *this; }
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   ac_fixed &operator-=(const ac_fixed<W2, I2, S2, Q2, O2> &o) { *this = this->operator-(o); return *this; }
+
+  // unary minus: one more integer bit, always signed (AC Datatypes rt_unary::neg); exact
+  ac_fixed<W + 1, I + 1, true> operator-() const {
+    ac_fixed<W + 1, I + 1, true> r;
+    r.v = -v;
+    return r;
+  }
+  // shifts move the bit pattern inside the same type: bits shifted out are lost, the binary point stays
+  ac_fixed operator>>(int n) const {
+    ac_fixed r;
+    r.v = n >= 0 ? ac_shim::wrap_bits(v >> n, W, S) : ac_shim::wrap_bits(v << -n, W, S);
+    return r;
+  }
+  ac_fixed operator<<(int n) const { return this->operator>>(-n); }
 
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   bool operator==(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {

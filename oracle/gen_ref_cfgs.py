@@ -23,6 +23,10 @@ def main(outdir):
     with open(os.path.join(outdir, "cfgs_pd.inc"), "w") as fh:
         for cid, (fi, fc, fa, fo, nt, df) in enumerate(rc.PD_CONFIGS):
             fh.write(f"X({cid}, {f(fi)}, {f(fc)}, {f(fa)}, {f(fo)}, {nt}, {df})\n")
+    with open(os.path.join(outdir, "cfgs_pi.inc"), "w") as fh:
+        for cid, cfg in enumerate(rc.PI_CONFIGS):
+            fi, fc, fa, fo, nt, IF, ft = cfg
+            fh.write(f"X({cid}, {f(fi)}, {f(fc)}, {f(fa)}, {f(fo)}, {nt}, {rc.pi_coeffsz(cfg)}, {IF}, {ft})\n")
     with open(os.path.join(outdir, "cfgs_id.inc"), "w") as fh:
         for cid, (fi, fa, fo, ns, chn) in enumerate(rc.ID_CONFIGS):
             fh.write(f"X({cid}, {f(fi)}, {f(fa)}, {f(fo)}, {ns}, {chn})\n")

@@ -96,6 +96,12 @@ def lib_b():
         L.ob_pd_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.ob_pd_run.restype = C.c_long
         L.ob_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.ob_pi_create.restype = C.c_void_p
+        L.ob_pi_create.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int, C.c_int, C.c_int]
+        L.ob_pi_destroy.argtypes = [C.c_void_p]
+        L.ob_pi_load.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
+        L.ob_pi_run.restype = C.c_long
+        L.ob_pi_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.ob_id_create.restype = C.c_void_p
         L.ob_id_create.argtypes = [C.POINTER(ObFmt)] * 3 + [C.c_int, C.c_int]
         L.ob_id_destroy.argtypes = [C.c_void_p]
@@ -143,6 +149,12 @@ def lib_a():
         L.acref_pd_run.restype = C.c_long
         L.acref_pd_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
         L.acref_pd_destroy.argtypes = [C.c_void_p]
+        L.acref_pi_create.restype = C.c_void_p
+        L.acref_pi_create.argtypes = [C.c_int]
+        L.acref_pi_load.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
+        L.acref_pi_run.restype = C.c_long
+        L.acref_pi_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+        L.acref_pi_destroy.argtypes = [C.c_void_p]
         L.acref_id_create.restype = C.c_void_p
         L.acref_id_create.argtypes = [C.c_int]
         L.acref_id_run.restype = C.c_long
@@ -411,6 +423,66 @@ class PdA:
 def id_frame_samples(n_sample, NS, CHN):
     """Samples (all channels) a frame with token n_sample consumes: n_sample * CHN if it dumps, else NS * CHN."""
     return (int(n_sample) if 1 <= int(n_sample) <= NS else NS) * CHN
+
+
+class PiB:
+    """Oracle B ac_poly_intr: load(coeffs, sign, corr); run(samples) -> IF outputs per step (folded forms: one step late)."""
+
+    def __init__(self, fin, fcoeff, facc, fout, ntaps, IF, ftype):
+        self.L = lib_b()
+        a, b, c, d = _obfmt(fin), _obfmt(fcoeff), _obfmt(facc), _obfmt(fout)
+        self.nt, self.IF, self.ftype = int(ntaps), int(IF), ftype
+        self.h = self.L.ob_pi_create(C.byref(a), C.byref(b), C.byref(c), C.byref(d), self.nt, self.IF, rc.PI_FTYPES.index(ftype))
+        self.coeffsz = rc.pi_coeffsz((None, None, None, None, self.nt, self.IF, ftype))
+
+    def load(self, coeffs, sign=None, corr=None):
+        c = _i64(coeffs)
+        assert c.size == self.coeffsz
+        sg = _i64(np.ones(self.IF) if sign is None else sign)
+        cr = _i64(np.arange(self.IF) if corr is None else corr)
+        self.L.ob_pi_load(self.h, _p(c), _p(sg), _p(cr))
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size * self.IF + 1, dtype=np.int64)
+        n = self.L.ob_pi_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ob_pi_destroy(self.h)
+            self.h = None
+
+
+class PiA:
+    """The real reference ac_poly_intr for one compiled-in configuration (index into ref_configs.PI_CONFIGS)."""
+
+    def __init__(self, cfg_id):
+        self.L = lib_a()
+        self.h = self.L.acref_pi_create(int(cfg_id))
+        if not self.h:
+            raise KeyError("configuration not instantiated in oracle/_ref")
+        cfg = rc.PI_CONFIGS[cfg_id]
+        self.nt, self.IF, self.ftype = cfg[4], cfg[5], cfg[6]
+        self.coeffsz = rc.pi_coeffsz(cfg)
+
+    def load(self, coeffs, sign=None, corr=None):
+        c = _i64(coeffs)
+        assert c.size == self.coeffsz
+        sg = _i64(np.ones(self.IF) if sign is None else sign)
+        cr = _i64(np.arange(self.IF) if corr is None else corr)
+        self.L.acref_pi_load(self.h, _p(c), _p(sg), _p(cr))
+
+    def run(self, x):
+        x = _i64(x)
+        out = np.empty(x.size * self.IF + 1, dtype=np.int64)
+        n = self.L.acref_pi_run(self.h, _p(x), x.size, _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_pi_destroy(self.h)
+            self.h = None
 
 
 class IdB:

@@ -307,6 +307,94 @@ long ob_pd_run(ob_pd *f, const int64_t *in, long n, int64_t *out) {
   return nout;
 }
 
+/* ------------------------------------------------------------------ ac_poly_intr */
+/* include/ac_dsp/ac_poly_intr.h:103-256.  One step = one input sample -> IF outputs.  NTAPS is the length of the low-rate
+ * delay line taps[] (:107,127-129).  Per phase j:
+ *   FOLD_EVEN (:122-166): acc = sum_{i=NTAPS/2-1..0} coeffs[i + j*NTAPS/2] * fold_i, fold_i = ACC_TYPE(taps[i] + tp),
+ *                         tp = sign[j] ? taps[NTAPS-1-i] : IN_TYPE(-taps[NTAPS-1-i])           (:137-146)
+ *   FOLD_ODD  (:172-226): i = 0 .. (NTAPS-1)/2 upwards, centre tap fold = ACC_TYPE(taps[i]), coeffs[i + (NTAPS/2+1)*j]
+ *   FOLD_ANTI (:232-251): plain polyphase MAC over taps[NTAPS-1..0] with coeffs[i + NTAPS*j], written at once.
+ * The folded forms keep the accumulators of the PREVIOUS step in acc_a / acc_b (ping-pong on `flip`) and, from the
+ * second step on (`init`), write per phase  t1 = prev[j]  or, when corr[j] != j (symmetric-pair coefficients),
+ * (t1 + (sign[j] ? -prev[corr[j]] : prev[corr[j]])) >> 1  (:147-164): the outputs of step t are a function of step t-1. */
+enum { PI_FOLD_EVEN, PI_FOLD_ODD, PI_FOLD_ANTI };
+typedef struct {
+  ob_fmt in, coeff, acc, out;
+  int nt, ifac, ftype, csz, init;
+  w128 *taps, *h, *prev;
+  int *sign, *corr;
+} ob_pi;
+
+ob_pi *ob_pi_create(const ob_fmt *in, const ob_fmt *coeff, const ob_fmt *acc, const ob_fmt *out, int ntaps, int ifac, int ftype) {
+  ob_pi *f = (ob_pi *)calloc(1, sizeof(ob_pi));
+  f->in = *in; f->coeff = *coeff; f->acc = *acc; f->out = *out; f->nt = ntaps; f->ifac = ifac; f->ftype = ftype;
+  f->csz = ifac * (ftype == PI_FOLD_EVEN ? ntaps / 2 : (ftype == PI_FOLD_ODD ? ntaps / 2 + 1 : ntaps));
+  f->taps = (w128 *)calloc((size_t)ntaps, sizeof(w128));
+  f->h = (w128 *)calloc((size_t)(f->csz > 0 ? f->csz : 1), sizeof(w128));
+  f->prev = (w128 *)calloc((size_t)ifac, sizeof(w128));
+  f->sign = (int *)calloc((size_t)ifac, sizeof(int));
+  f->corr = (int *)calloc((size_t)ifac, sizeof(int));
+  return f;
+}
+void ob_pi_destroy(ob_pi *f) { if (f) { free(f->taps); free(f->h); free(f->prev); free(f->sign); free(f->corr); free(f); } }
+int ob_pi_coeffsz(const ob_pi *f) { return f->csz; }
+/* ctrl_t = ctrl_st.read(); coeffs_t = coeffs_st.read(): :286-288 */
+void ob_pi_load(ob_pi *f, const int64_t *c, const int64_t *sign, const int64_t *corr) {
+  for (int i = 0; i < f->csz; i++) f->h[i] = ob_wrap((w128)c[i], f->coeff.W, f->coeff.S);
+  for (int j = 0; j < f->ifac; j++) { f->sign[j] = sign[j] != 0; f->corr[j] = (int)(corr[j] & 0xff); }
+}
+/* -x assigned to a variable of format g: exact negation (one more bit), then the overflow mode of g */
+static w128 pi_neg(w128 x, const ob_fmt *g) { return ob_convert(-x, F_of(g), g); }
+
+long ob_pi_run(ob_pi *f, const int64_t *in, long n, int64_t *out) {
+  const int NT = f->nt, IF = f->ifac;
+  const int Fin = F_of(&f->in), Fc = F_of(&f->coeff), Fa = F_of(&f->acc);
+  long nout = 0;
+  w128 *cur = (w128 *)calloc((size_t)IF, sizeof(w128));
+  for (long k = 0; k < n; k++) {
+    for (int i = NT - 1; i >= 1; i--) f->taps[i] = f->taps[i - 1];
+    f->taps[0] = ob_wrap((w128)in[k], f->in.W, f->in.S);
+    for (int j = 0; j < IF; j++) {
+      w128 acc = 0;
+      if (f->ftype == PI_FOLD_EVEN) {
+        for (int i = NT / 2 - 1; i >= 0; i--) {
+          w128 tp = f->sign[j] ? f->taps[NT - 1 - i] : pi_neg(f->taps[NT - 1 - i], &f->in);
+          w128 fold = ob_convert(f->taps[i] + tp, Fin, &f->acc);
+          acc = ob_macc(acc, &f->acc, f->h[i + j * (NT / 2)] * fold, Fc + Fa);
+        }
+      } else if (f->ftype == PI_FOLD_ODD) {
+        for (int i = 0; i < (NT - 1) / 2 + 1; i++) {
+          w128 fold;
+          if (i == (NT - 1) / 2) fold = ob_convert(f->taps[i], Fin, &f->acc);
+          else {
+            w128 tp = f->sign[j] ? f->taps[NT - 1 - i] : pi_neg(f->taps[NT - 1 - i], &f->in);
+            fold = ob_convert(f->taps[i] + tp, Fin, &f->acc);
+          }
+          acc = ob_macc(acc, &f->acc, f->h[i + (NT / 2 + 1) * j] * fold, Fc + Fa);
+        }
+      } else {
+        for (int i = NT - 1; i >= 0; i--) acc = ob_macc(acc, &f->acc, f->taps[i] * f->h[i + NT * j], Fin + Fc);
+        out[nout++] = (int64_t)ob_convert(acc, Fa, &f->out);
+        continue;
+      }
+      cur[j] = acc;
+      if (f->init) {
+        w128 t1 = f->prev[j];
+        if (j != f->corr[j]) {
+          w128 t2 = f->prev[f->corr[j]];
+          w128 tn = f->sign[j] ? pi_neg(t2, &f->acc) : t2;
+          out[nout++] = (int64_t)ob_convert((t1 + tn) >> 1, Fa, &f->out);   /* the sum has W_acc + 1 bits: >> 1 loses its LSB only */
+        } else {
+          out[nout++] = (int64_t)ob_convert(t1, Fa, &f->out);
+        }
+      }
+    }
+    if (f->ftype != PI_FOLD_ANTI) { memcpy(f->prev, cur, (size_t)IF * sizeof(w128)); f->init = 1; }
+  }
+  free(cur);
+  return nout;
+}
+
 /* ------------------------------------------------------------------ ac_intg_dump */
 /* include/ac_dsp/ac_intg_dump.h:84-151: integrate-and-dump over CHN interleaved channels.  Per frame one n_sample token
  * is read; samples j = 1 .. NS are added into temp[i] (ACC_TYPE, re-quantised at every add) and at j == n_sample the

@@ -135,6 +135,38 @@ PD_CONFIGS = [
 ]
 
 
+# ac_poly_intr instantiations: (in, coeff, acc, out, NTAPS, IF, ftype)
+# ftype is the polyphase enum of ac_poly_intr.h:95 (FOLD_EVEN / FOLD_ODD: symmetric-pair structures; FOLD_ANTI: the plain
+# polyphase form).  NTAPS = taps per phase (length of the low-rate delay line).
+PI_FTYPES = ["FOLD_EVEN", "FOLD_ODD", "FOLD_ANTI"]
+PI_CONFIGS = [
+    (_Q15, _Q15, _ACC40, _ACC40, 8, 4, "FOLD_EVEN"),
+    (_Q15, _Q15, _ACC40, _ACC40, 7, 4, "FOLD_ODD"),
+    (_Q15, _Q15, _ACC40, _ACC40, 16, 4, "FOLD_ANTI"),            # 64 taps in all: the DUC partner of the R = 4 CIC interpolator
+    (_Q15, _Q15, _ACC40, _ACC40, 32, 8, "FOLD_ANTI"),
+    (_Q15, _Q15, _ACC40, _ACC40, 2, 3, "FOLD_EVEN"),
+    (_Q15, _Q15, _ACC40, _ACC40, 1, 2, "FOLD_ODD"),
+    (_Q15, _Q15, _ACC40, _ACC40, 5, 1, "FOLD_ANTI"),
+    (fmt(32, 16), fmt(32, 16), fmt(64, 32), fmt(64, 32), 6, 3, "FOLD_EVEN"),   # the header's usage example (ac_poly_intr.h:46-49)
+    (fmt(32, 16), fmt(32, 16), fmt(64, 32), fmt(64, 32), 5, 2, "FOLD_ODD"),
+    (_Q15, _Q15, fmt(24, 4), fmt(16, 1), 8, 4, "FOLD_EVEN"),                  # fold and product both truncate
+    (_Q15, _Q15, fmt(24, 4, True, RND), fmt(16, 1, True, RND), 9, 3, "FOLD_ODD"),
+    (_Q15, _Q15, fmt(24, 4), fmt(16, 1), 6, 5, "FOLD_ANTI"),
+    (fmt(12, 0, False), fmt(14, 2), fmt(30, 6), fmt(20, 4), 6, 3, "FOLD_EVEN"),   # unsigned samples: -x wraps back into IN_TYPE
+    (_Q15, _Q15, fmt(18, 1), fmt(18, 1), 8, 2, "FOLD_EVEN"),                    # accumulator too narrow: wraps
+    # order-dependent accumulators / saturating sample negation
+    (fmt(16, 1, True, TRN, "AC_SAT"), _Q15, fmt(24, 4, True, TRN, "AC_SAT"), fmt(16, 1, True, "AC_RND_CONV", "AC_SAT_SYM"), 8, 4, "FOLD_EVEN"),
+    (_Q15, _Q15, fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), 5, 2, "FOLD_ODD"),
+    (_Q15, _Q15, fmt(24, 4, True, TRN, "AC_SAT"), fmt(16, 1), 7, 3, "FOLD_ANTI"),
+]
+
+
+def pi_coeffsz(cfg):
+    """COEFFSZ an instantiation reads: ac_poly_intr.h:141 (i + j*NTAPS/2), :199 (i + (NTAPS/2+1)*j), :249 (i + NTAPS*j)."""
+    nt, IF, ft = cfg[4], cfg[5], cfg[6]
+    return IF * (nt // 2 if ft == "FOLD_EVEN" else (nt // 2 + 1 if ft == "FOLD_ODD" else nt))
+
+
 # ac_intg_dump instantiations (SURVEY.md 8f, row N4): (in, acc, out, NS, CHN)
 ID_CONFIGS = [
     (_Q15, fmt(32, 17), fmt(32, 17), 64, 4),

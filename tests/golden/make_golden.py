@@ -18,7 +18,9 @@ Fixtures (all raw two's-complement integers, int64):
       outputs of the UNMODIFIED reference class ac_fir_reg_share (oracle/ref_driver_rs.cpp) for every configuration
       in oracle/ref_configs.RS_CONFIGS: samples, coefficient RAM image, outputs of three run batches, final
       ac_firProgCoeffs_delay_line value; and of the UNMODIFIED ac_poly_dec (oracle/ref_driver_pd.cpp) for every
-      configuration in PD_CONFIGS (samples, phase-ordered coefficients, outputs of three run batches).
+      configuration in PD_CONFIGS (samples, phase-ordered coefficients, outputs of three run batches), of the
+      UNMODIFIED ac_poly_intr (oracle/ref_driver_pi.cpp) for every configuration in PI_CONFIGS (two coefficient /
+      control sets, the second loaded half way through the stream) and of ac_intg_dump (ID_CONFIGS).
   ref_outputs.npz
       outputs of the UNMODIFIED reference classes (Oracle A) on seeded random inputs for every
       configuration in oracle/ref_configs.py x ftype (FIR) and every CIC configuration, fed in
@@ -171,6 +173,26 @@ def main():
             ys.append(f.run(x, ns)); xs.append(x); toks.append(ns)
         rs[f"id{cid}_x"], rs[f"id{cid}_ns"], rs[f"id{cid}_y"] = np.concatenate(xs), np.concatenate(toks), np.concatenate(ys)
         rs[f"id{cid}_xlen"] = np.array([v.size for v in xs], dtype=np.int64)
+    for cid, cfg in enumerate(rc.PI_CONFIGS):                           # ac_poly_intr (row N2), same file
+        fi, fc, fa, fo, nt, IF, ft = cfg
+        f = O.PiA(cid)
+        x = O.rand_raw(rng2, fi, 5 * nt + 41)
+        x[nt + 3] = -(1 << (fi[0] - 1)) if fi[2] else (1 << fi[0]) - 1      # the sample whose negation does not fit IN_TYPE
+        c1, c2 = O.rand_raw(rng2, fc, f.coeffsz), O.rand_raw(rng2, fc, f.coeffsz)
+        sign = rng2.integers(0, 2, size=IF)
+        corr = np.arange(IF)
+        if IF >= 2:                                                      # symmetric pairs (j, IF-1-j), as the technique pairs them
+            corr = IF - 1 - corr
+            corr[IF // 2:] = np.arange(IF)[IF // 2:] if cid % 2 else corr[IF // 2:]
+        half = x.size // 2
+        f.load(c1, sign, corr)
+        y1 = np.concatenate([f.run(x[:1]), f.run(x[1:9]), f.run(x[9:half])])
+        f.load(c2, 1 - sign, corr[::-1].copy())                          # reload between steps: the parked accumulators keep their values
+        y2 = f.run(x[half:])
+        rs[f"pi{cid}_x"], rs[f"pi{cid}_c1"], rs[f"pi{cid}_c2"] = x, c1, c2
+        rs[f"pi{cid}_sign"], rs[f"pi{cid}_corr"] = sign.astype(np.int64), corr.astype(np.int64)
+        rs[f"pi{cid}_y"] = np.concatenate([y1, y2])
+        rs[f"pi{cid}_half"] = np.array([half, y1.size], dtype=np.int64)
     np.savez_compressed(OUT + "/rs_outputs.npz", **rs)
     print("rs_outputs:", len(rs), "arrays")
     np.savez_compressed(OUT + "/ref_outputs.npz", **store)

@@ -141,6 +141,34 @@ def test_facade_poly_dec(bench_exe, tmp_path, cid, chunk):
     assert np.array_equal(y, g[f"pd{cid}_y"])
 
 
+@pytest.fixture(scope="module")
+def poly_intr_exe(engine, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("facade_pi") / "facade_poly_intr")
+    subprocess.check_call(["g++"] + CXXFLAGS + [os.path.join(ROOT, "tests", "cpp", "facade_poly_intr.cpp")] + LDFLAGS + ["-o", exe])
+    return exe
+
+
+def test_facade_poly_intr_compiles_and_fails_loudly_without_gpu(engine, poly_intr_exe, tmp_path):
+    if engine.load().b2d_device_count() > 0:
+        pytest.skip("GPU present: covered by the parity test")
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    ctl = np.concatenate([g["pi0_c1"], g["pi0_c2"], g["pi0_sign"], g["pi0_corr"], g["pi0_half"][:1]])
+    p, y = run_case(poly_intr_exe, tmp_path, "pi0", g["pi0_x"], ctl)
+    assert p.returncode == 70 and "engine_error" in p.stderr, (p.returncode, p.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", [0, 1, 2, 9])
+def test_facade_poly_intr(poly_intr_exe, tmp_path, cid):
+    """ac_poly_intr through its facade class (one run() per read_ctrl token, control / coefficient structs on channels,
+    a reload half way) against the committed outputs of the unmodified reference class."""
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    ctl = np.concatenate([g[f"pi{cid}_c1"], g[f"pi{cid}_c2"], g[f"pi{cid}_sign"], g[f"pi{cid}_corr"], g[f"pi{cid}_half"][:1]])
+    p, y = run_case(poly_intr_exe, tmp_path, f"pi{cid}", g[f"pi{cid}_x"], ctl)
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(y, g[f"pi{cid}_y"])
+
+
 # ------------------------------------------------------------------------ the reference's own benches, unmodified (row N3)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref")
 

@@ -674,3 +674,61 @@ def test_intg_dump_vector_path_geometries(engine, oracle, CHN, n, fi, fa):
     x = rng.integers(lo, hi, size=frames * n * CHN, endpoint=True).astype(np.int16 if S else np.uint16)
     y = f.run(torch.from_numpy(x.view(np.int16)).cuda(), np.full(frames, n)).cpu().numpy()     # picks the carry up
     assert np.array_equal(y.astype(np.int64), ob.run(x, np.full(frames, n)).reshape(frames, CHN))
+
+
+# ------------------------------------------------------------------------ ac_poly_intr
+@pytest.mark.parametrize("cid", range(len(rc.PI_CONFIGS)),
+                         ids=lambda i: f"pi{i}-{rc.PI_CONFIGS[i][6]}-NT{rc.PI_CONFIGS[i][4]}-IF{rc.PI_CONFIGS[i][5]}")
+def test_poly_intr_vs_reference_outputs(engine, cid, path):
+    """The engine against the committed outputs of the UNMODIFIED reference class ac_poly_intr: three runs, a reload of the
+    coefficient and control structures half way (the parked accumulators keep the values of the old set, the new
+    sign / corr apply at once), one more run."""
+    from test_oracle import pi_replay
+    g = golden("rs_outputs.npz")
+    fi, fc, fa, fo, nt, IF, ft = rc.PI_CONFIGS[cid]
+    f = engine.ac_poly_intr(fi, fc, fa, fo, nt, IF, ft)
+    assert np.array_equal(pi_replay(f, g, cid).astype(np.int64), g[f"pi{cid}_y"]), f.path
+    if path == "auto":
+        want = "polyintr_q15" if (ft == "FOLD_ANTI" and fi[0] <= 16 and fa[0] == 40 and IF in (2, 4, 8)) else None
+        assert want is None or f.path == want, f.path
+
+
+@pytest.mark.parametrize("ft,nt,IF", [("FOLD_ANTI", 16, 4), ("FOLD_ANTI", 3, 2), ("FOLD_ANTI", 33, 8), ("FOLD_ANTI", 9, 5),
+                                      ("FOLD_EVEN", 12, 4), ("FOLD_ODD", 11, 3)])
+def test_poly_intr_random_channels_and_device(engine, oracle, ft, nt, IF, path):
+    """Random streams against Oracle B: host and device paths, planar and interleaved channels with per-channel
+    coefficient / control sets, calls of ragged lengths (including single samples and an empty call)."""
+    import torch
+    rng = np.random.default_rng(nt * 100 + IF)
+    C = 3
+    csz = rc.pi_coeffsz((None, None, None, None, nt, IF, ft))
+    cs = [rng.integers(-32768, 32767, size=csz, endpoint=True) for _ in range(C)]
+    sg = [rng.integers(0, 2, size=IF) for _ in range(C)]
+    cr = [rng.integers(0, IF, size=IF) for _ in range(C)]
+    n = 30000
+    x = rng.integers(-32768, 32767, size=(C, n), endpoint=True).astype(np.int16)
+    x[:, 100:140] = -32768
+    want = []
+    for c in range(C):
+        ob = oracle.PiB(Q15, Q15, ACC40, ACC40, nt, IF, ft)
+        ob.load(cs[c], sg[c], cr[c])
+        want.append(ob.run(x[c]))
+    want = np.stack(want)
+    for layout in ("planar", "interleaved"):
+        for dev in (False, True):
+            f = engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, IF, ft, n_channels=C, layout=layout)
+            for c in range(C):
+                f.load(cs[c], sg[c], cr[c], channel=c)
+            ys, o = [], 0
+            for ln in (1, 0, 1, 7, 4096, 12345, n):
+                xi = x[:, o:min(o + ln, n)]
+                if layout == "interleaved":
+                    xi = np.ascontiguousarray(xi.T)
+                y = f.run(torch.from_numpy(np.ascontiguousarray(xi)).cuda()).cpu().numpy() if dev else f.run(xi)
+                ys.append(np.asarray(y).reshape(C, -1))
+                o = min(o + ln, n)
+            assert np.array_equal(np.concatenate(ys, axis=1).astype(np.int64), want), (layout, dev, f.path)
+    with pytest.raises(engine.B2dError):
+        engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, IF, ft).run(np.zeros(4, dtype=np.int16))     # nothing loaded yet
+    with pytest.raises(engine.B2dError):
+        engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, IF, ft, coeffs=np.zeros(csz), corr=np.full(IF, IF))   # corr out of range

@@ -179,6 +179,73 @@ def test_poly_dec_live_reference_equals_restatement(oracle):
             assert np.array_equal(a.run(x), b.run(x)), (cid, kind)
 
 
+# ------------------------------------------------------------------------ ac_poly_intr
+def _pi_ids(i):
+    return f"pi{i}-{rc.PI_CONFIGS[i][6]}-NT{rc.PI_CONFIGS[i][4]}-IF{rc.PI_CONFIGS[i][5]}"
+
+
+def pi_replay(f, g, cid, cuts=(1, 9)):
+    """The call sequence the fixture was generated with: first coefficient / control set, three runs, reload, one run."""
+    x, half = g[f"pi{cid}_x"], int(g[f"pi{cid}_half"][0])
+    sign, corr = g[f"pi{cid}_sign"], g[f"pi{cid}_corr"]
+    f.load(g[f"pi{cid}_c1"], sign, corr)
+    ys = [f.run(x[:cuts[0]]), f.run(x[cuts[0]:cuts[1]]), f.run(x[cuts[1]:half])]
+    f.load(g[f"pi{cid}_c2"], 1 - sign, corr[::-1].copy())
+    ys.append(f.run(x[half:]))
+    return np.concatenate([np.asarray(y).reshape(-1) for y in ys])
+
+
+@pytest.mark.parametrize("cid", range(len(rc.PI_CONFIGS)), ids=_pi_ids)
+def test_poly_intr_restatement_vs_reference_outputs(oracle, cid):
+    g = golden("rs_outputs.npz")
+    fi, fc, fa, fo, nt, IF, ft = rc.PI_CONFIGS[cid]
+    y = pi_replay(oracle.PiB(fi, fc, fa, fo, nt, IF, ft), g, cid)
+    n = g[f"pi{cid}_x"].size
+    assert y.size == IF * (n if ft == "FOLD_ANTI" else n - 1)        # the folded forms write one step late (ac_poly_intr.h:160)
+    assert np.array_equal(y, g[f"pi{cid}_y"])
+
+
+def test_poly_intr_live_reference_equals_restatement(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no reference tree)")
+    rng = np.random.default_rng(41)
+    for cid, (fi, fc, fa, fo, nt, IF, ft) in enumerate(rc.PI_CONFIGS):
+        a, b = oracle.PiA(cid), oracle.PiB(fi, fc, fa, fo, nt, IF, ft)
+        for kind in ("uniform", "min", "max", "alt"):
+            c = oracle.rand_raw(rng, fc, a.coeffsz, "uniform" if kind == "alt" else kind)
+            sign, corr = rng.integers(0, 2, size=IF), rng.integers(0, IF, size=IF)
+            a.load(c, sign, corr); b.load(c, sign, corr)
+            x = oracle.rand_raw(rng, fi, 4 * nt + 9, kind)
+            assert np.array_equal(a.run(x), b.run(x)), (cid, kind)
+
+
+def test_poly_intr_kat_plain_form_is_the_polyphase_fir(oracle):
+    """Derived from the semantics (not a reference test): FOLD_ANTI with exact accumulators equals the zero-stuffed input
+    filtered by the interleaved prototype h[IF*m + j] = coeffs[m + NTAPS*j]; a symmetric pair (corr = mirror phase) of the
+    folded form returns (sum + difference) / 2 of the two parked accumulators."""
+    rng = np.random.default_rng(8)
+    NT, IF = 6, 4
+    c = rng.integers(-2000, 2000, size=NT * IF)
+    x = rng.integers(-3000, 3000, size=50)
+    f = oracle.PiB((16, 1), (16, 1), (40, 8), (40, 8), NT, IF, "FOLD_ANTI")
+    f.load(c)
+    y = f.run(x)
+    proto = np.zeros(NT * IF, dtype=np.int64)
+    for j in range(IF):
+        proto[j::IF] = c[j * NT:(j + 1) * NT]
+    z = np.zeros(x.size * IF, dtype=np.int64)
+    z[::IF] = x
+    assert np.array_equal(y, np.convolve(z, proto)[:z.size] << 2)       # F_acc - F_in - F_c = 2
+    e = oracle.PiB((16, 1), (16, 1), (40, 8), (40, 8), NT, 2, "FOLD_EVEN")
+    ce = rng.integers(-2000, 2000, size=NT)
+    e.load(ce, [1, 0], [1, 0])
+    ye = e.run(x).reshape(-1, 2)
+    plain = oracle.PiB((16, 1), (16, 1), (40, 8), (40, 8), NT, 2, "FOLD_EVEN")
+    plain.load(ce, [1, 0], [0, 1])
+    yp = plain.run(x).reshape(-1, 2)                                    # the parked accumulators themselves: S (sum set), D (difference set)
+    assert np.array_equal(ye[:, 0], (yp[:, 0] - yp[:, 1]) >> 1) and np.array_equal(ye[:, 1], (yp[:, 1] + yp[:, 0]) >> 1)
+
+
 # ------------------------------------------------------------------------ ac_intg_dump (SURVEY.md 8f row N4)
 def _id_calls(g, cid):
     x, ns, xlen = g[f"id{cid}_x"], g[f"id{cid}_ns"], g[f"id{cid}_xlen"]
