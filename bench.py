@@ -63,6 +63,10 @@ WORKLOADS = {
     "polydec": dict(kind="polydec", taps=32, df=8, channels=2, layout="interleaved", n=1 << 30, unit_is_iq=True,
                     bytes_per_unit=6.0, macs_per_unit=64,
                     name="ac_poly_dec NTAPS=32 DF=8 (256 taps) <16,1> x <16,1> -> <40,8>, interleaved 16-bit IQ, 2^30 IQ inputs per GPU"),
+    # polyphase interpolator, plain form, 16 taps per phase x 4 phases (64-tap prototype)
+    "polyintr": dict(kind="polyintr", taps=16, IF=4, channels=1, layout="planar", n=1 << 26, unit_is_iq=False,
+                     bytes_per_unit=2.0 + 4 * 8.0, macs_per_unit=64,
+                     name="ac_poly_intr NTAPS=16 IF=4 FOLD_ANTI (64-tap prototype) <16,1> x <16,1> -> <40,8>, 1 real channel x 2^26 inputs per GPU"),
     # integrate-and-dump, 4 interleaved channels, 64 samples per dump
     "intgdump": dict(kind="intgdump", chn=4, nsamp=256, ns=1024, channels=1, layout="planar", n=1 << 30, unit_is_iq=False,
                      bytes_per_unit=2.0 + 4.0 / 256, macs_per_unit=0,
@@ -151,6 +155,16 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
                 return None
         make = IdRun
         per_thread = int(seconds_target * 8e6)
+    elif wl["kind"] == "polyintr":
+        cid = [i for i, c in enumerate(O.rc.PI_CONFIGS) if c[4] == wl["taps"] and c[5] == wl["IF"] and c[6] == "FOLD_ANTI" and c[0][0] == 16][0]
+        h = O.rand_raw(rng, Q15, wl["taps"] * wl["IF"])
+
+        def make():
+            f = O.PiA(cid) if kind == "reference" else O.PiB(Q15, Q15, ACC40, ACC40, wl["taps"], wl["IF"], "FOLD_ANTI")
+            f.load(h)
+            f.last_run_seconds = lambda: None
+            return f
+        per_thread = int(seconds_target * 0.5e6)
     elif wl["kind"] == "polydec":
         cid = [i for i, c in enumerate(O.rc.PD_CONFIGS) if c[4] == wl["taps"] and c[5] == wl["df"] and c[0][0] == 16][0]
         h = O.rand_raw(rng, Q15, wl["taps"] * wl["df"])
@@ -306,6 +320,10 @@ def main():
                 self.f.close()
         f = _Id()
         launches_per_step = 1
+    elif wl["kind"] == "polyintr":
+        h = rng.integers(-32768, 32767, size=wl["taps"] * wl["IF"], endpoint=True).astype(np.int16)
+        f = E.ac_poly_intr(Q15, Q15, ACC40, ACC40, wl["taps"], wl["IF"], "FOLD_ANTI", coeffs=h, n_channels=C, layout=wl["layout"], device=local)
+        launches_per_step = 2
     elif wl["kind"] == "polydec":
         h = rng.integers(-32768, 32767, size=wl["taps"] * wl["df"], endpoint=True).astype(np.int16)
         f = E.ac_poly_dec(Q15, Q15, ACC40, ACC40, wl["taps"], wl["df"], coeffs=h, n_channels=C, layout=wl["layout"], device=local)
@@ -329,7 +347,7 @@ def main():
 
     y = f.run(x)
     path = f.path
-    up = wl.get("R", 1) if (wl.get("mode") == "intr" or wl["kind"] == "cicfir") else 1
+    up = wl.get("R", 1) if (wl.get("mode") == "intr" or wl["kind"] == "cicfir") else wl.get("IF", 1)
     ybuf = torch.empty(max(y.numel(), C * n * up), dtype=y.dtype, device="cuda")
     del y
     for _ in range(args.warmup):
@@ -371,6 +389,9 @@ def main():
             tok2 = np.full(n2 // (wl["chn"] * wl["nsamp"]), wl["nsamp"], dtype=np.uint32)
             yh = torch.empty(tok2.size * wl["chn"], dtype=torch.int32).pin_memory()
             call = lambda: lib.b2d_intgdump_run(f._h, xn.ctypes.data, n2, tok2.ctypes.data, tok2.size, yh.data_ptr(), ct.byref(no))
+        elif wl["kind"] == "polyintr":
+            yh = torch.empty(lib.b2d_polyintr_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
+            call = lambda: lib.b2d_polyintr_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
         elif wl["kind"] == "polydec":
             yh = torch.empty(lib.b2d_polydec_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
             call = lambda: lib.b2d_polydec_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
@@ -428,6 +449,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
                           "polydec": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+                          "polyintr": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
                           "intgdump": "s16 -> s64 (exact integer sum, ac_fixed<32,17> wrap)",
                           "cic": "s16 -> u32 (modular integrate / comb)"}[wl["kind"]],
                 "data": "synthetic",
