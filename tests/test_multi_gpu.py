@@ -26,7 +26,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 comm = P.make_comm(rank, world, local)
 Q15, ACC40 = (16, 1), (40, 8)
 rng = np.random.default_rng(2026)                     # same stream on every rank: the job's full input
-C, n, taps = 8, 6000, 1024
+C, n, taps = 16, 4000, 1024          # >= 2 channels per rank at world = 8
 x = rng.integers(-32768, 32767, size=(C, n), endpoint=True).astype(np.int16)
 h = rng.integers(-32768, 32767, size=taps, endpoint=True).astype(np.int16)
 mine = P.local_channels(C, rank, world)
@@ -46,11 +46,11 @@ cf = E.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT
 box = [g if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
 cf.load(box[0])
-yc = np.asarray(cf.run(torch.from_numpy(x[mine][:, :3000].copy()).cuda()).cpu().numpy()).reshape(len(mine), -1)
+yc = np.asarray(cf.run(torch.from_numpy(x[mine][:, :2000].copy()).cuda()).cpu().numpy()).reshape(len(mine), -1)
 for i, c in enumerate(mine):
     oc, of = O.CicB("intr", Q15, (20, 5), 4, 1, 3), O.FirB((20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG")
     of.load(g)
-    assert np.array_equal(yc[i].astype(np.int64), of.run(oc.run(x[c][:3000]))), ("cicfir", rank, c)
+    assert np.array_equal(yc[i].astype(np.int64), of.run(oc.run(x[c][:2000]))), ("cicfir", rank, c)
 allc = [None] * world
 dist.all_gather_object(allc, crc)
 merged = {}
