@@ -107,6 +107,10 @@ def load():
         "b2d_intgdump_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dIntgdumpDesc)]), "b2d_intgdump_destroy": (C.c_int, [vp]),
         "b2d_intgdump_run": (C.c_int, [vp, vp, sz, vp, sz, vp, psz]), "b2d_intgdump_run_dev": (C.c_int, [vp, vp, sz, vp, sz, vp, psz, vp]),
         "b2d_intgdump_reset": (C.c_int, [vp]), "b2d_intgdump_path": (C.c_char_p, [vp]),
+        "b2d_cicfir_state_bytes": (C.c_int, [vp, psz]), "b2d_cicfir_get_state": (C.c_int, [vp, vp, sz]), "b2d_cicfir_set_state": (C.c_int, [vp, vp, sz]),
+        "b2d_polydec_state_bytes": (C.c_int, [vp, psz]), "b2d_polydec_get_state": (C.c_int, [vp, vp, sz]), "b2d_polydec_set_state": (C.c_int, [vp, vp, sz]),
+        "b2d_polyintr_state_bytes": (C.c_int, [vp, psz]), "b2d_polyintr_get_state": (C.c_int, [vp, vp, sz]), "b2d_polyintr_set_state": (C.c_int, [vp, vp, sz]),
+        "b2d_intgdump_state_bytes": (C.c_int, [vp, psz]), "b2d_intgdump_get_state": (C.c_int, [vp, vp, sz]), "b2d_intgdump_set_state": (C.c_int, [vp, vp, sz]),
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),

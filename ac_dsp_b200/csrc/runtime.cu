@@ -545,6 +545,35 @@ extern "C" int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw)
 
 struct StateHdr { uint32_t magic, version; uint64_t n_seen; uint32_t hist, channels, bytes, pad; };
 static const uint32_t kFirMagic = 0x46324442u, kCicMagic = 0x43324442u;
+static const uint32_t kDecMagic = 0x44324442u, kIntrMagic = 0x49324442u, kDumpMagic = 0x55324442u, kCasMagic = 0x4b324442u;
+
+// Checkpoint blobs of the later handle types: StateHdr followed by device arrays copied verbatim.
+struct StatePart { void *dev; size_t bytes; };
+static size_t state_total(const StatePart *parts, int np) {
+  size_t t = sizeof(StateHdr);
+  for (int i = 0; i < np; i++) t += parts[i].bytes;
+  return t;
+}
+static int state_get(const StateHdr &hd, const StatePart *parts, int np, void *blob, size_t bytes) {
+  if (!blob) return fail(B2D_EINVAL, "null argument");
+  if (bytes < state_total(parts, np)) return fail(B2D_EINVAL, "state blob needs %zu bytes", state_total(parts, np));
+  CU(cudaDeviceSynchronize());
+  memcpy(blob, &hd, sizeof(hd));
+  size_t o = sizeof(hd);
+  for (int i = 0; i < np; i++) { if (parts[i].bytes) CU(cudaMemcpy((char *)blob + o, parts[i].dev, parts[i].bytes, cudaMemcpyDeviceToHost)); o += parts[i].bytes; }
+  return B2D_OK;
+}
+static int state_set(const StateHdr &want, const StatePart *parts, int np, const void *blob, size_t bytes, StateHdr *got) {
+  if (!blob) return fail(B2D_EINVAL, "null argument");
+  if (bytes < state_total(parts, np)) return fail(B2D_EINVAL, "state blob needs %zu bytes", state_total(parts, np));
+  memcpy(got, blob, sizeof(*got));
+  if (got->magic != want.magic || got->hist != want.hist || got->channels != want.channels || got->bytes != want.bytes)
+    return fail(B2D_EINVAL, "state blob does not belong to this filter configuration");
+  CU(cudaDeviceSynchronize());
+  size_t o = sizeof(*got);
+  for (int i = 0; i < np; i++) { if (parts[i].bytes) CU(cudaMemcpy(parts[i].dev, (const char *)blob + o, parts[i].bytes, cudaMemcpyHostToDevice)); o += parts[i].bytes; }
+  return B2D_OK;
+}
 
 extern "C" int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes) {
   if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
@@ -1067,6 +1096,56 @@ extern "C" int b2d_cicfir_reset(b2d_cicfir *h) {
   return b2d_fir_reset(h->fir);
 }
 
+// Checkpoint of the cascade: fused = input history + count; two-stage = the two stage blobs back to back.
+extern "C" int b2d_cicfir_state_bytes(b2d_cicfir *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  if (h->fused) { *bytes = sizeof(StateHdr) + (size_t)h->H * h->cd.n_channels * 2; return B2D_OK; }
+  size_t a = 0, b = 0;
+  int st;
+  if ((st = b2d_cic_state_bytes(h->cic, &a)) || (st = b2d_fir_state_bytes(h->fir, &b))) return st;
+  *bytes = sizeof(StateHdr) + a + b;
+  return B2D_OK;
+}
+extern "C" int b2d_cicfir_get_state(b2d_cicfir *h, void *blob, size_t bytes) {
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  int st = use_device(h->device);
+  if (st) return st;
+  if (h->fused) {
+    const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->H * h->cd.n_channels * 2}};
+    return state_get(StateHdr{kCasMagic, 1, h->n_seen, (uint32_t)h->H, h->cd.n_channels, 2, 1}, parts, 1, blob, bytes);
+  }
+  size_t need = 0, a = 0;
+  if ((st = b2d_cicfir_state_bytes(h, &need))) return st;
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  b2d_cic_state_bytes(h->cic, &a);
+  const StateHdr hd{kCasMagic, 1, 0, 0, h->cd.n_channels, 2, 0};
+  memcpy(blob, &hd, sizeof(hd));
+  if ((st = b2d_cic_get_state(h->cic, (char *)blob + sizeof(hd), a))) return st;
+  return b2d_fir_get_state(h->fir, (char *)blob + sizeof(hd) + a, need - sizeof(hd) - a);
+}
+extern "C" int b2d_cicfir_set_state(b2d_cicfir *h, const void *blob, size_t bytes) {
+  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
+  int st = use_device(h->device);
+  if (st) return st;
+  if (h->fused) {
+    const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->H * h->cd.n_channels * 2}};
+    StateHdr got;
+    if ((st = state_set(StateHdr{kCasMagic, 1, 0, (uint32_t)h->H, h->cd.n_channels, 2, 1}, parts, 1, blob, bytes, &got))) return st;
+    if (got.pad != 1) return fail(B2D_EINVAL, "state blob was taken from a two-stage cascade");
+    h->n_seen = got.n_seen;
+    return B2D_OK;
+  }
+  size_t need = 0, a = 0;
+  if ((st = b2d_cicfir_state_bytes(h, &need))) return st;
+  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
+  StateHdr hd;
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kCasMagic || hd.pad != 0 || hd.channels != h->cd.n_channels) return fail(B2D_EINVAL, "state blob does not belong to this cascade");
+  b2d_cic_state_bytes(h->cic, &a);
+  if ((st = b2d_cic_set_state(h->cic, (const char *)blob + sizeof(hd), a))) return st;
+  return b2d_fir_set_state(h->fir, (const char *)blob + sizeof(hd) + a, need - sizeof(hd) - a);
+}
+
 // -------------------------------------------------------------------------------------------- ac_poly_dec
 struct b2d_polydec {
   b2d_polydec_desc d;
@@ -1260,6 +1339,29 @@ extern "C" int b2d_polydec_reset(b2d_polydec *h) {
   const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
   for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
   h->n_seen = 0;
+  return B2D_OK;
+}
+
+extern "C" int b2d_polydec_state_bytes(b2d_polydec *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  *bytes = sizeof(StateHdr) + (size_t)h->T * h->d.n_channels * h->in_bytes;
+  return B2D_OK;
+}
+extern "C" int b2d_polydec_get_state(b2d_polydec *h, void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->T * h->d.n_channels * h->in_bytes}};
+  return state_get(StateHdr{kDecMagic, 1, h->n_seen, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 1, blob, bytes);
+}
+extern "C" int b2d_polydec_set_state(b2d_polydec *h, const void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->T * h->d.n_channels * h->in_bytes}};
+  StateHdr got;
+  if ((st = state_set(StateHdr{kDecMagic, 1, 0, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 1, blob, bytes, &got))) return st;
+  h->n_seen = got.n_seen;
   return B2D_OK;
 }
 
@@ -1522,6 +1624,39 @@ extern "C" int b2d_polyintr_reset(b2d_polyintr *h) {
   return B2D_OK;
 }
 
+static void polyintr_parts(b2d_polyintr *h, StatePart *parts) {
+  parts[0] = StatePart{h->d_tail[h->cur], (size_t)h->H * h->d.n_channels * h->in_bytes};
+  parts[1] = StatePart{h->d_carry[h->ccur], (size_t)h->d.n_channels * h->d.intr_factor * sizeof(int64_t)};
+}
+extern "C" int b2d_polyintr_state_bytes(b2d_polyintr *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  StatePart parts[2];
+  polyintr_parts(h, parts);
+  *bytes = state_total(parts, 2);
+  return B2D_OK;
+}
+// the delay line, the parked accumulators of the last step (ac_poly_intr.h:108-110) and `init`
+extern "C" int b2d_polyintr_get_state(b2d_polyintr *h, void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  StatePart parts[2];
+  polyintr_parts(h, parts);
+  return state_get(StateHdr{kIntrMagic, 1, h->n_seen, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, h->init ? 1u : 0u}, parts, 2, blob, bytes);
+}
+extern "C" int b2d_polyintr_set_state(b2d_polyintr *h, const void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  StatePart parts[2];
+  polyintr_parts(h, parts);
+  StateHdr got;
+  if ((st = state_set(StateHdr{kIntrMagic, 1, 0, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 2, blob, bytes, &got))) return st;
+  h->n_seen = got.n_seen;
+  h->init = got.pad != 0;
+  return B2D_OK;
+}
+
 // -------------------------------------------------------------------------------------------- ac_intg_dump
 struct b2d_intgdump {
   b2d_intgdump_desc d;
@@ -1583,6 +1718,28 @@ extern "C" int b2d_intgdump_reset(b2d_intgdump *h) {
   CU(cudaDeviceSynchronize());
   for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_carry[i], 0, h->d.chn * sizeof(int64_t)));
   return B2D_OK;
+}
+
+// the running sums temp[CHN] (ac_intg_dump.h:78)
+extern "C" int b2d_intgdump_state_bytes(b2d_intgdump *h, size_t *bytes) {
+  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
+  *bytes = sizeof(StateHdr) + (size_t)h->d.chn * sizeof(int64_t);
+  return B2D_OK;
+}
+extern "C" int b2d_intgdump_get_state(b2d_intgdump *h, void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  const StatePart parts[1] = {{h->d_carry[h->cur], (size_t)h->d.chn * sizeof(int64_t)}};
+  return state_get(StateHdr{kDumpMagic, 1, 0, 0, h->d.chn, 8, 0}, parts, 1, blob, bytes);
+}
+extern "C" int b2d_intgdump_set_state(b2d_intgdump *h, const void *blob, size_t bytes) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  int st = use_device(h->device);
+  if (st) return st;
+  const StatePart parts[1] = {{h->d_carry[h->cur], (size_t)h->d.chn * sizeof(int64_t)}};
+  StateHdr got;
+  return state_set(StateHdr{kDumpMagic, 1, 0, 0, h->d.chn, 8, 0}, parts, 1, blob, bytes, &got);
 }
 
 // token sequence -> segments of the per-channel sample axis (control flow of ac_intg_dump.h:133-147)

@@ -29,6 +29,20 @@ def _container_dtype(fmt):
     return _NP_DT[L.load().b2d_container_bytes(fmt.W)]
 
 
+def _get_state(h, prefix):
+    lib = L.load()
+    n = C.c_size_t(0)
+    L.check(getattr(lib, f"b2d_{prefix}_state_bytes")(h, C.byref(n)))
+    buf = np.zeros(n.value, dtype=np.uint8)
+    L.check(getattr(lib, f"b2d_{prefix}_get_state")(h, buf.ctypes.data, buf.size))
+    return buf
+
+
+def _set_state(h, prefix, blob):
+    blob = np.ascontiguousarray(np.asarray(blob, dtype=np.uint8))
+    L.check(getattr(L.load(), f"b2d_{prefix}_set_state")(h, blob.ctypes.data, blob.size))
+
+
 class _Block:
     """Shared marshaling: channel layout, numpy / torch dispatch."""
 
@@ -343,6 +357,13 @@ class cic_intr_fir_cascade(_Block):
         lib = L.load()
         return self._run(data_in, lib.b2d_cicfir_run, lib.b2d_cicfir_run_dev, lambda n: lib.b2d_cicfir_max_out(self._h, n), True, out)
 
+    def get_state(self):
+        """Checkpoint blob (b2d_cicfir_get_state)."""
+        return _get_state(self._h, "cicfir")
+
+    def set_state(self, blob):
+        _set_state(self._h, "cicfir", blob)
+
     def reset(self):
         L.check(L.load().b2d_cicfir_reset(self._h))
 
@@ -390,6 +411,13 @@ class ac_poly_dec(_Block):
             self.load(coeffs_st)
         lib = L.load()
         return self._run(data_in, lib.b2d_polydec_run, lib.b2d_polydec_run_dev, lambda n: lib.b2d_polydec_max_out(self._h, n), True, out)
+
+    def get_state(self):
+        """Checkpoint blob (b2d_polydec_get_state)."""
+        return _get_state(self._h, "polydec")
+
+    def set_state(self, blob):
+        _set_state(self._h, "polydec", blob)
 
     def reset(self):
         L.check(L.load().b2d_polydec_reset(self._h))
@@ -450,6 +478,13 @@ class ac_poly_intr(_Block):
         lib = L.load()
         return self._run(data_in, lib.b2d_polyintr_run, lib.b2d_polyintr_run_dev, lambda n: lib.b2d_polyintr_max_out(self._h, n), True, out)
 
+    def get_state(self):
+        """Checkpoint blob (b2d_polyintr_get_state)."""
+        return _get_state(self._h, "polyintr")
+
+    def set_state(self, blob):
+        _set_state(self._h, "polyintr", blob)
+
     def reset(self):
         L.check(L.load().b2d_polyintr_reset(self._h))
 
@@ -498,6 +533,13 @@ class ac_intg_dump:
     @property
     def path(self):
         return L.load().b2d_intgdump_path(self._h).decode()
+
+    def get_state(self):
+        """Checkpoint blob (b2d_intgdump_get_state)."""
+        return _get_state(self._h, "intgdump")
+
+    def set_state(self, blob):
+        _set_state(self._h, "intgdump", blob)
 
     def reset(self):
         L.check(L.load().b2d_intgdump_reset(self._h))

@@ -181,6 +181,9 @@ int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n
 int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
 int b2d_cicfir_reset(b2d_cicfir *h);
 const char *b2d_cicfir_path(b2d_cicfir *h);
+int b2d_cicfir_state_bytes(b2d_cicfir *h, size_t *bytes);   /* checkpoint, as b2d_fir_get_state */
+int b2d_cicfir_get_state(b2d_cicfir *h, void *blob, size_t bytes);
+int b2d_cicfir_set_state(b2d_cicfir *h, const void *blob, size_t bytes);
 
 /* ---- polyphase decimator: ac_poly_dec ----------------------------------------------------------- */
 /* ac_poly_dec<IN, COEFF, STR_COEFF, ACC, OUT, NTAPS, DF>::run(data_in, data_out, coeffs_st)  (ac_poly_dec.h:87-137):
@@ -205,6 +208,9 @@ int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t 
 int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
 int b2d_polydec_reset(b2d_polydec *h);
 const char *b2d_polydec_path(b2d_polydec *h);
+int b2d_polydec_state_bytes(b2d_polydec *h, size_t *bytes);
+int b2d_polydec_get_state(b2d_polydec *h, void *blob, size_t bytes);
+int b2d_polydec_set_state(b2d_polydec *h, const void *blob, size_t bytes);
 
 /* ---- polyphase interpolating FIR: ac_poly_intr ---------------------------------------------------- */
 /* ac_poly_intr<IN, COEFF, ACC, OUT, STR_CTRL, STR_COEFF, NTAPS, COEFFSZ, IF, ftype>::run(data_in, data_out, ctrl_st,
@@ -240,6 +246,10 @@ int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_ou
 int b2d_polyintr_reset(b2d_polyintr *h);
 /* "polyintr_q15" (DP2A polyphase kernel, FOLD_ANTI on 16-bit operands), "polyintr_wide" (64-bit modular), "polyintr_generic" */
 const char *b2d_polyintr_path(b2d_polyintr *h);
+/* checkpoint: delay line, the parked accumulators acc_a / acc_b of the last step and `init` (ac_poly_intr.h:107-111) */
+int b2d_polyintr_state_bytes(b2d_polyintr *h, size_t *bytes);
+int b2d_polyintr_get_state(b2d_polyintr *h, void *blob, size_t bytes);
+int b2d_polyintr_set_state(b2d_polyintr *h, const void *blob, size_t bytes);
 
 /* ---- integrate and dump: ac_intg_dump ------------------------------------------------------------ */
 /* ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (ac_intg_dump.h:113-151).  One call =
@@ -261,6 +271,10 @@ int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_in, const u
 int b2d_intgdump_reset(b2d_intgdump *h);
 /* kernel family the last run took: "intgdump_vec" (128-bit loads, equal frames), "intgdump_warp", "intgdump_thread" */
 const char *b2d_intgdump_path(b2d_intgdump *h);
+/* checkpoint: the running sums temp[CHN] (ac_intg_dump.h:78) */
+int b2d_intgdump_state_bytes(b2d_intgdump *h, size_t *bytes);
+int b2d_intgdump_get_state(b2d_intgdump *h, void *blob, size_t bytes);
+int b2d_intgdump_set_state(b2d_intgdump *h, const void *blob, size_t bytes);
 
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128

@@ -732,3 +732,55 @@ def test_poly_intr_random_channels_and_device(engine, oracle, ft, nt, IF, path):
         engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, IF, ft).run(np.zeros(4, dtype=np.int16))     # nothing loaded yet
     with pytest.raises(engine.B2dError):
         engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, IF, ft, coeffs=np.zeros(csz), corr=np.full(IF, IF))   # corr out of range
+
+
+# ------------------------------------------------------------------------ checkpoint / resume of the later handle types
+@pytest.mark.parametrize("two_stage", ["0", "1"])
+def test_checkpoint_resume_cascade_polydec_polyintr_intgdump(engine, oracle, two_stage, monkeypatch):
+    """all filter state lives in object members; get_state after k samples + set_state into a fresh
+    handle must continue the stream exactly like the uninterrupted object (and a blob of another configuration is
+    refused)."""
+    monkeypatch.setenv("B2D_CICFIR_TWO_STAGE", two_stage)
+    rng = np.random.default_rng(99)
+    x = rng.integers(-32768, 32767, size=5000, endpoint=True).astype(np.int16)
+    cut = 1237
+    # cascade (BASELINE configs[4])
+    g = rng.integers(-32768, 32767, size=63, endpoint=True).astype(np.int16)
+    mk = lambda: engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT_REG", coeffs=g)
+    a, b = mk(), mk()
+    whole = a.run(x)
+    first = b.run(x[:cut])
+    c = mk()
+    c.set_state(b.get_state())
+    assert np.array_equal(np.concatenate([first, c.run(x[cut:])]), whole), a.path
+    with pytest.raises(engine.B2dError):
+        engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 31, "SHIFT_REG", coeffs=g[:31]).set_state(b.get_state())
+    if two_stage == "1":
+        return
+    # polyphase decimator
+    hp = rng.integers(-32768, 32767, size=64, endpoint=True).astype(np.int16)
+    mk = lambda: engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, 16, 4, coeffs=hp)
+    a, b, c = mk(), mk(), mk()
+    whole, first = a.run(x), b.run(x[:cut])
+    c.set_state(b.get_state())
+    assert np.array_equal(np.concatenate([first, c.run(x[cut:])]), whole)
+    # polyphase interpolator, folded form: the parked accumulators and `init` travel with the blob
+    for ft, nt in (("FOLD_EVEN", 8), ("FOLD_ANTI", 16)):
+        csz = rc.pi_coeffsz((None, None, None, None, nt, 4, ft))
+        hc = rng.integers(-32768, 32767, size=csz, endpoint=True).astype(np.int16)
+        mk = lambda: engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt, 4, ft, coeffs=hc, sign=[1, 0, 0, 1], corr=[3, 1, 2, 0])
+        a, b, c = mk(), mk(), mk()
+        whole, first = a.run(x), b.run(x[:cut])
+        c.set_state(b.get_state())
+        assert np.array_equal(np.concatenate([first, c.run(x[cut:])]), whole), ft
+        with pytest.raises(engine.B2dError):
+            engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, nt + 2, 4, ft).set_state(b.get_state())
+    # integrate-and-dump: a frame that does not dump leaves running sums behind
+    mk = lambda: engine.ac_intg_dump(Q15, (32, 17), (32, 17), 64, 4)
+    a, b, c = mk(), mk(), mk()
+    tok1, tok2 = np.array([64, 99, 0]), np.array([32, 64])
+    n1, n2 = (64 + 64 + 64) * 4, (32 + 64) * 4
+    whole = np.concatenate([a.run(x[:n1], tok1), a.run(x[n1:n1 + n2], tok2)])
+    first = b.run(x[:n1], tok1)
+    c.set_state(b.get_state())
+    assert np.array_equal(np.concatenate([first, c.run(x[n1:n1 + n2], tok2)]), whole)
