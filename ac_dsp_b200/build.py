@@ -40,9 +40,19 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libb200dsp.so")
     os.makedirs(LIBDIR, exist_ok=True)
     tmp = LIB + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    subprocess.check_call(cmd)
+    # one nvcc -c per source in parallel, then one link
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src + ".o")
+        subprocess.check_call([nvcc] + cflags + ["-c", os.path.join(CSRC, src), "-o", obj])
+        return obj
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + objs + ["-ldl"])
     os.replace(tmp, LIB)
     return LIB
 

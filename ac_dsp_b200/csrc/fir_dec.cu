@@ -167,7 +167,38 @@ __global__ void __launch_bounds__(kWideThreads) polydec_q15_kernel(DecQArgs a) {
   };
   const bool planar1 = NP == 1 && (!a.interleaved || a.C == 1);
   const int lg = (a.DF & (a.DF - 1)) == 0 ? 31 - __clz(a.DF) : -1;   // DF a power of two: (k, pos) by shift / mask, no chain
-  if (interior && (NP == 2 || planar1) && lg >= 0) {
+  if (interior && NP == 2 && lg >= 2 && ((((uintptr_t)((const uint32_t *)a.x + l0)) & 15) == 0)) {
+    // IQ words, DF a multiple of 4: a 128-bit load is 4 consecutive phases of one row k; two rows (k, k+1) of the same phase
+    // pack into one 32-bit shared-memory word per channel: 2 LDG.128 + 8 PRMT + 8 STS.32 per 8 IQ samples
+    const uint4 *x128 = (const uint4 *)((const uint32_t *)a.x + l0);
+    const int lg4 = lg - 2, G4 = a.DF >> 2, items = (XS >> 1) * G4, mask = a.DF - 1;
+    for (int it = threadIdx.x; it < items; it += 4 * kWideThreads) {
+      uint4 w0[4], w1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ii = it + u * kWideThreads;
+        if (ii < items) {
+          const int kkp = ii >> lg4, pg = ii & (G4 - 1);
+          w0[u] = x128[(size_t)(2 * kkp) * G4 + pg];
+          w1[u] = x128[(size_t)(2 * kkp + 1) * G4 + pg];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ii = it + u * kWideThreads;
+        if (ii < items) {
+          const int kkp = ii >> lg4, pg = ii & (G4 - 1);
+          const uint32_t a0[4] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w}, a1[4] = {w1[u].x, w1[u].y, w1[u].z, w1[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int r = mask - (4 * pg + i);
+            ((uint32_t *)(xs + (size_t)r * XS))[kkp] = __byte_perm(a0[i], a1[i], 0x5410);
+            ((uint32_t *)(xs + (size_t)(a.DF + r) * XS))[kkp] = __byte_perm(a0[i], a1[i], 0x7632);
+          }
+        }
+      }
+    }
+  } else if (interior && (NP == 2 || planar1) && lg >= 0) {
     const uint32_t *x32 = (const uint32_t *)a.x + l0;
     const uint16_t *x16 = (const uint16_t *)a.x + (size_t)c0 * a.n + l0;
     const int mask = a.DF - 1;

@@ -253,6 +253,26 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bind_near_gpu(local):
+    """Run this rank's host threads -- and, by first touch, its pinned staging buffers -- on the CPUs next to its GPU
+    (NVML's ideal affinity), so that the H2D / D2H streams of N ranks do not all cross the socket interconnect.
+    Returns the original affinity (restored before the CPU baseline, which uses every core) or None."""
+    try:
+        import pynvml
+        orig = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & orig
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return orig
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +297,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    orig_affinity = bind_near_gpu(local) if world > 1 else None
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -419,7 +440,8 @@ def main():
         u2 = n2 if wl["unit_is_iq"] else n2 * C
         e2e = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
                "d2h_bytes_per_step": int(no.value * C * yh.element_size()), "steps": k2,
-               "api": "b2d_fir_run / b2d_cic_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
+               "api": "b2d_*_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
+               "host_affinity": "NVML ideal CPUs of the GPU" if orig_affinity else "unchanged",
                "samples_per_step": u2}
 
     if rank == 0:
@@ -458,6 +480,8 @@ def main():
                            "parallelism": f"channels sharded over {world} GPU(s), one ncclBroadcast of the coefficient set at load()"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roof}
         if world == 1 and not args.no_cpu:
+            if orig_affinity:
+                os.sched_setaffinity(0, orig_affinity)
             cb = cpu_reference(wl)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
