@@ -427,6 +427,91 @@ def test_full_size_cic_windows(engine, oracle):
     assert int(ydc[0, -1]) == 3 * 8 ** 4 and int(ydc[1, 1000]) == 3 * 8 ** 4
 
 
+def test_full_size_cascade_and_prog1024_windows(engine, oracle):
+    """BASELINE configs[4] (interpolator R=4 N=3 + 63-tap FIR, one channel of 2^26 inputs = one GPU's share) and
+    configs[3] (1024 taps, one GPU's share: 8 channels x 2^27) at full size: random output windows re-derived by the
+    oracle from the same inputs, plus output count and a zero-input / DC property."""
+    import torch
+    rng = np.random.default_rng(20260104)
+    # ---- configs[4]
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(20260104)
+    x = torch.randint(-32768, 32768, (n,), dtype=torch.int16, device="cuda", generator=g)
+    hc = oracle.rand_raw(rng, Q15, 63)
+    f = engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT_REG", coeffs=hc)
+    y = f.run(x)
+    torch.cuda.synchronize()
+    assert f.path == "cicfir_fused" and y.shape == ((n - 1) * 4 + 1 - 2,)        # (K-1)R + 1 - (N-1): SURVEY.md 8a a15
+    for k in [0, 3, n - 600] + [int(v) for v in rng.integers(100, n - 1000, size=16)]:
+        k0 = max(0, k - 40)                         # 18 composite taps per phase + the comb run-in
+        xs = x[k0:k + 500].cpu().numpy()
+        oc, of = oracle.CicB("intr", Q15, (20, 5), 4, 1, 3), oracle.FirB((20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG")
+        of.load(hc)
+        want = of.run(oc.run(xs))                   # restarted k0 inputs early: exact once 63 + run-in outputs have passed
+        o_lo = (k - k0) * 4 + 100                   # compare from 100 outputs into period k
+        ref = want[o_lo:o_lo + 1500] if k0 > 0 else want[:1500]
+        first = (k * 4 + 100) if k0 > 0 else 0      # both streams drop their first N-1 outputs: index i of the restart is 4*k0 + i here
+        got = y[first:first + ref.size].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, ref), k
+    del y, f
+    # ---- configs[3], per-GPU share
+    C, n = 8, 1 << 27
+    x = torch.randint(-32768, 32768, (C, n), dtype=torch.int16, device="cuda", generator=g)
+    h = oracle.rand_raw(rng, Q15, 1024)
+    f = make_fir(engine, "prog", Q15, Q15, ACC40, ACC40, 1024, "SHIFT_REG", h, n_channels=C, layout="planar")
+    y = f.run(x)
+    torch.cuda.synchronize()
+    assert f.path == "fir_q15" and y.shape == (C, n)
+    for s in [0, n - 1500] + [int(v) for v in rng.integers(1100, n - 3000, size=10)]:
+        lo = max(0, s - 1023)
+        c = int(rng.integers(0, C))
+        want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, 1024, "SHIFT_REG", h, x[c, lo:s + 800].cpu().numpy())
+        assert np.array_equal(y[c, s:s + 800].cpu().numpy(), want[s - lo:]), (s, c)
+
+
+def test_full_size_polydec_polyintr_intgdump_windows(engine, oracle):
+    """Rows N2 / N4 at the bench sizes: windows re-derived by the oracle."""
+    import torch
+    rng = np.random.default_rng(20260105)
+    g = torch.Generator(device="cuda").manual_seed(20260105)
+    # polyphase decimator, 32 x 8 taps, 2^28 IQ inputs
+    n = 1 << 28
+    x = torch.randint(-32768, 32768, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    hp = oracle.rand_raw(rng, Q15, 256)
+    f = engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, 32, 8, coeffs=hp, n_channels=2, layout="interleaved")
+    y = f.run(x)
+    assert f.path == "polydec_q15" and y.shape == (2, n // 8)
+    for m in [0, n // 8 - 300] + [int(v) for v in rng.integers(100, n // 8 - 1000, size=12)]:
+        m0 = max(0, m - 32)
+        xs = x[m0 * 8:(m + 250) * 8].cpu().numpy()
+        for c in range(2):
+            ob = oracle.PdB(Q15, Q15, ACC40, ACC40, 32, 8)
+            ob.load(hp)
+            assert np.array_equal(y[c, m:m + 250].cpu().numpy().astype(np.int64), ob.run(xs[:, c])[m - m0:]), (m, c)
+    del x, y, f
+    # polyphase interpolator, 16 taps x 4 phases, 2^26 inputs
+    n = 1 << 26
+    x = torch.randint(-32768, 32768, (n,), dtype=torch.int16, device="cuda", generator=g)
+    hi = oracle.rand_raw(rng, Q15, 64)
+    f = engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, 16, 4, "FOLD_ANTI", coeffs=hi)
+    y = f.run(x)
+    assert f.path == "polyintr_q15" and y.shape == (4 * n,)
+    for k in [0, n - 400] + [int(v) for v in rng.integers(100, n - 1000, size=12)]:
+        k0 = max(0, k - 16)
+        ob = oracle.PiB(Q15, Q15, ACC40, ACC40, 16, 4, "FOLD_ANTI")
+        ob.load(hi)
+        want = ob.run(x[k0:k + 300].cpu().numpy())
+        assert np.array_equal(y[4 * k:4 * (k + 300)].cpu().numpy().astype(np.int64), want[4 * (k - k0):]), k
+    del y, f
+    # integrate-and-dump, 4 channels x 256 samples per dump, 2^28 samples: every output is a plain sum
+    f = engine.ac_intg_dump(Q15, (32, 17), (32, 17), 1024, 4)
+    xs = x[: 1 << 26]
+    frames = xs.numel() // 1024
+    yd = f.run(xs, np.full(frames, 256))
+    assert f.path == "intgdump_vec" and yd.shape == (frames, 4)
+    assert torch.equal(yd, xs.view(frames, 256, 4).to(torch.int32).sum(dim=1).to(torch.int32))
+
+
 def test_comm_single_rank_broadcast(engine, oracle):
     """The NCCL coefficient broadcast with a world of one (the multi-rank path is exercised by bench.py --gpus N)."""
     uid = engine.Comm.unique_id()
