@@ -14,13 +14,18 @@
 //   * -a   -> ac_fixed<W+1, I+1, true> (exact);  a >> n / a << n keep the type of a (bit-pattern shift)
 //   * conversion/assignment: drop fraction bits with quantisation mode Q, then drop
 //     integer bits with overflow mode O.  a += b  ==  a = a + b.
-// Raw values live in an __int128, so every width the hot path can produce
-// (<= 32+64+1 bits) is exact.  `ac_shim::from_raw / to_raw` are shim-only helpers used
-// by the oracle driver to move raw integers in and out.
+// Storage is tiered like the real package's (which keeps ceil(W/32) native words): the raw value of a
+// type that needs <= 32 bits lives in an int32_t, <= 64 bits in an int64_t, anything wider in an __int128
+// (every width the hot path can produce, <= 32+64+1 bits, is exact).  Each operator computes in the storage
+// type of its RESULT and each conversion in the narrowest tier that holds the re-scaled source plus one
+// carry bit, so the common <16,1> x <16,1> -> <40,8> path is plain 32/64-bit machine arithmetic and the CPU
+// timings taken with this shim are not handicapped by 128-bit emulation.  `ac_shim::from_raw / to_raw` are
+// shim-only helpers used by the oracle driver to move raw integers in and out.
 #ifndef B200DSP_ORACLE_AC_SHIM_AC_FIXED_H
 #define B200DSP_ORACLE_AC_SHIM_AC_FIXED_H
 
 #include <cmath>
+#include <stdint.h>
 #include <iostream>
 #include "ac_int.h"
 
@@ -30,22 +35,36 @@ enum ac_o_mode { AC_WRAP, AC_SAT, AC_SAT_ZERO, AC_SAT_SYM };
 namespace ac_shim {
 typedef __int128 wide_t;
 
-inline wide_t wrap_bits(wide_t v, int W, bool S) {
-  if (W >= 128) return v;
-  unsigned __int128 m = (((unsigned __int128)1) << W) - 1;
-  unsigned __int128 u = ((unsigned __int128)v) & m;
-  if (S && ((u >> (W - 1)) & 1)) u |= ~m;
-  return (wide_t)u;
-}
-inline wide_t max_val(int W, bool S) { return S ? ((((wide_t)1) << (W - 1)) - 1) : ((((wide_t)1) << W) - 1); }
-inline wide_t min_val(int W, bool S) { return S ? -(((wide_t)1) << (W - 1)) : 0; }
+template <bool C, class A, class B> struct tsel { typedef A type; };
+template <class A, class B> struct tsel<false, A, B> { typedef B type; };
+// narrowest signed container with at least BITS bits
+template <int BITS> struct store {
+  typedef typename tsel<(BITS <= 32), int32_t, typename tsel<(BITS <= 64), int64_t, wide_t>::type>::type type;
+};
+template <class T> struct uns;
+template <> struct uns<int32_t> { typedef uint32_t type; };
+template <> struct uns<int64_t> { typedef uint64_t type; };
+template <> struct uns<wide_t> { typedef unsigned __int128 type; };
 
-// q = floor(v / 2^sh) corrected per quantisation mode; sh > 0.
-inline wide_t quantize(wide_t v, int sh, ac_q_mode Q) {
-  wide_t q = v >> sh;                       // arithmetic shift = floor
-  wide_t rem = v - (q << sh);               // 0 <= rem < 2^sh
+template <class T>
+inline T wrap_bits(T v, int W, bool S) {
+  typedef typename uns<T>::type U;
+  const int TB = (int)sizeof(T) * 8;
+  if (W >= TB) return v;
+  if (S) return (T)((T)((U)v << (TB - W)) >> (TB - W));   // shift pair = sign-extend from bit W-1 (as the real package normalises)
+  return (T)(((U)v) & ((((U)1) << W) - 1));
+}
+template <class T> inline T max_val(int W, bool S) { return S ? (T)((((T)1) << (W - 1)) - 1) : (T)((((T)1) << W) - 1); }
+template <class T> inline T min_val(int W, bool S) { return S ? (T)(-(((T)1) << (W - 1))) : (T)0; }
+
+// q = floor(v / 2^sh) corrected per quantisation mode; 0 < sh < bits(T) - 1.
+template <class T>
+inline T quantize(T v, int sh, ac_q_mode Q) {
+  T q = v >> sh;                            // arithmetic shift = floor
+  if (Q == AC_TRN) return q;
+  T rem = v - (T)((typename uns<T>::type)q << sh);   // 0 <= rem < 2^sh
   bool msb = (rem >> (sh - 1)) & 1;
-  bool rest = (rem & ((((wide_t)1) << (sh - 1)) - 1)) != 0;
+  bool rest = (rem & ((((T)1) << (sh - 1)) - 1)) != 0;
   bool neg = v < 0;
   switch (Q) {
     case AC_TRN:          break;
@@ -59,28 +78,39 @@ inline wide_t quantize(wide_t v, int sh, ac_q_mode Q) {
   }
   return q;
 }
-inline wide_t overflow(wide_t v, int W, bool S, ac_o_mode O) {
-  wide_t hi = max_val(W, S), lo = min_val(W, S);
+// v must fit T with at least one bit to spare above W (+1 if unsigned): see conv_bits.
+template <class T>
+inline T overflow(T v, int W, bool S, ac_o_mode O) {
+  if (O == AC_WRAP) return wrap_bits<T>(v, W, S);
+  T hi = max_val<T>(W, S), lo = min_val<T>(W, S);
   switch (O) {
-    case AC_WRAP: return wrap_bits(v, W, S);
+    case AC_WRAP: break;
     case AC_SAT:  return v > hi ? hi : (v < lo ? lo : v);
-    case AC_SAT_ZERO: return (v > hi || v < lo) ? 0 : v;
+    case AC_SAT_ZERO: return (v > hi || v < lo) ? (T)0 : v;
     case AC_SAT_SYM: {
-      wide_t slo = S ? -hi : 0;
+      T slo = S ? (T)-hi : (T)0;
       return v > hi ? hi : (v < slo ? slo : v);
     }
   }
   return v;
 }
-// Re-scale raw value with F2 fraction bits into <W, F> with modes Q, O.
-inline wide_t convert(wide_t v, int F2, int W, int F, bool S, ac_q_mode Q, ac_o_mode O) {
-  if (F2 > F) v = quantize(v, F2 - F, Q);
-  else if (F > F2) v = v << (F - F2);
-  return overflow(v, W, S, O);
+// Re-scale raw value with F2 fraction bits into <W, F> with modes Q, O, computing in T.
+template <class T>
+inline T convert(T v, int F2, int W, int F, bool S, ac_q_mode Q, ac_o_mode O) {
+  if (F2 > F) v = quantize<T>(v, F2 - F, Q);
+  else if (F > F2) v = (T)((typename uns<T>::type)v << (F - F2));
+  return overflow<T>(v, W, S, O);
 }
 template <bool C, int A, int B> struct sel { enum { v = A }; };
 template <int A, int B> struct sel<false, A, B> { enum { v = B }; };
 template <int A, int B> struct imax { enum { v = (A > B) ? A : B }; };
+// bits the computation of a conversion needs: the source (SB bits as a signed number) moved to the destination's
+// binary point plus a carry / rounding bit, the destination's range (DB bits) plus one for the saturation
+// compares, and a right-shift count that stays below the container width
+template <int SB, int F2, int DB, int F> struct conv_bits {
+  enum { up = (F > F2) ? (F - F2) : 0, dn = (F2 > F) ? (F2 - F) : 0,
+         v = imax<imax<SB + up + 1, DB + 1>::v, dn + 2>::v };
+};
 }  // namespace ac_shim
 
 template <int W, int I, bool S = true, ac_q_mode Q = AC_TRN, ac_o_mode O = AC_WRAP>
@@ -93,13 +123,18 @@ public:
   static const ac_o_mode o_mode = O;
   enum { F = W - I };
 
-  ac_shim::wide_t v;  // canonical raw value (sign- or zero-extended from W bits)
+  enum { BITS = W + (S ? 0 : 1) };   // bits of the raw value read as a signed number
+  typedef typename ac_shim::store<BITS>::type raw_t;
+  raw_t v;  // canonical raw value (sign- or zero-extended from W bits)
 
   ac_fixed() : v(0) {}
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
-  ac_fixed(const ac_fixed<W2, I2, S2, Q2, O2> &o) { v = ac_shim::convert(o.v, W2 - I2, W, F, S, Q, O); }
+  ac_fixed(const ac_fixed<W2, I2, S2, Q2, O2> &o) {
+    typedef typename ac_shim::store<ac_shim::conv_bits<W2 + (S2 ? 0 : 1), W2 - I2, BITS, F>::v>::type CT;
+    v = (raw_t)ac_shim::convert<CT>((CT)o.v, W2 - I2, W, F, S, Q, O);
+  }
   template <int W2, bool S2>
-  ac_fixed(const ac_int<W2, S2> &o) { v = ac_shim::convert((ac_shim::wide_t)o.v, 0, W, F, S, Q, O); }
+  ac_fixed(const ac_int<W2, S2> &o) { set_int((ac_shim::wide_t)o.v); }
   ac_fixed(bool b) { set_int(b ? 1 : 0); }
   ac_fixed(char b) { set_int(b); }
   ac_fixed(short b) { set_int(b); }
@@ -115,8 +150,8 @@ public:
 
   template <ac_special_val V>
   ac_fixed &set_val() {
-    if (V == AC_VAL_MAX) v = ac_shim::max_val(W, S);
-    else if (V == AC_VAL_MIN) v = ac_shim::min_val(W, S);
+    if (V == AC_VAL_MAX) v = (raw_t)ac_shim::max_val<ac_shim::wide_t>(W, S);
+    else if (V == AC_VAL_MIN) v = (raw_t)ac_shim::min_val<ac_shim::wide_t>(W, S);
     else if (V == AC_VAL_QUANTUM) v = 1;
     else v = 0;  // AC_VAL_0; AC_VAL_DC ("don't care") is given a defined value here
     return *this;
@@ -124,24 +159,25 @@ public:
 
   double to_double() const { return (double)std::ldexp((long double)v, -F); }
   long double to_long_double() const { return std::ldexp((long double)v, -F); }
-  int to_int() const { return (int)(F >= 0 ? (v >> F) : (v << -F)); }
+  int to_int() const { return (int)(F >= 0 ? ((ac_shim::wide_t)v >> F) : ((ac_shim::wide_t)v << -F)); }
 
   // bit slices of the raw value (WS <= 64): read as ac_int<WS,S>, write from any ac_int
   template <int WS>
-  ac_int<WS, S> slc(int lsb) const { return ac_int<WS, S>((long long)(v >> lsb)); }
+  ac_int<WS, S> slc(int lsb) const { return ac_int<WS, S>((long long)((ac_shim::wide_t)v >> lsb)); }
   template <int W2, bool S2>
   ac_fixed &set_slc(int lsb, const ac_int<W2, S2> &s) {
     const unsigned __int128 m = (W2 >= 128 ? ~(unsigned __int128)0 : ((((unsigned __int128)1) << W2) - 1)) << lsb;
-    const unsigned __int128 u = (((unsigned __int128)v) & ~m) | ((((unsigned __int128)(ac_shim::wide_t)s.v) << lsb) & m);
-    v = ac_shim::wrap_bits((ac_shim::wide_t)u, W, S);
+    const unsigned __int128 u = (((unsigned __int128)(ac_shim::wide_t)v) & ~m) | ((((unsigned __int128)(ac_shim::wide_t)s.v) << lsb) & m);
+    v = (raw_t)ac_shim::wrap_bits<ac_shim::wide_t>((ac_shim::wide_t)u, W, S);
     return *this;
   }
 
   // --- arithmetic (result types follow the AC Datatypes width rules) ---
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   ac_fixed<W + W2, I + I2, S || S2> operator*(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {
-    ac_fixed<W + W2, I + I2, S || S2> r;
-    r.v = v * o.v;
+    typedef ac_fixed<W + W2, I + I2, S || S2> R;
+    R r;
+    r.v = (typename R::raw_t)v * (typename R::raw_t)o.v;
     return r;
   }
   template <int W2, int I2, bool S2>
@@ -157,16 +193,20 @@ public:
   };
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   typename rt<W2, I2, S2>::plus operator+(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {
-    typename rt<W2, I2, S2>::plus r;
+    typedef typename rt<W2, I2, S2>::plus R;
+    typedef typename ac_shim::uns<typename R::raw_t>::type U;
+    R r;
     const int rF = rt<W2, I2, S2>::pF;
-    r.v = (v << (rF - F)) + (o.v << (rF - (W2 - I2)));
+    r.v = (typename R::raw_t)(((U)(typename R::raw_t)v << (rF - F)) + ((U)(typename R::raw_t)o.v << (rF - (W2 - I2))));
     return r;
   }
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   typename rt<W2, I2, S2>::minus operator-(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {
-    typename rt<W2, I2, S2>::minus r;
+    typedef typename rt<W2, I2, S2>::minus R;
+    typedef typename ac_shim::uns<typename R::raw_t>::type U;
+    R r;
     const int rF = rt<W2, I2, S2>::pF;
-    r.v = (v << (rF - F)) - (o.v << (rF - (W2 - I2)));
+    r.v = (typename R::raw_t)(((U)(typename R::raw_t)v << (rF - F)) - ((U)(typename R::raw_t)o.v << (rF - (W2 - I2))));
     return r;
   }
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
@@ -177,13 +217,14 @@ public:
   // unary minus: one more integer bit, always signed (AC Datatypes rt_unary::neg); exact
   ac_fixed<W + 1, I + 1, true> operator-() const {
     ac_fixed<W + 1, I + 1, true> r;
-    r.v = -v;
+    r.v = -(typename ac_fixed<W + 1, I + 1, true>::raw_t)v;
     return r;
   }
   // shifts move the bit pattern inside the same type: bits shifted out are lost, the binary point stays
   ac_fixed operator>>(int n) const {
     ac_fixed r;
-    r.v = n >= 0 ? ac_shim::wrap_bits(v >> n, W, S) : ac_shim::wrap_bits(v << -n, W, S);
+    r.v = n >= 0 ? ac_shim::wrap_bits<raw_t>(v >> n, W, S)
+                 : ac_shim::wrap_bits<raw_t>((raw_t)((typename ac_shim::uns<raw_t>::type)v << -n), W, S);
     return r;
   }
   ac_fixed operator<<(int n) const { return this->operator>>(-n); }
@@ -191,13 +232,13 @@ public:
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   bool operator==(const ac_fixed<W2, I2, S2, Q2, O2> &o) const {
     const int rF = ac_shim::imax<F, W2 - I2>::v;
-    return (v << (rF - F)) == (o.v << (rF - (W2 - I2)));
+    return ((ac_shim::wide_t)v << (rF - F)) == ((ac_shim::wide_t)o.v << (rF - (W2 - I2)));
   }
   template <int W2, int I2, bool S2, ac_q_mode Q2, ac_o_mode O2>
   bool operator!=(const ac_fixed<W2, I2, S2, Q2, O2> &o) const { return !(*this == o); }
 
 private:
-  void set_int(ac_shim::wide_t b) { v = ac_shim::convert(b, 0, W, F, S, Q, O); }
+  void set_int(ac_shim::wide_t b) { v = (raw_t)ac_shim::convert<ac_shim::wide_t>(b, 0, W, F, S, Q, O); }
   void set_real(long double d) {
     // Scale to the LSB, split into floor + remainder, apply Q on the remainder, then O.
     long double sc = std::ldexp(d, F);
@@ -215,7 +256,7 @@ private:
       case AC_RND_CONV: q += (msb && (rest || (q & 1))); break;
       case AC_RND_CONV_ODD: q += (msb && (rest || !(q & 1))); break;
     }
-    v = ac_shim::overflow(q, W, S, O);
+    v = (raw_t)ac_shim::overflow<ac_shim::wide_t>(q, W, S, O);
   }
 };
 
@@ -226,7 +267,7 @@ inline std::ostream &operator<<(std::ostream &os, const ac_fixed<W, I, S, Q, O> 
 }
 
 namespace ac_shim {
-template <class T> inline T from_raw(long long raw) { T t; t.v = wrap_bits((wide_t)raw, T::width, T::sign); return t; }
+template <class T> inline T from_raw(long long raw) { T t; t.v = (typename T::raw_t)wrap_bits<wide_t>((wide_t)raw, T::width, T::sign); return t; }
 template <class T> inline long long to_raw(const T &t) { return (long long)t.v; }
 }  // namespace ac_shim
 
