@@ -42,6 +42,15 @@ def test_facade_compiles_and_fails_loudly_without_gpu(engine, bench_exe, tmp_pat
     assert p.returncode == 70 and "engine_error" in p.stderr, (p.returncode, p.stderr)
 
 
+def test_facade_marshaling_round_trips_every_storage_tier(engine, tmp_path):
+    """include/b200dsp/marshal.h moves ac_fixed values through slc / set_slc only; check it against the shim's
+    canonical raw value for 16..64-bit signed and unsigned types (no engine call, CPU)."""
+    exe = str(tmp_path / "marshal_roundtrip")
+    subprocess.check_call(["g++"] + CXXFLAGS + [os.path.join(ROOT, "tests", "cpp", "marshal_roundtrip.cpp")] + LDFLAGS + ["-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "bad=0" in p.stdout, p.stdout + p.stderr
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "tests", "rtest_ac_fir_load_coeffs.cpp")),
                     reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("name", ["ac_fir_const_coeffs", "ac_fir_load_coeffs", "ac_fir_prog_coeffs", "ac_cic_dec_full", "ac_cic_intr_full"])
