@@ -70,10 +70,17 @@ _lib_b = None
 _lib_a = None
 
 
+def _libpath(name, sub):
+    """B2D_ORACLE_LIBDIR points the loader at an alternative build of the two oracle libraries (the UBSan build that
+    `make -C oracle sanitize` leaves in oracle/_ref/san); default: the normal build."""
+    alt = os.environ.get("B2D_ORACLE_LIBDIR")
+    return os.path.join(alt, name) if alt else os.path.join(HERE, sub, name)
+
+
 def lib_b():
     global _lib_b
     if _lib_b is None:
-        path = os.path.join(HERE, "liboracle_b.so")
+        path = _libpath("liboracle_b.so", "")
         if not os.path.exists(path):
             build()
         L = C.CDLL(path)
@@ -126,7 +133,7 @@ def have_ref():
 def lib_a():
     global _lib_a
     if _lib_a is None:
-        L = C.CDLL(os.path.join(HERE, "_ref", "libacdsp_ref.so"))
+        L = C.CDLL(_libpath("libacdsp_ref.so", "_ref"))
         L.acref_fir_create.restype = C.c_void_p
         L.acref_fir_create.argtypes = [C.c_int, C.c_int, C.c_int]
         L.acref_fir_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
