@@ -46,8 +46,13 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
 
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [os.path.join(HERE, "..", "include", "b200dsp.h")]
+    t_hdr = max(os.path.getmtime(f) for f in hdrs)
+
     def compile_one(src):
         obj = os.path.join(objdir, src + ".o")
+        if not force and not verbose and os.path.exists(obj) and os.path.getmtime(obj) > max(t_hdr, os.path.getmtime(os.path.join(CSRC, src))):
+            return obj                       # object newer than its source and every header: keep it
         subprocess.check_call([nvcc] + cflags + ["-c", os.path.join(CSRC, src), "-o", obj])
         return obj
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.h"
 #include "nccl_dl.h"
 
@@ -23,6 +25,11 @@ static int fail(int status, const char *fmt, ...) {
   va_end(ap);
   return status;
 }
+// NVTX range per load / run entry point (tracing): header-only NVTX 3, a no-op unless a tool is attached
+struct TraceRange {
+  explicit TraceRange(const char *name) { nvtxRangePushA(name); }
+  ~TraceRange() { nvtxRangePop(); }
+};
 #define CU(expr)                                                                                      \
   do {                                                                                                \
     cudaError_t e__ = (expr);                                                                         \
@@ -362,6 +369,7 @@ extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
 }
 
 extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel) {
+  TraceRange trace__("b2d_fir_load");
   if (!h) return fail(B2D_EINVAL, "null handle");
   const size_t N = h->d.n_taps;
   const uint32_t C = h->d.n_channels;
@@ -425,6 +433,7 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
 }
 
 extern "C" int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_fir_run_dev");
   if (!h || (n && (!d_in || !d_out))) return fail(B2D_EINVAL, "null argument");
   if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
   int st = use_device(h->device);
@@ -435,6 +444,7 @@ extern "C" int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_o
 }
 
 extern "C" int b2d_fir_run(b2d_fir *h, const void *in, size_t n, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_fir_run");
   if (!h || (n && (!in || !out))) return fail(B2D_EINVAL, "null argument");
   if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
   if (n_out) *n_out = n;
@@ -481,6 +491,7 @@ extern "C" int b2d_fir_reset(b2d_fir *h) {
 }
 
 extern "C" int b2d_fir_load_blocked(b2d_fir *h, const void *ram, size_t n_ram, uint32_t mww, uint32_t bs, uint32_t bo, int32_t channel) {
+  TraceRange trace__("b2d_fir_load_blocked");
   if (!h) return fail(B2D_EINVAL, "null handle");
   if (bs < 1 || mww < 1) return fail(B2D_EINVAL, "mem_word_width and blk_sz must be >= 1");
   const size_t N = h->d.n_taps;
@@ -514,6 +525,7 @@ extern "C" int b2d_fir_delay_line_out(b2d_fir *h, void *out_raw) {
 }
 
 extern "C" int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw) {
+  TraceRange trace__("b2d_fir_run_window");
   if (!h || !window || !out_raw) return fail(B2D_EINVAL, "null argument");
   if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
   int st = use_device(h->device);
@@ -739,6 +751,7 @@ static int cic_launch(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_
 }
 
 extern "C" int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_cic_run_dev");
   if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
   const size_t no = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
   if (no && !d_out) return fail(B2D_EINVAL, "null output");
@@ -750,6 +763,7 @@ extern "C" int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_o
 }
 
 extern "C" int b2d_cic_run(b2d_cic *h, const void *in, size_t n, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_cic_run");
   if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
   const size_t no_total = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
   if (no_total && !out) return fail(B2D_EINVAL, "null output");
@@ -958,6 +972,7 @@ extern "C" const char *b2d_cicfir_path(b2d_cicfir *h) { return !h ? "" : (h->fus
 extern "C" size_t b2d_cicfir_max_out(b2d_cicfir *h, size_t n) { return h ? n * h->cd.R : 0; }
 
 extern "C" int b2d_cicfir_load(b2d_cicfir *h, const void *coeff_raw, size_t n, int32_t channel) {
+  TraceRange trace__("b2d_cicfir_load");
   if (!h) return fail(B2D_EINVAL, "null handle");
   int st = b2d_fir_load(h->fir, coeff_raw, n, channel);     // validation, wrapping to COEFF_TYPE, const-kind rule
   if (st || !h->fused) return st;
@@ -1031,6 +1046,7 @@ static int cicfir_ready(b2d_cicfir *h) {
 }
 
 extern "C" int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_cicfir_run_dev");
   if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
   int st = cicfir_ready(h);
   if (st) return st;
@@ -1043,6 +1059,7 @@ extern "C" int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, voi
 }
 
 extern "C" int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_cicfir_run");
   if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
   int st = cicfir_ready(h);
   if (st) return st;
@@ -1223,6 +1240,7 @@ extern "C" const char *b2d_polydec_path(b2d_polydec *h) { return !h ? "" : (h->w
 extern "C" size_t b2d_polydec_max_out(b2d_polydec *h, size_t n) { return h ? n / h->d.df + 1 : 0; }
 
 extern "C" int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t channel) {
+  TraceRange trace__("b2d_polydec_load");
   if (!h || !coeff_raw) return fail(B2D_EINVAL, "null argument");
   const size_t L = (size_t)h->d.n_taps * h->d.df;
   const uint32_t C = h->d.n_channels;
@@ -1281,6 +1299,7 @@ static int polydec_ready(const b2d_polydec *h) {
 }
 
 extern "C" int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_polydec_run_dev");
   if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
   int st = polydec_ready(h);
   if (st) return st;
@@ -1293,6 +1312,7 @@ extern "C" int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, v
 }
 
 extern "C" int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_polydec_run");
   if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
   int st = polydec_ready(h);
   if (st) return st;
@@ -1473,6 +1493,7 @@ extern "C" size_t b2d_polyintr_coeffsz(b2d_polyintr *h) { return h ? (size_t)h->
 extern "C" size_t b2d_polyintr_max_out(b2d_polyintr *h, size_t n) { return h ? n * h->d.intr_factor : 0; }
 
 extern "C" int b2d_polyintr_load(b2d_polyintr *h, const void *coeff_raw, size_t n, const uint8_t *sign, const uint8_t *corr, int32_t channel) {
+  TraceRange trace__("b2d_polyintr_load");
   if (!h || (!coeff_raw && h->csz)) return fail(B2D_EINVAL, "null argument");
   const uint32_t C = h->d.n_channels, IF = h->d.intr_factor;
   const size_t L = (size_t)h->csz;
@@ -1559,6 +1580,7 @@ static int polyintr_ready(const b2d_polyintr *h) {
 }
 
 extern "C" int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_polyintr_run_dev");
   if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
   int st = polyintr_ready(h);
   if (st) return st;
@@ -1571,6 +1593,7 @@ extern "C" int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n,
 }
 
 extern "C" int b2d_polyintr_run(b2d_polyintr *h, const void *in, size_t n, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_polyintr_run");
   if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
   int st = polyintr_ready(h);
   if (st) return st;
@@ -1775,6 +1798,7 @@ static int intgdump_plan(const b2d_intgdump *h, const uint32_t *n_sample, size_t
 
 extern "C" int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *d_out,
                                     size_t *n_out, void *cuda_stream) {
+  TraceRange trace__("b2d_intgdump_run_dev");
   if (!h || (n_frames && !n_sample) || (n_in && !d_in)) return fail(B2D_EINVAL, "null argument");
   int st = use_device(h->device);
   if (st) return st;
@@ -1813,6 +1837,7 @@ extern "C" int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_
 }
 
 extern "C" int b2d_intgdump_run(b2d_intgdump *h, const void *in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *out, size_t *n_out) {
+  TraceRange trace__("b2d_intgdump_run");
   if (!h || (n_frames && !n_sample) || (n_in && !in)) return fail(B2D_EINVAL, "null argument");
   int st = use_device(h->device);
   if (st) return st;
