@@ -399,6 +399,18 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
   }
 }
 
+// Grid size of the two persistent kernels, in units of "what is resident at once" (148 SMs x CTAs per SM).  1 = one
+// CTA per slot striding over the tiles.  ncu shows 16.6 of 24 resident warps per SM on average for that shape
+// (profiles/r01_source_level_notes.md): the warp scheduler favours the older CTAs of an SM, they finish their equal
+// share of tiles early and the SM runs the tail under-occupied.  B2D_UPFIR_WAVES = W (1..64) launches W x as many CTAs,
+// each with 1/W of the tiles, so the hardware CTA scheduler refills a slot as soon as it frees (A/B switch; the tile
+// loop is written for any grid size, results do not depend on it).
+static int up_grid_waves() {
+  const char *w = getenv("B2D_UPFIR_WAVES");
+  const int v = w ? atoi(w) : 1;
+  return v < 1 ? 1 : (v > 64 ? 64 : v);
+}
+
 template <int R, int JT, int PLANES, int NARROW>
 static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   constexpr int TILE = kUpThreads * JT;
@@ -416,7 +428,7 @@ static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW>, kUpThreads, smem);
   if (per_sm < 1) per_sm = 1;
   long long gx = a.ntiles;
-  const long long cap = (148LL * per_sm + a.C - 1) / a.C;
+  const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, a.C);
   upfir_lane_kernel<R, JT, PLANES, NARROW><<<grid, kUpThreads, smem, st>>>(a);
@@ -489,7 +501,7 @@ static cudaError_t launch_up(UpArgs a, cudaStream_t st) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_q15_kernel<R, KT, PLANES>, kUpThreads, smem);
   if (per_sm < 1) per_sm = 1;
   long long gx = a.ntiles;
-  const long long cap = (148LL * per_sm + a.C - 1) / a.C;
+  const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, a.C);
   upfir_q15_kernel<R, KT, PLANES><<<grid, kUpThreads, smem, st>>>(a);
