@@ -18,6 +18,7 @@
 // tap pairs are consumed four at a time with a 1..3 pair tail, so the taps per phase are padded to an even count
 // only.  CTAs are persistent; the next tile's samples are fetched into registers while the current one computes.
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kUpThreads) upfir_q15_kernel(UpArgs a) {
 // of a period are stored straight from registers as 128-bit words: consecutive lanes write consecutive R*8-byte
 // groups, so a pair of store instructions covers 1 KB contiguously -- no staging tile, no copy-out pass, and one
 // barrier per tile (the sample double buffer).
-template <int R, int JT, int PLANES, int NARROW>
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
 __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int WPP = PLANES == 3 ? 2 : 1;
@@ -300,15 +301,11 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
     const long long k_tile = kbase + tile * TILE;
     {
       int acc[JT][R][PLANES];
-#pragma unroll
-      for (int j = 0; j < JT; j++)
-#pragma unroll
-        for (int ph = 0; ph < R; ph++)
-#pragma unroll
-          for (int pl = 0; pl < PLANES; pl++) acc[j][ph][pl] = 0;
       const uint32_t *xq = xb + ((threadIdx.x & 1) ? XS : 0) + (threadIdx.x >> 1);   // period q = j*128 + tid: word q/2 + p
-#pragma unroll 2
-      for (int p = 0; p < TP; p++) {
+      // one tap pair of every phase for the JT periods of this lane; `first` (a compile-time flag) starts the
+      // accumulators from zero operands instead of reading them
+      auto pair = [&](const int p, auto first) {
+        constexpr bool FIRST = decltype(first)::value;
         uint32_t w[CW];
         if (CW % 4 == 0) {
 #pragma unroll
@@ -326,15 +323,29 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
 #pragma unroll
           for (int ph = 0; ph < R; ph++) {
             const uint32_t wa = w[ph * WPP];
-            acc[j][ph][0] = up_dp2a_lo_u(sx, wa, acc[j][ph][0]);
+            acc[j][ph][0] = up_dp2a_lo_u(sx, wa, FIRST ? 0 : acc[j][ph][0]);
             if (PLANES == 3) {
-              acc[j][ph][1] = up_dp2a_hi_u(sx, wa, acc[j][ph][1]);
-              acc[j][ph][2] = up_dp2a_lo_s(sx, w[ph * WPP + 1], acc[j][ph][2]);
+              acc[j][ph][1] = up_dp2a_hi_u(sx, wa, FIRST ? 0 : acc[j][ph][1]);
+              acc[j][ph][2] = up_dp2a_lo_s(sx, w[ph * WPP + 1], FIRST ? 0 : acc[j][ph][2]);
             } else {
-              acc[j][ph][1] = up_dp2a_hi_s(sx, wa, acc[j][ph][1]);
+              acc[j][ph][1] = up_dp2a_hi_s(sx, wa, FIRST ? 0 : acc[j][ph][1]);
             }
           }
         }
+      };
+      if (PEEL) {                                 // TP >= 1: the first pair initialises the accumulators (no zeroing pass)
+        pair(0, std::true_type());
+#pragma unroll 2
+        for (int p = 1; p < TP; p++) pair(p, std::false_type());
+      } else {
+#pragma unroll
+        for (int j = 0; j < JT; j++)
+#pragma unroll
+          for (int ph = 0; ph < R; ph++)
+#pragma unroll
+            for (int pl = 0; pl < PLANES; pl++) acc[j][ph][pl] = 0;
+#pragma unroll 2
+        for (int p = 0; p < TP; p++) pair(p, std::false_type());
       }
       // ---- results of period k: outputs k*R .. k*R+R-1
       const long long o_tile = k_tile * R;
@@ -411,7 +422,7 @@ static int up_grid_waves() {
   return v < 1 ? 1 : (v > 64 ? 64 : v);
 }
 
-template <int R, int JT, int PLANES, int NARROW>
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
 static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   constexpr int TILE = kUpThreads * JT;
   const long long kbase = a.out_first / R;
@@ -422,24 +433,29 @@ static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   const int XS = ((((nxs + 1) / 2 + 1) + 31) & ~31) + 16;
   const size_t smem = (size_t)((ncw + 3) & ~3) * 4 + (size_t)4 * XS * 4 + (size_t)TILE * R * 8;
   a.ntiles = (nper + TILE - 1) / TILE;
-  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW>, kUpThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, kUpThreads, smem);
   if (per_sm < 1) per_sm = 1;
   long long gx = a.ntiles;
   const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, a.C);
-  upfir_lane_kernel<R, JT, PLANES, NARROW><<<grid, kUpThreads, smem, st>>>(a);
+  upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL><<<grid, kUpThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 template <int R, int JT, int PLANES>
 static cudaError_t launch_up_lane(const UpArgs &a, cudaStream_t st) {
   // W_acc - lsh <= 40: bits of the upper planes above 2^32 fall off the accumulator (see the epilogue)
-  if (a.acc.W - a.lsh <= 40 && a.acc.W > 32 && a.lsh < 32)
+  if (a.acc.W - a.lsh <= 40 && a.acc.W > 32 && a.lsh < 32) {
+    // A/B switch (profiles/r01_source_level_notes.md): accumulators started by the first tap pair; instantiated for
+    // the two bench geometries (R = 4, JT = 4, signed <40,8>-style accumulator) only
+    const char *peel = getenv("B2D_UPFIR_PEEL");
+    if (R == 4 && JT == 4 && a.acc.S && peel && *peel == '1') return launch_up_lane_n<4, 4, PLANES, 1, true>(a, st);
     return a.acc.S ? launch_up_lane_n<R, JT, PLANES, 1>(a, st) : launch_up_lane_n<R, JT, PLANES, 2>(a, st);
+  }
   return launch_up_lane_n<R, JT, PLANES, 0>(a, st);
 }
 
