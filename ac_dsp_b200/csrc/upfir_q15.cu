@@ -301,39 +301,39 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
     const long long k_tile = kbase + tile * TILE;
     {
       int acc[JT][R][PLANES];
-      const uint32_t *xq = xb + ((threadIdx.x & 1) ? XS : 0) + (threadIdx.x >> 1);   // period q = j*128 + tid: word q/2 + p
-      // one tap pair of every phase for the JT periods of this lane; `first` (a compile-time flag) starts the
-      // accumulators from zero operands instead of reading them
-      auto pair = [&](const int p, auto first) {
-        constexpr bool FIRST = decltype(first)::value;
-        uint32_t w[CW];
-        if (CW % 4 == 0) {
+      if (PEEL) {                                 // A/B variant: the first tap pair (TP >= 1) initialises the accumulators, no zeroing pass
+        const uint32_t *xq = xb + ((threadIdx.x & 1) ? XS : 0) + (threadIdx.x >> 1);
+        // one tap pair of every phase for the JT periods of this lane; `first` (a compile-time flag) starts the
+        // accumulators from zero operands instead of reading them
+        auto pair = [&](const int p, auto first) {
+          constexpr bool FIRST = decltype(first)::value;
+          uint32_t w[CW];
+          if (CW % 4 == 0) {
 #pragma unroll
-          for (int i = 0; i < CW / 4; i++) {
-            const uint4 v = *(const uint4 *)(cw + p * CW + 4 * i);
-            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            for (int i = 0; i < CW / 4; i++) {
+              const uint4 v = *(const uint4 *)(cw + p * CW + 4 * i);
+              w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+          } else {                                                  // R = 2, two planes: 2 words per pair
+            const uint2 v = *(const uint2 *)(cw + p * CW);
+            w[0] = v.x; w[1] = v.y;
           }
-        } else {                                                  // R = 2, two planes: 2 words per pair
-          const uint2 v = *(const uint2 *)(cw + p * CW);
-          w[0] = v.x; w[1] = v.y;
-        }
 #pragma unroll
-        for (int j = 0; j < JT; j++) {
-          const uint32_t sx = xq[j * (kUpThreads / 2) + p];
+          for (int j = 0; j < JT; j++) {
+            const uint32_t sx = xq[j * (kUpThreads / 2) + p];
 #pragma unroll
-          for (int ph = 0; ph < R; ph++) {
-            const uint32_t wa = w[ph * WPP];
-            acc[j][ph][0] = up_dp2a_lo_u(sx, wa, FIRST ? 0 : acc[j][ph][0]);
-            if (PLANES == 3) {
-              acc[j][ph][1] = up_dp2a_hi_u(sx, wa, FIRST ? 0 : acc[j][ph][1]);
-              acc[j][ph][2] = up_dp2a_lo_s(sx, w[ph * WPP + 1], FIRST ? 0 : acc[j][ph][2]);
-            } else {
-              acc[j][ph][1] = up_dp2a_hi_s(sx, wa, FIRST ? 0 : acc[j][ph][1]);
+            for (int ph = 0; ph < R; ph++) {
+              const uint32_t wa = w[ph * WPP];
+              acc[j][ph][0] = up_dp2a_lo_u(sx, wa, FIRST ? 0 : acc[j][ph][0]);
+              if (PLANES == 3) {
+                acc[j][ph][1] = up_dp2a_hi_u(sx, wa, FIRST ? 0 : acc[j][ph][1]);
+                acc[j][ph][2] = up_dp2a_lo_s(sx, w[ph * WPP + 1], FIRST ? 0 : acc[j][ph][2]);
+              } else {
+                acc[j][ph][1] = up_dp2a_hi_s(sx, wa, FIRST ? 0 : acc[j][ph][1]);
+              }
             }
           }
-        }
-      };
-      if (PEEL) {                                 // TP >= 1: the first pair initialises the accumulators (no zeroing pass)
+        };
         pair(0, std::true_type());
 #pragma unroll 2
         for (int p = 1; p < TP; p++) pair(p, std::false_type());
@@ -344,8 +344,36 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
           for (int ph = 0; ph < R; ph++)
 #pragma unroll
             for (int pl = 0; pl < PLANES; pl++) acc[j][ph][pl] = 0;
+        const uint32_t *xq = xb + ((threadIdx.x & 1) ? XS : 0) + (threadIdx.x >> 1);   // period q = j*128 + tid: word q/2 + p
 #pragma unroll 2
-        for (int p = 0; p < TP; p++) pair(p, std::false_type());
+        for (int p = 0; p < TP; p++) {
+          uint32_t w[CW];
+          if (CW % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < CW / 4; i++) {
+              const uint4 v = *(const uint4 *)(cw + p * CW + 4 * i);
+              w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+          } else {                                                  // R = 2, two planes: 2 words per pair
+            const uint2 v = *(const uint2 *)(cw + p * CW);
+            w[0] = v.x; w[1] = v.y;
+          }
+#pragma unroll
+          for (int j = 0; j < JT; j++) {
+            const uint32_t sx = xq[j * (kUpThreads / 2) + p];
+#pragma unroll
+            for (int ph = 0; ph < R; ph++) {
+              const uint32_t wa = w[ph * WPP];
+              acc[j][ph][0] = up_dp2a_lo_u(sx, wa, acc[j][ph][0]);
+              if (PLANES == 3) {
+                acc[j][ph][1] = up_dp2a_hi_u(sx, wa, acc[j][ph][1]);
+                acc[j][ph][2] = up_dp2a_lo_s(sx, w[ph * WPP + 1], acc[j][ph][2]);
+              } else {
+                acc[j][ph][1] = up_dp2a_hi_s(sx, wa, acc[j][ph][1]);
+              }
+            }
+          }
+        }
       }
       // ---- results of period k: outputs k*R .. k*R+R-1
       const long long o_tile = k_tile * R;
