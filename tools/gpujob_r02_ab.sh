@@ -1,0 +1,27 @@
+# Round-2 opening GPU job: A/B the switches prepared at the end of round 1 (profiles/r01_source_level_notes.md).
+#   gpurun --timeout 600 -- 'bash tools/gpujob_r02_ab.sh'
+# Each variant first has to pass the parity tests of the kernels it touches, then is timed with bench.py (device-resident
+# inputs, no CPU arm); lines land in gpurun_out/r02_ab_*.json.
+mkdir -p gpurun_out
+K="cascade or cicfir or poly_intr or polyintr"
+run() {   # name, env assignments...
+  name=$1; shift
+  echo "== $name: $*" | tee -a gpurun_out/r02_ab_summary.txt
+  env "$@" timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$K" 2>&1 | tail -1 | tee -a gpurun_out/r02_ab_summary.txt
+  for wl in cicfir polyintr; do
+    env "$@" timeout 120 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/r02_ab_${name}_${wl}.json 2> gpurun_out/r02_ab_${name}_${wl}.err
+    python - gpurun_out/r02_ab_${name}_${wl}.json <<'PY' | tee -a gpurun_out/r02_ab_summary.txt
+import json, sys
+d = json.load(open(sys.argv[1]))
+print(f"   {d['config']['workload'][:40]:40s} {d['value']:10.1f} {d['unit']}  roofline {d['roofline']['frac']:.3f}")
+PY
+  done
+}
+run base     B2D_UPFIR_WAVES=1
+run waves2   B2D_UPFIR_WAVES=2
+run waves4   B2D_UPFIR_WAVES=4
+run waves8   B2D_UPFIR_WAVES=8
+run waves16  B2D_UPFIR_WAVES=16
+run peel     B2D_UPFIR_PEEL=1
+run peel_w4  B2D_UPFIR_PEEL=1 B2D_UPFIR_WAVES=4
+run peel_w8  B2D_UPFIR_PEEL=1 B2D_UPFIR_WAVES=8
