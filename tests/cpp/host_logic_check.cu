@@ -1,0 +1,189 @@
+// tests/cpp/host_logic_check.cu -- CPU checks of the engine's host-side logic (no kernel launch, no GPU):
+//   1. the fixed-point core shared by host and device code (csrc/common.cuh: convert / macc / tap_term) against the
+//      assignment and `+=` of the AC-datatypes shim the oracle is built on, over all 8 quantisation x 4 overflow modes;
+//   2. the coefficient packers (fir_q15_pack: effective direct-form taps of the folded architectures, reversed, two
+//      byte planes; upfir_q15_pack: per-phase reversed composite taps, two or three byte planes) against an
+//      independent expansion, and cic_history_len against DESIGN.md section 3.
+// Built with nvcc (host code only) and linked with libb200dsp.so by tests/test_abi.py.
+#include <ac_fixed.h>
+#include <ac_int.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace b2d;
+
+static int g_bad = 0;
+static long g_checks = 0;
+#define EXPECT(cond, ...)                                        \
+  do {                                                           \
+    g_checks++;                                                  \
+    if (!(cond)) {                                               \
+      if (g_bad < 20) { std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } \
+      g_bad++;                                                   \
+    }                                                            \
+  } while (0)
+
+static long long rnd64() { return ((long long)rand() << 42) ^ ((long long)rand() << 21) ^ rand(); }
+
+// ---- 1. convert / macc / tap_term vs the shim
+template <class SRC, class DST>
+static void check_convert() {
+  const Fmt fd{DST::width, DST::i_width, DST::sign ? 1 : 0, (int)DST::q_mode, (int)DST::o_mode};
+  for (int i = 0; i < 4000; i++) {
+    long long r = rnd64();
+    if (i < 8) r = (i & 1) ? -(long long)(i >> 1) - 1 : (i >> 1);          // small values around zero
+    else if (i < 16) r = (long long)((1ULL << (SRC::width - 1)) - 1ULL) - (i - 8);          // near the top of the range
+    const SRC s = ac_shim::from_raw<SRC>(r);
+    const DST d = s;                                                        // the shim's assignment: Q then O
+    const long long want = ac_shim::to_raw(d);
+    const long long got = convert((i128)ac_shim::to_raw(s), SRC::width - SRC::i_width, fd);
+    EXPECT(want == got, "convert <%d,%d,%d> -> <%d,%d,%d,Q%d,O%d> raw %lld: shim %lld engine %lld", SRC::width, SRC::i_width,
+           (int)SRC::sign, DST::width, DST::i_width, (int)DST::sign, (int)DST::q_mode, (int)DST::o_mode, ac_shim::to_raw(s), want, got);
+  }
+}
+
+template <class A, class B, class ACC>
+static void check_macc() {
+  const Fmt fa{ACC::width, ACC::i_width, ACC::sign ? 1 : 0, (int)ACC::q_mode, (int)ACC::o_mode};
+  const int Fp = (A::width - A::i_width) + (B::width - B::i_width);
+  ACC acc = ac_shim::from_raw<ACC>(0);
+  long long eacc = 0, emod = 0;
+  const int s = Fp - fa.F();
+  for (int i = 0; i < 3000; i++) {
+    const A a = ac_shim::from_raw<A>(rnd64());
+    const B b = ac_shim::from_raw<B>(rnd64());
+    acc += a * b;                                                           // the reference's tap: exact product, += re-quantises
+    const i128 p = (i128)ac_shim::to_raw(a) * (i128)ac_shim::to_raw(b);
+    eacc = macc(eacc, fa, p, Fp);
+    EXPECT(ac_shim::to_raw(acc) == eacc, "macc step %d: shim %lld engine %lld", i, ac_shim::to_raw(acc), eacc);
+    if (fa.O == B2D_WRAP && (fa.Q == B2D_TRN || fa.Q == B2D_RND)) {         // the order-free form the fast kernels use
+      emod += tap_term(p, s, fa.Q);
+      EXPECT(wrap_bits(emod, fa.W, fa.S) == eacc, "tap_term step %d", i);
+    }
+  }
+}
+
+template <ac_q_mode Q, ac_o_mode O>
+static void check_modes() {
+  check_convert<ac_fixed<40, 8, true>, ac_fixed<16, 1, true, Q, O> >();
+  check_convert<ac_fixed<33, 3, true>, ac_fixed<20, 5, false, Q, O> >();
+  check_convert<ac_fixed<16, 1, true>, ac_fixed<40, 8, true, Q, O> >();
+  check_convert<ac_fixed<64, 32, true>, ac_fixed<48, 32, true, Q, O> >();
+  check_convert<ac_fixed<31, 9, false>, ac_fixed<12, 2, true, Q, O> >();
+  check_macc<ac_fixed<16, 1, true>, ac_fixed<16, 1, true>, ac_fixed<40, 8, true, Q, O> >();
+  check_macc<ac_fixed<28, 6, true>, ac_fixed<23, 7, true>, ac_fixed<64, 32, true, Q, O> >();   // prog bench: per-tap truncation
+  check_macc<ac_fixed<16, 8, true>, ac_fixed<12, 2, false>, ac_fixed<24, 12, true, Q, O> >();
+}
+
+template <ac_q_mode Q>
+static void check_q() {
+  check_modes<Q, AC_WRAP>();
+  check_modes<Q, AC_SAT>();
+  check_modes<Q, AC_SAT_ZERO>();
+  check_modes<Q, AC_SAT_SYM>();
+}
+
+// ---- 2. packers
+static std::vector<int64_t> effective_taps(const std::vector<int64_t> &c, int N, int ft) {
+  // ac_fir_load_coeffs.h:231-259 / ac_fir_reg_share.h:151-205: taps i and N-1-i share h[i] (negated for _ANTI), the centre
+  // tap of an odd fold is unpaired
+  std::vector<int64_t> e(N, 0);
+  const bool even = ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI, odd = ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI;
+  const int64_t sg = (ft == B2D_FOLD_EVEN_ANTI || ft == B2D_FOLD_ODD_ANTI) ? -1 : 1;
+  for (int i = 0; i < N; i++) {
+    if (!even && !odd) { e[i] = c[i]; continue; }
+    const int half = even ? N / 2 : (N - 1) / 2 + 1;
+    if (i < half) e[i] = c[i];
+    else e[i] = sg * c[N - 1 - i];
+    if (even && (N & 1) && i == N / 2) e[i] = 0;                             // FOLD_EVEN on an odd count never reads the middle tap
+  }
+  return e;
+}
+
+static void check_fir_q15_pack() {
+  const Fmt fc{16, 1, 1, B2D_TRN, B2D_WRAP};
+  const int fts[] = {B2D_SHIFT_REG, B2D_ROTATE_SHIFT, B2D_C_BUFF, B2D_TRANSPOSED, B2D_FOLD_EVEN, B2D_FOLD_ODD, B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI};
+  const int Ns[] = {1, 2, 16, 27, 29, 63, 256, 1024};
+  for (int ft : fts)
+    for (int N : Ns) {
+      if ((ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI) && (N & 1)) continue;
+      if ((ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI) && !(N & 1)) continue;
+      std::vector<int64_t> c(N);
+      const bool anti = ft == B2D_FOLD_EVEN_ANTI || ft == B2D_FOLD_ODD_ANTI;
+      for (auto &v : c) v = anti ? (rand() % 32767) - 16383 : (rand() % 65536) - 32768;   // _ANTI: negated taps must stay 16-bit
+      const int words = fir_q15_pk_words(N, ft);
+      EXPECT(words * 2 >= N && words * 2 < N + 16 && (words * 2) % 16 == 0, "pk_words(%d) = %d", N, words);
+      std::vector<uint32_t> pk(words, 0xDEADBEEF);
+      fir_q15_pack(fc, c.data(), N, ft, pk.data(), words);
+      const std::vector<int64_t> e = effective_taps(c, N, ft);
+      for (int k = 0; k < 2 * words; k++) {
+        const uint32_t w = pk[k / 2];
+        const int el = k & 1;
+        const int64_t lo = (w >> (8 * el)) & 0xFF, hi = (int8_t)((w >> (16 + 8 * el)) & 0xFF);
+        const int64_t want = k < N ? e[N - 1 - k] : 0;                       // reversed: sample and tap index advance together
+        EXPECT(hi * 256 + lo == want, "fir_q15_pack ft %d N %d k %d: %lld vs %lld", ft, N, k, (long long)(hi * 256 + lo), (long long)want);
+      }
+    }
+}
+
+static void check_upfir_pack() {
+  const int Rs[] = {2, 4, 8};
+  const int Ts[] = {1, 5, 18, 72, 73, 200};
+  for (int planes = 2; planes <= 3; planes++)
+    for (int R : Rs)
+      for (int T : Ts) {
+        const int bits = planes == 3 ? 23 : 15;
+        std::vector<int64_t> c(T);
+        for (auto &v : c) v = (rnd64() & ((1LL << (bits + 1)) - 1)) - (1LL << bits);
+        EXPECT(upfir_q15_geometry(R, T, bits + 1), "geometry R %d T %d", R, T);
+        EXPECT(upfir_q15_planes(bits + 1) == planes, "planes for %d bits", bits + 1);
+        const int words = upfir_q15_words(R, T, planes), wpp = planes == 3 ? 2 : 1;
+        const int Tc = (T + R - 1) / R, TP = (Tc + 1) / 2;
+        EXPECT(words == R * TP * wpp, "words");
+        std::vector<uint32_t> pk(words, 0xDEADBEEF);
+        upfir_q15_pack(c.data(), T, R, planes, pk.data());
+        for (int ph = 0; ph < R; ph++)
+          for (int k = 0; k < 2 * TP; k++) {
+            const uint32_t wa = pk[(ph * TP + k / 2) * wpp], wb = planes == 3 ? pk[(ph * TP + k / 2) * wpp + 1] : 0;
+            const int el = k & 1;
+            const int64_t b0 = (wa >> (8 * el)) & 0xFF, b1 = (wa >> (16 + 8 * el)) & 0xFF, b2 = (int8_t)((wb >> (8 * el)) & 0xFF);
+            const int64_t got = planes == 3 ? b0 + 256 * b1 + 65536 * b2 : b0 + 256 * (int64_t)(int8_t)b1;
+            const int m = 2 * TP - 1 - k, idx = ph + R * m;                   // per phase reversed, zero padded on the oldest sample
+            const int64_t want = (m < Tc && idx < T) ? c[idx] : 0;
+            EXPECT(got == want, "upfir_q15_pack planes %d R %d T %d ph %d k %d: %lld vs %lld", planes, R, T, ph, k, (long long)got, (long long)want);
+          }
+      }
+  EXPECT(!upfir_q15_geometry(3, 63, 24) && !upfir_q15_geometry(4, 63, 25) && !upfir_q15_geometry(4, 4 * 128 + 1, 24), "geometry limits");
+}
+
+static void check_support_tables() {
+  const Fmt q15{16, 1, 1, B2D_TRN, B2D_WRAP}, acc40{40, 8, 1, B2D_TRN, B2D_WRAP};
+  Fmt sat = acc40; sat.O = B2D_SAT;
+  Fmt conv = acc40; conv.Q = B2D_RND_CONV;
+  Fmt acc24{24, 8, 1, B2D_TRN, B2D_WRAP};                                     // F_acc = 16 < 30: per-tap truncation, not the q15 path
+  EXPECT(fir_q15_supported(q15, q15, acc40, acc40, 256, B2D_SHIFT_REG), "cfg 2 must take fir_q15");
+  EXPECT(fir_q15_supported(q15, q15, acc40, acc40, 1024, B2D_TRANSPOSED), "cfg 4 must take fir_q15");
+  EXPECT(!fir_q15_supported(q15, q15, sat, sat, 256, B2D_SHIFT_REG), "saturating accumulators are order-dependent");
+  EXPECT(!fir_q15_supported(q15, q15, conv, conv, 256, B2D_SHIFT_REG), "parity-dependent rounding is order-dependent");
+  EXPECT(!fir_q15_supported(q15, q15, acc24, acc24, 256, B2D_SHIFT_REG), "per-tap truncation is not an exact shift");
+  EXPECT(!fir_q15_supported(q15, q15, acc40, acc40, 4096, B2D_SHIFT_REG), "tap limit");
+  EXPECT(!fir_q15_supported(q15, q15, acc40, acc40, 256, B2D_FOLD_EVEN_ANTI), "negated 16-bit taps need 17 bits");
+  EXPECT(fir_q15_supported(q15, q15, acc40, acc40, 255, B2D_FOLD_ODD), "exact ACC_TYPE pre-add");
+  EXPECT(cic_history_len(0, 8, 1, 4) == 4 * 1 * 8 + 4 - 1, "decimator history N*M*R + N - 1");
+  EXPECT(cic_history_len(1, 4, 1, 3) == 3 * 1 + 3 + 2, "interpolator history N*M + N + 2");
+}
+
+int main() {
+  srand(20260101);
+  check_q<AC_TRN>(); check_q<AC_RND>(); check_q<AC_TRN_ZERO>(); check_q<AC_RND_ZERO>();
+  check_q<AC_RND_INF>(); check_q<AC_RND_MIN_INF>(); check_q<AC_RND_CONV>(); check_q<AC_RND_CONV_ODD>();
+  check_fir_q15_pack();
+  check_upfir_pack();
+  check_support_tables();
+  std::printf("checks=%ld bad=%d\n", g_checks, g_bad);
+  return g_bad != 0;
+}

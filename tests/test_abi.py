@@ -104,3 +104,20 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("the CPU oracle", ""), f
+
+
+def test_host_logic_fixed_point_core_and_packers(engine, tmp_path):
+    """tests/cpp/host_logic_check.cu (host code only): csrc/common.cuh convert / macc / tap_term against the oracle
+    shim's assignment and `+=` for every Q x O mode, and the coefficient packers against an independent expansion."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    libdir = os.path.join(ROOT, "ac_dsp_b200", "lib")
+    exe = str(tmp_path / "host_logic_check")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-w", f"-I{ROOT}/ac_dsp_b200/csrc", f"-I{ROOT}/oracle/ac_shim",
+                           os.path.join(ROOT, "tests", "cpp", "host_logic_check.cu"), "-o", exe,
+                           f"-L{libdir}", "-lb200dsp", "-Xlinker", "-rpath", "-Xlinker", libdir])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "bad=0" in p.stdout, p.stdout[-3000:] + p.stderr[-1000:]
