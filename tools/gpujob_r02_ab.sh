@@ -25,3 +25,6 @@ run waves16  B2D_UPFIR_WAVES=16
 run peel     B2D_UPFIR_PEEL=1
 run peel_w4  B2D_UPFIR_PEEL=1 B2D_UPFIR_WAVES=4
 run peel_w8  B2D_UPFIR_PEEL=1 B2D_UPFIR_WAVES=8
+# source-level capture of the headline kernel (not taken in round 1): where do the 4 % non-IDP slots of the DP2A pipe go?
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:fir_q15_kernel --launch-skip 1 --launch-count 1 -f \
+  -o gpurun_out/r02_fir_q15_full python bench.py --workload fir256 --log2n 26 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_ncu_fir_q15.log 2>&1
