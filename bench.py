@@ -442,6 +442,7 @@ def main():
                "d2h_bytes_per_step": int(no.value * C * yh.element_size()), "steps": k2,
                "api": "b2d_*_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
                "host_affinity": "NVML ideal CPUs of the GPU" if orig_affinity else "unchanged",
+               "host_numa_alloc": os.environ.get("B2D_HOST_NUMA") == "1",
                "samples_per_step": u2}
 
     if rank == 0:

@@ -28,3 +28,6 @@ run peel_w8  B2D_UPFIR_PEEL=1 B2D_UPFIR_WAVES=8
 # source-level capture of the headline kernel (not taken in round 1): where do the 4 % non-IDP slots of the DP2A pipe go?
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:fir_q15_kernel --launch-skip 1 --launch-count 1 -f \
   -o gpurun_out/r02_fir_q15_full python bench.py --workload fir256 --log2n 26 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_ncu_fir_q15.log 2>&1
+# e2e at N GPUs is host-bound (round 1: 3.28 G IQ samples/s at 1 GPU, 3.94 G at 2, 5.30 G at 8).  A/B on a multi-GPU box:
+#   gpurun --gpus 8 --timeout 900 -- 'for v in 0 1; do B2D_HOST_NUMA=$v python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+#     --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu > gpurun_out/r02_e2e_n8_numa$v.json; done'
