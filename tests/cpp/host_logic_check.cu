@@ -130,6 +130,48 @@ static void check_fir_q15_pack() {
     }
 }
 
+static void check_fir_wide_and_polydec_pack() {
+  const int fts[] = {B2D_SHIFT_REG, B2D_FOLD_EVEN, B2D_FOLD_ODD, B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI};
+  for (int ft : fts)
+    for (int N : {2, 8, 27, 63, 64}) {
+      if ((ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI) && (N & 1)) continue;
+      if ((ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI) && !(N & 1)) continue;
+      std::vector<int64_t> c(N);
+      for (auto &v : c) v = (rand() % 2000001) - 1000000;
+      const int words = fir_wide_words(N);
+      EXPECT(words >= N && words % 8 == 0 && words < N + 8, "fir_wide_words(%d) = %d", N, words);
+      for (int mode = 0; mode < 3; mode++) {                                 // 0: folds expanded; 1, 2: the kernel folds itself, raw taps
+        std::vector<int32_t> out(words, 0x5A5A5A5A);
+        fir_wide_pack(c.data(), N, ft, mode, out.data(), words);
+        const std::vector<int64_t> e = mode == 0 ? effective_taps(c, N, ft) : c;
+        for (int i = 0; i < words; i++) EXPECT(out[i] == (i < N ? (int32_t)e[i] : 0), "fir_wide_pack ft %d N %d mode %d i %d", ft, N, mode, i);
+      }
+    }
+  // polyphase decimator: phase-major planes, zero padded per phase (ac_poly_dec.h:110-126 reads coeffs[tp + NTAPS*df])
+  for (int NT : {1, 7, 32})
+    for (int DF : {2, 3, 8}) {
+      std::vector<int64_t> c((size_t)NT * DF);
+      for (auto &v : c) v = (rand() % 65536) - 32768;
+      const int ntpad = polydec_words(NT);
+      std::vector<int32_t> out((size_t)ntpad * DF, 0x5A5A5A5A);
+      polydec_pack(c.data(), NT, DF, out.data());
+      for (int r = 0; r < DF; r++)
+        for (int tp = 0; tp < ntpad; tp++)
+          EXPECT(out[(size_t)r * ntpad + tp] == (tp < NT ? (int32_t)c[tp + NT * r] : 0), "polydec_pack NT %d DF %d r %d tp %d", NT, DF, r, tp);
+      const Fmt fc{16, 1, 1, B2D_TRN, B2D_WRAP};
+      const int pkw = polydec_q15_words(NT, DF) / DF;
+      std::vector<uint32_t> pk((size_t)pkw * DF, 0xDEADBEEF);
+      polydec_q15_pack(fc, c.data(), NT, DF, pk.data());
+      for (int r = 0; r < DF; r++)
+        for (int k = 0; k < 2 * pkw; k++) {
+          const uint32_t w = pk[(size_t)r * pkw + k / 2];
+          const int el = k & 1;
+          const int64_t got = (int64_t)((w >> (8 * el)) & 0xFF) + 256 * (int64_t)(int8_t)((w >> (16 + 8 * el)) & 0xFF);
+          EXPECT(got == (k < NT ? c[(size_t)NT * r + NT - 1 - k] : 0), "polydec_q15_pack NT %d DF %d r %d k %d", NT, DF, r, k);
+        }
+    }
+}
+
 static void check_upfir_pack() {
   const int Rs[] = {2, 4, 8};
   const int Ts[] = {1, 5, 18, 72, 73, 200};
@@ -183,6 +225,7 @@ int main() {
   check_q<AC_RND_INF>(); check_q<AC_RND_MIN_INF>(); check_q<AC_RND_CONV>(); check_q<AC_RND_CONV_ODD>();
   check_fir_q15_pack();
   check_upfir_pack();
+  check_fir_wide_and_polydec_pack();
   check_support_tables();
   std::printf("checks=%ld bad=%d\n", g_checks, g_bad);
   return g_bad != 0;
