@@ -703,6 +703,13 @@ static int cic_int_width(const b2d_cic_desc *d, int *outW) {
   return 0;
 }
 
+// Differential delay the reference's comb really has.  diffStage() shifts comb_dly_ln[k][0..M-1] with an ASCENDING copy
+// loop (ac_cic_full_core.h:247-251: `if (i != 0) dly[i] = dly[i-1]` for i = 0 .. M-1), so dly[0] smears through the line
+// and dly[M-1], read at the next step, is the input of two steps ago: the delay is min(M, 2) while the lossless width
+// (cic_int_width above) keeps growing with M.  Bit-exactness means following the code, not the intent; M <= 2 -- every
+// reference vector and BASELINE configuration -- is unaffected (pinned by tests/golden/cic_comb_quirk.npz).
+static uint32_t cic_comb_delay(uint32_t M) { return M > 2 ? 2u : M; }
+
 static int cic_check(const b2d_cic_desc *d, int *outW) {
   int st;
   if (!d) return fail(B2D_EINVAL, "null descriptor");
@@ -760,7 +767,7 @@ extern "C" int b2d_cic_create(b2d_cic **out, const b2d_cic_desc *desc) {
   if (!h) return fail(B2D_ENOMEM, "handle");
   h->d = *desc; h->fin = to_fmt(desc->in); h->fo = to_fmt(desc->out); h->device = dev; h->intW = w;
   h->in_bytes = container_bytes(desc->in.W); h->out_bytes = container_bytes(desc->out.W);
-  h->H = cic_history_len(desc->mode == B2D_CIC_INTR, desc->R, desc->M, desc->N);
+  h->H = cic_history_len(desc->mode == B2D_CIC_INTR, desc->R, cic_comb_delay(desc->M), desc->N);
   const size_t tail_bytes = (size_t)h->H * desc->n_channels * h->in_bytes;
   for (int i = 0; i < 2; i++) {
     cudaError_t e = cudaMalloc(&h->d_tail[i], tail_bytes);
@@ -772,11 +779,11 @@ extern "C" int b2d_cic_create(b2d_cic **out, const b2d_cic_desc *desc) {
     }
   }
   CicLaunch p{};
-  p.fin = h->fin; p.fout = h->fo; p.intW = w; p.R = desc->R; p.M = desc->M; p.N = desc->N;
+  p.fin = h->fin; p.fout = h->fo; p.intW = w; p.R = desc->R; p.M = cic_comb_delay(desc->M); p.N = desc->N;
   p.intr = desc->mode == B2D_CIC_INTR; p.C = desc->n_channels; p.interleaved = desc->layout == B2D_INTERLEAVED;
   h->fast = cic_fast_supported(p) ? 1 : (cic_intr_fast_supported(p) ? 2 : 0);
   const char *force = getenv("B2D_FORCE_GENERIC");
-  if (force && *force == '1') h->fast = 0;
+  if ((force && *force == '1') || desc->M > 2) h->fast = 0;   // M > 2: the width is not the one the fast kernels were instantiated for
   *out = h;
   return B2D_OK;
 }
@@ -801,7 +808,7 @@ extern "C" size_t b2d_cic_max_out(b2d_cic *h, size_t n) {
 static int cic_launch(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
   if (n == 0) return B2D_OK;
   CicLaunch p;
-  p.fin = h->fin; p.fout = h->fo; p.intW = h->intW; p.R = h->d.R; p.M = h->d.M; p.N = h->d.N;
+  p.fin = h->fin; p.fout = h->fo; p.intW = h->intW; p.R = h->d.R; p.M = cic_comb_delay(h->d.M); p.N = h->d.N;
   p.intr = h->d.mode == B2D_CIC_INTR; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
   p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
   p.n_seen = h->n_seen; p.out_first = cic_emitted(h, h->n_seen);
@@ -948,6 +955,7 @@ static bool cicfir_fusable(const b2d_cic_desc &cd, const b2d_fir_desc &fd, int i
   if (in.W > 16 || (!in.S && in.W == 16)) return false;
   if (!(mid.S && mid.F() == in.F() && mid.W >= intW)) return false;          // the lossless INT_TYPE passes unchanged
   if (fa.O != B2D_WRAP || (fa.Q != B2D_TRN && fa.Q != B2D_RND)) return false;
+  if (cd.M > 2) return false;                 // cic_comb_delay: the composite taps below assume delay M; two-stage path instead
   const int s = mid.F() + fc.F() - fa.F();
   if (s > 0 || -s > 40 || -s >= fa.W) return false;
   switch (fd.ftype) {

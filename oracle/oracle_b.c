@@ -481,14 +481,19 @@ static w128 cic_int_stage(ob_cic *c, w128 x) {
   c->intg[0] = ob_convert(x + c->intg[0], Fi, &c->it);
   return c->intg[c->N - 1];
 }
-/* comb + diffStage: ac_cic_full_core.h:228-255 */
+/* comb + diffStage: ac_cic_full_core.h:228-255.  The delay line is shifted with an ASCENDING copy loop
+ * (`for i = 0 .. M-1: if (i != 0) dly[i] = dly[i-1]`, :247-251), so dly[0] smears through the whole line: after a step
+ * every dly[i >= 1] holds the previous input and dly[M-1] read at the next step is the input of two steps ago.  The
+ * differential delay of the reference as written is therefore min(M, 2), not M, while the lossless width
+ * (find_inter_type_cic_*) still grows with M.  Found by the random-instantiation sweep (tests/test_oracle_fuzz.py):
+ * the reference's own vectors use M = 2, where both readings coincide.  Restated literally. */
 static w128 cic_comb(ob_cic *c, w128 x) {
   const int Fi = F_of(&c->it);
   w128 v = x;
   for (int k = 0; k < c->N; k++) {
     w128 *d = c->comb + (size_t)k * c->M;
     w128 o = ob_convert(v - d[c->M - 1], Fi, &c->it);
-    for (int i = c->M - 1; i > 0; i--) d[i] = d[i - 1];
+    for (int i = 1; i < c->M; i++) d[i] = d[i - 1];
     d[0] = v;
     v = o;
   }

@@ -245,3 +245,19 @@ def test_intg_dump_equal_frames_are_segment_sums(CHN):
     ref = O.IdB(Q15, (32, 17), (32, 17), 1024, CHN).run(x, np.full(frames, ns))
     seg = x.astype(np.int64).reshape(frames, ns, CHN).sum(axis=1)
     assert np.array_equal(np.asarray(ref).reshape(frames, CHN), seg)
+
+
+# ----------------------------------------------------------------- the reference's comb for M > 2 (a quirk, followed)
+@pytest.mark.parametrize("mode,R,M,N", [("dec", 4, 3, 2), ("dec", 2, 5, 3), ("intr", 3, 3, 2), ("intr", 5, 4, 3), ("dec", 8, 3, 1)])
+def test_comb_delay_of_the_reference_is_min_m_2(mode, R, M, N):
+    """ac_cic_full_core.h:247-251 shifts the comb delay line with an ascending copy loop, so its differential delay is
+    min(M, 2) while the lossless width still grows with M (oracle_b.c cic_comb, runtime.cu cic_comb_delay).  The engine
+    therefore runs an M > 2 instantiation as the M = 2 filter at the M-wide internal type: same outputs."""
+    rng = np.random.default_rng(M * 7 + N)
+    x = rand16(rng, 500)
+    W = O.cic_int_width(mode, Q15, R, M, N)
+    outf = (W, W - 15)
+    y_m = O.CicB(mode, Q15, outf, R, M, N).run(x)
+    y_2 = O.CicB(mode, Q15, outf, R, 2, N).run(x)
+    assert np.array_equal(y_m, y_2)
+    assert not np.array_equal(y_m, O.CicB(mode, Q15, outf, R, 1, N).run(x)) or N == 0

@@ -1,0 +1,192 @@
+"""Oracle A == Oracle B on RANDOM instantiations (dev container only: needs /root/reference).
+
+tests/test_oracle.py compares the two oracles on the hand-picked table in oracle/ref_configs.py.  Here the table is
+drawn at random -- formats (widths, binary points, signedness), all 8 quantisation and 4 overflow modes for the
+accumulator and the output, tap counts, R / M / N -- the unmodified reference templates are compiled for exactly
+those instantiations (a throw-away .so next to the test's tmp dir, same driver sources as oracle/_ref), and the
+plain-C restatement has to reproduce them bit for bit, single call and chunked.  Oracle B is what checks the CUDA
+engine on the GPU box, so this is the widest net under the parity chain.  B2D_FUZZ_SEED picks another draw.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("AC_DSP_REF", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "include", "ac_dsp", "ac_fir_load_coeffs.h")),
+                                reason="reference tree not present (GPU box): the committed fixtures pin Oracle B there")
+SEED = int(os.environ.get("B2D_FUZZ_SEED", "20260101"))
+Q_MODES, O_MODES = O.Q_MODES, O.O_MODES
+
+
+def cfmt(f):
+    W, I, S, Q, Om = f
+    return f"{W},{I},{'true' if S else 'false'},{Q},{Om}"
+
+
+def compile_driver(tmp, incs, sources, name):
+    """incs: {file name: text} placed under tmp/_ref/.  The drivers #include "_ref/cfgs_*.inc" with quotes, which is
+    looked up next to the including file first, so the (test-infrastructure) driver sources are copied into tmp and
+    compiled there: these lists replace oracle/_ref's."""
+    import shutil
+    os.makedirs(os.path.join(tmp, "_ref"), exist_ok=True)
+    for fn, text in incs.items():
+        with open(os.path.join(tmp, "_ref", fn), "w") as fh:
+            fh.write(text)
+    shutil.copy(os.path.join(ROOT, "oracle", "ref_driver_cic.h"), tmp)
+    objs = []
+    for src, defs in sources:
+        local = shutil.copy(os.path.join(ROOT, "oracle", src), tmp)
+        obj = os.path.join(tmp, src + "".join(defs).replace("-D", "_") + ".o")
+        subprocess.check_call(["g++", "-std=c++11", "-O1", "-fPIC", f"-I{tmp}", f"-I{ROOT}/oracle/ac_shim", f"-I{REF}/include",
+                               "-c", local, "-o", obj] + defs)
+        objs.append(obj)
+    lib = os.path.join(tmp, name)
+    subprocess.check_call(["g++", "-shared", "-o", lib] + objs)
+    return C.CDLL(lib)
+
+
+def rand_fmt(rng, wlo, whi, modes=False):
+    W = int(rng.integers(wlo, whi + 1))
+    I = int(rng.integers(-2, W + 3))
+    S = bool(rng.integers(0, 2)) or W == 1
+    Q = Q_MODES[int(rng.integers(0, 8))] if modes else "AC_TRN"
+    Om = O_MODES[int(rng.integers(0, 4))] if modes else "AC_WRAP"
+    return (W, I, S, Q, Om)
+
+
+# ------------------------------------------------------------------------------------------------ FIR
+def draw_fir(rng, k):
+    cfgs = []
+    while len(cfgs) < k:
+        fi, fc = rand_fmt(rng, 2, 32), rand_fmt(rng, 2, 32)
+        Fp = (fi[0] - fi[1]) + (fc[0] - fc[1])
+        Wa = int(rng.integers(8, 65))
+        Fa = Fp + int(rng.integers(-12, 7))                    # mostly dropping bits per tap, sometimes an exact shift
+        fa = (Wa, Wa - Fa, True if rng.integers(0, 4) else False, Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        Wo = int(rng.integers(4, 65))
+        fo = (Wo, Wo - (Fa - int(rng.integers(0, 10))), bool(rng.integers(0, 2)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        nt = int(rng.choice([2, 3, 4, 5, 8, 11, 16, 27, 40]))
+        # what the 128-bit shim (and the engine's 128-bit generic path) can hold: product, fold product, sums
+        if fi[0] + fc[0] > 64 or fc[0] + fa[0] > 96:
+            continue
+        if abs(fa[1]) > 70 or abs(fo[1]) > 70 or max(Fa, Fp) - min(Fa, Fp) > 40:
+            continue
+        cfgs.append((fi, fc, fa, fo, nt))
+    return cfgs
+
+
+@pytest.fixture(scope="module")
+def fir_fuzz(tmp_path_factory):
+    rng = np.random.default_rng(SEED)
+    cfgs = draw_fir(rng, 10)
+    inc = "".join(f"X({i}, {cfmt(fi)}, {cfmt(fc)}, {cfmt(fa)}, {cfmt(fo)}, {nt})\n" for i, (fi, fc, fa, fo, nt) in enumerate(cfgs))
+    L = compile_driver(str(tmp_path_factory.mktemp("firfuzz")), {"cfgs_fir.inc": inc}, [("ref_driver_fir.cpp", [])], "libfirfuzz.so")
+    L.acref_fir_create.restype = C.c_void_p
+    L.acref_fir_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.acref_fir_load.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.acref_fir_run.restype = C.c_long
+    L.acref_fir_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+    L.acref_fir_destroy.argtypes = [C.c_void_p]
+    return L, cfgs
+
+
+def p64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_fir_random_instantiation(fir_fuzz, i):
+    L, cfgs = fir_fuzz
+    fi, fc, fa, fo, nt = cfgs[i]
+    rng = np.random.default_rng(SEED + 100 + i)
+    x = O.rand_raw(rng, fi, 260)
+    x[:4] = [O.rand_raw(rng, fi, 1, "min")[0], O.rand_raw(rng, fi, 1, "max")[0], 0, O.rand_raw(rng, fi, 1, "min")[0]]
+    h = O.rand_raw(rng, fc, nt)
+    for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"):
+        if ft == "FOLD_EVEN" and nt % 2:
+            continue                      # reads h[0 .. N/2) only: legal, but B mirrors A either way -- keep the reference's intended use
+        if ft == "FOLD_ODD" and nt % 2 == 0:
+            continue
+        for cls in (0, 1, 2):
+            ha = L.acref_fir_create(i, cls, O.FTYPES.index(ft))
+            assert ha, (cfgs[i], ft, cls)
+            hh = np.ascontiguousarray(h, dtype=np.int64)
+            assert L.acref_fir_load(ha, p64(hh)) == 0
+            xa = np.ascontiguousarray(x, dtype=np.int64)
+            ya = np.empty(x.size, dtype=np.int64)
+            # the reference in two calls (state carried by the object), the restatement in three differently cut ones
+            n1 = L.acref_fir_run(ha, p64(xa), 97, p64(ya))
+            rest = np.ascontiguousarray(xa[97:])
+            yb_ = np.empty(rest.size, dtype=np.int64)
+            n2 = L.acref_fir_run(ha, p64(rest), rest.size, p64(yb_))
+            L.acref_fir_destroy(ha)
+            assert n1 == 97 and n2 == rest.size
+            ya = np.concatenate([ya[:97], yb_])
+            b = O.FirB(fi, fc, fa, fo, nt, ft)
+            b.load(h)
+            yb = np.concatenate([b.run(x[:1]), b.run(x[1:130]), b.run(x[130:])])
+            assert np.array_equal(ya, yb), (cfgs[i], ft, cls, int(np.flatnonzero(ya != yb)[0]))
+
+
+# ------------------------------------------------------------------------------------------------ CIC
+def draw_cic(rng, k, mode):
+    cfgs = []
+    while len(cfgs) < k:
+        R, M, N = int(rng.integers(2, 10)), int(rng.integers(1, 4)), int(rng.integers(1, 6))
+        W = int(rng.integers(3, 25))
+        fi = (W, int(rng.integers(-1, W + 2)), bool(rng.integers(0, 2)) or W < 4, "AC_TRN", "AC_WRAP")
+        intW = O.cic_int_width(mode, fi, R, M, N)
+        if intW > 64:
+            continue
+        Fin = fi[0] - fi[1]
+        Wo = int(rng.integers(4, 65))
+        fo = (Wo, Wo - (Fin - int(rng.integers(0, 6))), bool(rng.integers(0, 2)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        if rng.integers(0, 3) == 0:
+            fo = (intW, intW - Fin, True, "AC_TRN", "AC_WRAP")      # the lossless type, passed on unchanged
+        cfgs.append((R, M, N, fi, fo))
+    return cfgs
+
+
+@pytest.fixture(scope="module")
+def cic_fuzz(tmp_path_factory):
+    rng = np.random.default_rng(SEED + 7)
+    dec, intr = draw_cic(rng, 8, "dec"), draw_cic(rng, 8, "intr")
+    incs = {"cfgs_cic_dec.inc": "".join(f"X({i}, {R}, {M}, {N}, {cfmt(fi)}, {cfmt(fo)})\n" for i, (R, M, N, fi, fo) in enumerate(dec)),
+            "cfgs_cic_intr.inc": "".join(f"X({i}, {R}, {M}, {N}, {cfmt(fi)}, {cfmt(fo)})\n" for i, (R, M, N, fi, fo) in enumerate(intr))}
+    L = compile_driver(str(tmp_path_factory.mktemp("cicfuzz")), incs,
+                       [("ref_driver_cic.cpp", ["-DACREF_CIC_DEC"]), ("ref_driver_cic.cpp", ["-DACREF_CIC_INTR"])], "libcicfuzz.so")
+    for fn in (L.acref_cic_dec_create, L.acref_cic_intr_create):
+        fn.restype = C.c_void_p
+        fn.argtypes = [C.c_int]
+    L.acref_cic_run.restype = C.c_long
+    L.acref_cic_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.POINTER(C.c_int64)]
+    L.acref_cic_destroy.argtypes = [C.c_void_p]
+    return L, dec, intr
+
+
+@pytest.mark.parametrize("mode", ["dec", "intr"])
+@pytest.mark.parametrize("i", range(8))
+def test_cic_random_instantiation(cic_fuzz, mode, i):
+    L, dec, intr = cic_fuzz
+    R, M, N, fi, fo = (dec if mode == "dec" else intr)[i]
+    rng = np.random.default_rng(SEED + 300 + i)
+    x = np.ascontiguousarray(O.rand_raw(rng, fi, 400), dtype=np.int64)
+    ha = (L.acref_cic_dec_create if mode == "dec" else L.acref_cic_intr_create)(i)
+    assert ha
+    outs = []
+    for lo, hi in ((0, 1), (1, 58), (58, 61), (61, 400)):            # the reference itself in ragged calls
+        seg = np.ascontiguousarray(x[lo:hi])
+        buf = np.empty(seg.size * R + R + 8, dtype=np.int64)
+        n = L.acref_cic_run(ha, p64(seg), seg.size, p64(buf))
+        outs.append(buf[:n].copy())
+    L.acref_cic_destroy(ha)
+    ya = np.concatenate(outs)
+    b = O.CicB(mode, fi, fo, R, M, N)
+    yb = np.concatenate([b.run(x[:200]), b.run(x[200:])])
+    assert ya.size == yb.size and np.array_equal(ya, yb), ((R, M, N, fi, fo), ya.size, yb.size)
