@@ -190,3 +190,182 @@ def test_cic_random_instantiation(cic_fuzz, mode, i):
     b = O.CicB(mode, fi, fo, R, M, N)
     yb = np.concatenate([b.run(x[:200]), b.run(x[200:])])
     assert ya.size == yb.size and np.array_equal(ya, yb), ((R, M, N, fi, fo), ya.size, yb.size)
+
+
+# ------------------------------------------------------------------------------- ac_poly_dec / ac_poly_intr / ac_intg_dump
+def draw_mac_formats(rng):
+    """(in, coeff, acc, out) like draw_fir: random binary points, all modes on the accumulator and the output."""
+    while True:
+        fi, fc = rand_fmt(rng, 2, 32), rand_fmt(rng, 2, 32)
+        Fp = (fi[0] - fi[1]) + (fc[0] - fc[1])
+        Wa = int(rng.integers(8, 65))
+        Fa = Fp + int(rng.integers(-12, 7))
+        fa = (Wa, Wa - Fa, True if rng.integers(0, 4) else False, Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        Wo = int(rng.integers(4, 65))
+        fo = (Wo, Wo - (Fa - int(rng.integers(0, 10))), bool(rng.integers(0, 2)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        if fi[0] + fc[0] > 64 or fc[0] + fa[0] > 96 or abs(fa[1]) > 70 or abs(fo[1]) > 70 or abs(Fa - Fp) > 40:
+            continue
+        return fi, fc, fa, fo
+
+
+@pytest.fixture(scope="module")
+def poly_fuzz(tmp_path_factory):
+    rng = np.random.default_rng(SEED + 11)
+    pd = [draw_mac_formats(rng) + (int(rng.integers(1, 13)), int(rng.integers(2, 7))) for _ in range(8)]
+    pi = []
+    for _ in range(9):
+        ft = ["FOLD_EVEN", "FOLD_ODD", "FOLD_ANTI"][len(pi) % 3]
+        nt = int(rng.integers(1, 7)) * 2 if ft == "FOLD_EVEN" else (int(rng.integers(0, 6)) * 2 + 1 if ft == "FOLD_ODD" else int(rng.integers(1, 12)))
+        pi.append(draw_mac_formats(rng) + (nt, int(rng.integers(1, 6)), ft))
+    idc = []
+    for _ in range(8):
+        fi = rand_fmt(rng, 2, 32)
+        Fa = (fi[0] - fi[1]) + int(rng.integers(-8, 5))
+        Wa = int(rng.integers(8, 65))
+        fa = (Wa, Wa - Fa, bool(rng.integers(0, 4)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        Wo = int(rng.integers(4, 65))
+        fo = (Wo, Wo - (Fa - int(rng.integers(0, 8))), bool(rng.integers(0, 2)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+        idc.append((fi, fa, fo, int(rng.integers(4, 65)), int(rng.integers(1, 6))))
+    from oracle import ref_configs as rc
+    incs = {
+        "cfgs_pd.inc": "".join(f"X({i}, {cfmt(a)}, {cfmt(b)}, {cfmt(c)}, {cfmt(d)}, {nt}, {df})\n" for i, (a, b, c, d, nt, df) in enumerate(pd)),
+        "cfgs_pi.inc": "".join(f"X({i}, {cfmt(a)}, {cfmt(b)}, {cfmt(c)}, {cfmt(d)}, {nt}, {rc.pi_coeffsz((a, b, c, d, nt, IF, ft))}, {IF}, {ft})\n"
+                               for i, (a, b, c, d, nt, IF, ft) in enumerate(pi)),
+        "cfgs_id.inc": "".join(f"X({i}, {cfmt(a)}, {cfmt(b)}, {cfmt(c)}, {ns}, {chn})\n" for i, (a, b, c, ns, chn) in enumerate(idc)),
+    }
+    L = compile_driver(str(tmp_path_factory.mktemp("polyfuzz")), incs,
+                       [("ref_driver_pd.cpp", []), ("ref_driver_pi.cpp", []), ("ref_driver_id.cpp", [])], "libpolyfuzz.so")
+    P64 = C.POINTER(C.c_int64)
+    for name in ("pd", "pi", "id"):
+        getattr(L, f"acref_{name}_create").restype = C.c_void_p
+        getattr(L, f"acref_{name}_create").argtypes = [C.c_int]
+        getattr(L, f"acref_{name}_destroy").argtypes = [C.c_void_p]
+    L.acref_pd_load.argtypes = [C.c_void_p, P64]
+    L.acref_pd_run.restype = C.c_long
+    L.acref_pd_run.argtypes = [C.c_void_p, P64, C.c_long, P64]
+    L.acref_pi_load.argtypes = [C.c_void_p, P64, P64, P64]
+    L.acref_pi_run.restype = C.c_long
+    L.acref_pi_run.argtypes = [C.c_void_p, P64, C.c_long, P64]
+    L.acref_id_run.restype = C.c_long
+    L.acref_id_run.argtypes = [C.c_void_p, P64, C.c_long, P64, C.c_long, P64]
+    return L, pd, pi, idc
+
+
+def i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+@pytest.mark.parametrize("i", range(8))
+def test_poly_dec_random_instantiation(poly_fuzz, i):
+    L, pd, _pi, _id = poly_fuzz
+    fi, fc, fa, fo, nt, df = pd[i]
+    rng = np.random.default_rng(SEED + 500 + i)
+    x, h = i64(O.rand_raw(rng, fi, 50 * df + 3)), i64(O.rand_raw(rng, fc, nt * df))
+    ha = L.acref_pd_create(i)
+    L.acref_pd_load(ha, p64(h))
+    outs = []
+    for lo, hi in ((0, 1), (1, df + 2), (df + 2, x.size)):
+        seg = i64(x[lo:hi])
+        buf = np.empty(seg.size // df + 3, dtype=np.int64)
+        outs.append(buf[:L.acref_pd_run(ha, p64(seg), seg.size, p64(buf))].copy())
+    L.acref_pd_destroy(ha)
+    b = O.PdB(fi, fc, fa, fo, nt, df)
+    b.load(h)
+    yb = np.concatenate([b.run(x[:7]), b.run(x[7:])])
+    ya = np.concatenate(outs)
+    assert ya.size == yb.size and np.array_equal(ya, yb), (pd[i], ya.size, yb.size)
+
+
+@pytest.mark.parametrize("i", range(9))
+def test_poly_intr_random_instantiation(poly_fuzz, i):
+    L, _pd, pi, _id = poly_fuzz
+    fi, fc, fa, fo, nt, IF, ft = pi[i]
+    from oracle import ref_configs as rc
+    csz = rc.pi_coeffsz(pi[i])
+    rng = np.random.default_rng(SEED + 600 + i)
+    x, h = i64(O.rand_raw(rng, fi, 120)), i64(O.rand_raw(rng, fc, csz))
+    x[:3] = [O.rand_raw(rng, fi, 1, "min")[0], O.rand_raw(rng, fi, 1, "max")[0], O.rand_raw(rng, fi, 1, "min")[0]]
+    sign, corr = i64(rng.integers(0, 2, IF)), i64(rng.integers(0, IF, IF))
+    h2, sign2, corr2 = i64(O.rand_raw(rng, fc, csz)), i64(rng.integers(0, 2, IF)), i64(rng.integers(0, IF, IF))
+    ha = L.acref_pi_create(i)
+    b = O.PiB(fi, fc, fa, fo, nt, IF, ft)
+    ya, yb = [], []
+    for (lo, hi), (c, s, r) in zip(((0, 70), (70, 120)), ((h, sign, corr), (h2, sign2, corr2))):     # a reload mid-stream
+        L.acref_pi_load(ha, p64(c), p64(s), p64(r))
+        seg = i64(x[lo:hi])
+        buf = np.empty(seg.size * IF + 1, dtype=np.int64)
+        ya.append(buf[:L.acref_pi_run(ha, p64(seg), seg.size, p64(buf))].copy())
+        b.load(c, s, r)
+        yb.append(b.run(seg))
+    L.acref_pi_destroy(ha)
+    ya, yb = np.concatenate(ya), np.concatenate(yb)
+    assert ya.size == yb.size and np.array_equal(ya, yb), (pi[i], ya.size, yb.size)
+
+
+@pytest.mark.parametrize("i", range(8))
+def test_intg_dump_random_instantiation(poly_fuzz, i):
+    L, _pd, _pi, idc = poly_fuzz
+    fi, fa, fo, NS, CHN = idc[i]
+    rng = np.random.default_rng(SEED + 700 + i)
+    tok = rng.integers(1, NS + 1, 30)
+    tok[[4, 11, 20]] = [0, NS + 5, NS]                # tokens outside 1..NS consume NS samples and dump nothing
+    n = int(sum(O.id_frame_samples(v, NS, CHN) for v in tok))
+    x = i64(O.rand_raw(rng, fi, n))
+    ha = L.acref_id_create(i)
+    buf = np.empty(tok.size * CHN + 1, dtype=np.int64)
+    ya = buf[:L.acref_id_run(ha, p64(x), x.size, p64(i64(tok)), tok.size, p64(buf))].copy()
+    L.acref_id_destroy(ha)
+    yb = np.asarray(O.IdB(fi, fa, fo, NS, CHN).run(x, tok)).reshape(-1)
+    assert ya.size == yb.size and np.array_equal(ya, yb), (idc[i], ya.size, yb.size)
+
+
+# ------------------------------------------------------------------------------------------ ac_fir_reg_share
+@pytest.fixture(scope="module")
+def rs_fuzz(tmp_path_factory):
+    from oracle import ref_configs as rc
+    rng = np.random.default_rng(SEED + 13)
+    cfgs = []
+    while len(cfgs) < 10:
+        ft = ["SHIFT_REG", "FOLD_EVEN", "FOLD_ODD", "FOLD_EVEN_ANTI", "FOLD_ODD_ANTI"][len(cfgs) % 5]
+        N = int(rng.integers(1, 13)) * 2 if "EVEN" in ft else (int(rng.integers(0, 12)) * 2 + 1 if "ODD" in ft else int(rng.integers(1, 25)))
+        used = N if ft == "SHIFT_REG" else (N // 2 if "EVEN" in ft else (N - 1) // 2 + 1)
+        bs = int(rng.choice([d for d in range(1, used + 1) if used % d == 0]))     # the tap loop must be whole blocks (else the reference reads out of range)
+        mww = bs + int(rng.integers(0, 4))
+        bo = int(rng.integers(0, mww - bs + 1))
+        fi, fc, fa, fo = draw_mac_formats(rng)
+        cfgs.append((N, fi, fo, fc, fa, mww, bs, bo, ft))
+    inc = "".join(f"X({i}, {N}, {cfmt(fi)}, {cfmt(fo)}, {cfmt(fc)}, {cfmt(fa)}, {mww}, {bs}, {bo}, {ft}, {rc.rs_ram_words(c)})\n"
+                  for i, c in enumerate(cfgs) for (N, fi, fo, fc, fa, mww, bs, bo, ft) in [c])
+    L = compile_driver(str(tmp_path_factory.mktemp("rsfuzz")), {"cfgs_rs.inc": inc}, [("ref_driver_rs.cpp", [])], "librsfuzz.so")
+    P64 = C.POINTER(C.c_int64)
+    L.acref_rs_create.restype = C.c_void_p
+    L.acref_rs_create.argtypes = [C.c_int]
+    L.acref_rs_run.restype = C.c_long
+    L.acref_rs_run.argtypes = [C.c_void_p, P64, C.c_long, P64, P64]
+    L.acref_rs_delay_out.restype = C.c_longlong
+    L.acref_rs_delay_out.argtypes = [C.c_void_p]
+    L.acref_rs_destroy.argtypes = [C.c_void_p]
+    return L, cfgs
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_reg_share_random_instantiation(rs_fuzz, i):
+    from oracle import ref_configs as rc
+    L, cfgs = rs_fuzz
+    N, fi, fo, fc, fa, mww, bs, bo, ft = cfgs[i]
+    rng = np.random.default_rng(SEED + 800 + i)
+    x = i64(O.rand_raw(rng, fi, 4 * N + 30))
+    ram = i64(O.rand_raw(rng, fc, rc.rs_ram_words(cfgs[i])))
+    ram2 = i64(O.rand_raw(rng, fc, ram.size))                      # programmable: another coefficient set mid-stream
+    ha = L.acref_rs_create(i)
+    b = O.RsB(fi, fo, fc, fa, N, mww, bs, bo, ft)
+    ya, yb = [], []
+    for (lo, hi), r in (((0, 2 * N), ram), ((2 * N, x.size), ram2)):
+        seg = i64(x[lo:hi])
+        buf = np.empty(seg.size, dtype=np.int64)
+        assert L.acref_rs_run(ha, p64(seg), seg.size, p64(r), p64(buf)) == seg.size
+        ya.append(buf)
+        yb.append(b.run(seg, r))
+    assert np.array_equal(np.concatenate(ya), np.concatenate(yb)), cfgs[i]
+    assert int(L.acref_rs_delay_out(ha)) == b.delay_out(), cfgs[i]
+    L.acref_rs_destroy(ha)
