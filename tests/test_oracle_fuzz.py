@@ -109,10 +109,7 @@ def test_fir_random_instantiation(fir_fuzz, i):
     x[:4] = [O.rand_raw(rng, fi, 1, "min")[0], O.rand_raw(rng, fi, 1, "max")[0], 0, O.rand_raw(rng, fi, 1, "min")[0]]
     h = O.rand_raw(rng, fc, nt)
     for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"):
-        if ft == "FOLD_EVEN" and nt % 2:
-            continue                      # reads h[0 .. N/2) only: legal, but B mirrors A either way -- keep the reference's intended use
-        if ft == "FOLD_ODD" and nt % 2 == 0:
-            continue
+        # FOLD_EVEN on an odd count / FOLD_ODD on an even one are not the intended use but compile: compared as well
         for cls in (0, 1, 2):
             ha = L.acref_fir_create(i, cls, O.FTYPES.index(ft))
             assert ha, (cfgs[i], ft, cls)
@@ -139,6 +136,12 @@ def draw_cic(rng, k, mode):
     cfgs = []
     while len(cfgs) < k:
         R, M, N = int(rng.integers(2, 10)), int(rng.integers(1, 4)), int(rng.integers(1, 6))
+        if len(cfgs) == 0:
+            R, M, N = 256, 1, 2                                    # the 8-bit rate counter's limit (ac_cic_full_core.h:72-73)
+        elif len(cfgs) == 1:
+            R, M, N = int(rng.integers(100, 256)), 2, int(rng.integers(1, 3))
+        elif len(cfgs) == 2:
+            R, M, N = int(rng.integers(2, 5)), 1, int(rng.integers(6, 9))
         W = int(rng.integers(3, 25))
         fi = (W, int(rng.integers(-1, W + 2)), bool(rng.integers(0, 2)) or W < 4, "AC_TRN", "AC_WRAP")
         intW = O.cic_int_width(mode, fi, R, M, N)
@@ -176,11 +179,11 @@ def test_cic_random_instantiation(cic_fuzz, mode, i):
     L, dec, intr = cic_fuzz
     R, M, N, fi, fo = (dec if mode == "dec" else intr)[i]
     rng = np.random.default_rng(SEED + 300 + i)
-    x = np.ascontiguousarray(O.rand_raw(rng, fi, 400), dtype=np.int64)
+    x = np.ascontiguousarray(O.rand_raw(rng, fi, 400 if mode == "intr" or R < 50 else 3 * R + 77), dtype=np.int64)
     ha = (L.acref_cic_dec_create if mode == "dec" else L.acref_cic_intr_create)(i)
     assert ha
     outs = []
-    for lo, hi in ((0, 1), (1, 58), (58, 61), (61, 400)):            # the reference itself in ragged calls
+    for lo, hi in ((0, 1), (1, 58), (58, 61), (61, x.size)):         # the reference itself in ragged calls
         seg = np.ascontiguousarray(x[lo:hi])
         buf = np.empty(seg.size * R + R + 8, dtype=np.int64)
         n = L.acref_cic_run(ha, p64(seg), seg.size, p64(buf))
