@@ -264,17 +264,23 @@ def test_poly_dec_random_instantiation(poly_fuzz, i):
     fi, fc, fa, fo, nt, df = pd[i]
     rng = np.random.default_rng(SEED + 500 + i)
     x, h = i64(O.rand_raw(rng, fi, 50 * df + 3)), i64(O.rand_raw(rng, fc, nt * df))
+    h2 = i64(O.rand_raw(rng, fc, nt * df))
     ha = L.acref_pd_create(i)
     L.acref_pd_load(ha, p64(h))
-    outs = []
-    for lo, hi in ((0, 1), (1, df + 2), (df + 2, x.size)):
+    b = O.PdB(fi, fc, fa, fo, nt, df)
+    b.load(h)
+    outs, outs_b = [], []
+    cut = 20 * df + 1                                  # a new coefficient set arrives with a group half consumed
+    for lo, hi in ((0, 1), (1, df + 2), (df + 2, cut), (cut, x.size)):
+        if lo == cut:
+            L.acref_pd_load(ha, p64(h2))
+            b.load(h2)
         seg = i64(x[lo:hi])
         buf = np.empty(seg.size // df + 3, dtype=np.int64)
         outs.append(buf[:L.acref_pd_run(ha, p64(seg), seg.size, p64(buf))].copy())
+        outs_b.append(b.run(seg))
     L.acref_pd_destroy(ha)
-    b = O.PdB(fi, fc, fa, fo, nt, df)
-    b.load(h)
-    yb = np.concatenate([b.run(x[:7]), b.run(x[7:])])
+    yb = np.concatenate(outs_b)
     ya = np.concatenate(outs)
     assert ya.size == yb.size and np.array_equal(ya, yb), (pd[i], ya.size, yb.size)
 
