@@ -326,6 +326,7 @@ struct b2d_fir {
   b2d_comm *comm = nullptr;
   int root = 0;
   int64_t *d_dl = nullptr;        // REG_SHARE: OUT_TYPE(reg[N_TAPS-1]) per channel
+  bool ran = false;               // samples were filtered since create / reset (see the TRANSPOSED rule in b2d_fir_load)
   void *d_win = nullptr;          // run_window scratch: [C][N_TAPS-1] tail, [C] newest samples, [C] outputs, [C][N_TAPS-1] dummy tail
   Pipe pipe;
 };
@@ -458,6 +459,19 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
     }
   }
   if (h->comm && (st = comm_bcast_i64(h->comm, v.data(), N, h->root))) return st;
+  // TRANSPOSED keeps ACC_TYPE partial sums as its state (reg_trans[], ac_fir_load_coeffs.h:265-278): after a coefficient
+  // change the next N_TAPS-1 outputs of the reference mix old-tap partial sums with new-tap products, which a window of
+  // input history cannot reproduce.  Equal to the direct form only while the taps stay put -- so a CHANGE of taps on a
+  // filter that has already consumed samples is refused (reset() first), never approximated.  Re-loading the same taps
+  // (ac_fir_prog_coeffs passes its array on every call) is not a change.
+  if (h->d.ftype == B2D_TRANSPOSED && h->ran) {
+    for (uint32_t c = 0; c < C; c++) {
+      if (channel >= 0 && (uint32_t)channel != c) continue;
+      if (h->ch_loaded[c] && !std::equal(v.begin(), v.end(), h->h_coeff.begin() + (size_t)c * N))
+        return fail(B2D_EUNSUPPORTED, "coefficient change on a TRANSPOSED filter mid-stream: the reference's partial sums keep the "
+                                      "old taps for N_TAPS-1 outputs; call reset() first or use another architecture");
+    }
+  }
   // the coefficient set may be swapped between run() calls while earlier launches are still in flight
   CU(cudaDeviceSynchronize());
   for (uint32_t c = 0; c < C; c++) {
@@ -492,6 +506,7 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   if (h->d_dl) CU(launch_fir_delay_out(p, h->d_dl, st));
   CU(launch_fir_tail(p, st));
   h->cur ^= 1;
+  h->ran = true;
   return B2D_OK;
 }
 
@@ -550,6 +565,7 @@ extern "C" int b2d_fir_reset(b2d_fir *h) {
   const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
   for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
   if (h->d_dl) CU(cudaMemset(h->d_dl, 0, h->d.n_channels * sizeof(int64_t)));
+  h->ran = false;
   return B2D_OK;
 }
 
@@ -681,6 +697,7 @@ extern "C" int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes) {
   if (st) return st;
   CU(cudaDeviceSynchronize());
   if (need > sizeof(hd)) CU(cudaMemcpy(h->d_tail[h->cur], (const char *)blob + sizeof(hd), need - sizeof(hd), cudaMemcpyHostToDevice));
+  h->ran = true;                  // a restored history stands for consumed samples
   return B2D_OK;
 }
 
@@ -1087,6 +1104,7 @@ static int cicfir_launch(b2d_cicfir *h, const void *d_in, size_t n, void *d_out,
     p.n_seen = h->n_seen; p.out_first = intr_emitted(h->n_seen, h->cd.R, h->cd.N);
     p.tail = h->d_tail[h->cur]; p.H = h->H; p.cw = h->d_cw;
     CU(launch_upfir_q15(p, st));
+    h->fir->ran = true;           // the fused kernel is the direct form too: same TRANSPOSED rule in b2d_fir_load
     CicLaunch t{};
     t.fin = to_fmt(h->cd.in); t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;
     t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1]; t.H = h->H;
@@ -1178,6 +1196,7 @@ extern "C" int b2d_cicfir_reset(b2d_cicfir *h) {
   if (h->fused) {
     for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, (size_t)h->H * h->cd.n_channels * 2));
     h->n_seen = 0;
+    h->fir->ran = false;
     return B2D_OK;
   }
   if ((st = b2d_cic_reset(h->cic))) return st;
@@ -1221,6 +1240,7 @@ extern "C" int b2d_cicfir_set_state(b2d_cicfir *h, const void *blob, size_t byte
     if ((st = state_set(StateHdr{kCasMagic, 1, 0, (uint32_t)h->H, h->cd.n_channels, 2, 1}, parts, 1, blob, bytes, &got))) return st;
     if (got.pad != 1) return fail(B2D_EINVAL, "state blob was taken from a two-stage cascade");
     h->n_seen = got.n_seen;
+    h->fir->ran = true;
     return B2D_OK;
   }
   size_t need = 0, a = 0;

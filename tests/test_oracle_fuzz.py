@@ -108,6 +108,7 @@ def test_fir_random_instantiation(fir_fuzz, i):
     x = O.rand_raw(rng, fi, 260)
     x[:4] = [O.rand_raw(rng, fi, 1, "min")[0], O.rand_raw(rng, fi, 1, "max")[0], 0, O.rand_raw(rng, fi, 1, "min")[0]]
     h = O.rand_raw(rng, fc, nt)
+    h2 = np.ascontiguousarray(O.rand_raw(rng, fc, nt), dtype=np.int64)
     for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"):
         # FOLD_EVEN on an odd count / FOLD_ODD on an even one are not the intended use but compile: compared as well
         for cls in (0, 1, 2):
@@ -119,6 +120,9 @@ def test_fir_random_instantiation(fir_fuzz, i):
             ya = np.empty(x.size, dtype=np.int64)
             # the reference in two calls (state carried by the object), the restatement in three differently cut ones
             n1 = L.acref_fir_run(ha, p64(xa), 97, p64(ya))
+            reload_ = cls != 0                             # load / prog classes: another coefficient set mid-stream, delay line kept
+            if reload_:
+                assert L.acref_fir_load(ha, p64(h2)) == 0
             rest = np.ascontiguousarray(xa[97:])
             yb_ = np.empty(rest.size, dtype=np.int64)
             n2 = L.acref_fir_run(ha, p64(rest), rest.size, p64(yb_))
@@ -127,7 +131,10 @@ def test_fir_random_instantiation(fir_fuzz, i):
             ya = np.concatenate([ya[:97], yb_])
             b = O.FirB(fi, fc, fa, fo, nt, ft)
             b.load(h)
-            yb = np.concatenate([b.run(x[:1]), b.run(x[1:130]), b.run(x[130:])])
+            yb = [b.run(x[:1]), b.run(x[1:97])]
+            if reload_:
+                b.load(h2)
+            yb = np.concatenate(yb + [b.run(x[97:130]), b.run(x[130:])])
             assert np.array_equal(ya, yb), (cfgs[i], ft, cls, int(np.flatnonzero(ya != yb)[0]))
 
 

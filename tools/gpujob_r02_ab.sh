@@ -18,7 +18,7 @@ PY
   done
 }
 # the random-format engine sweep written at the end of round 1 (never run on a GPU yet)
-B2D_ENGINE_FUZZ=1 timeout 600 python -m pytest tests/test_zz_engine_fuzz.py tests/test_zz_comb_quirk.py -m gpu -q 2>&1 | tail -15 | tee -a gpurun_out/r02_ab_summary.txt
+B2D_ENGINE_FUZZ=1 timeout 600 python -m pytest tests/test_zz_engine_fuzz.py tests/test_zz_reference_quirks.py -m gpu -q 2>&1 | tail -15 | tee -a gpurun_out/r02_ab_summary.txt
 run base     B2D_UPFIR_WAVES=1
 run waves2   B2D_UPFIR_WAVES=2
 run waves4   B2D_UPFIR_WAVES=4
