@@ -328,8 +328,14 @@ def test_intg_dump_random_instantiation(poly_fuzz, i):
     n = int(sum(O.id_frame_samples(v, NS, CHN) for v in tok))
     x = i64(O.rand_raw(rng, fi, n))
     ha = L.acref_id_create(i)
-    buf = np.empty(tok.size * CHN + 1, dtype=np.int64)
-    ya = buf[:L.acref_id_run(ha, p64(x), x.size, p64(i64(tok)), tok.size, p64(buf))].copy()
+    ya = []
+    cut_f = 13                                        # two calls, split at a frame boundary (sums of non-dumping frames run on)
+    cut_s = int(sum(O.id_frame_samples(v, NS, CHN) for v in tok[:cut_f]))
+    for xs, ts in ((x[:cut_s], tok[:cut_f]), (x[cut_s:], tok[cut_f:])):
+        xs, ts = i64(xs), i64(ts)
+        buf = np.empty(ts.size * CHN + 1, dtype=np.int64)
+        ya.append(buf[:L.acref_id_run(ha, p64(xs), xs.size, p64(ts), ts.size, p64(buf))].copy())
+    ya = np.concatenate(ya)
     L.acref_id_destroy(ha)
     yb = np.asarray(O.IdB(fi, fa, fo, NS, CHN).run(x, tok)).reshape(-1)
     assert ya.size == yb.size and np.array_equal(ya, yb), (idc[i], ya.size, yb.size)
