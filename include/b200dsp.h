@@ -112,7 +112,10 @@ int b2d_fir_destroy(b2d_fir *h);
  *   CONST: the constructor's pointer (ac_fir_const_coeffs.h:314) -- allowed once.
  *   LOAD : the ld=true phase of run() (ac_fir_load_coeffs.h:324-331).
  *   PROG : the array argument of run() (ac_fir_prog_coeffs.h:277); may change between run() calls,
- *          the delay line is kept.
+ *          the delay line is kept.  Exception: B2D_TRANSPOSED keeps ACC_TYPE partial sums, not samples
+ *          (ac_fir_load_coeffs.h:265-278), so after a change the reference's next n_taps-1 outputs mix old and
+ *          new taps; a CHANGE of taps on a TRANSPOSED filter that has consumed samples returns
+ *          B2D_EUNSUPPORTED (b2d_fir_reset first).  Loading equal values again is not a change.
  * channel = -1 loads every channel.  With a communicator attached (b2d_fir_set_comm) the values of
  * rank `root` are broadcast to all ranks with one ncclBroadcast; other ranks may pass NULL. */
 int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel);
@@ -145,6 +148,9 @@ int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
 const char *b2d_fir_path(b2d_fir *h);
 
 /* ---- CIC: ac_cic_dec_full / ac_cic_intr_full ---------------------------------------------- */
+/* Note on M > 2: the reference's comb shifts its delay line with an ascending copy loop (ac_cic_full_core.h:247-251),
+ * which makes the differential delay min(M, 2) while the lossless internal width still grows with M; the engine
+ * reproduces exactly that. */
 int b2d_cic_create(b2d_cic **h, const b2d_cic_desc *desc);
 int b2d_cic_destroy(b2d_cic *h);
 /* Lossless internal width of find_inter_type_cic_dec / _intr (ac_cic_dec_full.h:132, ac_cic_intr_full.h:122). */
