@@ -42,6 +42,26 @@ def test_facade_compiles_and_fails_loudly_without_gpu(engine, bench_exe, tmp_pat
     assert p.returncode == 70 and "engine_error" in p.stderr, (p.returncode, p.stderr)
 
 
+FACADE_HEADERS = ["ac_fir_const_coeffs", "ac_fir_load_coeffs", "ac_fir_prog_coeffs", "ac_cic_dec_full", "ac_cic_intr_full",
+                  "ac_fir_reg_share", "ac_poly_dec", "ac_poly_intr", "ac_intg_dump"]
+
+
+def test_facade_headers_are_self_contained_and_combinable(tmp_path):
+    """Each facade header compiles on its own (and twice: include guards); all of them share one translation unit --
+    including both CIC headers, which the reference cannot (unguarded `power` template, ac_cic_dec_full.h:94-108 /
+    ac_cic_intr_full.h:90-98) -- except ac_poly_intr, whose polyphase FTYPE enum clashes with the FIR one in the
+    reference as well."""
+    def syntax_only(name, includes):
+        src = tmp_path / (name + ".cpp")
+        src.write_text("".join(f"#include <ac_dsp/{h}.h>\n" for h in includes) + "int main() { return 0; }\n")
+        p = subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", f"-I{ROOT}/include/b200dsp",
+                            f"-I{ROOT}/oracle/ac_shim", str(src)], capture_output=True, text=True)
+        assert p.returncode == 0, (name, p.stderr[-2000:])
+    for h in FACADE_HEADERS:
+        syntax_only(h, [h, h])
+    syntax_only("all", [h for h in FACADE_HEADERS if h != "ac_poly_intr"])
+
+
 def test_facade_marshaling_round_trips_every_storage_tier(engine, tmp_path):
     """include/b200dsp/marshal.h moves ac_fixed values through slc / set_slc only; check it against the shim's
     canonical raw value for 16..64-bit signed and unsigned types (no engine call, CPU)."""
