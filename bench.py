@@ -212,22 +212,28 @@ def cpu_reference(wl, seconds_target=12.0, threads=None):
 
     secs = [0.0] * threads
 
+    passes = [0] * threads
+
     def work(i):
-        t = time.perf_counter()
-        objs[i].run(xs[i])
-        # the reference arm times run() alone (channels pre-filled, drained afterwards): BASELINE.md section 3
-        inner = objs[i].last_run_seconds() if kind == "reference" else None
-        secs[i] = inner if inner else time.perf_counter() - t
+        # the block is filtered again (the object's state simply continues) until the bounded sample has cost about
+        # seconds_target of CPU time per thread; the hot loop got faster than the constants above assumed
+        while passes[i] < 8 and secs[i] < 0.7 * seconds_target:
+            t = time.perf_counter()
+            objs[i].run(xs[i])
+            # the reference arm times run() alone (channels pre-filled, drained afterwards): BASELINE.md section 3
+            inner = objs[i].last_run_seconds() if kind == "reference" else None
+            secs[i] += inner if inner else time.perf_counter() - t
+            passes[i] += 1
     ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     for t in ths:
         t.start()
     for t in ths:
         t.join()
-    rate_real = sum(per_thread / s for s in secs)            # instances run concurrently: rates add
+    rate_real = sum(per_thread * p / s for p, s in zip(passes, secs))   # instances run concurrently: rates add
     rate = rate_real / 2 if wl["unit_is_iq"] else rate_real
     dt = max(secs)
     return {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "seconds": dt,
-            "sample": f"{threads} independent filter instances (one per host thread) x {per_thread} real samples each, "
+            "sample": f"{threads} independent filter instances (one per host thread) x {per_thread} real samples x {max(passes)} pass(es) each, "
                       f"{'reference C++ templates over the ac_types shim (oracle/_ref)' if kind == 'reference' else 'oracle_b.c integer restatement'}"}
 
 
