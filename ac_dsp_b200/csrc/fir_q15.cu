@@ -271,8 +271,10 @@ bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fm
       if (coeff.W + (coeff.S ? 0 : 1) > 15) return false;
       // fall through
     case B2D_FOLD_ODD:
-      // `fold` is ACC_TYPE (ac_fir_load_coeffs.h:248-255): exact only if the pre-add neither truncates nor wraps there
-      return acc.F() >= in.F() && in.W + 1 + (in.S ? 0 : 1) + (acc.F() - in.F()) <= acc.W;
+      // `fold` is ACC_TYPE (ac_fir_load_coeffs.h:248-255): exact only if the pre-add neither truncates nor wraps there;
+      // an unsigned ACC_TYPE wraps every negative pre-add (signed samples, or the _ANTI pre-subtract) before the multiply
+      if (!acc.S && (in.S || ftype == B2D_FOLD_ODD_ANTI)) return false;
+      return acc.F() >= in.F() && in.W + 1 + (in.S ? 0 : 1) + (acc.F() - in.F()) <= acc.W + (acc.S ? 0 : 1);
     default: return false;
   }
 }
@@ -348,7 +350,9 @@ cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st) {
   const size_t stride = (tile + a.Npad + 8 + 7) & ~(size_t)7;
   const size_t smem = (size_t)np * a.pkw * 4 + (size_t)np * stride * 2;
   dim3 grid((unsigned)((p.n + tile - 1) / tile), np == 2 ? 1 : p.C);
-  const int xs = p.fin.S ? 1 : 0, cs = p.fcoeff.S ? 1 : 0;
+  // the mirrored taps of the _ANTI folds are negated by fir_q15_pack: the effective taps are signed whatever COEFF_TYPE is
+  const bool anti = p.ftype == B2D_FOLD_EVEN_ANTI || p.ftype == B2D_FOLD_ODD_ANTI;
+  const int xs = p.fin.S ? 1 : 0, cs = (p.fcoeff.S || anti) ? 1 : 0;
   if (xs && cs) return launch_sc<1, 1>(a, np, fastout, grid, smem, st);
   if (xs && !cs) return launch_sc<1, 0>(a, np, fastout, grid, smem, st);
   if (!xs && cs) return launch_sc<0, 1>(a, np, fastout, grid, smem, st);

@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(kWideThreads) fir_wide_kernel(WideArgs a) {
 // ------------------------------------------------------------------------------------------ host side
 static bool fits_i32(const Fmt &f) { return f.W + (f.S ? 0 : 1) <= 32; }
 
-static bool fold_odd_exact(const Fmt &in, const Fmt &acc) {
-  // `fold` is ACC_TYPE (ac_fir_load_coeffs.h:248-255): exact iff the pre-add neither drops fraction bits nor wraps there
-  return acc.F() >= in.F() && in.W + 1 + (in.S ? 0 : 1) + (acc.F() - in.F()) <= acc.W;
+static bool fold_odd_exact(const Fmt &in, const Fmt &acc, bool anti) {
+  // `fold` is ACC_TYPE (ac_fir_load_coeffs.h:248-255): exact iff the pre-add neither drops fraction bits nor wraps there;
+  // an unsigned ACC_TYPE wraps every negative pre-add (signed samples, or the _ANTI pre-subtract) before the multiply
+  if (!acc.S && (in.S || anti)) return false;
+  return acc.F() >= in.F() && in.W + 1 + (in.S ? 0 : 1) + (acc.F() - in.F()) <= acc.W + (acc.S ? 0 : 1);
 }
 
 int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, int ftype) {
@@ -120,7 +122,7 @@ int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, i
   if (s < -63 || s > 61) return -1;
   const bool anti = ftype == B2D_FOLD_EVEN_ANTI || ftype == B2D_FOLD_ODD_ANTI;
   const bool fold = ftype == B2D_FOLD_EVEN || ftype == B2D_FOLD_ODD || anti;
-  if ((ftype == B2D_FOLD_ODD || ftype == B2D_FOLD_ODD_ANTI) && !fold_odd_exact(in, acc)) return -1;
+  if ((ftype == B2D_FOLD_ODD || ftype == B2D_FOLD_ODD_ANTI) && !fold_odd_exact(in, acc, ftype == B2D_FOLD_ODD_ANTI)) return -1;
   if (s <= 0) return (anti && coeff.W + (coeff.S ? 0 : 1) > 31) ? -1 : 0;   // the mirrored taps are negated
   if (!fold) return 1;
   if (in.W + (in.S ? 0 : 1) > 31) return -1;     // |h * (xa + xb)| must stay below 2^62

@@ -978,7 +978,7 @@ static bool cicfir_fusable(const b2d_cic_desc &cd, const b2d_fir_desc &fd, int i
   switch (fd.ftype) {
     case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: break;
     case B2D_FOLD_ODD:
-      if (!(fa.F() >= mid.F() && mid.W + 1 + (fa.F() - mid.F()) <= fa.W)) return false;
+      if (!fa.S || !(fa.F() >= mid.F() && mid.W + 1 + (fa.F() - mid.F()) <= fa.W)) return false;   // mid is signed: an unsigned fold wraps
       break;
     default: return false;
   }

@@ -39,6 +39,8 @@ FIR_FORMATS = [
     # order-dependent accumulators: saturation / sign-dependent rounding (the reference's tap order matters)
     ("q15_sat", fmt(16, 1), fmt(16, 1), fmt(24, 4, True, TRN, "AC_SAT"), fmt(16, 1, True, "AC_RND_CONV", "AC_SAT_SYM"), [9, 16]),
     ("q15_tz", fmt(16, 1), fmt(16, 1), fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), [10]),
+    # unsigned ACC_TYPE: FOLD_ODD's `fold = ACC_TYPE(a + b)` wraps every negative pre-add before the multiply
+    ("uacc", fmt(16, 1), fmt(16, 1), fmt(40, 8, False), fmt(40, 8, False), [9, 16]),
 ]
 
 
@@ -114,6 +116,11 @@ RS_CONFIGS = [
     (10, _Q15, fmt(12, 1, True, "AC_RND_INF", "AC_SAT"), _Q15, fmt(30, 6, True, "AC_TRN_ZERO", "AC_SAT_ZERO"), 1, 1, 0, "FOLD_EVEN_ANTI"),
     # accumulator too narrow for the pre-add (wrap inside FOLD_ODD_ANTI's `fold`)
     (7, _Q15, fmt(18, 1), _Q15, fmt(18, 1), 1, 1, 0, "FOLD_ODD_ANTI"),
+    # unsigned COEFF_TYPE with an _ANTI fold: the mirrored taps are negative, the effective taps signed
+    (16, _Q15, _ACC40, fmt(14, 1, False), _ACC40, 1, 1, 0, "FOLD_EVEN_ANTI"),
+    (15, _Q15, _ACC40, fmt(12, 0, False), _ACC40, 1, 1, 0, "FOLD_ODD_ANTI"),
+    # everything unsigned: the pre-subtract wraps in the unsigned ACC_TYPE `fold`
+    (9, fmt(12, 0, False), fmt(30, 6, False), fmt(14, 2, False), fmt(30, 6, False), 1, 1, 0, "FOLD_ODD_ANTI"),
 ]
 
 

@@ -18,7 +18,10 @@ PY
   done
 }
 # the random-format engine sweep written at the end of round 1 (never run on a GPU yet)
-B2D_ENGINE_FUZZ=1 timeout 600 python -m pytest tests/test_zz_engine_fuzz.py tests/test_zz_reference_quirks.py -m gpu -q 2>&1 | tail -15 | tee -a gpurun_out/r02_ab_summary.txt
+for seed in 0 1 2 3 4 5; do
+  echo "== engine fuzz seed $seed" | tee -a gpurun_out/r02_ab_summary.txt
+  B2D_FUZZ_SEED=$seed B2D_ENGINE_FUZZ=1 timeout 900 python -m pytest tests/test_zz_engine_fuzz.py tests/test_zz_reference_quirks.py -m gpu -q -rf 2>&1 | tail -40 | tee gpurun_out/r02_engine_fuzz_seed$seed.txt | tail -3 | tee -a gpurun_out/r02_ab_summary.txt
+done
 run base     B2D_UPFIR_WAVES=1
 run waves2   B2D_UPFIR_WAVES=2
 run waves4   B2D_UPFIR_WAVES=4

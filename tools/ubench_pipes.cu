@@ -13,13 +13,15 @@
 
 enum Op { IMAD_LO, IMAD_WIDE, IMAD_WIDE_U, IMAD_HI, DP4A, DP2A, FFMA, FFMA2, DFMA, IADD, IADD64, LOP3,
           MIX_IMAD_IADD, MIX_WIDE_DFMA, MIX_IMAD_FFMA, MIX_IMAD_DFMA, MIX_WIDE_IADD, MIX_WIDE_FFMA, MIX_WIDE_DFMA_21,
-          MIX_WIDE_LDS, MIX_DFMA_IADD, MIX_WIDE_DFMA_IADD, MIX_IMAD_LOP3, MIX_IMAD_SHF, MIX_IMAD_PRMT, MIX_IMAD2_DFMA, MIX_IMAD_DP4A, MIX_IMAD_LDS, SHF, PRMT, NOPS };
+          MIX_WIDE_LDS, MIX_DFMA_IADD, MIX_WIDE_DFMA_IADD, MIX_IMAD_LOP3, MIX_IMAD_SHF, MIX_IMAD_PRMT, MIX_IMAD2_DFMA, MIX_IMAD_DP4A, MIX_IMAD_LDS, SHF, PRMT,
+          MIX_DP2A_FFMA_21, MIX_DP2A_FFMA_41, MIX_DP2A_FFMA_81, MIX_DP2A_IADD_41, MIX_DP2A_PRMT_81, NOPS };
 static const char *kNames[] = {"imad.lo.s32", "imad.wide.s32", "imad.wide.u32", "imad.hi.s32", "dp4a.s32", "dp2a.lo.s32", "ffma.f32",
                                "ffma2.f32x2(2 fma/lane)", "dfma.f64", "iadd.s32", "iadd.s64", "lop3",
                                "mix imad.lo+iadd 1:1", "mix imad.wide+dfma 1:1", "mix imad.lo+ffma 1:1", "mix imad.lo+dfma 1:1",
                                "mix imad.wide+iadd 1:1", "mix imad.wide+ffma 1:1", "mix imad.wide+dfma 2:1",
                                "mix imad.wide+lds32 4:1", "mix dfma+iadd 1:1", "mix imad.wide+dfma+iadd 1:1:1",
-                               "mix imad.lo+lop3 1:1", "mix imad.lo+shf 1:1", "mix imad.lo+prmt 1:1", "mix imad.lo+dfma 2:1", "mix imad.lo+dp4a 1:1", "mix imad.lo+lds32 8:1", "shf.r", "prmt"};
+                               "mix imad.lo+lop3 1:1", "mix imad.lo+shf 1:1", "mix imad.lo+prmt 1:1", "mix imad.lo+dfma 2:1", "mix imad.lo+dp4a 1:1", "mix imad.lo+lds32 8:1", "shf.r", "prmt",
+                               "mix dp2a+ffma 2:1", "mix dp2a+ffma 4:1", "mix dp2a+ffma 8:1", "mix dp2a+iadd 4:1", "mix dp2a+prmt 8:1"};
 
 constexpr int K = 8;        // independent accumulators per thread
 constexpr int UNROLL = 32;  // "taps" per loop trip; every (x[(k+u)&7], h[u]) product in a trip is distinct
@@ -34,6 +36,9 @@ __global__ void __launch_bounds__(512, 1) bench(int iters, int32_t a0, int32_t b
   __syncthreads();
   constexpr bool kInt = (OP != FFMA && OP != FFMA2 && OP != DFMA && OP != MIX_DFMA_IADD);
   constexpr bool kF32 = (OP == FFMA || OP == MIX_IMAD_FFMA || OP == MIX_WIDE_FFMA);
+  // r02: would the FMA-lite pipe take exact-integer FFMAs next to a full DP2A stream?  
+  constexpr int kSide = OP == MIX_DP2A_FFMA_21 ? 2 : ((OP == MIX_DP2A_FFMA_41 || OP == MIX_DP2A_IADD_41) ? 4 : ((OP == MIX_DP2A_FFMA_81 || OP == MIX_DP2A_PRMT_81) ? 8 : 0));
+  constexpr bool kSideF = (OP == MIX_DP2A_FFMA_21 || OP == MIX_DP2A_FFMA_41 || OP == MIX_DP2A_FFMA_81);
   constexpr bool kF64 = (OP == MIX_IMAD2_DFMA || OP == DFMA || OP == MIX_WIDE_DFMA || OP == MIX_IMAD_DFMA || OP == MIX_WIDE_DFMA_21 || OP == MIX_DFMA_IADD || OP == MIX_WIDE_DFMA_IADD);
   int32_t b = b0 - threadIdx.x;
   int32_t x[8], h[UNROLL], r[K], q[K];
@@ -82,8 +87,14 @@ __global__ void __launch_bounds__(512, 1) bench(int iters, int32_t a0, int32_t b
           asm volatile("mad.hi.s32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(x[xi]), "r"(h[u]));
         if (OP == DP4A)
           asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(x[xi]), "r"(h[u]));
-        if (OP == DP2A)
+        if (OP == DP2A || kSide)
           asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(x[xi]), "r"(h[u]));
+        if (kSide && kSideF && (k % kSide) == 0)
+          asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f[k]) : "f"(xf[xi]), "f"(hf[u]));
+        if (OP == MIX_DP2A_IADD_41 && (k % kSide) == 0)
+          asm volatile("add.s32 %0, %0, %1;" : "+r"(q[k]) : "r"(x[xi]));
+        if (OP == MIX_DP2A_PRMT_81 && (k % kSide) == 0)
+          asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(q[k]) : "r"(x[xi]), "r"(h[u]));
         if (kF32)
           asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f[k]) : "f"(xf[xi]), "f"(hf[u]));
         if (OP == FFMA2)
@@ -106,7 +117,7 @@ __global__ void __launch_bounds__(512, 1) bench(int iters, int32_t a0, int32_t b
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       if (kInt) x[i] += b;
-      if (kF32) xf[i] += 1e-7f;
+      if (kF32 || kSideF) xf[i] += 1e-7f;
       if (kF64) xd[i] += 1e-9;
       if (OP == FFMA2) x2[i] += 2;
     }
@@ -149,7 +160,12 @@ int run_one(int sms, int blocks_per_sm, long long *d_sink, long long *d_cyc) {
   free(h);
   double lane_ops_per_sm = (double)iters * UNROLL * K * ops_per_body(OP) * 512.0 * blocks_per_sm;
   if (OP == MIX_WIDE_LDS || OP == MIX_IMAD_LDS) lane_ops_per_sm = (double)iters * UNROLL * K * 512.0 * blocks_per_sm;  // count the IMADs only
+  double side = 0;   // r02 mixes: report the DP2A rate; the side stream rides along at 1/ratio of it
+  if (OP == MIX_DP2A_FFMA_21) side = 2; else if (OP == MIX_DP2A_FFMA_41 || OP == MIX_DP2A_IADD_41) side = 4; else if (OP == MIX_DP2A_FFMA_81 || OP == MIX_DP2A_PRMT_81) side = 8;
   double total = lane_ops_per_sm * sms;
+  if (side > 0)
+    printf("{\"op\": \"%s\", \"dp2a_lane_ops_per_clk_per_sm\": %.2f, \"side_lane_ops_per_clk_per_sm\": %.2f, \"note\": \"dp2a alone = 63.7\"}\n",
+           kNames[OP], lane_ops_per_sm / (double)mx, lane_ops_per_sm / (double)mx / side);
   printf("{\"op\": \"%s\", \"blocks_per_sm\": %d, \"lane_ops_per_clk_per_sm\": %.2f, \"tera_ops_per_s\": %.3f, \"ms\": %.3f, \"eff_clock_mhz\": %.0f}\n",
          kNames[OP], blocks_per_sm, lane_ops_per_sm / (double)mx, total / (ms * 1e-3) / 1e12, ms, (double)mx / (ms * 1e3));
   return 0;
