@@ -12,6 +12,7 @@ O_MODES = ["AC_WRAP", "AC_SAT", "AC_SAT_ZERO", "AC_SAT_SYM"]
 FTYPES = ["SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED", "FOLD_EVEN_ANTI", "FOLD_ODD_ANTI"]
 FIR_KINDS = ["const", "load", "prog", "reg_share"]
 PLANAR, INTERLEAVED = 0, 1
+WIRE_CONTAINER, WIRE_PACKED = 0, 1
 
 OK, EUNSUPPORTED, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6
 
@@ -114,6 +115,9 @@ def load():
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),
+        "b2d_wire_bytes": (C.c_int, [i32, i32]), "b2d_unpack_wire": (C.c_int, [vp, sz, i32, i32, vp]),
+        "b2d_fir_set_wire": (C.c_int, [vp, i32]), "b2d_cic_set_wire": (C.c_int, [vp, i32]), "b2d_cicfir_set_wire": (C.c_int, [vp, i32]),
+        "b2d_polydec_set_wire": (C.c_int, [vp, i32]), "b2d_polyintr_set_wire": (C.c_int, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -26,23 +26,29 @@ struct FirGenArgs {
   size_t n;
   const void *tail;
   const int64_t *h;
+  // TRANSPOSED across a coefficient change (see launch_fir_pending below): outputs i < n_limit only; the accumulator of
+  // output i < N-1 starts from acc_init[c][i] (the partial sums the old taps left in reg_trans[]); acc_out != null: the
+  // inputs of this call are zeros and the raw ACC_TYPE accumulators are written to acc_out[c][i] instead of y.
+  size_t n_limit;
+  const int64_t *acc_init;
+  int64_t *acc_out;
 };
 
 __device__ __forceinline__ int64_t fir_gen_sample(const FirGenArgs &a, uint32_t c, size_t i, int k) {
   const int T = a.N - 1;
-  if ((size_t)k <= i) return load_raw(a.x, elem_index(i - k, c, a.n, a.C, a.interleaved), a.in_bytes, a.in.S);
+  if ((size_t)k <= i) return a.acc_out ? 0 : load_raw(a.x, elem_index(i - k, c, a.n, a.C, a.interleaved), a.in_bytes, a.in.S);
   return load_raw(a.tail, (size_t)c * T + (size_t)(T - (k - (int64_t)i)), a.in_bytes, a.in.S);
 }
 
 __global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
-  const size_t total = a.n * a.C;
+  const size_t total = a.n_limit * a.C;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t c = a.interleaved ? (uint32_t)(t % a.C) : (uint32_t)(t / a.n);
-    const size_t i = a.interleaved ? t / a.C : t % a.n;
+    const uint32_t c = a.interleaved ? (uint32_t)(t % a.C) : (uint32_t)(t / a.n_limit);
+    const size_t i = a.interleaved ? t / a.C : t % a.n_limit;
     const int64_t *h = a.h + (size_t)c * a.N;
     const int N = a.N;
     const int Fin = a.in.F(), Fc = a.coeff.F(), Fa = a.acc.F();
-    int64_t acc = 0;
+    int64_t acc = (a.acc_init && i < (size_t)(N - 1)) ? a.acc_init[(size_t)c * (N - 1) + i] : 0;
     // _ANTI: pre-subtract instead of pre-add (ac_fir_reg_share.h:151-165,186-205)
     const int anti = a.ftype == B2D_FOLD_EVEN_ANTI || a.ftype == B2D_FOLD_ODD_ANTI;
     switch (a.ftype) {
@@ -81,7 +87,8 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
         break;
       default: break;
     }
-    store_raw(a.y, elem_index(i, c, a.n, a.C, a.interleaved), a.out_bytes, convert((i128)acc, Fa, a.out));
+    if (a.acc_out) a.acc_out[(size_t)c * (N - 1) + i] = acc;
+    else store_raw(a.y, elem_index(i, c, a.n, a.C, a.interleaved), a.out_bytes, convert((i128)acc, Fa, a.out));
   }
 }
 
@@ -92,10 +99,49 @@ cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st) {
   a.N = p.n_taps; a.ftype = p.ftype; a.ascending = p.ascending; a.C = p.C; a.interleaved = p.interleaved;
   a.in_bytes = container_bytes(p.fin.W); a.out_bytes = container_bytes(p.fout.W);
   a.x = p.in; a.y = p.out; a.n = p.n; a.tail = p.tail; a.h = p.coeff64;
+  a.n_limit = p.n; a.acc_init = nullptr; a.acc_out = nullptr;
   const size_t total = p.n * p.C;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
   fir_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// TRANSPOSED keeps ACC_TYPE partial sums, not samples (reg_trans[], ac_fir_load_coeffs.h:265-278, ac_fir_prog_coeffs.h:232-247):
+//   y[n] = q(..q(q(x[n-N+1] h'[N-1]) + x[n-N+2] h''[N-2]).. + x[n] h[0]),  each tap taken from the set that was active
+// when ITS sample arrived.  The engine carries samples; at a coefficient change the runtime turns the history into the
+// N-1 pending partial sums (old taps over the history followed by zeros: acc_out mode), clears the history, and the first
+// N-1 outputs after the change start their accumulators from those sums (acc_init mode) -- in the reference's own order
+// (oldest first), so saturating / sign-dependent ACC_TYPEs come out right as well.
+cudaError_t launch_fir_pending(const FirLaunch &p, size_t n_limit, const int64_t *acc_init, int64_t *acc_out, cudaStream_t st) {
+  if (n_limit == 0 || p.n_taps < 2) return cudaSuccess;
+  FirGenArgs a;
+  a.in = p.fin; a.coeff = p.fcoeff; a.acc = p.facc; a.out = p.fout;
+  a.N = p.n_taps; a.ftype = B2D_TRANSPOSED; a.ascending = 0; a.C = p.C; a.interleaved = p.interleaved;
+  a.in_bytes = container_bytes(p.fin.W); a.out_bytes = container_bytes(p.fout.W);
+  a.x = p.in; a.y = p.out; a.n = p.n; a.tail = p.tail; a.h = p.coeff64;
+  a.n_limit = n_limit; a.acc_init = acc_init; a.acc_out = acc_out;
+  const size_t total = n_limit * p.C;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  fir_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// pending[c][j] <- pending[c][j + n] (zeros shifted in): n more outputs have consumed their partial sums
+__global__ void fir_pending_shift_kernel(const int64_t *src, int64_t *dst, size_t n, int T, uint32_t C) {
+  const size_t total = (size_t)T * C;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = t % T;
+    dst[t] = j + n < (size_t)T ? src[t + n] : 0;
+  }
+}
+cudaError_t launch_fir_pending_shift(const int64_t *src, int64_t *dst, size_t n, int T, uint32_t C, cudaStream_t st) {
+  if (T <= 0) return cudaSuccess;
+  const size_t total = (size_t)T * C;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  fir_pending_shift_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n, T, C);
   return cudaGetLastError();
 }
 

@@ -24,6 +24,10 @@ struct FirLaunch {
 
 // generic path: every format / ftype / Q / O, reference tap order, 128-bit intermediates.
 cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st);
+// TRANSPOSED across a coefficient change (fir_generic.cu): outputs i < n_limit with accumulators started from
+// acc_init[C][n_taps-1] (may be null); acc_out != null: zero inputs, raw ACC_TYPE accumulators to acc_out[C][n_taps-1].
+cudaError_t launch_fir_pending(const FirLaunch &p, size_t n_limit, const int64_t *acc_init, int64_t *acc_out, cudaStream_t st);
+cudaError_t launch_fir_pending_shift(const int64_t *src, int64_t *dst, size_t n, int T, uint32_t C, cudaStream_t st);
 // q15 path: W_in, W_c <= 16 in int16 containers, exact left-shift accumulate, DP2A byte planes.
 bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
 void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
@@ -143,5 +147,8 @@ int upfir_q15_planes(int max_abs_bits);
 int upfir_q15_words(int R, int taps_total, int planes);
 void upfir_q15_pack(const int64_t *c, int taps_total, int R, int planes, uint32_t *out);
 cudaError_t launch_upfir_q15(const UpLaunch &p, cudaStream_t st);
+
+// Packed host-link format (wire.cu): `count` values in 2 / 4 / 8-byte containers -> wire_bytes (< container) bytes each.
+cudaError_t launch_pack_wire(const void *src, int container_bytes, void *dst, int wire_bytes, size_t count, cudaStream_t st);
 
 }  // namespace b2d

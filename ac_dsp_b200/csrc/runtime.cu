@@ -1,49 +1,28 @@
-// runtime.cu -- host runtime behind the C-ABI of include/b200dsp.h: handles, descriptor validation,
-// kernel-family dispatch, history carry between run() calls, the pipelined host-buffer path and the
-// NCCL coefficient broadcast.  No CPU compute path exists: every run() ends in a CUDA kernel launch.
-#include <algorithm>
-#include <cstdarg>
-#include <cstdio>
+// runtime.cu -- the part of the host runtime behind include/b200dsp.h that every handle family shares: error text,
+// page-locked host buffers, the device slots and streams of the pipelined host-buffer path (the loop itself is the
+// template in rt_common.h), the NCCL communicator and checkpoint blobs.  The handle families live in rt_fir.cu, rt_cic.cu,
+// rt_poly.cu, rt_intgdump.cu and rt_mvavg.cu.  No CPU compute path exists: every run() ends in a CUDA kernel launch.
 #include <cctype>
-#include <cstdlib>
-#include <cstring>
 #include <map>
 #include <mutex>
-#include <new>
-#include <string>
-#include <vector>
 
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 
-#include <nvtx3/nvToolsExt.h>
-
-#include "kernels.h"
-#include "nccl_dl.h"
+#include "rt_common.h"
 
 using namespace b2d;
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-static int fail(int status, const char *fmt, ...) {
+int b2d::fail(int status, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return status;
 }
-// NVTX range per load / run entry point (tracing): header-only NVTX 3, a no-op unless a tool is attached
-struct TraceRange {
-  explicit TraceRange(const char *name) { nvtxRangePushA(name); }
-  ~TraceRange() { nvtxRangePop(); }
-};
-#define CU(expr)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e__ = (expr);                                                                         \
-    if (e__ != cudaSuccess) return fail(B2D_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
-
 extern "C" const char *b2d_version(void) { return "b200dsp 0.1 (sm_100a)"; }
 extern "C" const char *b2d_last_error(void) { return g_err; }
 extern "C" const char *b2d_strerror(int s) {
@@ -129,8 +108,7 @@ extern "C" int b2d_host_free(void *p) {
   return B2D_OK;
 }
 
-static Fmt to_fmt(const b2d_fmt &f) { return Fmt{f.W, f.I, f.S ? 1 : 0, f.Q, f.O}; }
-static int check_fmt(const b2d_fmt &f, int maxW, const char *what) {
+int b2d::check_fmt(const b2d_fmt &f, int maxW, const char *what) {
   if (f.W < 1 || f.W > 64) return fail(B2D_EINVAL, "%s: width %d outside 1..64", what, f.W);
   if (f.W > maxW) return fail(B2D_EUNSUPPORTED, "%s: width %d > %d", what, f.W, maxW);
   if (f.I < -64 || f.I > 128) return fail(B2D_EUNSUPPORTED, "%s: integer width %d outside -64..128", what, f.I);
@@ -138,7 +116,7 @@ static int check_fmt(const b2d_fmt &f, int maxW, const char *what) {
   if (f.O < B2D_WRAP || f.O > B2D_SAT_SYM) return fail(B2D_EINVAL, "%s: bad overflow mode %d", what, f.O);
   return B2D_OK;
 }
-static int use_device(int dev) {
+int b2d::use_device(int dev) {
   int cur = -1;
   CU(cudaGetDevice(&cur));
   if (cur != dev) CU(cudaSetDevice(dev));
@@ -149,58 +127,51 @@ static int use_device(int dev) {
 // run() on HOST buffers: the stream is cut into chunks; chunk i+1 is copied in while chunk i computes
 // and chunk i-1 is copied out (three streams, three device slots).  Each chunk is an ordinary run_dev()
 // call, so the result is the reference's own "several run() calls" behaviour by construction.
-struct Pipe {
-  static const int S = 3;
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  cudaEvent_t e_in[S] = {}, e_k[S] = {}, e_out[S] = {};
-  void *d_in[S] = {}, *d_out[S] = {};
-  size_t cap_in = 0, cap_out = 0;
-  bool ready = false;
-  int init() {
-    if (ready) return B2D_OK;
-    CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < S; i++) {
-      CU(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming));
-    }
-    ready = true;
-    return B2D_OK;
+int Pipe::init() {
+  if (ready) return B2D_OK;
+  CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < S; i++) {
+    CU(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming));
   }
-  int ensure(size_t in_bytes, size_t out_bytes) {
-    if (in_bytes > cap_in) {
-      for (int i = 0; i < S; i++) { if (d_in[i]) cudaFree(d_in[i]); d_in[i] = nullptr; }
-      cap_in = 0;
-      for (int i = 0; i < S; i++) if (cudaMalloc(&d_in[i], in_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", in_bytes); }
-      cap_in = in_bytes;
-    }
-    if (out_bytes > cap_out) {
-      for (int i = 0; i < S; i++) { if (d_out[i]) cudaFree(d_out[i]); d_out[i] = nullptr; }
-      cap_out = 0;
-      for (int i = 0; i < S; i++) if (cudaMalloc(&d_out[i], out_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", out_bytes); }
-      cap_out = out_bytes;
-    }
-    return B2D_OK;
+  ready = true;
+  return B2D_OK;
+}
+static int grow_slots(void **slots, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return B2D_OK;
+  for (int i = 0; i < Pipe::S; i++) { if (slots[i]) cudaFree(slots[i]); slots[i] = nullptr; }
+  *cap = 0;
+  for (int i = 0; i < Pipe::S; i++)
+    if (cudaMalloc(&slots[i], bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", bytes); }
+  *cap = bytes;
+  return B2D_OK;
+}
+int Pipe::ensure(size_t in_bytes, size_t out_bytes, size_t pk_bytes) {
+  int st;
+  if ((st = grow_slots(d_in, &cap_in, in_bytes))) return st;
+  if ((st = grow_slots(d_out, &cap_out, out_bytes))) return st;
+  return grow_slots(d_pk, &cap_pk, pk_bytes);
+}
+void Pipe::destroy() {
+  for (int i = 0; i < S; i++) {
+    if (d_in[i]) cudaFree(d_in[i]);
+    if (d_out[i]) cudaFree(d_out[i]);
+    if (d_pk[i]) cudaFree(d_pk[i]);
+    if (e_in[i]) cudaEventDestroy(e_in[i]);
+    if (e_k[i]) cudaEventDestroy(e_k[i]);
+    if (e_out[i]) cudaEventDestroy(e_out[i]);
   }
-  void destroy() {
-    for (int i = 0; i < S; i++) {
-      if (d_in[i]) cudaFree(d_in[i]);
-      if (d_out[i]) cudaFree(d_out[i]);
-      if (e_in[i]) cudaEventDestroy(e_in[i]);
-      if (e_k[i]) cudaEventDestroy(e_k[i]);
-      if (e_out[i]) cudaEventDestroy(e_out[i]);
-    }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_k) cudaStreamDestroy(s_k);
-    if (s_out) cudaStreamDestroy(s_out);
-  }
-};
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_k) cudaStreamDestroy(s_k);
+  if (s_out) cudaStreamDestroy(s_out);
+}
 
 // copy `len` samples per channel starting at time `off` between a full buffer (n_full per channel) and a
 // compact chunk buffer (len per channel)
-static cudaError_t copy_chunk(void *dst, const void *src, bool to_device, int bytes, uint32_t C, int interleaved,
+cudaError_t b2d::copy_chunk(void *dst, const void *src, bool to_device, int bytes, uint32_t C, int interleaved,
                               size_t n_full, size_t off, size_t len, cudaStream_t st) {
   if (len == 0) return cudaSuccess;
   const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
@@ -213,14 +184,6 @@ static cudaError_t copy_chunk(void *dst, const void *src, bool to_device, int by
 }
 
 // ----------------------------------------------------------------------------------------------- comm
-struct b2d_comm {
-  ncclComm_t comm = nullptr;
-  int rank = 0, world = 1, device = 0;
-  cudaStream_t stream = nullptr;
-  void *d_buf = nullptr;
-  size_t cap = 0;
-};
-
 static int nccl_fail(const NcclApi *api, int rc, const char *what) {
   return fail(B2D_ENCCL, "%s: %s", what, api->GetErrorString(rc));
 }
@@ -293,7 +256,7 @@ extern "C" int b2d_comm_barrier(b2d_comm *c) {
   return B2D_OK;
 }
 // values[0..n) of rank `root` -> every rank (int64 payload), synchronous.
-static int comm_bcast_i64(b2d_comm *c, int64_t *values, size_t n, int root) {
+int b2d::comm_bcast_i64(b2d_comm *c, int64_t *values, size_t n, int root) {
   const NcclApi *api = nccl_api(nullptr);
   int st = use_device(c->device);
   if (st) return st;
@@ -306,346 +269,13 @@ static int comm_bcast_i64(b2d_comm *c, int64_t *values, size_t n, int root) {
   return B2D_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ FIR
-enum { PATH_GENERIC = 0, PATH_Q15 = 1, PATH_WIDE = 2 };
-
-struct b2d_fir {
-  b2d_fir_desc d;
-  Fmt fin, fc, fa, fo;
-  int device = 0, T = 0, in_bytes = 2, out_bytes = 2, c_bytes = 2;
-  int path = PATH_GENERIC;
-  std::vector<int64_t> h_coeff;   // [C][N] raw, wrapped to COEFF_TYPE
-  std::vector<char> ch_loaded;    // per channel
-  int64_t *d_coeff64 = nullptr;
-  uint32_t *d_coeff_pk = nullptr;
-  int pk_words = 0;
-  int32_t *d_coeff32 = nullptr;
-  int wide_words = 0, wide_mode = 0;
-  void *d_tail[2] = {nullptr, nullptr};
-  int cur = 0;
-  b2d_comm *comm = nullptr;
-  int root = 0;
-  int64_t *d_dl = nullptr;        // REG_SHARE: OUT_TYPE(reg[N_TAPS-1]) per channel
-  bool ran = false;               // samples were filtered since create / reset (see the TRANSPOSED rule in b2d_fir_load)
-  void *d_win = nullptr;          // run_window scratch: [C][N_TAPS-1] tail, [C] newest samples, [C] outputs, [C][N_TAPS-1] dummy tail
-  Pipe pipe;
-};
-
-static bool all_loaded(const b2d_fir *h) {
-  for (char c : h->ch_loaded) if (!c) return false;
-  return true;
-}
-
-extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
-  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int st;
-  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
-  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
-  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
-  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
-  if (desc->n_taps < 1 || desc->n_taps > (1u << 20)) return fail(B2D_EINVAL, "n_taps %u outside 1..2^20", desc->n_taps);
-  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
-  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
-  if (desc->kind < B2D_FIR_CONST || desc->kind > B2D_FIR_REG_SHARE) return fail(B2D_EINVAL, "bad kind");
-  if (desc->ftype < B2D_SHIFT_REG || desc->ftype > B2D_FOLD_ODD_ANTI) return fail(B2D_EINVAL, "bad ftype");
-  const bool anti_ft = desc->ftype == B2D_FOLD_EVEN_ANTI || desc->ftype == B2D_FOLD_ODD_ANTI;
-  if (desc->kind != B2D_FIR_REG_SHARE && anti_ft)
-    return fail(B2D_EUNSUPPORTED, "the const / load / prog FIR classes do not dispatch the _ANTI architectures (output left unwritten)");
-  if (desc->kind == B2D_FIR_REG_SHARE && (desc->ftype == B2D_ROTATE_SHIFT || desc->ftype == B2D_C_BUFF || desc->ftype == B2D_TRANSPOSED))
-    return fail(B2D_EUNSUPPORTED, "ac_fir_reg_share does not dispatch this architecture (output left unwritten)");
-  Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
-  {  // bit budget of the 128-bit generic evaluation
-    const int Fp = desc->ftype == B2D_FOLD_ODD ? fc.F() + fa.F() : fin.F() + fc.F();
-    const int Wp = desc->ftype == B2D_FOLD_ODD ? fc.W + fa.W : fin.W + fc.W + 2;
-    const int rF = std::max(Fp, fa.F());
-    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + std::max(0, fo.F() - fa.F()) > 125 ||
-        (desc->ftype == B2D_FOLD_ODD && fin.W + 1 + std::max(0, fa.F() - fin.F()) > 125))
-      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
-  }
-  int dev = desc->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_fir *h = new (std::nothrow) b2d_fir();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
-  h->T = (int)desc->n_taps - 1;
-  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
-  const uint32_t C = desc->n_channels;
-  const size_t N = desc->n_taps;
-  h->h_coeff.assign(C * N, 0);
-  h->ch_loaded.assign(C, 0);
-  h->path = fir_q15_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q15
-            : (fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_WIDE : PATH_GENERIC);
-  const char *force = getenv("B2D_FORCE_GENERIC");
-  if (force && *force == '1') h->path = PATH_GENERIC;
-  if (force && *force == '2' && fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype)) h->path = PATH_WIDE;
-  cudaError_t e = cudaMalloc(&h->d_coeff64, C * N * sizeof(int64_t));
-  const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-    e = cudaMalloc(&h->d_tail[i], tail_bytes);
-    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
-  }
-  if (e == cudaSuccess && h->path == PATH_Q15) {
-    h->pk_words = fir_q15_pk_words((int)N, desc->ftype);
-    e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
-  }
-  if (e == cudaSuccess && desc->kind == B2D_FIR_REG_SHARE) {
-    e = cudaMalloc(&h->d_dl, C * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMemset(h->d_dl, 0, C * sizeof(int64_t));
-  }
-  if (e == cudaSuccess && h->path == PATH_WIDE) {
-    h->wide_words = fir_wide_words((int)N);
-    h->wide_mode = fir_wide_mode(fin, fc, fa, (int)N, desc->ftype);
-    e = cudaMalloc(&h->d_coeff32, (size_t)C * h->wide_words * sizeof(int32_t));
-  }
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    b2d_fir_destroy(h);
-    return fail(e == cudaErrorMemoryAllocation ? B2D_ENOMEM : B2D_ECUDA, "b2d_fir_create: %s", cudaGetErrorString(e));
-  }
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_destroy(b2d_fir *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  h->pipe.destroy();
-  if (h->d_coeff64) cudaFree(h->d_coeff64);
-  if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
-  if (h->d_coeff32) cudaFree(h->d_coeff32);
-  if (h->d_dl) cudaFree(h->d_dl);
-  if (h->d_win) cudaFree(h->d_win);
-  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
-  delete h;
-  return B2D_OK;
-}
-
-extern "C" const char *b2d_fir_path(b2d_fir *h) { return !h ? "" : (h->path == PATH_Q15 ? "fir_q15" : (h->path == PATH_WIDE ? "fir_wide" : "fir_generic")); }
-
-extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  if (comm && (root < 0 || root >= comm->world)) return fail(B2D_EINVAL, "root %d outside the communicator", root);
-  h->comm = comm; h->root = root;
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel) {
-  TraceRange trace__("b2d_fir_load");
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  const size_t N = h->d.n_taps;
-  const uint32_t C = h->d.n_channels;
-  if (n != N) return fail(B2D_EINVAL, "expected %zu coefficients, got %zu", N, n);
-  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
-  const bool have_local = !h->comm || h->comm->rank == h->root;
-  if (have_local && !coeff_raw) return fail(B2D_EINVAL, "null coefficient pointer");
-  if (h->d.kind == B2D_FIR_CONST) {  // ac_fir_const_coeffs: the pointer is bound once, at construction
-    for (uint32_t c = 0; c < C; c++)
-      if ((channel < 0 || (uint32_t)channel == c) && h->ch_loaded[c])
-        return fail(B2D_ESTATE, "constant-coefficient filter: coefficients are fixed at construction");
-  }
-  int st = use_device(h->device);
-  if (st) return st;
-  std::vector<int64_t> v(N, 0);
-  if (have_local) {
-    for (size_t i = 0; i < N; i++) {
-      int64_t r;
-      if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
-      else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
-      else r = ((const int64_t *)coeff_raw)[i];
-      v[i] = wrap_bits(r, h->fc.W, h->fc.S);
-    }
-  }
-  if (h->comm && (st = comm_bcast_i64(h->comm, v.data(), N, h->root))) return st;
-  // TRANSPOSED keeps ACC_TYPE partial sums as its state (reg_trans[], ac_fir_load_coeffs.h:265-278): after a coefficient
-  // change the next N_TAPS-1 outputs of the reference mix old-tap partial sums with new-tap products, which a window of
-  // input history cannot reproduce.  Equal to the direct form only while the taps stay put -- so a CHANGE of taps on a
-  // filter that has already consumed samples is refused (reset() first), never approximated.  Re-loading the same taps
-  // (ac_fir_prog_coeffs passes its array on every call) is not a change.
-  if (h->d.ftype == B2D_TRANSPOSED && h->ran) {
-    for (uint32_t c = 0; c < C; c++) {
-      if (channel >= 0 && (uint32_t)channel != c) continue;
-      if (h->ch_loaded[c] && !std::equal(v.begin(), v.end(), h->h_coeff.begin() + (size_t)c * N))
-        return fail(B2D_EUNSUPPORTED, "coefficient change on a TRANSPOSED filter mid-stream: the reference's partial sums keep the "
-                                      "old taps for N_TAPS-1 outputs; call reset() first or use another architecture");
-    }
-  }
-  // the coefficient set may be swapped between run() calls while earlier launches are still in flight
-  CU(cudaDeviceSynchronize());
-  for (uint32_t c = 0; c < C; c++) {
-    if (channel >= 0 && (uint32_t)channel != c) continue;
-    std::copy(v.begin(), v.end(), h->h_coeff.begin() + c * N);
-    h->ch_loaded[c] = 1;
-    CU(cudaMemcpy(h->d_coeff64 + c * N, v.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (h->path == PATH_Q15) {
-      std::vector<uint32_t> pk(h->pk_words, 0);
-      fir_q15_pack(h->fc, v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
-      CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    }
-    if (h->path == PATH_WIDE) {
-      std::vector<int32_t> w(h->wide_words, 0);
-      fir_wide_pack(v.data(), (int)N, h->d.ftype, h->wide_mode, w.data(), h->wide_words);
-      CU(cudaMemcpy(h->d_coeff32 + (size_t)c * h->wide_words, w.data(), h->wide_words * sizeof(int32_t), cudaMemcpyHostToDevice));
-    }
-  }
-  return B2D_OK;
-}
-
-static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaStream_t st) {
-  if (n == 0) return B2D_OK;
-  FirLaunch p;
-  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
-  p.n_taps = (int)h->d.n_taps; p.ftype = h->d.ftype; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
-  p.ascending = h->d.kind == B2D_FIR_REG_SHARE;
-  p.in = d_in; p.out = d_out; p.n = n;
-  p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1];
-  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
-  CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : (h->path == PATH_WIDE ? launch_fir_wide(p, st) : launch_fir_generic(p, st)));
-  if (h->d_dl) CU(launch_fir_delay_out(p, h->d_dl, st));
-  CU(launch_fir_tail(p, st));
-  h->cur ^= 1;
-  h->ran = true;
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_fir_run_dev");
-  if (!h || (n && (!d_in || !d_out))) return fail(B2D_EINVAL, "null argument");
-  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
-  int st = use_device(h->device);
-  if (st) return st;
-  if ((st = fir_launch(h, d_in, n, d_out, (cudaStream_t)cuda_stream))) return st;
-  if (n_out) *n_out = n;
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_run(b2d_fir *h, const void *in, size_t n, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_fir_run");
-  if (!h || (n && (!in || !out))) return fail(B2D_EINVAL, "null argument");
-  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
-  if (n_out) *n_out = n;
-  if (n == 0) return B2D_OK;
-  int st = use_device(h->device);
-  if (st) return st;
-  Pipe &P = h->pipe;
-  if ((st = P.init())) return st;
-  const uint32_t C = h->d.n_channels;
-  const int il = h->d.layout == B2D_INTERLEAVED;
-  const size_t per = (size_t)C * (h->in_bytes + h->out_bytes);
-  size_t L = std::max<size_t>((size_t)(96u << 20) / per, 4096);  // ~96 MiB of traffic per chunk
-  L = std::min(L, n);
-  if ((st = P.ensure(L * C * h->in_bytes, L * C * h->out_bytes))) return st;
-  size_t i = 0;
-  for (size_t off = 0; off < n; off += L, i++) {
-    const int s = (int)(i % Pipe::S);
-    const size_t len = std::min(L, n - off);
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
-    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
-    CU(cudaEventRecord(P.e_in[s], P.s_in));
-    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
-    if ((st = fir_launch(h, P.d_in[s], len, P.d_out[s], P.s_k))) return st;
-    CU(cudaEventRecord(P.e_k[s], P.s_k));
-    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
-    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, il, n, off, len, P.s_out));
-    CU(cudaEventRecord(P.e_out[s], P.s_out));
-  }
-  CU(cudaStreamSynchronize(P.s_out));
-  CU(cudaStreamSynchronize(P.s_k));
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_reset(b2d_fir *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
-  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
-  if (h->d_dl) CU(cudaMemset(h->d_dl, 0, h->d.n_channels * sizeof(int64_t)));
-  h->ran = false;
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_load_blocked(b2d_fir *h, const void *ram, size_t n_ram, uint32_t mww, uint32_t bs, uint32_t bo, int32_t channel) {
-  TraceRange trace__("b2d_fir_load_blocked");
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  if (bs < 1 || mww < 1) return fail(B2D_EINVAL, "mem_word_width and blk_sz must be >= 1");
-  const size_t N = h->d.n_taps;
-  const int ft = h->d.ftype;
-  const size_t used = (ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI) ? N / 2 : ((ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI) ? (N - 1) / 2 + 1 : N);
-  if (used % bs) return fail(B2D_EUNSUPPORTED, "tap loop length %zu is not a multiple of blk_sz %u (the reference reads its delay line out of range)", used, bs);
-  const size_t need = used ? (used / bs - 1) * (size_t)mww + bo + bs : 0;
-  const bool have_local = !h->comm || h->comm->rank == h->root;
-  if (have_local && (!ram || n_ram < need)) return fail(B2D_EINVAL, "coefficient RAM needs %zu words, got %zu", need, n_ram);
-  std::vector<unsigned char> taps(N * (size_t)h->c_bytes, 0);
-  if (have_local)
-    for (size_t t = 0; t < used; t++)
-      memcpy(&taps[t * h->c_bytes], (const char *)ram + ((t / bs) * (size_t)mww + bo + t % bs) * h->c_bytes, h->c_bytes);
-  return b2d_fir_load(h, have_local ? taps.data() : nullptr, N, channel);
-}
-
-extern "C" int b2d_fir_delay_line_out(b2d_fir *h, void *out_raw) {
-  if (!h || !out_raw) return fail(B2D_EINVAL, "null argument");
-  if (!h->d_dl) return fail(B2D_ESTATE, "delay-line output exists for B2D_FIR_REG_SHARE handles only");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  std::vector<int64_t> v(h->d.n_channels);
-  CU(cudaMemcpy(v.data(), h->d_dl, v.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
-  for (size_t c = 0; c < v.size(); c++) {
-    if (h->out_bytes == 2) ((int16_t *)out_raw)[c] = (int16_t)v[c];
-    else if (h->out_bytes == 4) ((int32_t *)out_raw)[c] = (int32_t)v[c];
-    else ((int64_t *)out_raw)[c] = v[c];
-  }
-  return B2D_OK;
-}
-
-extern "C" int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw) {
-  TraceRange trace__("b2d_fir_run_window");
-  if (!h || !window || !out_raw) return fail(B2D_EINVAL, "null argument");
-  if (!all_loaded(h)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
-  int st = use_device(h->device);
-  if (st) return st;
-  const uint32_t C = h->d.n_channels;
-  const size_t N = h->d.n_taps, T = N - 1, ib = h->in_bytes, ob = h->out_bytes;
-  const size_t tail_b = (std::max<size_t>(T * C * ib, 16) + 15) & ~(size_t)15, in_b = (C * ib + 15) & ~(size_t)15, out_b = (C * ob + 15) & ~(size_t)15;
-  if (!h->d_win) CU(cudaMalloc(&h->d_win, 2 * tail_b + in_b + out_b));
-  // reg order (newest first) -> planar tail, oldest first, + the newest sample as the one-sample input
-  std::vector<unsigned char> host(tail_b + in_b, 0);
-  for (uint32_t c = 0; c < C; c++) {
-    const unsigned char *w = (const unsigned char *)window + (size_t)c * N * ib;
-    for (size_t j = 0; j < T; j++) memcpy(&host[(c * T + j) * ib], w + (T - j) * ib, ib);   // tail[j] = reg[T - j]
-    memcpy(&host[tail_b + c * ib], w, ib);
-  }
-  char *base = (char *)h->d_win;
-  CU(cudaMemcpy(base, host.data(), host.size(), cudaMemcpyHostToDevice));
-  FirLaunch p;
-  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
-  p.n_taps = (int)N; p.ftype = h->d.ftype; p.C = C; p.interleaved = 1;   // one sample per channel: [1][C]
-  p.ascending = h->d.kind == B2D_FIR_REG_SHARE;
-  p.in = base + tail_b; p.out = base + tail_b + in_b; p.n = 1;
-  p.tail = base; p.tail_next = base + tail_b + in_b + out_b;
-  p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
-  CU(h->path == PATH_Q15 ? launch_fir_q15(p, nullptr) : (h->path == PATH_WIDE ? launch_fir_wide(p, nullptr) : launch_fir_generic(p, nullptr)));
-  CU(cudaMemcpy(out_raw, p.out, C * ob, cudaMemcpyDeviceToHost));
-  return B2D_OK;
-}
-
-struct StateHdr { uint32_t magic, version; uint64_t n_seen; uint32_t hist, channels, bytes, pad; };
-static const uint32_t kFirMagic = 0x46324442u, kCicMagic = 0x43324442u;
-static const uint32_t kDecMagic = 0x44324442u, kIntrMagic = 0x49324442u, kDumpMagic = 0x55324442u, kCasMagic = 0x4b324442u;
-
-// Checkpoint blobs of the later handle types: StateHdr followed by device arrays copied verbatim.
-struct StatePart { void *dev; size_t bytes; };
-static size_t state_total(const StatePart *parts, int np) {
+// ---------------------------------------------------------------------------------------- checkpoints
+size_t b2d::state_total(const StatePart *parts, int np) {
   size_t t = sizeof(StateHdr);
   for (int i = 0; i < np; i++) t += parts[i].bytes;
   return t;
 }
-static int state_get(const StateHdr &hd, const StatePart *parts, int np, void *blob, size_t bytes) {
+int b2d::state_get(const StateHdr &hd, const StatePart *parts, int np, void *blob, size_t bytes) {
   if (!blob) return fail(B2D_EINVAL, "null argument");
   if (bytes < state_total(parts, np)) return fail(B2D_EINVAL, "state blob needs %zu bytes", state_total(parts, np));
   CU(cudaDeviceSynchronize());
@@ -654,7 +284,7 @@ static int state_get(const StateHdr &hd, const StatePart *parts, int np, void *b
   for (int i = 0; i < np; i++) { if (parts[i].bytes) CU(cudaMemcpy((char *)blob + o, parts[i].dev, parts[i].bytes, cudaMemcpyDeviceToHost)); o += parts[i].bytes; }
   return B2D_OK;
 }
-static int state_set(const StateHdr &want, const StatePart *parts, int np, const void *blob, size_t bytes, StateHdr *got) {
+int b2d::state_set(const StateHdr &want, const StatePart *parts, int np, const void *blob, size_t bytes, StateHdr *got) {
   if (!blob) return fail(B2D_EINVAL, "null argument");
   if (bytes < state_total(parts, np)) return fail(B2D_EINVAL, "state blob needs %zu bytes", state_total(parts, np));
   memcpy(got, blob, sizeof(*got));
@@ -666,1283 +296,49 @@ static int state_set(const StateHdr &want, const StatePart *parts, int np, const
   return B2D_OK;
 }
 
-extern "C" int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  *bytes = sizeof(StateHdr) + (size_t)h->T * h->d.n_channels * h->in_bytes;
-  return B2D_OK;
-}
-extern "C" int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes) {
-  size_t need = 0;
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  b2d_fir_state_bytes(h, &need);
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  StateHdr hd{kFirMagic, 1, 0, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0};
-  memcpy(blob, &hd, sizeof(hd));
-  if (need > sizeof(hd)) CU(cudaMemcpy((char *)blob + sizeof(hd), h->d_tail[h->cur], need - sizeof(hd), cudaMemcpyDeviceToHost));
-  return B2D_OK;
-}
-extern "C" int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes) {
-  size_t need = 0;
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  b2d_fir_state_bytes(h, &need);
-  StateHdr hd;
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  memcpy(&hd, blob, sizeof(hd));
-  if (hd.magic != kFirMagic || hd.hist != (uint32_t)h->T || hd.channels != h->d.n_channels || hd.bytes != (uint32_t)h->in_bytes)
-    return fail(B2D_EINVAL, "state blob does not belong to this filter configuration");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  if (need > sizeof(hd)) CU(cudaMemcpy(h->d_tail[h->cur], (const char *)blob + sizeof(hd), need - sizeof(hd), cudaMemcpyHostToDevice));
-  h->ran = true;                  // a restored history stands for consumed samples
-  return B2D_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ CIC
-static int log2_ceil_u128(unsigned __int128 v) {
-  int k = 0;
-  while ((((unsigned __int128)1) << k) < v) k++;
-  return k;
-}
-
-// find_inter_type_cic_dec (ac_cic_dec_full.h:116-137): outW = log2_ceil(R^N * M^N) + W + !S
-// find_inter_type_cic_intr (ac_cic_intr_full.h:107-127): outW = log2_ceil(R^(N-1) * M^N) + W + !S
-static int cic_int_width(const b2d_cic_desc *d, int *outW) {
-  unsigned __int128 g = 1;
-  const unsigned __int128 lim = ((unsigned __int128)1) << 100;
-  const uint32_t nr = d->mode == B2D_CIC_INTR ? d->N - 1 : d->N;
-  for (uint32_t i = 0; i < nr; i++) { g *= d->R; if (g > lim) return -1; }
-  for (uint32_t i = 0; i < d->N; i++) { g *= d->M; if (g > lim) return -1; }
-  *outW = log2_ceil_u128(g) + d->in.W + (d->in.S ? 0 : 1);
-  return 0;
-}
-
-// Differential delay the reference's comb really has.  diffStage() shifts comb_dly_ln[k][0..M-1] with an ASCENDING copy
-// loop (ac_cic_full_core.h:247-251: `if (i != 0) dly[i] = dly[i-1]` for i = 0 .. M-1), so dly[0] smears through the line
-// and dly[M-1], read at the next step, is the input of two steps ago: the delay is min(M, 2) while the lossless width
-// (cic_int_width above) keeps growing with M.  Bit-exactness means following the code, not the intent; M <= 2 -- every
-// reference vector and BASELINE configuration -- is unaffected (pinned by tests/golden/cic_comb_quirk.npz).
-static uint32_t cic_comb_delay(uint32_t M) { return M > 2 ? 2u : M; }
-
-static int cic_check(const b2d_cic_desc *d, int *outW) {
-  int st;
-  if (!d) return fail(B2D_EINVAL, "null descriptor");
-  if ((st = check_fmt(d->in, 32, "IN_TYPE"))) return st;
-  if ((st = check_fmt(d->out, 64, "OUT_TYPE"))) return st;
-  if (d->mode != B2D_CIC_DEC && d->mode != B2D_CIC_INTR) return fail(B2D_EINVAL, "bad mode");
-  // rate counters of the reference are 8 bits wide (ac_cic_full_core.h:72-73,91); R = 1 never re-reads in the interpolator
-  if (d->R < 2 || d->R > 256) return fail(B2D_EINVAL, "R = %u outside 2..256", d->R);
-  if (d->M < 1 || d->N < 1 || d->N > 255) return fail(B2D_EINVAL, "M = %u, N = %u invalid", d->M, d->N);
-  if (d->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
-  if (d->layout != B2D_PLANAR && d->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
-  if (cic_int_width(d, outW) || *outW > 64) return fail(B2D_EUNSUPPORTED, "lossless internal width exceeds 64 bits");
-  if (d->N > 16 || (uint64_t)d->N * d->M > 64) return fail(B2D_EUNSUPPORTED, "N > 16 or N*M > 64");
-  return B2D_OK;
-}
-
-struct b2d_cic {
-  b2d_cic_desc d;
-  Fmt fin, fo;
-  int device = 0, intW = 0, H = 0, in_bytes = 2, out_bytes = 4;
-  int fast = 0;
-  unsigned long long n_seen = 0;
-  void *d_tail[2] = {nullptr, nullptr};
-  int cur = 0;
-  Pipe pipe;
-};
-
-extern "C" int b2d_cic_int_width(const b2d_cic_desc *desc, int32_t *outW) {
-  if (!outW) return fail(B2D_EINVAL, "null argument");
-  int w = 0;
-  int st = cic_check(desc, &w);
-  if (st) return st;
-  *outW = w;
-  return B2D_OK;
-}
-
-static unsigned long long cic_emitted(const b2d_cic *h, unsigned long long K) {
-  const long long R = h->d.R, N = h->d.N;
-  if (h->d.mode == B2D_CIC_DEC) return (K + R - 1) / R;  // inputs 0, R, 2R, ... are forwarded
-  if (K == 0) return 0;
-  const long long e = ((long long)K - 1) * R + 1 - (N - 1);  // integrator steps so far minus the N-1 dropped
-  return e > 0 ? (unsigned long long)e : 0;
-}
-
-extern "C" int b2d_cic_create(b2d_cic **out, const b2d_cic_desc *desc) {
-  if (!out) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int w = 0;
-  int st = cic_check(desc, &w);
-  if (st) return st;
-  int dev = desc->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_cic *h = new (std::nothrow) b2d_cic();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->d = *desc; h->fin = to_fmt(desc->in); h->fo = to_fmt(desc->out); h->device = dev; h->intW = w;
-  h->in_bytes = container_bytes(desc->in.W); h->out_bytes = container_bytes(desc->out.W);
-  h->H = cic_history_len(desc->mode == B2D_CIC_INTR, desc->R, cic_comb_delay(desc->M), desc->N);
-  const size_t tail_bytes = (size_t)h->H * desc->n_channels * h->in_bytes;
-  for (int i = 0; i < 2; i++) {
-    cudaError_t e = cudaMalloc(&h->d_tail[i], tail_bytes);
-    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      b2d_cic_destroy(h);
-      return fail(B2D_ECUDA, "b2d_cic_create: %s", cudaGetErrorString(e));
-    }
-  }
-  CicLaunch p{};
-  p.fin = h->fin; p.fout = h->fo; p.intW = w; p.R = desc->R; p.M = cic_comb_delay(desc->M); p.N = desc->N;
-  p.intr = desc->mode == B2D_CIC_INTR; p.C = desc->n_channels; p.interleaved = desc->layout == B2D_INTERLEAVED;
-  h->fast = cic_fast_supported(p) ? 1 : (cic_intr_fast_supported(p) ? 2 : 0);
-  const char *force = getenv("B2D_FORCE_GENERIC");
-  if ((force && *force == '1') || desc->M > 2) h->fast = 0;   // M > 2: the width is not the one the fast kernels were instantiated for
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cic_destroy(b2d_cic *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  h->pipe.destroy();
-  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
-  delete h;
-  return B2D_OK;
-}
-
-extern "C" const char *b2d_cic_path(b2d_cic *h) { return !h ? "" : (h->fast == 1 ? "cic_fast" : (h->fast == 2 ? "cic_intr_fast" : "cic_generic")); }
-
-extern "C" size_t b2d_cic_max_out(b2d_cic *h, size_t n) {
-  if (!h) return 0;
-  return h->d.mode == B2D_CIC_DEC ? n / h->d.R + 1 : n * h->d.R;
-}
-
-static int cic_launch(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
-  if (n == 0) return B2D_OK;
-  CicLaunch p;
-  p.fin = h->fin; p.fout = h->fo; p.intW = h->intW; p.R = h->d.R; p.M = cic_comb_delay(h->d.M); p.N = h->d.N;
-  p.intr = h->d.mode == B2D_CIC_INTR; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
-  p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
-  p.n_seen = h->n_seen; p.out_first = cic_emitted(h, h->n_seen);
-  p.tail = h->d_tail[h->cur]; p.tail_next = h->d_tail[h->cur ^ 1]; p.H = h->H;
-  CU(h->fast == 1 ? launch_cic_fast(p, st) : (h->fast == 2 ? launch_cic_intr_fast(p, st) : launch_cic_generic(p, st)));
-  CU(launch_cic_tail(p, st));
-  h->cur ^= 1;
-  h->n_seen += n;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_cic_run_dev");
-  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
-  const size_t no = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
-  if (no && !d_out) return fail(B2D_EINVAL, "null output");
-  int st = use_device(h->device);
-  if (st) return st;
-  if ((st = cic_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
-  if (n_out) *n_out = no;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cic_run(b2d_cic *h, const void *in, size_t n, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_cic_run");
-  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
-  const size_t no_total = (size_t)(cic_emitted(h, h->n_seen + n) - cic_emitted(h, h->n_seen));
-  if (no_total && !out) return fail(B2D_EINVAL, "null output");
-  if (n_out) *n_out = no_total;
-  if (n == 0) return B2D_OK;
-  int st = use_device(h->device);
-  if (st) return st;
-  Pipe &P = h->pipe;
-  if ((st = P.init())) return st;
-  const uint32_t C = h->d.n_channels;
-  const int il = h->d.layout == B2D_INTERLEAVED;
-  const bool dec = h->d.mode == B2D_CIC_DEC;
-  const double out_per_in = dec ? 1.0 / h->d.R : (double)h->d.R;
-  const double per = C * (h->in_bytes + h->out_bytes * out_per_in);
-  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
-  L = std::min(L, n);
-  const size_t Lout = dec ? L / h->d.R + 1 : L * h->d.R;
-  if ((st = P.ensure(L * C * h->in_bytes, Lout * C * h->out_bytes))) return st;
-  size_t i = 0, off_out = 0;
-  for (size_t off = 0; off < n; off += L, i++) {
-    const int s = (int)(i % Pipe::S);
-    const size_t len = std::min(L, n - off);
-    const size_t no = (size_t)(cic_emitted(h, h->n_seen + len) - cic_emitted(h, h->n_seen));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
-    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
-    CU(cudaEventRecord(P.e_in[s], P.s_in));
-    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
-    if ((st = cic_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
-    CU(cudaEventRecord(P.e_k[s], P.s_k));
-    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
-    // outputs are PLANAR with a channel stride of the whole call's output count
-    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
-    CU(cudaEventRecord(P.e_out[s], P.s_out));
-    off_out += no;
-  }
-  CU(cudaStreamSynchronize(P.s_out));
-  CU(cudaStreamSynchronize(P.s_k));
-  return B2D_OK;
-}
-
-extern "C" int b2d_cic_reset(b2d_cic *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, (size_t)h->H * h->d.n_channels * h->in_bytes));
-  h->n_seen = 0;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cic_state_bytes(b2d_cic *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  *bytes = sizeof(StateHdr) + (size_t)h->H * h->d.n_channels * h->in_bytes;
-  return B2D_OK;
-}
-extern "C" int b2d_cic_get_state(b2d_cic *h, void *blob, size_t bytes) {
-  size_t need = 0;
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  b2d_cic_state_bytes(h, &need);
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  StateHdr hd{kCicMagic, 1, h->n_seen, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, 0};
-  memcpy(blob, &hd, sizeof(hd));
-  CU(cudaMemcpy((char *)blob + sizeof(hd), h->d_tail[h->cur], need - sizeof(hd), cudaMemcpyDeviceToHost));
-  return B2D_OK;
-}
-extern "C" int b2d_cic_set_state(b2d_cic *h, const void *blob, size_t bytes) {
-  size_t need = 0;
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  b2d_cic_state_bytes(h, &need);
-  StateHdr hd;
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  memcpy(&hd, blob, sizeof(hd));
-  if (hd.magic != kCicMagic || hd.hist != (uint32_t)h->H || hd.channels != h->d.n_channels || hd.bytes != (uint32_t)h->in_bytes)
-    return fail(B2D_EINVAL, "state blob does not belong to this filter configuration");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(h->d_tail[h->cur], (const char *)blob + sizeof(hd), need - sizeof(hd), cudaMemcpyHostToDevice));
-  h->n_seen = hd.n_seen;
-  return B2D_OK;
-}
-
-// -------------------------------------------------------------------------------------------- cascade
-// ac_cic_intr_full -> ac_fir_* as one handle: fused polyphase kernel when exact, else the two kernels back to back.
-struct b2d_cicfir {
-  b2d_cic_desc cd;
-  b2d_fir_desc fd;
-  int device = 0, fused = 0;
-  // fused
-  Fmt fa, fo;
-  int R = 0, taps_total = 0, planes = 3, words = 0, H = 0, lsh = 0, in_bytes = 2, out_bytes = 8;
-  std::vector<int64_t> hcic;
-  std::vector<char> ch_loaded;
-  uint32_t *d_cw = nullptr;
-  void *d_tail[2] = {nullptr, nullptr};
-  int cur = 0;
-  unsigned long long n_seen = 0;
-  // two-stage
-  b2d_cic *cic = nullptr;
-  b2d_fir *fir = nullptr;
-  void *d_mid = nullptr;
-  size_t mid_cap = 0;
-  Pipe pipe;
-};
-
-static unsigned long long intr_emitted(unsigned long long K, long long R, long long N) {
-  if (K == 0) return 0;
-  const long long e = ((long long)K - 1) * R + 1 - (N - 1);
-  return e > 0 ? (unsigned long long)e : 0;
-}
-
-// Can the pair be evaluated as one exact integer FIR on the 16-bit input?  (see upfir_q15.cu)
-static bool cicfir_fusable(const b2d_cic_desc &cd, const b2d_fir_desc &fd, int intW, int *lsh, int *taps_total, int *planes) {
-  const Fmt in = to_fmt(cd.in), mid = to_fmt(cd.out), fc = to_fmt(fd.coeff), fa = to_fmt(fd.acc);
-  if (in.W > 16 || (!in.S && in.W == 16)) return false;
-  if (!(mid.S && mid.F() == in.F() && mid.W >= intW)) return false;          // the lossless INT_TYPE passes unchanged
-  if (fa.O != B2D_WRAP || (fa.Q != B2D_TRN && fa.Q != B2D_RND)) return false;
-  if (cd.M > 2) return false;                 // cic_comb_delay: the composite taps below assume delay M; two-stage path instead
-  const int s = mid.F() + fc.F() - fa.F();
-  if (s > 0 || -s > 40 || -s >= fa.W) return false;
-  switch (fd.ftype) {
-    case B2D_SHIFT_REG: case B2D_ROTATE_SHIFT: case B2D_C_BUFF: case B2D_TRANSPOSED: case B2D_FOLD_EVEN: break;
-    case B2D_FOLD_ODD:
-      if (!fa.S || !(fa.F() >= mid.F() && mid.W + 1 + (fa.F() - mid.F()) <= fa.W)) return false;   // mid is signed: an unsigned fold wraps
-      break;
-    default: return false;
-  }
-  // composite tap magnitude: |c| <= 2^(Wc-1) * (R*M)^N
-  unsigned __int128 g = 1;
-  for (uint32_t i = 0; i < cd.N; i++) { g *= (unsigned __int128)cd.R * cd.M; if (g > ((unsigned __int128)1 << 40)) return false; }
-  const int bits = fc.W + (fc.S ? 0 : 1) + log2_ceil_u128(g);
-  const int total = (int)fd.n_taps + (int)cd.N * ((int)cd.R * (int)cd.M - 1);
-  if (!upfir_q15_geometry((int)cd.R, total, bits)) return false;
-  *lsh = -s; *taps_total = total; *planes = upfir_q15_planes(bits);
-  return true;
-}
-
-extern "C" int b2d_cicfir_destroy(b2d_cicfir *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  h->pipe.destroy();
-  if (h->cic) b2d_cic_destroy(h->cic);
-  if (h->fir) b2d_fir_destroy(h->fir);
-  if (h->d_mid) cudaFree(h->d_mid);
-  if (h->d_cw) cudaFree(h->d_cw);
-  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
-  delete h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cicfir_create(b2d_cicfir **out, const b2d_cic_desc *cd, const b2d_fir_desc *fd) {
-  if (!out || !cd || !fd) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int intW = 0;
-  int st = cic_check(cd, &intW);
-  if (st) return st;
-  if (cd->mode != B2D_CIC_INTR) return fail(B2D_EINVAL, "the cascade takes an interpolator (B2D_CIC_INTR) first stage");
-  if (fd->in.W != cd->out.W || fd->in.I != cd->out.I || (fd->in.S != 0) != (cd->out.S != 0))
-    return fail(B2D_EINVAL, "fir->in must be the interpolator's OUT_TYPE");
-  if (fd->n_channels != cd->n_channels) return fail(B2D_EINVAL, "both stages must have the same n_channels");
-  int dev = cd->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_cicfir *h = new (std::nothrow) b2d_cicfir();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->cd = *cd; h->fd = *fd; h->device = dev;
-  h->cd.device = dev; h->fd.device = dev; h->fd.layout = B2D_PLANAR;
-  h->fa = to_fmt(fd->acc); h->fo = to_fmt(fd->out);
-  h->out_bytes = container_bytes(fd->out.W);
-  h->R = (int)cd->R;
-  const uint32_t C = cd->n_channels;
-  h->ch_loaded.assign(C, 0);
-  const char *force = getenv("B2D_CICFIR_TWO_STAGE");
-  h->fused = cicfir_fusable(*cd, *fd, intW, &h->lsh, &h->taps_total, &h->planes) && !(force && *force == '1');
-  // the FIR descriptor is validated by creating the second-stage object in either mode (it also serves reset/load checks)
-  if ((st = b2d_fir_create(&h->fir, &h->fd))) { b2d_cicfir_destroy(h); return st; }
-  if (h->fused) {
-    // boxcar(R*M)^N, ac_cic_intr_full.h:150-215 as one FIR (cic_intr_fast.cu)
-    h->hcic.assign(1, 1);
-    for (uint32_t s = 0; s < cd->N; s++) {
-      std::vector<int64_t> nx(h->hcic.size() + cd->R * cd->M - 1, 0);
-      for (size_t i = 0; i < h->hcic.size(); i++)
-        for (uint32_t j = 0; j < cd->R * cd->M; j++) nx[i + j] += h->hcic[i];
-      h->hcic.swap(nx);
-    }
-    h->words = upfir_q15_words(h->R, h->taps_total, h->planes);
-    h->H = (h->taps_total + h->R - 1) / h->R + 2;
-    cudaError_t e = cudaMalloc(&h->d_cw, (size_t)C * h->words * sizeof(uint32_t));
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-      e = cudaMalloc(&h->d_tail[i], (size_t)h->H * C * 2);
-      if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, (size_t)h->H * C * 2);
-    }
-    if (e != cudaSuccess) { cudaGetLastError(); b2d_cicfir_destroy(h); return fail(B2D_ECUDA, "b2d_cicfir_create: %s", cudaGetErrorString(e)); }
-  } else {
-    if ((st = b2d_cic_create(&h->cic, &h->cd))) { b2d_cicfir_destroy(h); return st; }
-  }
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" const char *b2d_cicfir_path(b2d_cicfir *h) { return !h ? "" : (h->fused ? "cicfir_fused" : "cicfir_two_stage"); }
-extern "C" size_t b2d_cicfir_max_out(b2d_cicfir *h, size_t n) { return h ? n * h->cd.R : 0; }
-
-extern "C" int b2d_cicfir_load(b2d_cicfir *h, const void *coeff_raw, size_t n, int32_t channel) {
-  TraceRange trace__("b2d_cicfir_load");
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = b2d_fir_load(h->fir, coeff_raw, n, channel);     // validation, wrapping to COEFF_TYPE, const-kind rule
-  if (st || !h->fused) return st;
-  const size_t N = h->fd.n_taps;
-  const uint32_t C = h->cd.n_channels;
-  for (uint32_t c = 0; c < C; c++) {
-    if (channel >= 0 && (uint32_t)channel != c) continue;
-    const int64_t *g = h->fir->h_coeff.data() + c * N;
-    std::vector<int64_t> eff(g, g + N);
-    if (h->fd.ftype == B2D_FOLD_EVEN) {
-      std::fill(eff.begin(), eff.end(), 0);
-      for (size_t i = 0; i < N / 2; i++) { eff[i] = g[i]; eff[N - 1 - i] = g[i]; }
-    } else if (h->fd.ftype == B2D_FOLD_ODD) {
-      std::fill(eff.begin(), eff.end(), 0);
-      for (size_t i = 0; i < (N - 1) / 2 + 1; i++) { eff[i] = g[i]; if (i != (N - 1) / 2) eff[N - 1 - i] = g[i]; }
-    }
-    std::vector<int64_t> comp((size_t)h->taps_total, 0);
-    for (size_t i = 0; i < h->hcic.size(); i++)
-      for (size_t j = 0; j < N; j++) comp[i + j] += h->hcic[i] * eff[j];
-    std::vector<uint32_t> pk((size_t)h->words, 0);
-    upfir_q15_pack(comp.data(), h->taps_total, h->R, h->planes, pk.data());
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(h->d_cw + (size_t)c * h->words, pk.data(), (size_t)h->words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    h->ch_loaded[c] = 1;
-  }
-  return B2D_OK;
-}
-
-static size_t cicfir_count(const b2d_cicfir *h, size_t n) {
-  const unsigned long long seen = h->fused ? h->n_seen : h->cic->n_seen;
-  return (size_t)(intr_emitted(seen + n, h->cd.R, h->cd.N) - intr_emitted(seen, h->cd.R, h->cd.N));
-}
-
-static int cicfir_launch(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
-  if (n == 0) return B2D_OK;
-  if (h->fused) {
-    UpLaunch p;
-    p.facc = h->fa; p.fout = h->fo; p.R = h->R; p.taps_total = h->taps_total; p.planes = h->planes; p.lsh = h->lsh;
-    p.C = h->cd.n_channels; p.interleaved = h->cd.layout == B2D_INTERLEAVED;
-    p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out;
-    p.n_seen = h->n_seen; p.out_first = intr_emitted(h->n_seen, h->cd.R, h->cd.N);
-    p.tail = h->d_tail[h->cur]; p.H = h->H; p.cw = h->d_cw;
-    CU(launch_upfir_q15(p, st));
-    h->fir->ran = true;           // the fused kernel is the direct form too: same TRANSPOSED rule in b2d_fir_load
-    CicLaunch t{};
-    t.fin = to_fmt(h->cd.in); t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;
-    t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1]; t.H = h->H;
-    CU(launch_cic_tail(t, st));
-    h->cur ^= 1;
-    h->n_seen += n;
-    return B2D_OK;
-  }
-  const uint32_t C = h->cd.n_channels;
-  const size_t mid_bytes = (size_t)container_bytes(h->cd.out.W) * C * std::max<size_t>(n_out, 1);
-  if (mid_bytes > h->mid_cap) {
-    if (h->d_mid) cudaFree(h->d_mid);
-    h->d_mid = nullptr; h->mid_cap = 0;
-    if (cudaMalloc(&h->d_mid, mid_bytes) != cudaSuccess) { cudaGetLastError(); return fail(B2D_ENOMEM, "cudaMalloc(%zu)", mid_bytes); }
-    h->mid_cap = mid_bytes;
-  }
-  size_t n_mid = 0, n_fir = 0;
-  int s = b2d_cic_run_dev(h->cic, d_in, n, h->d_mid, &n_mid, st);
-  if (s) return s;
-  if (n_mid != n_out) return fail(B2D_ESTATE, "cascade count mismatch");
-  return b2d_fir_run_dev(h->fir, h->d_mid, n_mid, d_out, &n_fir, st);
-}
-
-static int cicfir_ready(b2d_cicfir *h) {
-  if (h->fused) { for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded"); }
-  else if (!all_loaded(h->fir)) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
-  return B2D_OK;
-}
-
-extern "C" int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_cicfir_run_dev");
-  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
-  int st = cicfir_ready(h);
-  if (st) return st;
-  const size_t no = cicfir_count(h, n);
-  if (no && !d_out) return fail(B2D_EINVAL, "null output");
-  if ((st = use_device(h->device))) return st;
-  if ((st = cicfir_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
-  if (n_out) *n_out = no;
-  return B2D_OK;
-}
-
-extern "C" int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_cicfir_run");
-  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
-  int st = cicfir_ready(h);
-  if (st) return st;
-  const size_t no_total = cicfir_count(h, n);
-  if (no_total && !out) return fail(B2D_EINVAL, "null output");
-  if (n_out) *n_out = no_total;
-  if (n == 0) return B2D_OK;
-  if ((st = use_device(h->device))) return st;
-  Pipe &P = h->pipe;
-  if ((st = P.init())) return st;
-  const uint32_t C = h->cd.n_channels;
-  const int il = h->cd.layout == B2D_INTERLEAVED;
-  const int in_bytes = container_bytes(h->cd.in.W);
-  const double per = C * (in_bytes + (double)h->out_bytes * h->cd.R);
-  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
-  L = std::min(L, n);
-  if ((st = P.ensure(L * C * in_bytes, L * h->cd.R * C * h->out_bytes))) return st;
-  size_t i = 0, off_out = 0;
-  for (size_t off = 0; off < n; off += L, i++) {
-    const int s = (int)(i % Pipe::S);
-    const size_t len = std::min(L, n - off);
-    const size_t no = cicfir_count(h, len);
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
-    CU(copy_chunk(P.d_in[s], in, true, in_bytes, C, il, n, off, len, P.s_in));
-    CU(cudaEventRecord(P.e_in[s], P.s_in));
-    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
-    if ((st = cicfir_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
-    CU(cudaEventRecord(P.e_k[s], P.s_k));
-    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
-    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
-    CU(cudaEventRecord(P.e_out[s], P.s_out));
-    off_out += no;
-  }
-  CU(cudaStreamSynchronize(P.s_out));
-  CU(cudaStreamSynchronize(P.s_k));
-  return B2D_OK;
-}
-
-extern "C" int b2d_cicfir_reset(b2d_cicfir *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  if (h->fused) {
-    for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, (size_t)h->H * h->cd.n_channels * 2));
-    h->n_seen = 0;
-    h->fir->ran = false;
-    return B2D_OK;
-  }
-  if ((st = b2d_cic_reset(h->cic))) return st;
-  return b2d_fir_reset(h->fir);
-}
-
-// Checkpoint of the cascade: fused = input history + count; two-stage = the two stage blobs back to back.
-extern "C" int b2d_cicfir_state_bytes(b2d_cicfir *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  if (h->fused) { *bytes = sizeof(StateHdr) + (size_t)h->H * h->cd.n_channels * 2; return B2D_OK; }
-  size_t a = 0, b = 0;
-  int st;
-  if ((st = b2d_cic_state_bytes(h->cic, &a)) || (st = b2d_fir_state_bytes(h->fir, &b))) return st;
-  *bytes = sizeof(StateHdr) + a + b;
-  return B2D_OK;
-}
-extern "C" int b2d_cicfir_get_state(b2d_cicfir *h, void *blob, size_t bytes) {
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  int st = use_device(h->device);
-  if (st) return st;
-  if (h->fused) {
-    const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->H * h->cd.n_channels * 2}};
-    return state_get(StateHdr{kCasMagic, 1, h->n_seen, (uint32_t)h->H, h->cd.n_channels, 2, 1}, parts, 1, blob, bytes);
-  }
-  size_t need = 0, a = 0;
-  if ((st = b2d_cicfir_state_bytes(h, &need))) return st;
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  b2d_cic_state_bytes(h->cic, &a);
-  const StateHdr hd{kCasMagic, 1, 0, 0, h->cd.n_channels, 2, 0};
-  memcpy(blob, &hd, sizeof(hd));
-  if ((st = b2d_cic_get_state(h->cic, (char *)blob + sizeof(hd), a))) return st;
-  return b2d_fir_get_state(h->fir, (char *)blob + sizeof(hd) + a, need - sizeof(hd) - a);
-}
-extern "C" int b2d_cicfir_set_state(b2d_cicfir *h, const void *blob, size_t bytes) {
-  if (!h || !blob) return fail(B2D_EINVAL, "null argument");
-  int st = use_device(h->device);
-  if (st) return st;
-  if (h->fused) {
-    const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->H * h->cd.n_channels * 2}};
-    StateHdr got;
-    if ((st = state_set(StateHdr{kCasMagic, 1, 0, (uint32_t)h->H, h->cd.n_channels, 2, 1}, parts, 1, blob, bytes, &got))) return st;
-    if (got.pad != 1) return fail(B2D_EINVAL, "state blob was taken from a two-stage cascade");
-    h->n_seen = got.n_seen;
-    h->fir->ran = true;
-    return B2D_OK;
-  }
-  size_t need = 0, a = 0;
-  if ((st = b2d_cicfir_state_bytes(h, &need))) return st;
-  if (bytes < need) return fail(B2D_EINVAL, "state blob needs %zu bytes", need);
-  StateHdr hd;
-  memcpy(&hd, blob, sizeof(hd));
-  if (hd.magic != kCasMagic || hd.pad != 0 || hd.channels != h->cd.n_channels) return fail(B2D_EINVAL, "state blob does not belong to this cascade");
-  b2d_cic_state_bytes(h->cic, &a);
-  if ((st = b2d_cic_set_state(h->cic, (const char *)blob + sizeof(hd), a))) return st;
-  return b2d_fir_set_state(h->fir, (const char *)blob + sizeof(hd) + a, need - sizeof(hd) - a);
-}
-
-// -------------------------------------------------------------------------------------------- ac_poly_dec
-struct b2d_polydec {
-  b2d_polydec_desc d;
-  Fmt fin, fc, fa, fo;
-  int device = 0, in_bytes = 2, out_bytes = 8, c_bytes = 2, wide = 0, T = 0;
-  std::vector<char> ch_loaded;
-  int64_t *d_coeff64 = nullptr;
-  int32_t *d_coeff32 = nullptr;
-  uint32_t *d_coeff_pk = nullptr;
-  void *d_tail[2] = {nullptr, nullptr};
-  int cur = 0;
-  unsigned long long n_seen = 0;
-  Pipe pipe;
-};
-
-extern "C" int b2d_polydec_destroy(b2d_polydec *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  h->pipe.destroy();
-  if (h->d_coeff64) cudaFree(h->d_coeff64);
-  if (h->d_coeff32) cudaFree(h->d_coeff32);
-  if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
-  for (int i = 0; i < 2; i++) if (h->d_tail[i]) cudaFree(h->d_tail[i]);
-  delete h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_polydec_create(b2d_polydec **out, const b2d_polydec_desc *desc) {
-  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int st;
-  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
-  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
-  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
-  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
-  if (desc->n_taps < 1 || desc->df < 1 || (uint64_t)desc->n_taps * desc->df > (1u << 20)) return fail(B2D_EINVAL, "NTAPS = %u, DF = %u invalid", desc->n_taps, desc->df);
-  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
-  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
-  const Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
-  {  // bit budget of the 128-bit generic evaluation (as for the FIR classes)
-    const int Fp = fin.F() + fc.F(), Wp = fin.W + fc.W + 2, rF = std::max(Fp, fa.F());
-    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + std::max(0, fo.F() - fa.F()) > 125)
-      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
-  }
-  int dev = desc->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_polydec *h = new (std::nothrow) b2d_polydec();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
-  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
-  const uint32_t C = desc->n_channels;
-  const size_t L = (size_t)desc->n_taps * desc->df;
-  h->T = (int)L - 1;
-  h->ch_loaded.assign(C, 0);
-  h->wide = polydec_wide_mode(fin, fc, fa, (int)desc->n_taps, (int)desc->df) >= 0;
-  const char *force = getenv("B2D_FORCE_GENERIC");
-  if (h->wide && polydec_q15_supported(fin, fc, fa, (int)desc->n_taps, (int)desc->df) && !(force && *force == '2')) h->wide = 2;
-  if (force && *force == '1') h->wide = 0;
-  cudaError_t e = cudaMalloc(&h->d_coeff64, C * L * sizeof(int64_t));
-  if (e == cudaSuccess && h->wide == 2) e = cudaMalloc(&h->d_coeff_pk, (size_t)C * polydec_q15_words((int)desc->n_taps, (int)desc->df) * sizeof(uint32_t));
-  if (e == cudaSuccess && h->wide == 1) e = cudaMalloc(&h->d_coeff32, (size_t)C * desc->df * polydec_words((int)desc->n_taps) * sizeof(int32_t));
-  const size_t tail_bytes = std::max<size_t>((size_t)h->T * C * h->in_bytes, 16);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-    e = cudaMalloc(&h->d_tail[i], tail_bytes);
-    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
-  }
-  if (e != cudaSuccess) { cudaGetLastError(); b2d_polydec_destroy(h); return fail(B2D_ECUDA, "b2d_polydec_create: %s", cudaGetErrorString(e)); }
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" const char *b2d_polydec_path(b2d_polydec *h) { return !h ? "" : (h->wide == 2 ? "polydec_q15" : (h->wide ? "polydec_wide" : "polydec_generic")); }
-extern "C" size_t b2d_polydec_max_out(b2d_polydec *h, size_t n) { return h ? n / h->d.df + 1 : 0; }
-
-extern "C" int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t channel) {
-  TraceRange trace__("b2d_polydec_load");
-  if (!h || !coeff_raw) return fail(B2D_EINVAL, "null argument");
-  const size_t L = (size_t)h->d.n_taps * h->d.df;
-  const uint32_t C = h->d.n_channels;
-  if (n != L) return fail(B2D_EINVAL, "expected %zu coefficients (NTAPS * DF), got %zu", L, n);
-  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
-  int st = use_device(h->device);
-  if (st) return st;
-  std::vector<int64_t> v(L);
-  for (size_t i = 0; i < L; i++) {
+// ------------------------------------------------------------------------------------ shared helpers
+void b2d::widen_coeffs(const void *raw, size_t n, int c_bytes, const Fmt &fc, int64_t *out) {
+  for (size_t i = 0; i < n; i++) {
     int64_t r;
-    if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
-    else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
-    else r = ((const int64_t *)coeff_raw)[i];
-    v[i] = wrap_bits(r, h->fc.W, h->fc.S);
+    if (c_bytes == 2) r = fc.S ? (int64_t)((const int16_t *)raw)[i] : (int64_t)((const uint16_t *)raw)[i];
+    else if (c_bytes == 4) r = fc.S ? (int64_t)((const int32_t *)raw)[i] : (int64_t)((const uint32_t *)raw)[i];
+    else r = ((const int64_t *)raw)[i];
+    out[i] = wrap_bits(r, fc.W, fc.S);
   }
-  CU(cudaDeviceSynchronize());
-  const int words = polydec_words((int)h->d.n_taps);
-  std::vector<int32_t> pk;
-  std::vector<uint32_t> pq;
-  if (h->wide == 1) { pk.assign((size_t)h->d.df * words, 0); polydec_pack(v.data(), (int)h->d.n_taps, (int)h->d.df, pk.data()); }
-  if (h->wide == 2) { pq.assign((size_t)polydec_q15_words((int)h->d.n_taps, (int)h->d.df), 0); polydec_q15_pack(h->fc, v.data(), (int)h->d.n_taps, (int)h->d.df, pq.data()); }
-  for (uint32_t c = 0; c < C; c++) {
-    if (channel >= 0 && (uint32_t)channel != c) continue;
-    CU(cudaMemcpy(h->d_coeff64 + c * L, v.data(), L * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (h->wide == 1) CU(cudaMemcpy(h->d_coeff32 + (size_t)c * pk.size(), pk.data(), pk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (h->wide == 2) CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * pq.size(), pq.data(), pq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    h->ch_loaded[c] = 1;
+}
+
+int b2d::hist_wait(cudaEvent_t &ev, cudaStream_t st) {
+  if (ev) CU(cudaStreamWaitEvent(st, ev, 0));
+  return B2D_OK;
+}
+int b2d::hist_mark(cudaEvent_t &ev, cudaStream_t st) {
+  if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, st));
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ wire format
+int b2d::check_wire(int32_t wire) {
+  if (wire != B2D_WIRE_CONTAINER && wire != B2D_WIRE_PACKED) return fail(B2D_EINVAL, "bad wire format %d", wire);
+  return B2D_OK;
+}
+extern "C" int b2d_wire_bytes(int32_t W, int32_t wire) {
+  if (W < 1 || W > 64 || (wire != B2D_WIRE_CONTAINER && wire != B2D_WIRE_PACKED)) return 0;
+  return wire_bytes_of(W, wire);
+}
+// Packed values (ceil(W/8) little-endian bytes each) -> sign- / zero-extended containers, on the host.
+extern "C" int b2d_unpack_wire(const void *packed, size_t count, int32_t W, int32_t S, void *out) {
+  if (W < 1 || W > 64) return fail(B2D_EINVAL, "width %d outside 1..64", W);
+  if (count && (!packed || !out)) return fail(B2D_EINVAL, "null argument");
+  const int pb = (W + 7) / 8, cb = container_bytes(W);
+  const unsigned char *p = (const unsigned char *)packed;
+  for (size_t i = 0; i < count; i++, p += pb) {
+    uint64_t u = 0;
+    for (int b = 0; b < pb; b++) u |= (uint64_t)p[b] << (8 * b);
+    const int64_t v = wrap_bits((int64_t)u, W, S ? 1 : 0);
+    if (cb == 2) ((int16_t *)out)[i] = (int16_t)v;
+    else if (cb == 4) ((int32_t *)out)[i] = (int32_t)v;
+    else ((int64_t *)out)[i] = v;
   }
-  return B2D_OK;
-}
-
-static size_t polydec_count(const b2d_polydec *h, size_t n) {
-  return (size_t)((h->n_seen + n) / h->d.df - h->n_seen / h->d.df);
-}
-
-static int polydec_launch(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t n_out, cudaStream_t st) {
-  if (n == 0) return B2D_OK;
-  DecLaunch p;
-  p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
-  p.nt = (int)h->d.n_taps; p.df = (int)h->d.df; p.wide = h->wide; p.C = h->d.n_channels; p.interleaved = h->d.layout == B2D_INTERLEAVED;
-  p.in = d_in; p.out = d_out; p.n = n; p.n_out = n_out; p.n_seen = h->n_seen; p.tail = h->d_tail[h->cur];
-  p.coeff64 = h->d_coeff64; p.coeff32 = h->d_coeff32; p.coeff_pk = h->d_coeff_pk;
-  CU(launch_polydec(p, st));
-  FirLaunch t{};                    // history carry: the last NTAPS*DF - 1 samples, exactly as for an FIR of that length
-  t.fin = h->fin; t.n_taps = h->T + 1; t.C = p.C; t.interleaved = p.interleaved; t.in = d_in; t.n = n;
-  t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1];
-  CU(launch_fir_tail(t, st));
-  h->cur ^= 1;
-  h->n_seen += n;
-  return B2D_OK;
-}
-
-static int polydec_ready(const b2d_polydec *h) {
-  for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the coefficients of every channel were loaded");
-  return B2D_OK;
-}
-
-extern "C" int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_polydec_run_dev");
-  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
-  int st = polydec_ready(h);
-  if (st) return st;
-  const size_t no = polydec_count(h, n);
-  if (no && !d_out) return fail(B2D_EINVAL, "null output");
-  if ((st = use_device(h->device))) return st;
-  if ((st = polydec_launch(h, d_in, n, d_out, no, (cudaStream_t)cuda_stream))) return st;
-  if (n_out) *n_out = no;
-  return B2D_OK;
-}
-
-extern "C" int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_polydec_run");
-  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
-  int st = polydec_ready(h);
-  if (st) return st;
-  const size_t no_total = polydec_count(h, n);
-  if (no_total && !out) return fail(B2D_EINVAL, "null output");
-  if (n_out) *n_out = no_total;
-  if (n == 0) return B2D_OK;
-  if ((st = use_device(h->device))) return st;
-  Pipe &P = h->pipe;
-  if ((st = P.init())) return st;
-  const uint32_t C = h->d.n_channels;
-  const int il = h->d.layout == B2D_INTERLEAVED;
-  const double per = C * (h->in_bytes + (double)h->out_bytes / h->d.df);
-  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
-  L = std::min(L, n);
-  if ((st = P.ensure(L * C * h->in_bytes, (L / h->d.df + 1) * C * h->out_bytes))) return st;
-  size_t i = 0, off_out = 0;
-  for (size_t off = 0; off < n; off += L, i++) {
-    const int s = (int)(i % Pipe::S);
-    const size_t len = std::min(L, n - off);
-    const size_t no = polydec_count(h, len);
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
-    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
-    CU(cudaEventRecord(P.e_in[s], P.s_in));
-    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
-    if ((st = polydec_launch(h, P.d_in[s], len, P.d_out[s], no, P.s_k))) return st;
-    CU(cudaEventRecord(P.e_k[s], P.s_k));
-    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
-    CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
-    CU(cudaEventRecord(P.e_out[s], P.s_out));
-    off_out += no;
-  }
-  CU(cudaStreamSynchronize(P.s_out));
-  CU(cudaStreamSynchronize(P.s_k));
-  return B2D_OK;
-}
-
-extern "C" int b2d_polydec_reset(b2d_polydec *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  const size_t tail_bytes = std::max<size_t>((size_t)h->T * h->d.n_channels * h->in_bytes, 16);
-  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
-  h->n_seen = 0;
-  return B2D_OK;
-}
-
-extern "C" int b2d_polydec_state_bytes(b2d_polydec *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  *bytes = sizeof(StateHdr) + (size_t)h->T * h->d.n_channels * h->in_bytes;
-  return B2D_OK;
-}
-extern "C" int b2d_polydec_get_state(b2d_polydec *h, void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->T * h->d.n_channels * h->in_bytes}};
-  return state_get(StateHdr{kDecMagic, 1, h->n_seen, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 1, blob, bytes);
-}
-extern "C" int b2d_polydec_set_state(b2d_polydec *h, const void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  const StatePart parts[1] = {{h->d_tail[h->cur], (size_t)h->T * h->d.n_channels * h->in_bytes}};
-  StateHdr got;
-  if ((st = state_set(StateHdr{kDecMagic, 1, 0, (uint32_t)h->T, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 1, blob, bytes, &got))) return st;
-  h->n_seen = got.n_seen;
-  return B2D_OK;
-}
-
-// -------------------------------------------------------------------------------------------- ac_poly_intr
-struct b2d_polyintr {
-  b2d_polyintr_desc d;
-  Fmt fin, fc, fa, fo;
-  int device = 0, in_bytes = 2, out_bytes = 8, c_bytes = 2, csz = 0, H = 0;
-  int mode = 0;                      // 0 generic, 1 wide (64-bit modular), 2 q15 (upfir_lane DP2A kernel)
-  int lsh = 0, planes = 2, words = 0;
-  bool init = false;                 // folded forms: a step has been taken (ac_poly_intr.h:165)
-  std::vector<char> ch_loaded;
-  int64_t *d_coeff64 = nullptr;
-  uint32_t *d_cw = nullptr;
-  uint8_t *d_sign = nullptr, *d_corr = nullptr;
-  int64_t *d_carry[2] = {nullptr, nullptr};
-  void *d_tail[2] = {nullptr, nullptr};
-  int cur = 0, ccur = 0;
-  unsigned long long n_seen = 0;
-  Pipe pipe;
-};
-
-extern "C" int b2d_polyintr_destroy(b2d_polyintr *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  h->pipe.destroy();
-  if (h->d_coeff64) cudaFree(h->d_coeff64);
-  if (h->d_cw) cudaFree(h->d_cw);
-  if (h->d_sign) cudaFree(h->d_sign);
-  if (h->d_corr) cudaFree(h->d_corr);
-  for (int i = 0; i < 2; i++) { if (h->d_tail[i]) cudaFree(h->d_tail[i]); if (h->d_carry[i]) cudaFree(h->d_carry[i]); }
-  delete h;
-  return B2D_OK;
-}
-
-static int polyintr_csz(uint32_t nt, uint32_t ifac, int ftype) {
-  return (int)(ifac * (ftype == B2D_PI_FOLD_EVEN ? nt / 2 : (ftype == B2D_PI_FOLD_ODD ? nt / 2 + 1 : nt)));
-}
-
-// FOLD_ANTI on 16-bit operands with an exact wrapping accumulator is the plain polyphase FIR of upfir_q15.cu
-static bool polyintr_q15_ok(const b2d_polyintr_desc &d, int *lsh) {
-  const Fmt in = to_fmt(d.in), fc = to_fmt(d.coeff), fa = to_fmt(d.acc);
-  if (d.ftype != B2D_PI_FOLD_ANTI) return false;
-  if (in.W > 16 || (!in.S && in.W == 16) || fc.W > 16 || (!fc.S && fc.W == 16)) return false;
-  if (fa.O != B2D_WRAP || (fa.Q != B2D_TRN && fa.Q != B2D_RND)) return false;
-  const int s = in.F() + fc.F() - fa.F();
-  if (s > 0 || -s > 40 || -s >= fa.W) return false;
-  if (!upfir_q15_geometry((int)d.intr_factor, (int)(d.n_taps * d.intr_factor), 16)) return false;
-  *lsh = -s;
-  return true;
-}
-
-extern "C" int b2d_polyintr_create(b2d_polyintr **out, const b2d_polyintr_desc *desc) {
-  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int st;
-  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
-  if ((st = check_fmt(desc->coeff, 32, "COEFF_TYPE"))) return st;
-  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
-  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
-  if (desc->n_taps < 1 || desc->n_taps > (1u << 16)) return fail(B2D_EINVAL, "NTAPS = %u outside 1..65536", desc->n_taps);
-  if (desc->intr_factor < 1 || desc->intr_factor > 255) return fail(B2D_EINVAL, "IF = %u outside 1..255", desc->intr_factor);
-  if (desc->ftype < B2D_PI_FOLD_EVEN || desc->ftype > B2D_PI_FOLD_ANTI) return fail(B2D_EINVAL, "bad ftype");
-  if (desc->n_channels < 1) return fail(B2D_EINVAL, "n_channels must be >= 1");
-  if (desc->layout != B2D_PLANAR && desc->layout != B2D_INTERLEAVED) return fail(B2D_EINVAL, "bad layout");
-  const Fmt fin = to_fmt(desc->in), fc = to_fmt(desc->coeff), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
-  {  // bit budget of the 128-bit generic evaluation: the folded forms multiply COEFF_TYPE by an ACC_TYPE fold
-    const bool folded = desc->ftype != B2D_PI_FOLD_ANTI;
-    const int Fp = (folded ? fa.F() : fin.F()) + fc.F(), Wp = (folded ? fa.W : fin.W) + fc.W + 2, rF = std::max(Fp, fa.F());
-    if (fa.W + (rF - fa.F()) > 125 || Wp + (rF - Fp) > 125 || fa.W + 2 + std::max(0, fo.F() - fa.F()) > 125 ||
-        fin.W + 2 + std::max(0, fa.F() - fin.F()) > 125)
-      return fail(B2D_EUNSUPPORTED, "format combination exceeds the 128-bit intermediate budget");
-  }
-  int dev = desc->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_polyintr *h = new (std::nothrow) b2d_polyintr();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->d = *desc; h->fin = fin; h->fc = fc; h->fa = fa; h->fo = fo; h->device = dev;
-  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W); h->c_bytes = container_bytes(fc.W);
-  h->csz = polyintr_csz(desc->n_taps, desc->intr_factor, desc->ftype);
-  const uint32_t C = desc->n_channels, IF = desc->intr_factor;
-  h->H = (int)desc->n_taps + 2;
-  h->ch_loaded.assign(C, 0);
-  h->mode = polyintr_fast_supported(fin, fc, fa, desc->ftype) ? 1 : 0;
-  const char *force = getenv("B2D_FORCE_GENERIC");
-  if (h->mode && polyintr_q15_ok(*desc, &h->lsh) && !(force && *force == '2')) h->mode = 2;
-  if (force && *force == '1') h->mode = 0;
-  if (h->mode == 2) { h->planes = 2; h->words = upfir_q15_words((int)IF, (int)(desc->n_taps * IF), h->planes); }
-  cudaError_t e = cudaMalloc(&h->d_coeff64, (size_t)C * std::max(h->csz, 1) * sizeof(int64_t));
-  if (e == cudaSuccess && h->mode == 2) e = cudaMalloc(&h->d_cw, (size_t)C * h->words * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_sign, (size_t)C * IF);
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_corr, (size_t)C * IF);
-  const size_t tail_bytes = std::max<size_t>((size_t)h->H * C * h->in_bytes, 16);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-    e = cudaMalloc(&h->d_tail[i], tail_bytes);
-    if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_carry[i], (size_t)C * IF * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMemset(h->d_carry[i], 0, (size_t)C * IF * sizeof(int64_t));
-  }
-  if (e != cudaSuccess) { cudaGetLastError(); b2d_polyintr_destroy(h); return fail(B2D_ECUDA, "b2d_polyintr_create: %s", cudaGetErrorString(e)); }
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" const char *b2d_polyintr_path(b2d_polyintr *h) { return !h ? "" : (h->mode == 2 ? "polyintr_q15" : (h->mode ? "polyintr_wide" : "polyintr_generic")); }
-extern "C" size_t b2d_polyintr_coeffsz(b2d_polyintr *h) { return h ? (size_t)h->csz : 0; }
-extern "C" size_t b2d_polyintr_max_out(b2d_polyintr *h, size_t n) { return h ? n * h->d.intr_factor : 0; }
-
-extern "C" int b2d_polyintr_load(b2d_polyintr *h, const void *coeff_raw, size_t n, const uint8_t *sign, const uint8_t *corr, int32_t channel) {
-  TraceRange trace__("b2d_polyintr_load");
-  if (!h || (!coeff_raw && h->csz)) return fail(B2D_EINVAL, "null argument");
-  const uint32_t C = h->d.n_channels, IF = h->d.intr_factor;
-  const size_t L = (size_t)h->csz;
-  if (n != L) return fail(B2D_EINVAL, "expected %zu coefficients, got %zu", L, n);
-  if (channel < -1 || channel >= (int32_t)C) return fail(B2D_EINVAL, "channel %d outside -1..%u", channel, C - 1);
-  std::vector<uint8_t> sg(IF, 1), cr(IF);
-  for (uint32_t j = 0; j < IF; j++) {
-    cr[j] = corr ? corr[j] : (uint8_t)j;
-    if (sign) sg[j] = sign[j] ? 1 : 0;
-    if (cr[j] >= IF) return fail(B2D_EINVAL, "corr[%u] = %u outside 0..IF-1 (the reference would index acc_a / acc_b out of range)", j, cr[j]);
-  }
-  int st = use_device(h->device);
-  if (st) return st;
-  std::vector<int64_t> v(std::max<size_t>(L, 1));
-  for (size_t i = 0; i < L; i++) {
-    int64_t r;
-    if (h->c_bytes == 2) r = h->fc.S ? (int64_t)((const int16_t *)coeff_raw)[i] : (int64_t)((const uint16_t *)coeff_raw)[i];
-    else if (h->c_bytes == 4) r = h->fc.S ? (int64_t)((const int32_t *)coeff_raw)[i] : (int64_t)((const uint32_t *)coeff_raw)[i];
-    else r = ((const int64_t *)coeff_raw)[i];
-    v[i] = wrap_bits(r, h->fc.W, h->fc.S);
-  }
-  CU(cudaDeviceSynchronize());
-  std::vector<uint32_t> pk;
-  if (h->mode == 2) {      // composite taps of the polyphase form: c[ph + IF*m] = coeffs[m + NTAPS*ph]
-    const int NT = (int)h->d.n_taps;
-    std::vector<int64_t> comp((size_t)NT * IF);
-    for (uint32_t ph = 0; ph < IF; ph++)
-      for (int m = 0; m < NT; m++) comp[ph + (size_t)IF * m] = v[m + (size_t)NT * ph];
-    pk.assign((size_t)h->words, 0);
-    upfir_q15_pack(comp.data(), NT * (int)IF, (int)IF, h->planes, pk.data());
-  }
-  for (uint32_t c = 0; c < C; c++) {
-    if (channel >= 0 && (uint32_t)channel != c) continue;
-    if (L) CU(cudaMemcpy(h->d_coeff64 + c * L, v.data(), L * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (h->mode == 2) CU(cudaMemcpy(h->d_cw + (size_t)c * h->words, pk.data(), pk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_sign + (size_t)c * IF, sg.data(), IF, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_corr + (size_t)c * IF, cr.data(), IF, cudaMemcpyHostToDevice));
-    h->ch_loaded[c] = 1;
-  }
-  return B2D_OK;
-}
-
-static size_t polyintr_rows(const b2d_polyintr *h, size_t n) {
-  if (h->d.ftype == B2D_PI_FOLD_ANTI || h->init) return n;
-  return n ? n - 1 : 0;
-}
-
-static int polyintr_launch(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t n_rows, cudaStream_t st) {
-  if (n == 0) return B2D_OK;
-  const uint32_t C = h->d.n_channels;
-  const bool il = h->d.layout == B2D_INTERLEAVED;
-  if (h->mode == 2) {
-    UpLaunch p;
-    p.facc = h->fa; p.fout = h->fo; p.R = (int)h->d.intr_factor; p.taps_total = (int)(h->d.n_taps * h->d.intr_factor);
-    p.planes = h->planes; p.lsh = h->lsh; p.C = C; p.interleaved = il;
-    p.in = d_in; p.out = d_out; p.n = n; p.n_out = n * h->d.intr_factor;
-    p.n_seen = h->n_seen; p.out_first = h->n_seen * h->d.intr_factor;
-    p.tail = h->d_tail[h->cur]; p.H = h->H; p.cw = h->d_cw;
-    CU(launch_upfir_q15(p, st));
-  } else {
-    PiLaunch p;
-    p.fin = h->fin; p.fcoeff = h->fc; p.facc = h->fa; p.fout = h->fo;
-    p.nt = (int)h->d.n_taps; p.ifac = (int)h->d.intr_factor; p.ftype = h->d.ftype; p.csz = h->csz; p.fast = h->mode == 1;
-    p.C = C; p.interleaved = il; p.in = d_in; p.out = d_out; p.n = n; p.n_rows = n_rows;
-    p.row_shift = (h->d.ftype != B2D_PI_FOLD_ANTI && h->init) ? 1 : 0;
-    p.tail = h->d_tail[h->cur]; p.H = h->H; p.coeff64 = h->d_coeff64; p.sign = h->d_sign; p.corr = h->d_corr;
-    p.carry = h->d_carry[h->ccur]; p.carry_next = h->d_carry[h->ccur ^ 1];
-    CU(launch_polyintr(p, st));
-    if (h->d.ftype != B2D_PI_FOLD_ANTI) h->ccur ^= 1;
-  }
-  CicLaunch t{};
-  t.fin = h->fin; t.C = C; t.interleaved = il; t.in = d_in; t.n = n;
-  t.tail = h->d_tail[h->cur]; t.tail_next = h->d_tail[h->cur ^ 1]; t.H = h->H;
-  CU(launch_cic_tail(t, st));
-  h->cur ^= 1;
-  h->n_seen += n;
-  h->init = true;
-  return B2D_OK;
-}
-
-static int polyintr_ready(const b2d_polyintr *h) {
-  for (char c : h->ch_loaded) if (!c) return fail(B2D_ESTATE, "run() before the control / coefficient structures of every channel were loaded");
-  return B2D_OK;
-}
-
-extern "C" int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_polyintr_run_dev");
-  if (!h || (n && !d_in)) return fail(B2D_EINVAL, "null argument");
-  int st = polyintr_ready(h);
-  if (st) return st;
-  const size_t rows = polyintr_rows(h, n);
-  if (rows && !d_out) return fail(B2D_EINVAL, "null output");
-  if ((st = use_device(h->device))) return st;
-  if ((st = polyintr_launch(h, d_in, n, d_out, rows, (cudaStream_t)cuda_stream))) return st;
-  if (n_out) *n_out = rows * h->d.intr_factor;
-  return B2D_OK;
-}
-
-extern "C" int b2d_polyintr_run(b2d_polyintr *h, const void *in, size_t n, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_polyintr_run");
-  if (!h || (n && !in)) return fail(B2D_EINVAL, "null argument");
-  int st = polyintr_ready(h);
-  if (st) return st;
-  const uint32_t C = h->d.n_channels, IF = h->d.intr_factor;
-  const size_t rows_total = polyintr_rows(h, n), no_total = rows_total * IF;
-  if (no_total && !out) return fail(B2D_EINVAL, "null output");
-  if (n_out) *n_out = no_total;
-  if (n == 0) return B2D_OK;
-  if ((st = use_device(h->device))) return st;
-  Pipe &P = h->pipe;
-  if ((st = P.init())) return st;
-  const int il = h->d.layout == B2D_INTERLEAVED;
-  const double per = C * (h->in_bytes + (double)h->out_bytes * IF);
-  size_t L = std::max<size_t>((size_t)((double)(96u << 20) / per), 4096);
-  L = std::min(L, n);
-  if ((st = P.ensure(L * C * h->in_bytes, L * IF * C * h->out_bytes))) return st;
-  size_t i = 0, off_out = 0;
-  for (size_t off = 0; off < n; off += L, i++) {
-    const int s = (int)(i % Pipe::S);
-    const size_t len = std::min(L, n - off);
-    const size_t no = polyintr_rows(h, len) * IF;
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_in, P.e_k[s], 0));
-    CU(copy_chunk(P.d_in[s], in, true, h->in_bytes, C, il, n, off, len, P.s_in));
-    CU(cudaEventRecord(P.e_in[s], P.s_in));
-    CU(cudaStreamWaitEvent(P.s_k, P.e_in[s], 0));
-    if (i >= (size_t)Pipe::S) CU(cudaStreamWaitEvent(P.s_k, P.e_out[s], 0));
-    if ((st = polyintr_launch(h, P.d_in[s], len, P.d_out[s], no / IF, P.s_k))) return st;
-    CU(cudaEventRecord(P.e_k[s], P.s_k));
-    CU(cudaStreamWaitEvent(P.s_out, P.e_k[s], 0));
-    if (no) CU(copy_chunk(out, P.d_out[s], false, h->out_bytes, C, 0, no_total, off_out, no, P.s_out));
-    CU(cudaEventRecord(P.e_out[s], P.s_out));
-    off_out += no;
-  }
-  CU(cudaStreamSynchronize(P.s_out));
-  CU(cudaStreamSynchronize(P.s_k));
-  return B2D_OK;
-}
-
-extern "C" int b2d_polyintr_reset(b2d_polyintr *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  const size_t tail_bytes = std::max<size_t>((size_t)h->H * h->d.n_channels * h->in_bytes, 16);
-  for (int i = 0; i < 2; i++) {
-    CU(cudaMemset(h->d_tail[i], 0, tail_bytes));
-    CU(cudaMemset(h->d_carry[i], 0, (size_t)h->d.n_channels * h->d.intr_factor * sizeof(int64_t)));
-  }
-  h->n_seen = 0;
-  h->init = false;
-  return B2D_OK;
-}
-
-static void polyintr_parts(b2d_polyintr *h, StatePart *parts) {
-  parts[0] = StatePart{h->d_tail[h->cur], (size_t)h->H * h->d.n_channels * h->in_bytes};
-  parts[1] = StatePart{h->d_carry[h->ccur], (size_t)h->d.n_channels * h->d.intr_factor * sizeof(int64_t)};
-}
-extern "C" int b2d_polyintr_state_bytes(b2d_polyintr *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  StatePart parts[2];
-  polyintr_parts(h, parts);
-  *bytes = state_total(parts, 2);
-  return B2D_OK;
-}
-// the delay line, the parked accumulators of the last step (ac_poly_intr.h:108-110) and `init`
-extern "C" int b2d_polyintr_get_state(b2d_polyintr *h, void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  StatePart parts[2];
-  polyintr_parts(h, parts);
-  return state_get(StateHdr{kIntrMagic, 1, h->n_seen, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, h->init ? 1u : 0u}, parts, 2, blob, bytes);
-}
-extern "C" int b2d_polyintr_set_state(b2d_polyintr *h, const void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  StatePart parts[2];
-  polyintr_parts(h, parts);
-  StateHdr got;
-  if ((st = state_set(StateHdr{kIntrMagic, 1, 0, (uint32_t)h->H, h->d.n_channels, (uint32_t)h->in_bytes, 0}, parts, 2, blob, bytes, &got))) return st;
-  h->n_seen = got.n_seen;
-  h->init = got.pad != 0;
-  return B2D_OK;
-}
-
-// -------------------------------------------------------------------------------------------- ac_intg_dump
-struct b2d_intgdump {
-  b2d_intgdump_desc d;
-  Fmt fin, fa, fo;
-  int device = 0, in_bytes = 2, out_bytes = 8;
-  int64_t *d_carry[2] = {nullptr, nullptr};
-  int cur = 0;
-  unsigned long long *d_table = nullptr;
-  size_t table_cap = 0;
-  void *d_in = nullptr, *d_out = nullptr;
-  size_t cap_in = 0, cap_out = 0;
-  const char *path = "none";
-};
-
-extern "C" const char *b2d_intgdump_path(b2d_intgdump *h) { return h ? h->path : "none"; }
-
-extern "C" int b2d_intgdump_destroy(b2d_intgdump *h) {
-  if (!h) return B2D_OK;
-  use_device(h->device);
-  cudaDeviceSynchronize();
-  for (int i = 0; i < 2; i++) if (h->d_carry[i]) cudaFree(h->d_carry[i]);
-  if (h->d_table) cudaFree(h->d_table);
-  if (h->d_in) cudaFree(h->d_in);
-  if (h->d_out) cudaFree(h->d_out);
-  delete h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_intgdump_create(b2d_intgdump **out, const b2d_intgdump_desc *desc) {
-  if (!out || !desc) return fail(B2D_EINVAL, "null argument");
-  *out = nullptr;
-  int st;
-  if ((st = check_fmt(desc->in, 32, "IN_TYPE"))) return st;
-  if ((st = check_fmt(desc->acc, 64, "ACC_TYPE"))) return st;
-  if ((st = check_fmt(desc->out, 64, "OUT_TYPE"))) return st;
-  if (desc->ns < 1 || desc->chn < 1 || desc->chn > 65536) return fail(B2D_EINVAL, "NS = %u, CHN = %u invalid", desc->ns, desc->chn);
-  const Fmt fin = to_fmt(desc->in), fa = to_fmt(desc->acc), fo = to_fmt(desc->out);
-  if (std::abs(fin.F() - fa.F()) > 60 || fa.W + std::max(0, fo.F() - fa.F()) > 125) return fail(B2D_EUNSUPPORTED, "format combination exceeds the intermediate budget");
-  int dev = desc->device;
-  if (dev < 0) CU(cudaGetDevice(&dev));
-  if ((st = use_device(dev))) return st;
-  b2d_intgdump *h = new (std::nothrow) b2d_intgdump();
-  if (!h) return fail(B2D_ENOMEM, "handle");
-  h->d = *desc; h->fin = fin; h->fa = fa; h->fo = fo; h->device = dev;
-  h->in_bytes = container_bytes(fin.W); h->out_bytes = container_bytes(fo.W);
-  for (int i = 0; i < 2; i++) {
-    cudaError_t e = cudaMalloc(&h->d_carry[i], desc->chn * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMemset(h->d_carry[i], 0, desc->chn * sizeof(int64_t));
-    if (e != cudaSuccess) { cudaGetLastError(); b2d_intgdump_destroy(h); return fail(B2D_ECUDA, "b2d_intgdump_create: %s", cudaGetErrorString(e)); }
-  }
-  *out = h;
-  return B2D_OK;
-}
-
-extern "C" int b2d_intgdump_reset(b2d_intgdump *h) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  CU(cudaDeviceSynchronize());
-  for (int i = 0; i < 2; i++) CU(cudaMemset(h->d_carry[i], 0, h->d.chn * sizeof(int64_t)));
-  return B2D_OK;
-}
-
-// the running sums temp[CHN] (ac_intg_dump.h:78)
-extern "C" int b2d_intgdump_state_bytes(b2d_intgdump *h, size_t *bytes) {
-  if (!h || !bytes) return fail(B2D_EINVAL, "null argument");
-  *bytes = sizeof(StateHdr) + (size_t)h->d.chn * sizeof(int64_t);
-  return B2D_OK;
-}
-extern "C" int b2d_intgdump_get_state(b2d_intgdump *h, void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  const StatePart parts[1] = {{h->d_carry[h->cur], (size_t)h->d.chn * sizeof(int64_t)}};
-  return state_get(StateHdr{kDumpMagic, 1, 0, 0, h->d.chn, 8, 0}, parts, 1, blob, bytes);
-}
-extern "C" int b2d_intgdump_set_state(b2d_intgdump *h, const void *blob, size_t bytes) {
-  if (!h) return fail(B2D_EINVAL, "null handle");
-  int st = use_device(h->device);
-  if (st) return st;
-  const StatePart parts[1] = {{h->d_carry[h->cur], (size_t)h->d.chn * sizeof(int64_t)}};
-  StateHdr got;
-  return state_set(StateHdr{kDumpMagic, 1, 0, 0, h->d.chn, 8, 0}, parts, 1, blob, bytes, &got);
-}
-
-// token sequence -> segments of the per-channel sample axis (control flow of ac_intg_dump.h:133-147)
-static int intgdump_plan(const b2d_intgdump *h, const uint32_t *n_sample, size_t n_frames, size_t n_in, std::vector<unsigned long long> &bounds,
-                         size_t *nseg_out, int *has_tail, bool *regular) {
-  const unsigned long long NS = h->d.ns, CHN = h->d.chn;
-  bounds.clear();
-  unsigned long long pos = 0;
-  // equal dumping frames (the common case) need no boundary table: one vectorisable pass over the tokens
-  uint32_t diff = 0;
-  const uint32_t n0 = n_frames ? n_sample[0] : 0;
-  for (size_t f = 0; f < n_frames; f++) diff |= n_sample[f] ^ n0;
-  *regular = n_frames > 0 && diff == 0 && n0 >= 1 && n0 <= NS;
-  if (*regular) {
-    pos = (unsigned long long)n0 * n_frames;
-    if (pos * CHN != n_in) return fail(B2D_EINVAL, "the frames consume %llu samples, got %zu", pos * CHN, n_in);
-    *nseg_out = n_frames;
-    *has_tail = 0;
-    return B2D_OK;
-  }
-  bounds.push_back(0);
-  for (size_t f = 0; f < n_frames; f++) {
-    const unsigned long long n = n_sample[f];
-    if (n >= 1 && n <= NS) { pos += n; bounds.push_back(pos); }
-    else pos += NS;
-  }
-  if (pos * CHN != n_in) return fail(B2D_EINVAL, "the frames consume %llu samples, got %zu", pos * CHN, n_in);
-  *nseg_out = bounds.size() - 1;
-  *has_tail = pos > bounds.back() ? 1 : 0;
-  if (*has_tail) bounds.push_back(pos);
-  return B2D_OK;
-}
-
-extern "C" int b2d_intgdump_run_dev(b2d_intgdump *h, const void *d_in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *d_out,
-                                    size_t *n_out, void *cuda_stream) {
-  TraceRange trace__("b2d_intgdump_run_dev");
-  if (!h || (n_frames && !n_sample) || (n_in && !d_in)) return fail(B2D_EINVAL, "null argument");
-  int st = use_device(h->device);
-  if (st) return st;
-  std::vector<unsigned long long> bounds;
-  size_t nseg_out = 0;
-  int has_tail = 0;
-  bool regular = false;
-  if ((st = intgdump_plan(h, n_sample, n_frames, n_in, bounds, &nseg_out, &has_tail, &regular))) return st;
-  if (nseg_out && !d_out) return fail(B2D_EINVAL, "null output");
-  if (n_out) *n_out = nseg_out * h->d.chn;
-  if (nseg_out == 0 && !has_tail) return B2D_OK;
-  cudaStream_t stream = (cudaStream_t)cuda_stream;
-  IdLaunch p;
-  p.fin = h->fin; p.facc = h->fa; p.fout = h->fo; p.chn = (int)h->d.chn;
-  { const char *f = getenv("B2D_FORCE_GENERIC"); p.force_thread = (f && *f == '1') ? 1 : 0; }
-  p.in = d_in; p.out = d_out; p.carry = h->d_carry[h->cur]; p.carry_next = h->d_carry[h->cur ^ 1];
-  p.nseg_out = nseg_out; p.has_tail = has_tail; p.table = nullptr; p.n_reg = 0; p.tail_end = 0;
-  if (regular) p.n_reg = n_sample[0];
-  else {
-    if (bounds.size() > h->table_cap) {
-      if (h->d_table) cudaFree(h->d_table);
-      h->d_table = nullptr; h->table_cap = 0;
-      CU(cudaMalloc(&h->d_table, bounds.size() * sizeof(unsigned long long)));
-      h->table_cap = bounds.size();
-    }
-    CU(cudaMemcpyAsync(h->d_table, bounds.data(), bounds.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    CU(cudaStreamSynchronize(stream));          // `bounds` is a local
-    p.table = h->d_table;
-  }
-  // a call without a tail segment leaves temp[] cleared (the last dump zeroed it)
-  if (!has_tail) CU(cudaMemsetAsync(h->d_carry[h->cur ^ 1], 0, h->d.chn * sizeof(int64_t), stream));
-  h->path = intgdump_path(p);
-  CU(launch_intgdump(p, stream));
-  h->cur ^= 1;
-  return B2D_OK;
-}
-
-extern "C" int b2d_intgdump_run(b2d_intgdump *h, const void *in, size_t n_in, const uint32_t *n_sample, size_t n_frames, void *out, size_t *n_out) {
-  TraceRange trace__("b2d_intgdump_run");
-  if (!h || (n_frames && !n_sample) || (n_in && !in)) return fail(B2D_EINVAL, "null argument");
-  int st = use_device(h->device);
-  if (st) return st;
-  size_t n_dump = 0;
-  for (size_t f = 0; f < n_frames; f++) n_dump += (n_sample[f] >= 1 && n_sample[f] <= h->d.ns) ? 1 : 0;
-  if (n_dump && !out) return fail(B2D_EINVAL, "null output");
-  const size_t in_b = n_in * h->in_bytes, out_b = n_dump * h->d.chn * h->out_bytes;
-  if (in_b > h->cap_in) { if (h->d_in) cudaFree(h->d_in); h->d_in = nullptr; h->cap_in = 0; CU(cudaMalloc(&h->d_in, in_b)); h->cap_in = in_b; }
-  if (out_b > h->cap_out) { if (h->d_out) cudaFree(h->d_out); h->d_out = nullptr; h->cap_out = 0; CU(cudaMalloc(&h->d_out, out_b)); h->cap_out = out_b; }
-  if (in_b) CU(cudaMemcpy(h->d_in, in, in_b, cudaMemcpyHostToDevice));
-  size_t no = 0;
-  if ((st = b2d_intgdump_run_dev(h, h->d_in, n_in, n_sample, n_frames, h->d_out, &no, nullptr))) return st;
-  CU(cudaDeviceSynchronize());
-  if (no) CU(cudaMemcpy(out, h->d_out, no * h->out_bytes, cudaMemcpyDeviceToHost));
-  if (n_out) *n_out = no;
   return B2D_OK;
 }

@@ -46,7 +46,26 @@ def _set_state(h, prefix, blob):
 class _Block:
     """Shared marshaling: channel layout, numpy / torch dispatch."""
 
+    _prefix = None      # C-ABI family prefix ("fir", "cic", ...) of the subclasses that have b2d_<prefix>_set_wire
+
+    def set_wire(self, wire):
+        """Format of the output array of the numpy (host-buffer) run(): "container" (default) or "packed" --
+        ceil(W_out / 8) little-endian bytes per value (b200dsp.h: b2d_wire).  Packed runs return a uint8 array shaped
+        like the container result with a trailing axis of that many bytes; unpack_wire() widens it on the host."""
+        w = L.WIRE_PACKED if wire in ("packed", L.WIRE_PACKED) else L.WIRE_CONTAINER
+        L.check(getattr(L.load(), f"b2d_{self._prefix}_set_wire")(self._h, w))
+        self._wire = w
+
+    def unpack_wire(self, packed):
+        """Packed host output -> containers (b2d_unpack_wire), same shape without the trailing byte axis."""
+        p = np.ascontiguousarray(packed, dtype=np.uint8)
+        out = np.empty(p.shape[:-1], dtype=self._out_dt)
+        L.check(L.load().b2d_unpack_wire(p.ctypes.data, out.size, self._out_W, self._out_S, out.ctypes.data))
+        return out
+
     def _setup_io(self, fin, fout, n_channels, layout):
+        self._wire = L.WIRE_CONTAINER
+        self._out_W, self._out_S = int(fout.W), int(fout.S)
         self._C = int(n_channels)
         self._layout = L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR
         self._in_dt = _container_dtype(fin)
@@ -96,6 +115,11 @@ class _Block:
         x = np.ascontiguousarray(np.asarray(x).astype(self._in_dt, copy=False))
         n = self._n_per_channel(x.shape)
         cap = max_out(n)
+        if self._wire == L.WIRE_PACKED:
+            pb = lib.b2d_wire_bytes(self._out_W, L.WIRE_PACKED)
+            yb = np.empty(self._C * max(cap, 1) * pb, dtype=np.uint8)
+            L.check(fn_host(self._h, x.ctypes.data, n, yb.ctypes.data, C.byref(n_out)))
+            return yb[: self._C * n_out.value * pb].reshape(self._out_shape(n_out.value, rate_changing) + (pb,)).copy()
         y = np.empty(self._C * max(cap, 1), dtype=self._out_dt)
         L.check(fn_host(self._h, x.ctypes.data, n, y.ctypes.data, C.byref(n_out)))
         return y[: self._C * n_out.value].reshape(self._out_shape(n_out.value, rate_changing)).copy()
@@ -103,6 +127,7 @@ class _Block:
 
 class _Fir(_Block):
     _kind = "load"
+    _prefix = "fir"
 
     def __init__(self, IN_TYPE, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype="SHIFT_REG", n_channels=1,
                  layout="planar", device=-1, comm=None, root=0):
@@ -262,6 +287,8 @@ class ac_fir_reg_share(_Fir):
 class _Cic(_Block):
     _mode = 0
 
+    _prefix = "cic"
+
     def __init__(self, IN_TYPE, OUT_TYPE, R, M, N, n_channels=1, layout="planar", device=-1):
         lib = L.load()
         self._h = None
@@ -327,8 +354,10 @@ class cic_intr_fir_cascade(_Block):
     same stream-edge behaviour.  When no stage drops bits the engine fuses both into a single polyphase kernel on the
     16-bit input (path 'cicfir_fused'); otherwise the two kernels run back to back on the device."""
 
+    _prefix = "cicfir"
+
     def __init__(self, IN_TYPE, MID_TYPE, R, M, N, OUT_TYPE, COEFF_TYPE, ACC_TYPE, N_TAPS, ftype="SHIFT_REG", coeffs=None,
-                 n_channels=1, layout="planar", device=-1):
+                 n_channels=1, layout="planar", device=-1, fir_class="load"):
         lib = L.load()
         self._h = None
         self.N_TAPS = int(N_TAPS)
@@ -336,7 +365,7 @@ class cic_intr_fir_cascade(_Block):
         ft = L.FTYPES.index(ftype) if isinstance(ftype, str) else int(ftype)
         cd = L.B2dCicDesc(L.make_fmt(IN_TYPE), L.make_fmt(MID_TYPE), int(R), int(M), int(N), 1, int(n_channels), lay, int(device))
         fd = L.B2dFirDesc(L.make_fmt(MID_TYPE), L.make_fmt(COEFF_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(OUT_TYPE),
-                          self.N_TAPS, ft, 1, int(n_channels), L.PLANAR, int(device))
+                          self.N_TAPS, ft, L.FIR_KINDS.index(fir_class), int(n_channels), L.PLANAR, int(device))
         h = C.c_void_p()
         L.check(lib.b2d_cicfir_create(C.byref(h), C.byref(cd), C.byref(fd)))
         self._h = h
@@ -383,6 +412,8 @@ class ac_poly_dec(_Block):
     """ac_poly_dec<IN, COEFF, STR_COEFF, ACC, OUT, NTAPS, DF>::run(data_in, data_out, coeffs_st)
     (reference ac_poly_dec.h:87-137): polyphase decimator, one output per DF inputs, coefficients
     coeffs[NTAPS * DF] in phase order.  A call consumes whole groups of DF samples; the rest stays pending."""
+
+    _prefix = "polydec"
 
     def __init__(self, IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE, NTAPS, DF, coeffs=None, n_channels=1, layout="planar", device=-1):
         lib = L.load()
@@ -439,6 +470,8 @@ class ac_poly_intr(_Block):
     coeffs_st, read_ctrl_chan)  (reference ac_poly_intr.h:261-312): polyphase interpolator, IF
     outputs per input.  ftype is "FOLD_EVEN" / "FOLD_ODD" (symmetric-pair structures: outputs one step late, sign[] and
     corr[] from the control struct) or "FOLD_ANTI" (plain polyphase form).  load() is the read_ctrl = true call."""
+
+    _prefix = "polyintr"
 
     def __init__(self, IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE, NTAPS, IF, ftype="FOLD_ANTI", coeffs=None, sign=None, corr=None,
                  n_channels=1, layout="planar", device=-1):

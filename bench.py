@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric on the B200 engine, with the reference's CPU path beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir256|fir1024|cic_dec|cic_intr] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir256|fir1024|cic_dec|cic_intr|...] [--impl reference]
 
 A step is one run() of the hot path over one batch of synthetic 16-bit samples already resident in HBM
 (default workload: BASELINE.json configs[1], the 256-tap ac_fixed<16,1> -> <40,8> FIR over 2^30 interleaved IQ
-samples per GPU).  Rank 0 prints ONE JSON line.  `value` is device-resident throughput (CUDA events, max over
-ranks); `e2e` is the same metric through the C-ABI host-buffer call (b2d_*_run on pinned host memory, copies
-inside the timed region); `roofline` is the dominant kernel's algorithmic HBM bytes / its event-timed duration
-against MEASURED_PEAKS.json; `cpu_baseline` is the reference's own C++ templates (oracle/_ref, built in the dev
-container from /root/reference over the clean-room ac_types shim) on this box's host cores over a bounded sample.
-`--impl reference` prints that CPU run as its own line.  The oracle is only ever the thing timed as the
-CPU baseline here -- never part of the GPU path.
+samples per GPU).  Rank 0 prints ONE JSON line:
+  value        device-resident throughput (CUDA events on the launching stream, max over ranks)
+  roofline     the dominant kernel's algorithmic HBM bytes / its event-timed duration against MEASURED_PEAKS.json
+  e2e          the same metric through the C-ABI host-buffer call (b2d_*_run on page-locked host memory from
+               b2d_host_alloc, H2D / D2H copies inside the timed region), outputs in their int64 containers;
+               pcie_ceiling / frac put it against the bare-cudaMemcpyAsync ceiling of the box (tools/ubench_pcie.cu)
+  e2e_packed   the same call with the packed host-link format (B2D_WIRE_PACKED: 5 bytes per <40,8> value) -- a
+               different output format, reported separately, never mixed with e2e
+  parity       after the timed region every rank re-derives windows of its last output with the integer restatement
+               (oracle/oracle_b.c): mismatches summed over ranks -- the N-GPU runs carry their own parity check
+  cpu_baseline the reference's own C++ templates (oracle/_ref, built in the dev container from /root/reference over the
+               clean-room ac_types shim) on this box's host cores over a bounded sample (rank 0, one GPU)
+  secondary    {"cic_dec": ...}: the second workload north_star names (R=8, N=4 CIC decimator, BASELINE configs[2],
+               2^30 IQ inputs) with the same fields, measured in the same run at every N
+`--impl reference` prints the CPU run as its own line.  The oracle is only ever the thing timed as the CPU baseline or
+the checker of the parity probe here -- never part of the GPU path.
 """
 import argparse
 import json
@@ -279,46 +288,93 @@ def bind_near_gpu(local):
     return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="fir256", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2n", type=int, default=None, help="override samples per channel per step (power of two)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU seconds per step (bounded sample)")
-    args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.log2n:
-        wl["n"] = 1 << args.log2n
-    if args.impl == "reference":
-        return run_reference(args, wl)
-    args.warmup = max(args.warmup, 3)
+def host_buffer(lib, nbytes):
+    """Page-locked host memory from the engine's own allocator (b2d_host_alloc: cudaHostAlloc, or pages next to the GPU
+    with B2D_HOST_NUMA=1) as a uint8 numpy view, plus the pointer for b2d_host_free."""
+    import ctypes as ct
+    p = ct.c_void_p()
+    assert lib.b2d_host_alloc(ct.byref(p), nbytes) == 0, lib.b2d_last_error()
+    return np.ctypeslib.as_array((ct.c_uint8 * nbytes).from_address(p.value)), p
 
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    orig_affinity = bind_near_gpu(local) if world > 1 else None
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import ac_dsp_b200 as E
-    from ac_dsp_b200 import build as _b
-    if rank == 0:
-        _b.build()
-    if world > 1:
-        dist.barrier()
-    E.load()
 
-    # ---- coefficient set: rank 0 owns it, one ncclBroadcast at load() (the only collective on this path)
-    from ac_dsp_b200 import parallel as P
-    comm = P.make_comm(rank, world, local)
+def pcie_ceiling(world, in_bytes_per_unit, out_bytes_per_unit):
+    """Units/s the host link of this box can carry for this byte mix: the slower of the two directions, each taken from
+    the bare pinned-cudaMemcpyAsync measurement with `world` GPUs copying at once (tools/ubench_pcie.cu ->
+    profiles/r02_ubench_pcie.jsonl).  An upper bound (single-direction figures); None when no measurement is committed."""
+    path = os.path.join(ROOT, "profiles", "r02_ubench_pcie.jsonl")
+    if not os.path.exists(path):
+        return None
+    h2d = d2h = None
+    for ln in open(path):
+        try:
+            r = json.loads(ln)
+        except ValueError:
+            continue
+        if r.get("n_gpus") != world or r.get("h2d_source") != "default":
+            continue
+        if r.get("pattern") == "h2d":
+            h2d = r["h2d_gbs_sum"]
+        if r.get("pattern") == "d2h":
+            d2h = r["d2h_gbs_sum"]
+    if not h2d or not d2h:
+        return None
+    t = max(in_bytes_per_unit / (h2d * 1e9), out_bytes_per_unit / (d2h * 1e9))
+    return {"value": 1.0 / t / 1e6, "unit": "Msamples/s", "h2d_gbs": h2d, "d2h_gbs": d2h,
+            "source": f"profiles/r02_ubench_pcie.jsonl: bare pinned cudaMemcpyAsync, {world} GPU(s) at once, each direction alone"}
+
+
+def parity_probe(wl, x, y, n, C, il, h, rank):
+    """A few windows of the LAST timed step's output re-derived on the CPU by the integer restatement (oracle/oracle_b.c,
+    the checker -- never on the measured path): every rank checks its own bytes, so an N-GPU run carries N parity results."""
+    from oracle import oracle as O
+    O.build()
+    rng = np.random.default_rng(SEED + 7919 * (rank + 1))
+    W = 192
+    bad, checked, windows = 0, 0, []
+    if wl["kind"] == "fir":
+        T = wl["taps"] - 1
+        infmt = wl.get("infmt", Q15)
+        offs = [0, int(rng.integers(T + 1, n - W - 1)), n - W]
+        for off in offs:
+            for c in sorted(set((0, C - 1))):
+                col = (lambda a, lo, hi: a[lo:hi, c] if il and C > 1 else (a[c, lo:hi] if C > 1 else a[lo:hi]))
+                if off == 0:   # the step before fed the same block: the history is its last T samples
+                    seg = np.concatenate([col(x, n - T, n).cpu().numpy(), col(x, 0, W).cpu().numpy()])
+                else:
+                    seg = col(x, off - T, off + W).cpu().numpy()
+                ob = O.FirB(infmt, Q15, ACC40, ACC40, wl["taps"], "SHIFT_REG")
+                ob.load(h)
+                want = ob.run(seg)[T:]
+                got = col(y, off, off + W).cpu().numpy().astype(np.int64)
+                bad += int(np.count_nonzero(got != want))
+                checked += W
+            windows.append(off)
+    elif wl["kind"] == "cic" and wl["mode"] == "dec":
+        R = wl["R"]
+        n_out = n // R
+        yy = y.reshape(C, -1) if C > 1 else y.reshape(1, -1)
+        lead = 2 * wl["N"] * wl["M"] + 8        # outputs before the window: the restatement's run-in from a zero state
+        for m0 in (lead, int(rng.integers(lead + 1, n_out - W - 1)), n_out - W):
+            for c in sorted(set((0, C - 1))):
+                lo, hi = R * (m0 - lead), R * (m0 + W)
+                seg = (x[lo:hi, c] if il and C > 1 else (x[c, lo:hi] if C > 1 else x[lo:hi])).cpu().numpy()
+                want = O.CicB("dec", Q15, wl["out"], R, wl["M"], wl["N"]).run(seg)[lead:lead + W]
+                got = yy[c, m0:m0 + W].cpu().numpy().astype(np.int64)
+                bad += int(np.count_nonzero(got != want))
+                checked += W
+            windows.append(m0)
+    else:
+        return None
+    return {"windows": len(windows), "outputs_checked": checked, "mismatches": bad, "ok": bad == 0,
+            "checker": "oracle/oracle_b.c (integer restatement of the reference), after the timed region", "rank": rank}
+
+
+def measure(name, wl, args, ctx, want_cpu):
+    """One workload on this rank's GPU: device-resident throughput, roofline, e2e through the C-ABI host path (both
+    host-link formats), parity probe, CPU baseline (rank 0, one GPU).  Returns the fields of its JSON object."""
+    import ctypes as ct
+    torch, dist, E = ctx["torch"], ctx["dist"], ctx["E"]
+    rank, world, local, comm = ctx["rank"], ctx["world"], ctx["local"], ctx["comm"]
     rng = np.random.default_rng(SEED)
     C, n, il = wl["channels"], wl["n"], wl["layout"] == "interleaved"
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
@@ -326,11 +382,12 @@ def main():
     infmt = wl.get("infmt", Q15)
     lim = 1 << (infmt[0] - 1)
     x = torch.randint(-lim, lim, shape, dtype=torch.int16 if infmt[0] <= 16 else torch.int32, device="cuda", generator=gen)
+    h = None
     if wl["kind"] == "fir":
         h = rng.integers(-32768, 32767, size=wl["taps"], endpoint=True).astype(np.int16)
         f = E.ac_fir_load_coeffs(infmt, ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG", n_channels=C, layout=wl["layout"],
                                  device=local, comm=comm, root=0)
-        f.load(h if rank == 0 else None)
+        f.load(h if rank == 0 else None)     # rank 0 owns the set: one ncclBroadcast (the only collective on this path)
         launches_per_step = 2          # fir_q15_kernel + history carry
     elif wl["kind"] == "intgdump":
         class _Id:   # adapter: fixed token array, out= ignored (outputs are 1/64 of the input)
@@ -397,71 +454,104 @@ def main():
     value = units_per_step * world / (ms_per_step * 1e-3) / 1e6
     out_bytes = y.numel() * y.element_size()
     in_bytes = x.numel() * x.element_size()
+
+    # ---- parity of the bytes just produced, on every rank
+    parity = None
+    if not args.no_parity:
+        mine = parity_probe(wl, x, y, n, C, il, h, rank)
+        if mine is not None:
+            t = torch.tensor([mine["mismatches"], mine["outputs_checked"], mine["windows"]], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            tot = [int(v) for v in t.tolist()]
+            parity = {"ranks": world, "windows": tot[2], "outputs_checked": tot[1], "mismatches": tot[0], "ok": tot[0] == 0,
+                      "checker": mine["checker"]}
     del y
 
-    # ---- end to end through the C-ABI host-buffer call (pinned host memory, copies inside the timed region)
-    e2e = None
+    # ---- end to end through the C-ABI host-buffer call (page-locked host memory, copies inside the timed region)
+    e2e = e2e_packed = None
     if not args.no_e2e:
-        n2 = min(n, 1 << 27 if wl["kind"] == "fir" else 1 << 28)
-        shape2 = (n2, C) if il else ((C, n2) if C > 1 else (n2,))
-        xh = torch.empty(shape2, dtype=x.dtype).pin_memory()
-        xh.copy_(x[:n2] if (il or C == 1) else x[:, :n2])
-        xn = xh.numpy()
         lib = E.load()
-        import ctypes as ct
+        n2 = min(n, 1 << 27 if wl["kind"] == "fir" else 1 << 28)
+        u2 = n2 if wl["unit_is_iq"] else n2 * C
+        xin = (x[:n2] if (il or C == 1) else x[:, :n2]).contiguous()
+        xb, xptr = host_buffer(lib, xin.numel() * xin.element_size())
+        xb[:] = xin.cpu().numpy().view(np.uint8).reshape(-1)
+        del xin
+        no = ct.c_size_t(n2)
+        tok2 = None
         if wl["kind"] == "fir":
-            yh = torch.empty(n2 * C, dtype=torch.int64).pin_memory()
-            call = lambda: lib.b2d_fir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), None)
+            cap, W_out, fn, setw = n2, 40, lib.b2d_fir_run, lib.b2d_fir_set_wire
         elif wl["kind"] == "intgdump":
             tok2 = np.full(n2 // (wl["chn"] * wl["nsamp"]), wl["nsamp"], dtype=np.uint32)
-            yh = torch.empty(tok2.size * wl["chn"], dtype=torch.int32).pin_memory()
-            call = lambda: lib.b2d_intgdump_run(f._h, xn.ctypes.data, n2, tok2.ctypes.data, tok2.size, yh.data_ptr(), ct.byref(no))
+            cap, W_out, fn, setw = tok2.size * wl["chn"], 32, lib.b2d_intgdump_run, None
         elif wl["kind"] == "polyintr":
-            yh = torch.empty(lib.b2d_polyintr_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
-            call = lambda: lib.b2d_polyintr_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
+            cap, W_out, fn, setw = lib.b2d_polyintr_max_out(f._h, n2), 40, lib.b2d_polyintr_run, lib.b2d_polyintr_set_wire
         elif wl["kind"] == "polydec":
-            yh = torch.empty(lib.b2d_polydec_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
-            call = lambda: lib.b2d_polydec_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
+            cap, W_out, fn, setw = lib.b2d_polydec_max_out(f._h, n2), 40, lib.b2d_polydec_run, lib.b2d_polydec_set_wire
         elif wl["kind"] == "cicfir":
-            yh = torch.empty(lib.b2d_cicfir_max_out(f._h, n2) * C, dtype=torch.int64).pin_memory()
-            call = lambda: lib.b2d_cicfir_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
+            cap, W_out, fn, setw = lib.b2d_cicfir_max_out(f._h, n2), 40, lib.b2d_cicfir_run, lib.b2d_cicfir_set_wire
         else:
-            cap = lib.b2d_cic_max_out(f._h, n2)
-            yh = torch.empty(cap * C, dtype=torch.int32).pin_memory()
-            call = lambda: lib.b2d_cic_run(f._h, xn.ctypes.data, n2, yh.data_ptr(), ct.byref(no))
-        no = ct.c_size_t(n2)
-        for _ in range(2):
-            assert call() == 0, lib.b2d_last_error()
-        sync_all()
-        t0 = time.perf_counter()
-        k2 = max(3, min(args.steps, 5))
-        for _ in range(k2):
-            assert call() == 0, lib.b2d_last_error()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        u2 = n2 if wl["unit_is_iq"] else n2 * C
-        e2e = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
-               "d2h_bytes_per_step": int(no.value * C * yh.element_size()), "steps": k2,
-               "api": "b2d_*_run (C-ABI, pinned host buffers, 3-slot copy/compute pipeline)",
-               "host_affinity": "NVML ideal CPUs of the GPU" if orig_affinity else "unchanged",
-               "host_numa_alloc": os.environ.get("B2D_HOST_NUMA") == "1",
-               "samples_per_step": u2}
+            cap, W_out, fn, setw = lib.b2d_cic_max_out(f._h, n2), wl["out"][0], lib.b2d_cic_run, lib.b2d_cic_set_wire
+        cbytes = lib.b2d_container_bytes(W_out)
+        yb, yptr = host_buffer(lib, max(cap, 1) * (C if wl["kind"] != "intgdump" else 1) * cbytes)
+        if tok2 is not None:
+            call = lambda: fn(f._h, xb.ctypes.data, n2, tok2.ctypes.data, tok2.size, yb.ctypes.data, ct.byref(no))
+        else:
+            call = lambda: fn(f._h, xb.ctypes.data, n2, yb.ctypes.data, ct.byref(no))
 
+        def timed(wire):
+            if setw is not None:
+                assert setw(f._h, wire) == 0, lib.b2d_last_error()
+            for _ in range(2):
+                assert call() == 0, lib.b2d_last_error()
+            sync_all()
+            t0 = time.perf_counter()
+            k2 = max(3, min(args.steps, 5))
+            for _ in range(k2):
+                assert call() == 0, lib.b2d_last_error()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            wb = lib.b2d_wire_bytes(W_out, wire)
+            n_vals = no.value * (C if wl["kind"] != "intgdump" else 1)
+            res = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xb.size),
+                   "d2h_bytes_per_step": int(n_vals * wb), "steps": k2,
+                   "api": f"b2d_{'cic' if wl['kind'] == 'cic' else wl['kind']}_run (C-ABI, page-locked host buffers from b2d_host_alloc, 3-slot copy/compute pipeline)",
+                   "out_format": "B2D_WIRE_PACKED: %d bytes per ac_fixed<%d,.> value" % (wb, W_out) if wire else "containers: %d bytes per value" % cbytes,
+                   "host_affinity": "NVML ideal CPUs of the GPU" if ctx["orig_affinity"] else "unchanged",
+                   "host_numa_alloc": os.environ.get("B2D_HOST_NUMA") == "1",
+                   "samples_per_step": u2,
+                   "note": "one step = one C-ABI call over %d units per GPU (the device-resident `value` runs %d per step)" % (u2, units_per_step)}
+            ceil = pcie_ceiling(world, xb.size / u2, n_vals * wb / u2)
+            if ceil:
+                res["pcie_ceiling"] = ceil
+                res["frac"] = res["value"] / ceil["value"]
+            return res
+        e2e = timed(0)
+        if setw is not None and lib.b2d_wire_bytes(W_out, 1) < cbytes:
+            e2e_packed = timed(1)
+            setw(f._h, 0)
+        lib.b2d_host_free(xptr)
+        lib.b2d_host_free(yptr)
+
+    res = {"name": name, "value": value, "ms_per_step": ms_per_step, "units_per_step": units_per_step, "path": path,
+           "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "parity": parity, "gpu_launches": launches_per_step * args.steps}
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = wl["bytes_per_unit"] * units_per_step
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            t = json.load(open(tp)).get(args.workload)
+        for tp in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            t = json.load(open(tp)).get(name) if os.path.exists(tp) else None
             if t:   # measured DRAM bytes per unit (one ncu --set full capture) scaled to this launch's units
                 traffic = t["dram_bytes_per_unit"] * units_per_step
                 traffic_src = f"{t['source']}: {t['dram_bytes']} B measured at {t['capture_units']} units/launch, scaled"
+                break
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": path,
                 "algorithmic_bytes_per_launch": alg_bytes, "actual_io_bytes_per_launch": in_bytes + out_bytes}
@@ -473,26 +563,97 @@ def main():
             roof["int_pipe"] = {"achieved_tmac_s": tmacs, "ceiling_tmac_s": 148 * 64 * sm_mhz * 1e6 / 1e12,
                                 "frac": tmacs / (148 * 64 * sm_mhz * 1e6 / 1e12),
                                 "note": "CUDA-core IDP.2A issue ceiling at the sampled SM clock (tensor cores excluded by the north star)"}
-        line = {"metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
-                "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
-                          "polydec": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
-                          "polyintr": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
-                          "intgdump": "s16 -> s64 (exact integer sum, ac_fixed<32,17> wrap)",
-                          "cic": "s16 -> u32 (modular integrate / comb)"}[wl["kind"]],
-                "data": "synthetic",
-                "config": {"workload": wl["name"], "samples_per_step_per_gpu": units_per_step, "kernel_path": path,
-                           "l2": "inputs per step exceed L2 (>= 0.5 GiB vs 126 MB); no flush needed",
-                           "parallelism": f"channels sharded over {world} GPU(s), one ncclBroadcast of the coefficient set at load()"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roof}
-        if world == 1 and not args.no_cpu:
-            if orig_affinity:
-                os.sched_setaffinity(0, orig_affinity)
+        res["roofline"] = roof
+        if want_cpu:
+            if ctx["orig_affinity"]:
+                os.sched_setaffinity(0, ctx["orig_affinity"])
             cb = cpu_reference(wl)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        emit(line)
+            res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     f.close()
+    del x, ybuf
+    torch.cuda.empty_cache()
+    return res
+
+
+DTYPES = {"fir": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)", "cicfir": "s16 x s24 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+          "polydec": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+          "polyintr": "s16 x s16 -> s64 (exact integer, ac_fixed<40,8> wrap)",
+          "intgdump": "s16 -> s64 (exact integer sum, ac_fixed<32,17> wrap)",
+          "cic": "s16 -> u32 (modular integrate / comb)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="fir256", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=None, help="override samples per channel per step (power of two)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default run: skip the second north-star target (cic_dec)")
+    ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU seconds per step (bounded sample)")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.log2n:
+        wl["n"] = 1 << args.log2n
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    orig_affinity = bind_near_gpu(local) if world > 1 else None
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import ac_dsp_b200 as E
+    from ac_dsp_b200 import build as _b
+    if rank == 0:
+        _b.build()
+    if world > 1:
+        dist.barrier()
+    E.load()
+    from ac_dsp_b200 import parallel as P
+    comm = P.make_comm(rank, world, local)
+    ctx = dict(torch=torch, dist=dist, E=E, rank=rank, world=world, local=local, comm=comm, orig_affinity=orig_affinity)
+    want_cpu = world == 1 and not args.no_cpu
+
+    m = measure(args.workload, wl, args, ctx, want_cpu)
+    # the second target workload north_star names (R=8, N=4 CIC decimator, BASELINE configs[2]) rides along with the
+    # default run, at every N, so that the driver's BENCH / SCALE records carry it
+    sec = None
+    if args.workload == "fir256" and not args.no_secondary and not args.log2n:
+        sec = measure("cic_dec", dict(WORKLOADS["cic_dec"]), args, ctx, want_cpu)
+
+    if rank == 0:
+        line = {"metric": "Msamples/s (16b IQ, 256-tap FIR)" if args.workload == "fir256" else f"Msamples/s ({args.workload})",
+                "value": m["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": DTYPES[wl["kind"]], "data": "synthetic",
+                "config": {"workload": wl["name"], "samples_per_step_per_gpu": m["units_per_step"], "kernel_path": m["path"],
+                           "l2": "inputs per step exceed L2 (>= 0.5 GiB vs 126 MB); no flush needed",
+                           "e2e_samples_per_call_per_gpu": (m["e2e"] or {}).get("samples_per_step"),
+                           "parallelism": f"channels sharded over {world} GPU(s), one ncclBroadcast of the coefficient set at load()"},
+                "clocks": m["clocks"], "e2e": m["e2e"], "e2e_packed": m["e2e_packed"], "gpu_launches": m["gpu_launches"],
+                "roofline": m["roofline"], "parity": m["parity"]}
+        if "cpu_baseline" in m:
+            line["cpu_baseline"] = m["cpu_baseline"]
+        if sec:
+            swl = WORKLOADS["cic_dec"]
+            line["secondary"] = {"cic_dec": {
+                "metric": "Msamples/s (16b IQ, R=8 N=4 CIC decimator)", "value": sec["value"], "unit": "Msamples/s", "ms_per_step": sec["ms_per_step"],
+                "dtype": DTYPES["cic"], "config": {"workload": swl["name"], "samples_per_step_per_gpu": sec["units_per_step"], "kernel_path": sec["path"]},
+                "roofline": sec["roofline"], "e2e": sec["e2e"], "e2e_packed": sec["e2e_packed"], "parity": sec["parity"],
+                "clocks": sec["clocks"], "gpu_launches": sec["gpu_launches"],
+                **({"cpu_baseline": sec["cpu_baseline"]} if "cpu_baseline" in sec else {})}}
+        emit(line)
     if comm:
         comm.close()
     if world > 1:

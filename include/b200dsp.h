@@ -47,10 +47,11 @@ typedef enum {
 typedef enum { B2D_TRN = 0, B2D_RND, B2D_TRN_ZERO, B2D_RND_ZERO, B2D_RND_INF, B2D_RND_MIN_INF, B2D_RND_CONV, B2D_RND_CONV_ODD } b2d_qmode;
 typedef enum { B2D_WRAP = 0, B2D_SAT, B2D_SAT_ZERO, B2D_SAT_SYM } b2d_omode;
 
-/* ac_fixed<W, I, S, Q, O>.  Supported: inputs/coefficients W <= 32; accumulator W <= 64 with
- * Q in {TRN, RND} and O = WRAP (these make the per-tap `acc += a*b` re-quantisation
- * order-independent, which is what lets taps and outputs run in parallel); outputs W <= 64 with any
- * Q / O. */
+/* ac_fixed<W, I, S, Q, O>.  Supported: inputs / coefficients W <= 32; accumulators and outputs W <= 64 with every
+ * quantisation and overflow mode.  Accumulators with Q in {TRN, RND} and O = WRAP make the per-tap `acc += a*b`
+ * re-quantisation order-independent and run on the fast kernel families (b2d_*_path); saturating or sign-dependent
+ * accumulators are evaluated tap by tap in the reference's own order by the generic kernels (slower, still on the GPU).
+ * Combinations whose intermediates exceed 128 bits are rejected with B2D_EUNSUPPORTED at create time. */
 typedef struct { int32_t W, I, S, Q, O; } b2d_fmt;
 
 /* FTYPE enum of the reference (ac_fir_const_coeffs.h:96). The three hot classes dispatch the first
@@ -70,6 +71,13 @@ typedef enum { B2D_CIC_DEC = 0, B2D_CIC_INTR = 1 } b2d_cic_mode;
  * (16-bit IQ = 2 interleaved channels sharing one coefficient set). */
 typedef enum { B2D_PLANAR = 0, B2D_INTERLEAVED = 1 } b2d_layout;
 
+/* Format of the OUTPUT array of the host-buffer run() calls (b2d_*_run; the _run_dev calls always use containers).
+ * CONTAINER (default): one int16 / int32 / int64 container per value, as everywhere else.
+ * PACKED: ceil(W_out / 8) little-endian bytes per value, same element order -- an ac_fixed<40,8> result is 5 bytes
+ * instead of 8.  run() on host memory is bound by the host link, so fewer bytes per value is more samples per second;
+ * b2d_unpack_wire() widens a packed array to containers on the host.  b2d_wire_bytes() gives the bytes per value. */
+typedef enum { B2D_WIRE_CONTAINER = 0, B2D_WIRE_PACKED = 1 } b2d_wire;
+
 typedef struct {
   b2d_fmt in, coeff, acc, out;  /* IN_TYPE, COEFF_TYPE, ACC_TYPE, OUT_TYPE                           */
   uint32_t n_taps;              /* N_TAPS >= 1                                                      */
@@ -82,7 +90,7 @@ typedef struct {
 
 typedef struct {
   b2d_fmt in, out;              /* IN_TYPE, OUT_TYPE; the lossless INT_TYPE is derived internally   */
-  uint32_t R, M, N;             /* rate change 2..256, differential delay >= 1, stages 1..255       */
+  uint32_t R, M, N;             /* rate change 2..256 (R = 1: B2D_EUNSUPPORTED), differential delay >= 1, stages 1..16 */
   int32_t mode;                 /* b2d_cic_mode                                                     */
   uint32_t n_channels;
   int32_t layout;
@@ -103,6 +111,9 @@ int b2d_device_count(void);                       /* number of visible CUDA devi
  * buffers are page-locked (these, or any cudaHostAlloc / cudaHostRegister / torch pinned memory). */
 int b2d_host_alloc(void **p, size_t bytes);
 int b2d_host_free(void *p);
+int b2d_wire_bytes(int32_t W, int32_t wire);      /* bytes per value of a W-bit format in a host output array */
+/* `count` packed values (B2D_WIRE_PACKED) of an ac_fixed<W,.,S> format -> containers (b2d_container_bytes(W) each), host side. */
+int b2d_unpack_wire(const void *packed, size_t count, int32_t W, int32_t S, void *out_containers);
 
 /* ---- FIR: ac_fir_const_coeffs / ac_fir_load_coeffs / ac_fir_prog_coeffs -------------------- */
 /* Class instantiation + constructor: zeroed delay line (ac_fir_load_coeffs.h:134-139). */
@@ -112,10 +123,10 @@ int b2d_fir_destroy(b2d_fir *h);
  *   CONST: the constructor's pointer (ac_fir_const_coeffs.h:314) -- allowed once.
  *   LOAD : the ld=true phase of run() (ac_fir_load_coeffs.h:324-331).
  *   PROG : the array argument of run() (ac_fir_prog_coeffs.h:277); may change between run() calls,
- *          the delay line is kept.  Exception: B2D_TRANSPOSED keeps ACC_TYPE partial sums, not samples
- *          (ac_fir_load_coeffs.h:265-278), so after a change the reference's next n_taps-1 outputs mix old and
- *          new taps; a CHANGE of taps on a TRANSPOSED filter that has consumed samples returns
- *          B2D_EUNSUPPORTED (b2d_fir_reset first).  Loading equal values again is not a change.
+ *          the delay line is kept.  B2D_TRANSPOSED keeps ACC_TYPE partial sums, not samples
+ *          (ac_fir_load_coeffs.h:265-278, ac_fir_prog_coeffs.h:232-247): after a change the reference's next
+ *          n_taps-1 outputs are old-tap partial sums plus new-tap products, and so are the engine's (the history
+ *          is converted into those pending sums at the change).
  * channel = -1 loads every channel.  With a communicator attached (b2d_fir_set_comm) the values of
  * rank `root` are broadcast to all ranks with one ncclBroadcast; other ranks may pass NULL. */
 int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t channel);
@@ -139,12 +150,14 @@ int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw);
  * buffers and is asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). */
 int b2d_fir_run(b2d_fir *h, const void *in, size_t n, void *out, size_t *n_out);
 int b2d_fir_run_dev(b2d_fir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_fir_set_wire(b2d_fir *h, int32_t wire);   /* b2d_wire: format of b2d_fir_run's output array          */
 int b2d_fir_reset(b2d_fir *h);                    /* back to the constructed state, coefficients kept */
 /* Checkpoint: the delay line etc. as an opaque blob (size via _state_bytes). */
 int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes);
 int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes);
 int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
-/* Name of the kernel family chosen for this descriptor ("fir_q15x2", "fir_generic", ...). */
+/* Name of the kernel family chosen for this descriptor: "fir_q15" (16-bit operands, DP2A byte planes), "fir_wide"
+ * (operands <= 32 bits, wrapping 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order). */
 const char *b2d_fir_path(b2d_fir *h);
 
 /* ---- CIC: ac_cic_dec_full / ac_cic_intr_full ---------------------------------------------- */
@@ -163,6 +176,7 @@ size_t b2d_cic_max_out(b2d_cic *h, size_t n);
  * PLANAR outputs use a channel stride of *n_out. */
 int b2d_cic_run(b2d_cic *h, const void *in, size_t n, void *out, size_t *n_out);
 int b2d_cic_run_dev(b2d_cic *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_cic_set_wire(b2d_cic *h, int32_t wire);
 int b2d_cic_reset(b2d_cic *h);
 int b2d_cic_state_bytes(b2d_cic *h, size_t *bytes);
 int b2d_cic_get_state(b2d_cic *h, void *blob, size_t bytes);
@@ -185,6 +199,7 @@ int b2d_cicfir_load(b2d_cicfir *h, const void *coeff_raw, size_t n, int32_t chan
 size_t b2d_cicfir_max_out(b2d_cicfir *h, size_t n);
 int b2d_cicfir_run(b2d_cicfir *h, const void *in, size_t n, void *out, size_t *n_out);
 int b2d_cicfir_run_dev(b2d_cicfir *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_cicfir_set_wire(b2d_cicfir *h, int32_t wire);
 int b2d_cicfir_reset(b2d_cicfir *h);
 const char *b2d_cicfir_path(b2d_cicfir *h);
 int b2d_cicfir_state_bytes(b2d_cicfir *h, size_t *bytes);   /* checkpoint, as b2d_fir_get_state */
@@ -212,6 +227,7 @@ int b2d_polydec_load(b2d_polydec *h, const void *coeff_raw, size_t n, int32_t ch
 size_t b2d_polydec_max_out(b2d_polydec *h, size_t n);
 int b2d_polydec_run(b2d_polydec *h, const void *in, size_t n, void *out, size_t *n_out);
 int b2d_polydec_run_dev(b2d_polydec *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_polydec_set_wire(b2d_polydec *h, int32_t wire);
 int b2d_polydec_reset(b2d_polydec *h);
 const char *b2d_polydec_path(b2d_polydec *h);
 int b2d_polydec_state_bytes(b2d_polydec *h, size_t *bytes);
@@ -249,6 +265,7 @@ int b2d_polyintr_load(b2d_polyintr *h, const void *coeff_raw, size_t n, const ui
 size_t b2d_polyintr_max_out(b2d_polyintr *h, size_t n);
 int b2d_polyintr_run(b2d_polyintr *h, const void *in, size_t n, void *out, size_t *n_out);
 int b2d_polyintr_run_dev(b2d_polyintr *h, const void *d_in, size_t n, void *d_out, size_t *n_out, void *cuda_stream);
+int b2d_polyintr_set_wire(b2d_polyintr *h, int32_t wire);
 int b2d_polyintr_reset(b2d_polyintr *h);
 /* "polyintr_q15" (DP2A polyphase kernel, FOLD_ANTI on 16-bit operands), "polyintr_wide" (64-bit modular), "polyintr_generic" */
 const char *b2d_polyintr_path(b2d_polyintr *h);

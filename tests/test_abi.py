@@ -67,10 +67,31 @@ def test_descriptor_validation_without_gpu(engine):
         base.update(kw)
         return lib.b2d_cic_create(C.byref(h), C.byref(L.B2dCicDesc(*[base[k] for k, _ in L.B2dCicDesc._fields_])))
 
-    assert cic(R=1) == L.EINVAL and cic(R=257) == L.EINVAL                     # 8-bit rate counters; R = 1 never re-reads
+    assert cic(R=0) == L.EINVAL and cic(R=257) == L.EINVAL                     # 8-bit rate counters
+    assert cic(R=1) == L.EUNSUPPORTED                                          # a valid instantiation the engine does not build
     assert cic(N=0) == L.EINVAL and cic(M=0) == L.EINVAL
     assert cic(R=256, N=8) == L.EUNSUPPORTED                                   # lossless width 80 > 64
     assert lib.b2d_device_count() >= 0
+
+
+def test_wire_format_helpers(engine):
+    """b2d_wire_bytes / b2d_unpack_wire are host-side: packed ceil(W/8)-byte values widen back to containers."""
+    import numpy as np
+    lib = engine.load()
+    assert [lib.b2d_wire_bytes(w, 1) for w in (1, 8, 9, 16, 20, 24, 28, 32, 33, 40, 48, 56, 57, 64)] == [1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 8]
+    assert [lib.b2d_wire_bytes(w, 0) for w in (8, 20, 40)] == [2, 4, 8] and lib.b2d_wire_bytes(40, 2) == 0
+    rng = np.random.default_rng(4)
+    for W, S in ((40, 1), (40, 0), (20, 1), (7, 1), (56, 1), (33, 0)):
+        lo, hi = (-(1 << (W - 1)), (1 << (W - 1)) - 1) if S else (0, (1 << W) - 1)
+        v = rng.integers(lo, hi, size=1001, endpoint=True, dtype=np.int64)
+        v[:2] = [lo, hi]
+        pb = (W + 7) // 8
+        packed = np.zeros((v.size, pb), dtype=np.uint8)
+        for b in range(pb):
+            packed[:, b] = ((v.astype(np.uint64) >> np.uint64(8 * b)) & np.uint64(0xFF)).astype(np.uint8)
+        out = np.zeros(v.size, dtype={2: np.int16, 4: np.int32, 8: np.int64}[lib.b2d_container_bytes(W)])
+        assert lib.b2d_unpack_wire(packed.ctypes.data, v.size, W, S, out.ctypes.data) == 0
+        assert np.array_equal(out.astype(np.int64), v), (W, S)
 
 
 def test_shard_count(engine):

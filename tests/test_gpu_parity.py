@@ -540,7 +540,8 @@ CASCADES = [  # (R, M, N, MID, taps, ftype, coeff fmt, expected path)
     (4, 1, 3, (20, 5), 63, "FOLD_ODD", Q15, "cicfir_fused"),
     (4, 1, 3, (20, 5), 16, "FOLD_EVEN", Q15, "cicfir_fused"),
     (4, 1, 3, (20, 5), 1, "SHIFT_REG", Q15, "cicfir_fused"),
-    (4, 1, 3, (24, 9), 30, "TRANSPOSED", (12, 1), "cicfir_fused"),     # wider MID than the lossless type, 2 byte planes?
+    (4, 1, 3, (24, 9), 30, "TRANSPOSED", (12, 1), "cicfir_two_stage"), # loadable TRANSPOSED keeps partial sums across a change: FIR object
+    (4, 1, 3, (24, 9), 30, "C_BUFF", (12, 1), "cicfir_fused"),         # wider MID than the lossless type
     (4, 1, 3, (20, 5), 21, "SHIFT_REG", (8, 1), "cicfir_fused"),          # composite taps fit 16 bits: two byte planes
     (2, 1, 4, (19, 4), 33, "C_BUFF", Q15, "cicfir_fused"),
     (2, 2, 3, (21, 6), 8, "SHIFT_REG", (10, 2, False), "cicfir_fused"),
@@ -573,6 +574,24 @@ def test_cic_fir_cascade(engine, oracle, case, two_stage, monkeypatch):
     cuts = [0, 1, 2, 3, 7, 8, 1000, 1001, 9999, n]
     parts = [f.run(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
     assert np.array_equal(np.concatenate(parts).astype(np.int64), want)
+    if ft == "TRANSPOSED" and two_stage == "0":
+        # the constant-coefficient class can never change its taps: fused; the loadable one follows the reference's
+        # partial sums across a change mid-stream (ac_fir_load_coeffs.h:265-278)
+        g = engine.cic_intr_fir_cascade(Q15, mid, R, M, N, ACC40, fc, ACC40, taps, ft, coeffs=h, fir_class="const")
+        assert g.path == "cicfir_fused"
+        assert np.array_equal(g.run(x).astype(np.int64), want)
+        h2 = oracle.rand_raw(rng, fc, taps)
+        oc, of = oracle.CicB("intr", Q15, mid, R, M, N), oracle.FirB(mid, fc, ACC40, ACC40, taps, ft)
+        of.load(h)
+        w = [of.run(oc.run(x[:5000]))]
+        of.load(h2)
+        w.append(of.run(oc.run(x[5000:])))
+        f.reset()
+        f.load(h)
+        y2 = [f.run(x[:5000])]
+        f.load(h2)
+        y2.append(f.run(x[5000:]))
+        assert np.array_equal(np.concatenate(y2).astype(np.int64), np.concatenate(w))
 
 
 def test_cic_fir_cascade_channels_device_and_extremes(engine, oracle):
@@ -869,3 +888,61 @@ def test_checkpoint_resume_cascade_polydec_polyintr_intgdump(engine, oracle, two
     first = b.run(x[:n1], tok1)
     c.set_state(b.get_state())
     assert np.array_equal(np.concatenate([first, c.run(x[n1:n1 + n2], tok2)]), whole)
+
+
+# ------------------------------------------------------------------------------------------------ packed host-link format
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_bytes", ["", "40000"])
+def test_packed_wire_format_matches_containers(engine, oracle, chunk_bytes, monkeypatch):
+    """B2D_WIRE_PACKED (b200dsp.h): the host-buffer run() writes ceil(W_out / 8) little-endian bytes per value, same
+    element order; widened back on the host it is the container result (and the oracle's), for every handle family,
+    across several pipeline chunks and with counts that are not multiples of the pack kernel's group of four."""
+    if chunk_bytes:
+        monkeypatch.setenv("B2D_PIPE_CHUNK_BYTES", chunk_bytes)     # dozens of chunks through the three pipeline slots
+    rng = np.random.default_rng(2026)
+    n = 70001
+    xi = oracle.rand_raw(rng, Q15, 2 * n).astype(np.int16).reshape(n, 2)
+    h = oracle.rand_raw(rng, Q15, 64)
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 64, "SHIFT_REG", n_channels=2, layout="interleaved")
+    f.load(h)
+    want = f.run(xi)
+    f.reset()
+    f.set_wire("packed")
+    yp = f.run(xi)
+    assert yp.dtype == np.uint8 and yp.shape == (n, 2, 5)
+    assert np.array_equal(f.unpack_wire(yp), want)
+    ob = oracle.FirB(Q15, Q15, ACC40, ACC40, 64, "SHIFT_REG")
+    ob.load(h)
+    assert np.array_equal(want[:, 1].astype(np.int64), ob.run(xi[:, 1]))
+    f.set_wire("container")
+    f.reset()
+    assert np.array_equal(f.run(xi), want)
+    # planar multi-channel FIR with a 24-bit output (3 bytes on the wire, 4 in the container)
+    xp = oracle.rand_raw(rng, Q15, 3 * 9999).astype(np.int16).reshape(3, 9999)
+    g = engine.ac_fir_load_coeffs(Q15, (24, 4), Q15, (30, 6), 16, "C_BUFF", n_channels=3)
+    g.load(h[:16])
+    wg = g.run(xp)
+    g.reset()
+    g.set_wire("packed")
+    assert np.array_equal(g.unpack_wire(g.run(xp)), wg)
+    # rate-changing families: planar outputs with the call's output count as stride
+    x1 = xi[:, 0].copy()
+    cases = [
+        (engine.ac_cic_dec_full(Q15, (20, 5), 8, 1, 4, n_channels=2, layout="interleaved"), xi),
+        (engine.ac_cic_intr_full(Q15, (20, 5), 4, 1, 3), x1[:20001]),
+        (engine.cic_intr_fir_cascade(Q15, (20, 5), 4, 1, 3, ACC40, Q15, ACC40, 63, "SHIFT_REG", coeffs=h[:63]), x1[:20001]),
+        (engine.ac_poly_dec(Q15, Q15, ACC40, ACC40, 8, 8, coeffs=h), x1),
+        (engine.ac_poly_intr(Q15, Q15, ACC40, ACC40, 16, 4, "FOLD_ANTI", coeffs=h), x1[:20001]),
+    ]
+    for obj, x in cases:
+        monkeypatch.delenv("B2D_PIPE_CHUNK_BYTES", raising=False)
+        w = obj.run(x)                                  # one chunk, containers
+        if chunk_bytes:
+            monkeypatch.setenv("B2D_PIPE_CHUNK_BYTES", chunk_bytes)
+            obj.reset()
+            assert np.array_equal(obj.run(x), w), type(obj).__name__      # many chunks, containers
+        obj.reset()
+        obj.set_wire("packed")
+        got = obj.run(x)
+        assert got.dtype == np.uint8 and got.shape[:-1] == w.shape, type(obj).__name__
+        assert np.array_equal(obj.unpack_wire(got), w), type(obj).__name__

@@ -1,19 +1,17 @@
-"""Engine == Oracle B on RANDOM formats (GPU; opt-in with B2D_ENGINE_FUZZ=1 until it has been run once on a B200).
+"""Engine == Oracle B on RANDOM formats (GPU; part of the default `-m gpu` run).
 
 tests/test_oracle_fuzz.py pins the restatement to the unmodified reference templates on drawn instantiations; this is
 the same draw through the CUDA engine: formats outside the hand-picked tables, all 8 x 4 accumulator / output modes
-(the generic kernels), whatever fast path the predicates select, chunked calls.  Written after round 1's GPU budget was
-spent -- hence opt-in rather than part of the default `-m gpu` run; the first GPU job of the next round runs it.
+(the generic kernels), whatever fast path the predicates select, chunked calls, coefficient changes mid-stream (every
+architecture, TRANSPOSED included).  First run on a B200 at the start of round 2 with six seeds (B2D_FUZZ_SEED=0..5,
+profiles/r02_upfir_ab_and_engine_fuzz.txt): all green; B2D_FUZZ_SEED draws again.
 """
-import os
-
 import numpy as np
 import pytest
 
 import test_oracle_fuzz as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2D_ENGINE_FUZZ") != "1", reason="opt-in: B2D_ENGINE_FUZZ=1 (not yet run on a GPU)")]
+pytestmark = [pytest.mark.gpu]
 SEED = F.SEED
 
 
@@ -34,16 +32,24 @@ def test_fir_random_formats(engine, oracle, i):
     rng = np.random.default_rng(SEED + 9000 + i)
     fi, fc, fa, fo, nt = F.draw_fir(rng, 1)[0]
     x = oracle.rand_raw(rng, fi, 3000)
-    h = oracle.rand_raw(rng, fc, nt)
-    for ft in ("SHIFT_REG", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"):
+    h, h2 = oracle.rand_raw(rng, fc, nt), oracle.rand_raw(rng, fc, nt)
+    cuts = ((0, 1), (1, nt + 3), (nt + 3, nt + 5), (nt + 5, 3000))
+    for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"):
         if (ft == "FOLD_EVEN" and nt % 2) or (ft == "FOLD_ODD" and nt % 2 == 0):
             continue
+        reload_ = i % 3 != 0                       # load / prog classes: other taps mid-stream (twice, 2 samples apart)
         b = oracle.FirB(fi, fc, fa, fo, nt, ft)
-        b.load(h)
-        want = b.run(x)
         f = make_fir(engine, i % 3, fi, fc, fa, fo, nt, ft, h)
-        y = np.concatenate([np.atleast_1d(f.run(x[a:c])) for a, c in ((0, 1), (1, nt + 3), (nt + 3, 3000))])
-        assert np.array_equal(y.astype(np.int64), want), ((fi, fc, fa, fo, nt), ft, f.path)
+        b.load(h)
+        want, got = [], []
+        for k, (a, c) in enumerate(cuts):
+            if reload_ and k in (2, 3):
+                hh = h2 if k == 2 else h
+                b.load(hh)
+                f.load(hh)
+            want.append(b.run(x[a:c]))
+            got.append(np.atleast_1d(f.run(x[a:c])))
+        assert np.array_equal(np.concatenate(got).astype(np.int64), np.concatenate(want)), ((fi, fc, fa, fo, nt), ft, f.path, reload_)
 
 
 @pytest.mark.parametrize("mode", ["dec", "intr"])
