@@ -33,6 +33,11 @@ bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fm
 void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
 int fir_q15_pk_words(int n_taps, int ftype);
 cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st);
+// q24 path: W_in 17..24 in int32 containers, W_c <= 16: coefficient pairs in the DP2A 16-bit lanes, three sample byte planes.
+bool fir_q24_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
+void fir_q24_pack(const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
+int fir_q24_pk_words(int n_taps);
+cudaError_t launch_fir_q24(const FirLaunch &p, cudaStream_t st);
 // wide path: operands <= 32 bits, wrapping 64-bit accumulator with Q in {TRN, RND}; IMAD.WIDE per tap.
 bool fir_wide_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
 int fir_wide_mode(const Fmt &in, const Fmt &coeff, const Fmt &acc, int n_taps, int ftype);

@@ -46,7 +46,8 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
   h->h_coeff.assign(C * N, 0);
   h->ch_loaded.assign(C, 0);
   h->path = fir_q15_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q15
-            : (fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_WIDE : PATH_GENERIC);
+            : (fir_q24_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_Q24
+            : (fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype) ? PATH_WIDE : PATH_GENERIC));
   const char *force = getenv("B2D_FORCE_GENERIC");
   if (force && *force == '1') h->path = PATH_GENERIC;
   if (force && *force == '2' && fir_wide_supported(fin, fc, fa, fo, (int)N, desc->ftype)) h->path = PATH_WIDE;
@@ -56,8 +57,8 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
     e = cudaMalloc(&h->d_tail[i], tail_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->d_tail[i], 0, tail_bytes);
   }
-  if (e == cudaSuccess && h->path == PATH_Q15) {
-    h->pk_words = fir_q15_pk_words((int)N, desc->ftype);
+  if (e == cudaSuccess && (h->path == PATH_Q15 || h->path == PATH_Q24)) {
+    h->pk_words = h->path == PATH_Q15 ? fir_q15_pk_words((int)N, desc->ftype) : fir_q24_pk_words((int)N);
     e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
   }
   if (e == cudaSuccess && desc->kind == B2D_FIR_REG_SHARE) {
@@ -94,7 +95,19 @@ extern "C" int b2d_fir_destroy(b2d_fir *h) {
   return B2D_OK;
 }
 
-extern "C" const char *b2d_fir_path(b2d_fir *h) { return !h ? "" : (h->path == PATH_Q15 ? "fir_q15" : (h->path == PATH_WIDE ? "fir_wide" : "fir_generic")); }
+static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream_t st) {
+  switch (h->path) {
+    case PATH_Q15: return launch_fir_q15(p, st);
+    case PATH_Q24: return launch_fir_q24(p, st);
+    case PATH_WIDE: return launch_fir_wide(p, st);
+    default: return launch_fir_generic(p, st);
+  }
+}
+
+extern "C" const char *b2d_fir_path(b2d_fir *h) {
+  static const char *names[] = {"fir_generic", "fir_q15", "fir_wide", "fir_q24"};
+  return !h ? "" : names[h->path];
+}
 
 extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
   if (!h) return fail(B2D_EINVAL, "null handle");
@@ -164,9 +177,10 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
     std::copy(v.begin(), v.end(), h->h_coeff.begin() + c * N);
     h->ch_loaded[c] = 1;
     CU(cudaMemcpy(h->d_coeff64 + c * N, v.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (h->path == PATH_Q15) {
+    if (h->path == PATH_Q15 || h->path == PATH_Q24) {
       std::vector<uint32_t> pk(h->pk_words, 0);
-      fir_q15_pack(h->fc, v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
+      if (h->path == PATH_Q15) fir_q15_pack(h->fc, v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
+      else fir_q24_pack(v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
       CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     if (h->path == PATH_WIDE) {
@@ -189,7 +203,7 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
   int hs = hist_wait(h->e_hist, st);
   if (hs) return hs;
-  CU(h->path == PATH_Q15 ? launch_fir_q15(p, st) : (h->path == PATH_WIDE ? launch_fir_wide(p, st) : launch_fir_generic(p, st)));
+  CU(fir_dispatch(h, p, st));
   if (h->pend_rem) {   // TRANSPOSED after a coefficient change: the first outputs start from the old taps' partial sums
     const size_t m = std::min(n, h->pend_rem);
     CU(launch_fir_pending(p, m, h->d_pend[h->pcur], nullptr, st));
@@ -318,7 +332,7 @@ extern "C" int b2d_fir_run_window(b2d_fir *h, const void *window, void *out_raw)
   p.in = base + tail_b; p.out = base + tail_b + in_b; p.n = 1;
   p.tail = base; p.tail_next = base + tail_b + in_b + out_b;
   p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
-  CU(h->path == PATH_Q15 ? launch_fir_q15(p, nullptr) : (h->path == PATH_WIDE ? launch_fir_wide(p, nullptr) : launch_fir_generic(p, nullptr)));
+  CU(fir_dispatch(h, p, nullptr));
   CU(cudaMemcpy(out_raw, p.out, C * ob, cudaMemcpyDeviceToHost));
   return B2D_OK;
 }

@@ -2,14 +2,6 @@
 // page-locked host buffers, the device slots and streams of the pipelined host-buffer path (the loop itself is the
 // template in rt_common.h), the NCCL communicator and checkpoint blobs.  The handle families live in rt_fir.cu, rt_cic.cu,
 // rt_poly.cu, rt_intgdump.cu and rt_mvavg.cu.  No CPU compute path exists: every run() ends in a CUDA kernel launch.
-#include <cctype>
-#include <map>
-#include <mutex>
-
-#include <sys/mman.h>
-#include <sys/syscall.h>
-#include <unistd.h>
-
 #include "rt_common.h"
 
 using namespace b2d;
@@ -43,67 +35,17 @@ extern "C" int b2d_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
-// Page-locked host buffers.  Default: cudaHostAlloc.  B2D_HOST_NUMA=1 (A/B switch): the pages
-// are taken from the NUMA node the current GPU hangs off (mmap + mbind(MPOL_PREFERRED) + cudaHostRegister), so that the
-// H2D / D2H streams of a rank whose CPU set sits on the other socket do not cross the socket interconnect.  Any
-// failure on that path (no sysfs entry, mbind refused by the cgroup, registration refused) falls back to cudaHostAlloc.
-static std::mutex g_host_mu;
-static std::map<void *, size_t> g_host_mapped;
-
-static int gpu_numa_node(int dev) {
-  char bdf[32] = "";
-  if (cudaDeviceGetPCIBusId(bdf, (int)sizeof(bdf), dev) != cudaSuccess) { cudaGetLastError(); return -1; }
-  for (char *c = bdf; *c; ++c) *c = (char)tolower((unsigned char)*c);
-  const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/numa_node";
-  FILE *f = fopen(path.c_str(), "r");
-  if (!f) return -1;
-  int node = -1;
-  if (fscanf(f, "%d", &node) != 1) node = -1;
-  fclose(f);
-  return node;
-}
-
-static void *host_alloc_near_gpu(size_t bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  const int node = gpu_numa_node(dev);
-  if (node < 0 || node >= 1024) return nullptr;
-  const size_t len = (bytes + 4095) & ~(size_t)4095;
-  void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-  if (m == MAP_FAILED) return nullptr;
-  unsigned long mask[16] = {};
-  mask[node / 64] = 1UL << (node % 64);
-  (void)syscall(SYS_mbind, m, len, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(node + 2), 0u);   // best effort
-  if (cudaHostRegister(m, len, cudaHostRegisterPortable) != cudaSuccess) {
-    cudaGetLastError();
-    munmap(m, len);
-    return nullptr;
-  }
-  std::lock_guard<std::mutex> lk(g_host_mu);
-  g_host_mapped[m] = len;
-  return m;
-}
-
+// Page-locked host buffers (cudaHostAlloc, portable across devices).  Round 1 prepared a variant that took the pages from
+// the GPU's own NUMA node (mmap + mbind + cudaHostRegister); the 8-GPU A/B of round 2 showed no difference on this class of
+// box (one NUMA node, every GPU behind the same host bridge: profiles/r02_bench_numa1_n8.json vs r02_bench_default_n8.json,
+// 5313 vs 5307 M IQ samples/s), so it was removed.
 extern "C" int b2d_host_alloc(void **p, size_t bytes) {
   if (!p) return fail(B2D_EINVAL, "null pointer");
-  const char *numa = getenv("B2D_HOST_NUMA");
-  if (numa && *numa == '1' && (*p = host_alloc_near_gpu(bytes ? bytes : 1)) != nullptr) return B2D_OK;
   CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
   return B2D_OK;
 }
 extern "C" int b2d_host_free(void *p) {
   if (!p) return B2D_OK;
-  size_t len = 0;
-  {
-    std::lock_guard<std::mutex> lk(g_host_mu);
-    auto it = g_host_mapped.find(p);
-    if (it != g_host_mapped.end()) { len = it->second; g_host_mapped.erase(it); }
-  }
-  if (len) {
-    CU(cudaHostUnregister(p));
-    munmap(p, len);
-    return B2D_OK;
-  }
   CU(cudaFreeHost(p));
   return B2D_OK;
 }

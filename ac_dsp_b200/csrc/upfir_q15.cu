@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(kUpThreads) upfir_q15_kernel(UpArgs a) {
 // of a period are stored straight from registers as 128-bit words: consecutive lanes write consecutive R*8-byte
 // groups, so a pair of store instructions covers 1 KB contiguously -- no staging tile, no copy-out pass, and one
 // barrier per tile (the sample double buffer).
-template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
-__global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false, int MINB = 0>
+__global__ void __launch_bounds__(kUpThreads, MINB) upfir_lane_kernel(UpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int WPP = PLANES == 3 ? 2 : 1;
   constexpr int CW = R * WPP;                      // coefficient words per tap pair, all phases
@@ -392,6 +392,8 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
           if (NARROW) {
             // 32 < W_acc <= 40 + lsh: only the low W_acc - lsh bits of the sum count, so the upper planes combine modulo
             // 2^32 and the 64-bit sum, shift and sign extension are done on 32-bit halves (no IMAD.WIDE on the DP2A pipe)
+            // (a 32-bit-only form -- low word (acc0 + (m << 8)) << lsh, high bits from m + (acc0 >> 8) -- saves four instructions
+            // per result but ptxas turns its shift-adds into IMADs on the DP2A pipe: 103.5 vs 111.3 G inputs/s, r02 A/B)
             const uint32_t m = PLANES == 3 ? (uint32_t)acc[j][ph][1] + ((uint32_t)acc[j][ph][2] << 8) : (uint32_t)acc[j][ph][1];
             uint32_t tl, th;
             asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(tl), "=r"(th)
@@ -446,11 +448,11 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
 // loop is written for any grid size, results do not depend on it).
 static int up_grid_waves() {
   const char *w = getenv("B2D_UPFIR_WAVES");
-  const int v = w ? atoi(w) : 1;
+  const int v = w ? atoi(w) : 8;          // r02 A/B on a B200 (profiles/r02_upfir_ab_and_engine_fuzz.txt): 1 -> 8 is +8.6 % on cicfir, +7.6 % on polyintr
   return v < 1 ? 1 : (v > 64 ? 64 : v);
 }
 
-template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false, int MINB = 0>
 static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   constexpr int TILE = kUpThreads * JT;
   const long long kbase = a.out_first / R;
@@ -461,16 +463,16 @@ static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   const int XS = ((((nxs + 1) / 2 + 1) + 31) & ~31) + 16;
   const size_t smem = (size_t)((ncw + 3) & ~3) * 4 + (size_t)4 * XS * 4 + (size_t)TILE * R * 8;
   a.ntiles = (nper + TILE - 1) / TILE;
-  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, kUpThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB>, kUpThreads, smem);
   if (per_sm < 1) per_sm = 1;
   long long gx = a.ntiles;
   const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, a.C);
-  upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL><<<grid, kUpThreads, smem, st>>>(a);
+  upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB><<<grid, kUpThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -480,8 +482,12 @@ static cudaError_t launch_up_lane(const UpArgs &a, cudaStream_t st) {
   if (a.acc.W - a.lsh <= 40 && a.acc.W > 32 && a.lsh < 32) {
     // A/B switch (profiles/r01_source_level_notes.md): accumulators started by the first tap pair; instantiated for
     // the two bench geometries (R = 4, JT = 4, signed <40,8>-style accumulator) only
+    // three planes: +3 % with the peeled start (72 registers instead of 80); two planes: -6 % (70 instead of 54 registers)
     const char *peel = getenv("B2D_UPFIR_PEEL");
-    if (R == 4 && JT == 4 && a.acc.S && peel && *peel == '1') return launch_up_lane_n<4, 4, PLANES, 1, true>(a, st);
+    const bool use_peel = peel ? *peel == '1' : PLANES == 3;
+    const char *lb = getenv("B2D_UPFIR_LB6");       // A/B: __launch_bounds__(128, 6) keeps the prefetched samples out of local memory
+    if (R == 4 && JT == 4 && a.acc.S && use_peel && lb && *lb == '1') return launch_up_lane_n<4, 4, PLANES, 1, true, 6>(a, st);
+    if (R == 4 && JT == 4 && a.acc.S && use_peel) return launch_up_lane_n<4, 4, PLANES, 1, true>(a, st);
     return a.acc.S ? launch_up_lane_n<R, JT, PLANES, 1>(a, st) : launch_up_lane_n<R, JT, PLANES, 2>(a, st);
   }
   return launch_up_lane_n<R, JT, PLANES, 0>(a, st);

@@ -289,8 +289,7 @@ def bind_near_gpu(local):
 
 
 def host_buffer(lib, nbytes):
-    """Page-locked host memory from the engine's own allocator (b2d_host_alloc: cudaHostAlloc, or pages next to the GPU
-    with B2D_HOST_NUMA=1) as a uint8 numpy view, plus the pointer for b2d_host_free."""
+    """Page-locked host memory from the engine's own allocator (b2d_host_alloc) as a uint8 numpy view, plus the pointer for b2d_host_free."""
     import ctypes as ct
     p = ct.c_void_p()
     assert lib.b2d_host_alloc(ct.byref(p), nbytes) == 0, lib.b2d_last_error()
@@ -312,10 +311,10 @@ def pcie_ceiling(world, in_bytes_per_unit, out_bytes_per_unit):
             continue
         if r.get("n_gpus") != world or r.get("h2d_source") != "default":
             continue
-        if r.get("pattern") == "h2d":
-            h2d = r["h2d_gbs_sum"]
+        if r.get("pattern") == "h2d":      # all GPUs together, by the wall clock around the slowest one
+            h2d = r["aggregate_gbs_wall"]
         if r.get("pattern") == "d2h":
-            d2h = r["d2h_gbs_sum"]
+            d2h = r["aggregate_gbs_wall"]
     if not h2d or not d2h:
         return None
     t = max(in_bytes_per_unit / (h2d * 1e9), out_bytes_per_unit / (d2h * 1e9))
@@ -523,7 +522,6 @@ def measure(name, wl, args, ctx, want_cpu):
                    "api": f"b2d_{'cic' if wl['kind'] == 'cic' else wl['kind']}_run (C-ABI, page-locked host buffers from b2d_host_alloc, 3-slot copy/compute pipeline)",
                    "out_format": "B2D_WIRE_PACKED: %d bytes per ac_fixed<%d,.> value" % (wb, W_out) if wire else "containers: %d bytes per value" % cbytes,
                    "host_affinity": "NVML ideal CPUs of the GPU" if ctx["orig_affinity"] else "unchanged",
-                   "host_numa_alloc": os.environ.get("B2D_HOST_NUMA") == "1",
                    "samples_per_step": u2,
                    "note": "one step = one C-ABI call over %d units per GPU (the device-resident `value` runs %d per step)" % (u2, units_per_step)}
             ceil = pcie_ceiling(world, xb.size / u2, n_vals * wb / u2)

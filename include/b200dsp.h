@@ -156,8 +156,9 @@ int b2d_fir_reset(b2d_fir *h);                    /* back to the constructed sta
 int b2d_fir_state_bytes(b2d_fir *h, size_t *bytes);
 int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes);
 int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
-/* Name of the kernel family chosen for this descriptor: "fir_q15" (16-bit operands, DP2A byte planes), "fir_wide"
- * (operands <= 32 bits, wrapping 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order). */
+/* Name of the kernel family chosen for this descriptor: "fir_q15" (16-bit operands, DP2A byte planes), "fir_q24"
+ * (samples of 17..24 bits, taps <= 16 bits: DP2A on three sample byte planes), "fir_wide" (operands <= 32 bits, wrapping
+ * 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order). */
 const char *b2d_fir_path(b2d_fir *h);
 
 /* ---- CIC: ac_cic_dec_full / ac_cic_intr_full ---------------------------------------------- */

@@ -130,6 +130,39 @@ static void check_fir_q15_pack() {
     }
 }
 
+// fir_q24: effective direct-form taps, reversed, two signed 16-bit taps per word (the DP2A 16-bit lanes)
+static void check_fir_q24_pack() {
+  const int fts[] = {B2D_SHIFT_REG, B2D_FOLD_EVEN, B2D_FOLD_ODD, B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI};
+  for (int ft : fts)
+    for (int N : {1, 2, 15, 16, 17, 63, 64, 200}) {
+      if ((ft == B2D_FOLD_EVEN || ft == B2D_FOLD_EVEN_ANTI) && (N & 1)) continue;
+      if ((ft == B2D_FOLD_ODD || ft == B2D_FOLD_ODD_ANTI) && !(N & 1)) continue;
+      const bool anti = ft == B2D_FOLD_EVEN_ANTI || ft == B2D_FOLD_ODD_ANTI;
+      std::vector<int64_t> c(N);
+      for (auto &v : c) v = anti ? (rand() % 32767) - 16383 : (rand() % 65536) - 32768;
+      const int words = fir_q24_pk_words(N);
+      EXPECT(2 * words >= N && (2 * words) % 16 == 0 && 2 * words < N + 16, "fir_q24_pk_words(%d) = %d", N, words);
+      std::vector<uint32_t> pk(words, 0xDEADBEEF);
+      fir_q24_pack(c.data(), N, ft, pk.data(), words);
+      const std::vector<int64_t> e = effective_taps(c, N, ft);
+      for (int k = 0; k < 2 * words; k++) {
+        const int64_t got = (int16_t)((pk[k / 2] >> (16 * (k & 1))) & 0xFFFF);
+        EXPECT(got == (k < N ? e[N - 1 - k] : 0), "fir_q24_pack ft %d N %d k %d", ft, N, k);
+      }
+    }
+  const Fmt q15{16, 1, 1, B2D_TRN, B2D_WRAP}, s20{20, 5, 1, B2D_TRN, B2D_WRAP}, acc40{40, 8, 1, B2D_TRN, B2D_WRAP}, u24{24, 4, 0, B2D_TRN, B2D_WRAP};
+  const Fmt s24{24, 4, 1, B2D_TRN, B2D_WRAP}, c17{17, 1, 1, B2D_TRN, B2D_WRAP}, sat{40, 8, 1, B2D_TRN, B2D_SAT};
+  EXPECT(fir_q24_supported(s20, q15, acc40, acc40, 63, B2D_SHIFT_REG), "BASELINE configs[4] second stage");
+  const Fmt acc48{48, 12, 1, B2D_TRN, B2D_WRAP};
+  EXPECT(fir_q24_supported(s24, q15, acc48, acc48, 2048, B2D_TRANSPOSED), "24-bit signed samples");
+  EXPECT(!fir_q24_supported(s24, q15, acc40, acc40, 2048, B2D_TRANSPOSED), "per-tap truncation (s > 0) is not an exact shift");
+  EXPECT(!fir_q24_supported(q15, q15, acc40, acc40, 63, B2D_SHIFT_REG), "16-bit samples belong to fir_q15");
+  EXPECT(!fir_q24_supported(u24, q15, acc40, acc40, 63, B2D_SHIFT_REG), "unsigned 24-bit samples need 25 bits");
+  EXPECT(!fir_q24_supported(s20, c17, acc40, acc40, 63, B2D_SHIFT_REG), "17-bit taps do not fit the 16-bit lane");
+  EXPECT(!fir_q24_supported(s20, q15, sat, acc40, 63, B2D_SHIFT_REG), "saturating accumulators are order-dependent");
+  EXPECT(!fir_q24_supported(s20, q15, acc40, acc40, 64, B2D_FOLD_EVEN_ANTI), "negated 16-bit taps need 17 bits");
+}
+
 static void check_fir_wide_and_polydec_pack() {
   const int fts[] = {B2D_SHIFT_REG, B2D_FOLD_EVEN, B2D_FOLD_ODD, B2D_FOLD_EVEN_ANTI, B2D_FOLD_ODD_ANTI};
   for (int ft : fts)
@@ -226,6 +259,7 @@ int main() {
   check_fir_q15_pack();
   check_upfir_pack();
   check_fir_wide_and_polydec_pack();
+  check_fir_q24_pack();
   check_support_tables();
   std::printf("checks=%ld bad=%d\n", g_checks, g_bad);
   return g_bad != 0;

@@ -63,7 +63,8 @@ def test_q15_path_is_taken_for_the_baseline_formats(engine):
     h = np.ones(256, dtype=np.int16)
     for ft in ("SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "TRANSPOSED", "FOLD_EVEN", "FOLD_ODD"):
         assert make_fir(engine, "load", Q15, Q15, ACC40, ACC40, 256, ft, h).path == "fir_q15"
-    assert make_fir(engine, "load", (20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", h[:63]).path == "fir_wide"
+    assert make_fir(engine, "load", (20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", h[:63]).path == "fir_q24"
+    assert make_fir(engine, "load", (32, 16), Q15, (64, 32), (64, 32), 27, "SHIFT_REG", h[:27]).path == "fir_wide"
     # order-dependent accumulators (saturation, sign-dependent rounding) only exist on the generic kernel
     assert make_fir(engine, "load", Q15, Q15, (24, 4, True, "AC_TRN", "AC_SAT"), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"
     assert make_fir(engine, "load", Q15, Q15, (24, 4, True, "AC_TRN_ZERO"), Q15, 16, "SHIFT_REG", h[:16]).path == "fir_generic"
@@ -946,3 +947,65 @@ def test_packed_wire_format_matches_containers(engine, oracle, chunk_bytes, monk
         got = obj.run(x)
         assert got.dtype == np.uint8 and got.shape[:-1] == w.shape, type(obj).__name__
         assert np.array_equal(obj.unpack_wire(got), w), type(obj).__name__
+
+
+# ------------------------------------------------------------------------------------------------ fir_q24
+Q24_CASES = [
+    # (in, coeff, acc, out, taps, ftype, layout/channels): samples of 17..24 bits, taps <= 16 bits, exact-shift accumulators
+    ((20, 5), Q15, ACC40, ACC40, 63, "SHIFT_REG", 1),                       # BASELINE configs[4], second stage
+    ((20, 5), Q15, ACC40, ACC40, 63, "FOLD_ODD", 1),
+    ((24, 4), Q15, (48, 12), (48, 12), 256, "C_BUFF", 1),                   # full 24-bit samples, two accumulation blocks
+    ((24, 4), Q15, (48, 12), (20, 3, True, "AC_RND", "AC_SAT"), 300, "TRANSPOSED", 3),   # odd tap count, converted output, planar channels
+    ((23, 3, False), (12, 2, False), (44, 10, False), (44, 10, False), 40, "FOLD_EVEN", 2),   # everything unsigned
+    ((17, 1), (9, 1), ACC40, (24, 8), 1, "SHIFT_REG", 1),                   # one tap
+    ((18, 2), (15, 1), (40, 9), (40, 9), 16, "ROTATE_SHIFT", 2),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", Q24_CASES, ids=lambda c: f"in{c[0][0]}-c{c[1][0]}-{c[4]}{c[5]}-C{c[6]}")
+def test_fir_q24_path(engine, oracle, case):
+    """Three sample byte planes x 16-bit coefficient lanes (fir_q24.cu) against the restatement: full-range random data,
+    the extremes of every plane, chunked calls (history carry), multi-channel in both layouts, coefficient reload."""
+    fi, fc, fa, fo, taps, ft, C = case
+    rng = np.random.default_rng(taps * 7 + C)
+    n = 9001
+    h = oracle.rand_raw(rng, fc, taps)
+    if ft in ("FOLD_EVEN", "FOLD_ODD"):
+        h = np.concatenate([h[: (taps + 1) // 2], h[: taps // 2][::-1]])
+    for kind in ("rand", "min", "max", "alt"):
+        x = np.stack([oracle.rand_raw(rng, fi, n, kind) for _ in range(C)])
+        want = []
+        for c in range(C):
+            ob = oracle.FirB(fi, fc, fa, fo, taps, ft)
+            ob.load(h)
+            want.append(ob.run(x[c]))
+        want = np.stack(want)
+        for layout in (("planar",) if C == 1 else ("planar", "interleaved")):
+            f = engine.ac_fir_load_coeffs(fi, fo, fc, fa, taps, ft, n_channels=C, layout=layout)
+            f.load(h)
+            assert f.path == "fir_q24", f.path
+            xin = x[0] if C == 1 else (x if layout == "planar" else np.ascontiguousarray(x.T))
+            cuts = sorted({0, 1, 2, 9, taps + 3, 4096 + 5, n})
+            parts = []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                seg = xin[a:b] if (C == 1 or layout == "interleaved") else xin[:, a:b]
+                parts.append(np.atleast_1d(f.run(seg)))
+            y = np.concatenate(parts, axis=(1 if (C > 1 and layout == "planar") else 0)).astype(np.int64)
+            if C > 1 and layout == "interleaved":
+                y = y.T
+            assert np.array_equal(y.reshape(C, -1), want), (case, kind, layout)
+    # the wide kernel and the generic kernel agree on the same configuration
+    import os
+    for force in ("2", "1"):
+        os.environ["B2D_FORCE_GENERIC"] = force
+        try:
+            g = engine.ac_fir_load_coeffs(fi, fo, fc, fa, taps, ft)
+            g.load(h)
+            assert g.path in ("fir_wide", "fir_generic")
+            ob = oracle.FirB(fi, fc, fa, fo, taps, ft)
+            ob.load(h)
+            xs = oracle.rand_raw(rng, fi, 700)
+            assert np.array_equal(np.atleast_1d(g.run(xs)).astype(np.int64), ob.run(xs)), (case, force)
+        finally:
+            del os.environ["B2D_FORCE_GENERIC"]

@@ -79,6 +79,13 @@ def _run(world, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(w)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
+    if p.returncode != 0 or p.stdout.count("-ok") != world:      # keep the ranks' own words where a gpurun call brings them back
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"multi_gpu_world{world}_failure.txt"), "w") as fh:
+                fh.write(p.stdout[-20000:] + "\n==== stderr ====\n" + p.stderr[-40000:])
+        except OSError:
+            pass
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert p.stdout.count("-ok") == world, p.stdout
     return [l for l in p.stdout.splitlines() if l.startswith("CRC ")][0]

@@ -78,7 +78,70 @@ static void worker(int dev, size_t chunk, int reps, const Pattern &pt, bool wc, 
   cudaStreamDestroy(s_in); cudaStreamDestroy(s_out);
 }
 
+// The engine's host pipeline in miniature (rt_common.h: run_host_pipeline): three slots, H2D / kernel / D2H on three
+// streams chained by events, 4 B in : 16 B out per unit.  `busy_us` > 0 runs a kernel that keeps every SM busy for about
+// that long per chunk (the FIR kernel's place); 0 launches nothing.  Answers: does the D2H leg reach the bare-copy rate
+// when small H2D copies and a compute kernel run beside it?
+__global__ void spin_kernel(long long cycles, int *sink) {
+  const long long t0 = clock64();
+  int v = 0;
+  while (clock64() - t0 < cycles) v++;
+  if (v == -1) *sink = v;
+}
+
+static void pipeline_probe(size_t chunk, int nchunks, int busy_us, int same_stream_copies) {
+  CK(cudaSetDevice(0));
+  const size_t out_b = chunk, in_b = chunk / 4;
+  void *h_in, *h_out, *d_in[3], *d_out[3];
+  CK(cudaHostAlloc(&h_in, in_b * nchunks, cudaHostAllocPortable));
+  CK(cudaHostAlloc(&h_out, out_b * nchunks, cudaHostAllocPortable));
+  memset(h_in, 1, in_b * nchunks); memset(h_out, 0, out_b * nchunks);
+  for (int i = 0; i < 3; i++) { CK(cudaMalloc(&d_in[i], in_b)); CK(cudaMalloc(&d_out[i], out_b)); }
+  cudaStream_t s_in, s_k, s_out;
+  CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  if (same_stream_copies) s_out = s_in;
+  cudaEvent_t e_in[3], e_k[3], e_out[3], t0, t1;
+  for (int i = 0; i < 3; i++) { cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming); }
+  CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+  int *sink; CK(cudaMalloc(&sink, 4));
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  const long long cycles = (long long)busy_us * (p.clockRate / 1000);
+  for (int rep = 0; rep < 2; rep++) {
+    CK(cudaDeviceSynchronize());
+    const auto w0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < nchunks; i++) {
+      const int s = i % 3;
+      if (i >= 3) CK(cudaStreamWaitEvent(s_in, e_k[s], 0));
+      CK(cudaMemcpyAsync(d_in[s], (char *)h_in + (size_t)i * in_b, in_b, cudaMemcpyHostToDevice, s_in));
+      CK(cudaEventRecord(e_in[s], s_in));
+      CK(cudaStreamWaitEvent(s_k, e_in[s], 0));
+      if (i >= 3) CK(cudaStreamWaitEvent(s_k, e_out[s], 0));
+      if (busy_us > 0) spin_kernel<<<p.multiProcessorCount * 4, 128, 0, s_k>>>(cycles, sink);
+      CK(cudaEventRecord(e_k[s], s_k));
+      CK(cudaStreamWaitEvent(s_out, e_k[s], 0));
+      CK(cudaMemcpyAsync((char *)h_out + (size_t)i * out_b, d_out[s], out_b, cudaMemcpyDeviceToHost, s_out));
+      CK(cudaEventRecord(e_out[s], s_out));
+    }
+    CK(cudaDeviceSynchronize());
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    if (rep == 1)
+      printf("{\"pattern\": \"pipeline\", \"chunk_mib\": %.1f, \"chunks\": %d, \"kernel_busy_us\": %d, \"copies_share_a_stream\": %d, \"d2h_gbs\": %.1f, \"h2d_gbs\": %.1f, \"wall_ms\": %.2f}\n",
+             chunk / 1048576.0, nchunks, busy_us, same_stream_copies, (double)out_b * nchunks / (ms * 1e-3) / 1e9, (double)in_b * nchunks / (ms * 1e-3) / 1e9, ms);
+  }
+  fflush(stdout);
+  cudaFreeHost(h_in); cudaFreeHost(h_out);
+  for (int i = 0; i < 3; i++) { cudaFree(d_in[i]); cudaFree(d_out[i]); }
+}
+
 int main(int argc, char **argv) {
+  if (argc > 1 && !strcmp(argv[1], "pipeline")) {
+    for (int busy : {0, 50, 100, 300})
+      for (size_t mib : {20, 80}) pipeline_probe(mib << 20, (int)(2048 / mib), busy, 0);
+    pipeline_probe((size_t)20 << 20, 100, 100, 1);
+    return 0;
+  }
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   const size_t chunk = (size_t)(argc > 1 ? atoi(argv[1]) : 256) << 20;   // MiB per D2H copy
