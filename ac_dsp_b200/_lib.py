@@ -49,6 +49,14 @@ class B2dIntgdumpDesc(C.Structure):
     _fields_ = [("fin", B2dFmt), ("acc", B2dFmt), ("out", B2dFmt), ("ns", C.c_uint32), ("chn", C.c_uint32), ("device", C.c_int32)]
 
 
+class B2dMvavgDesc(C.Structure):
+    _fields_ = [("fin", B2dFmt), ("out", B2dFmt), ("acc", B2dFmt), ("coeff", B2dFmt), ("max_sample", C.c_uint32), ("taps", C.c_uint32),
+                ("win_type", C.c_int32), ("device", C.c_int32)]
+
+
+WIN_MODES = ["AC_WIN", "AC_CLIP", "AC_MIRROR"]   # b2d_window_mode
+
+
 class B2dError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(msg)
@@ -115,6 +123,9 @@ def load():
         "b2d_shard_count": (C.c_int, [u32, i32, i32, C.POINTER(u32)]), "b2d_comm_unique_id": (C.c_int, [vp]),
         "b2d_comm_create": (C.c_int, [C.POINTER(vp), vp, i32, i32, i32]), "b2d_comm_destroy": (C.c_int, [vp]),
         "b2d_comm_barrier": (C.c_int, [vp]),
+        "b2d_mvavg_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dMvavgDesc), vp]), "b2d_mvavg_destroy": (C.c_int, [vp]),
+        "b2d_mvavg_max_out": (sz, [vp, sz]), "b2d_mvavg_run": (C.c_int, [vp, vp, sz, sz, vp, psz]),
+        "b2d_mvavg_run_dev": (C.c_int, [vp, vp, sz, sz, vp, psz, vp]), "b2d_mvavg_path": (C.c_char_p, [vp]),
         "b2d_wire_bytes": (C.c_int, [i32, i32]), "b2d_unpack_wire": (C.c_int, [vp, sz, i32, i32, vp]),
         "b2d_fir_set_wire": (C.c_int, [vp, i32]), "b2d_cic_set_wire": (C.c_int, [vp, i32]), "b2d_cicfir_set_wire": (C.c_int, [vp, i32]),
         "b2d_polydec_set_wire": (C.c_int, [vp, i32]), "b2d_polyintr_set_wire": (C.c_int, [vp, i32]),

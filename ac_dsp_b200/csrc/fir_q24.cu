@@ -55,6 +55,10 @@ __device__ __forceinline__ int q24_sample(const Q24Args &a, uint32_t c, long lon
   return ((const int *)a.x)[elem_index((size_t)g, c, a.n, a.C, a.interleaved)];
 }
 
+// LEAD = (-(N_TAPS - 1)) mod 4: where the first staged sample of a tile sits inside its 16-byte group (tiles are multiples
+// of 1024 outputs, so it is the same for every tile of a launch) -- a template parameter, so that picking four samples out
+// of two aligned 128-bit loads costs no moves.
+template <int LEAD>
 __global__ void __launch_bounds__(kQ24Threads) fir_q24_kernel(Q24Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tile = kQ24Threads * kQ24T * a.passes;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(kQ24Threads) fir_q24_kernel(Q24Args a) {
   const uint32_t c = blockIdx.y;
   const long long out0 = (long long)blockIdx.x * tile;
   const long long g0 = out0 - (a.N - 1);
-  const int lead = (int)(((g0 % 4) + 4) % 4);                        // the same for every tile (tile is a multiple of 1024)
+  constexpr int lead = LEAD;
 
   for (int i = threadIdx.x; i < a.pkw; i += kQ24Threads) cw[i] = a.cpk[(size_t)c * a.pkw + i];
   // ---- stage: groups of four samples -> one word per plane
@@ -232,13 +236,20 @@ cudaError_t launch_fir_q24(const FirLaunch &p, cudaStream_t st) {
   const size_t tile = per_pass * passes;
   const size_t stride = (tile + a.Npad + 16 + 15) & ~(size_t)15;
   const size_t smem = (size_t)((a.pkw + 3) & ~3) * 4 + 3 * stride;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(fir_q24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
   dim3 grid((unsigned)((p.n + tile - 1) / tile), p.C);
-  fir_q24_kernel<<<grid, kQ24Threads, smem, st>>>(a);
-  return cudaGetLastError();
+  const int lead = (4 - ((p.n_taps - 1) & 3)) & 3;
+  cudaError_t e = cudaSuccess;
+#define B2D_Q24_LAUNCH(L)                                                                                                    \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(fir_q24_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) fir_q24_kernel<L><<<grid, kQ24Threads, smem, st>>>(a);                                             \
+  } while (0)
+  if (lead == 0) B2D_Q24_LAUNCH(0);
+  else if (lead == 1) B2D_Q24_LAUNCH(1);
+  else if (lead == 2) B2D_Q24_LAUNCH(2);
+  else B2D_Q24_LAUNCH(3);
+#undef B2D_Q24_LAUNCH
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace b2d

@@ -153,6 +153,17 @@ int upfir_q15_words(int R, int taps_total, int planes);
 void upfir_q15_pack(const int64_t *c, int taps_total, int R, int planes, uint32_t *out);
 cudaError_t launch_upfir_q15(const UpLaunch &p, cudaStream_t st);
 
+// Weighted moving average over bursts (ac_mv_avg): mv_avg.cu
+struct MvLaunch {
+  Fmt fin, fcoeff, facc, fout;
+  int taps, win;             // window span (odd), b2d_window_mode
+  const void *in;            // whole bursts of n_sample samples
+  void *out;                 // `per` outputs per burst
+  const int64_t *coeff64;    // [taps]
+  size_t n_sample, per, n_out;
+};
+cudaError_t launch_mvavg(const MvLaunch &p, cudaStream_t st);
+
 // Packed host-link format (wire.cu): `count` values in 2 / 4 / 8-byte containers -> wire_bytes (< container) bytes each.
 cudaError_t launch_pack_wire(const void *src, int container_bytes, void *dst, int wire_bytes, size_t count, cudaStream_t st);
 

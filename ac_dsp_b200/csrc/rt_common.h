@@ -100,6 +100,24 @@ int run_host_pipeline(Pipe &P, const HostRun &r, Count count, Launch launch) {
   if (st) return st;
   const bool packed = r.wire_bytes < r.out_bytes;
   if ((st = P.ensure(r.L * r.C * r.in_bytes, r.Lout * r.C * r.out_bytes, packed ? r.Lout * r.C * r.wire_bytes + 16 : 0))) return st;
+  if (r.n <= r.L) {
+    // one chunk: there is nothing to overlap -- copy in, compute, copy out on the compute stream, one synchronisation.
+    // This is the path of the reference-signature calls that move a handful of samples (ac_fir_prog_coeffs::run: one).
+    const size_t no = count(r.n);
+    CU(copy_chunk(P.d_in[0], r.in, true, r.in_bytes, r.C, r.il, r.n, 0, r.n, P.s_k));
+    if ((st = launch(P.d_in[0], r.n, P.d_out[0], no, P.s_k))) return st;
+    const void *src = P.d_out[0];
+    if (packed && no) {
+      CU(launch_pack_wire(P.d_out[0], r.out_bytes, P.d_pk[0], r.wire_bytes, no * r.C, P.s_k));
+      src = P.d_pk[0];
+    }
+    if (no) {
+      if (r.out_like_in) CU(copy_chunk(r.out, src, false, r.wire_bytes, r.C, r.il, r.n, 0, r.n, P.s_k));
+      else CU(copy_chunk(r.out, src, false, r.wire_bytes, r.C, 0, r.no_total, 0, no, P.s_k));
+    }
+    CU(cudaStreamSynchronize(P.s_k));
+    return B2D_OK;
+  }
   // B2D_PIPE_TRACE=1 (diagnosis): timestamps around every copy and launch, printed per call on stderr
   const char *trace_env = getenv("B2D_PIPE_TRACE");
   const bool trace = trace_env && *trace_env == '1';

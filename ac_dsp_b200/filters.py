@@ -533,6 +533,57 @@ class ac_poly_intr(_Block):
             pass
 
 
+class ac_mv_avg:
+    """ac_mv_avg<MAX_SAMPLE, TAPS, WIN_TYPE, IN, OUT, ACC, COEFF, S_TYPE>(coeffs)::run(data_in, data_out, n_sample)
+    (reference ac_mv_avg.h:140-204): run(whole bursts of n_sample samples, n_sample) -> the smoothed
+    bursts (n_sample outputs each for AC_CLIP / AC_MIRROR, n_sample - TAPS + 1 for AC_WIN).  Parity unpinned: the window
+    class lives in ac_math (absent); its boundary rules are restated from the manual."""
+
+    def __init__(self, MAX_SAMPLE, TAPS, WIN_TYPE, IN_TYPE, OUT_TYPE, ACC_TYPE, COEFF_TYPE, coeffs, device=-1):
+        lib = L.load()
+        self._h = None
+        w = L.WIN_MODES.index(WIN_TYPE) if isinstance(WIN_TYPE, str) else int(WIN_TYPE)
+        d = L.B2dMvavgDesc(L.make_fmt(IN_TYPE), L.make_fmt(OUT_TYPE), L.make_fmt(ACC_TYPE), L.make_fmt(COEFF_TYPE), int(MAX_SAMPLE), int(TAPS),
+                           w, int(device))
+        c = np.ascontiguousarray(np.asarray(coeffs).astype(_container_dtype(d.coeff), copy=False))
+        if c.size != int(TAPS):
+            raise ValueError("expected TAPS coefficients")
+        h = C.c_void_p()
+        L.check(lib.b2d_mvavg_create(C.byref(h), C.byref(d), c.ctypes.data))
+        self._h = h
+        self._in_dt, self._out_dt = _container_dtype(d.fin), _container_dtype(d.out)
+
+    def run(self, data_in, n_sample):
+        lib = L.load()
+        n_out = C.c_size_t(0)
+        if _is_torch(data_in):
+            import torch
+            x = data_in.contiguous()
+            y = torch.empty(max(x.numel(), 1), dtype={np.int16: torch.int16, np.int32: torch.int32, np.int64: torch.int64}[self._out_dt], device=x.device)
+            L.check(lib.b2d_mvavg_run_dev(self._h, x.data_ptr(), x.numel(), int(n_sample), y.data_ptr(), C.byref(n_out),
+                                          torch.cuda.current_stream(x.device).cuda_stream))
+            return y[: n_out.value]
+        x = np.ascontiguousarray(np.asarray(data_in).astype(self._in_dt, copy=False)).reshape(-1)
+        y = np.empty(max(x.size, 1), dtype=self._out_dt)
+        L.check(lib.b2d_mvavg_run(self._h, x.ctypes.data, x.size, int(n_sample), y.ctypes.data, C.byref(n_out)))
+        return y[: n_out.value].copy()
+
+    @property
+    def path(self):
+        return L.load().b2d_mvavg_path(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().b2d_mvavg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ac_intg_dump:
     """ac_intg_dump<IN, ACC, OUT, N_TYPE, NS, CHN>::run(data_in, data_out, n_sample)  (reference ac_intg_dump.h:113-151,
     SURVEY.md 8f row N4): run(samples interleaved over CHN, n_sample tokens) -> (dumping frames, CHN) sums."""

@@ -300,6 +300,31 @@ int b2d_intgdump_state_bytes(b2d_intgdump *h, size_t *bytes);
 int b2d_intgdump_get_state(b2d_intgdump *h, void *blob, size_t bytes);
 int b2d_intgdump_set_state(b2d_intgdump *h, const void *blob, size_t bytes);
 
+/* ---- weighted moving average: ac_mv_avg ------------------------------------------------------------- */
+/* ac_mv_avg<MAX_SAMPLE, TAPS, WIN_TYPE, IN, OUT, ACC, COEFF, S_TYPE>::run(data_in, data_out, n_sample)  (ac_mv_avg.h:140-204):
+ * the input is processed in bursts of n_sample samples (TAPS <= n_sample <= MAX_SAMPLE); within a burst
+ * out[i] = sum_{j=-TAPS/2..TAPS/2} (ACC_TYPE) x~[i+j] * coeffs[j + TAPS/2], the sum re-quantised to ACC_TYPE at every tap.
+ * x~ extends the burst at its two ends: B2D_CLIP repeats the edge sample, B2D_MIRROR reflects about it (n_sample outputs
+ * per burst); B2D_WIN has no boundary processing and emits only the n_sample - TAPS + 1 points whose window is full.
+ * The weights are the constructor's const array (TAPS raw COEFF_TYPE values, HOST memory).  No state survives a run().
+ * PARITY UNPINNED: the window semantics come from ac_math's ac_window.h, which neither the reference tree nor this
+ * image contains and for which the reference ships no vector; they are restated from the manual. */
+typedef enum { B2D_WIN = 0, B2D_CLIP = 1, B2D_MIRROR = 2 } b2d_window_mode;
+typedef struct {
+  b2d_fmt in, out, acc, coeff;   /* IN_TYPE, OUT_TYPE, ACC_TYPE, COEFF_TYPE                                       */
+  uint32_t max_sample, taps;     /* MAX_SAMPLE; TAPS (odd)                                                        */
+  int32_t win_type;              /* b2d_window_mode                                                               */
+  int32_t device;
+} b2d_mvavg_desc;
+typedef struct b2d_mvavg b2d_mvavg;
+int b2d_mvavg_create(b2d_mvavg **h, const b2d_mvavg_desc *desc, const void *coeff_raw);
+int b2d_mvavg_destroy(b2d_mvavg *h);
+size_t b2d_mvavg_max_out(b2d_mvavg *h, size_t n);
+/* n_in samples = whole bursts of n_sample; *n_out = outputs of all bursts, burst-major. */
+int b2d_mvavg_run(b2d_mvavg *h, const void *in, size_t n_in, size_t n_sample, void *out, size_t *n_out);
+int b2d_mvavg_run_dev(b2d_mvavg *h, const void *d_in, size_t n_in, size_t n_sample, void *d_out, size_t *n_out, void *cuda_stream);
+const char *b2d_mvavg_path(b2d_mvavg *h);
+
 /* ---- multi-GPU: one process per GPU, channels sharded, coefficients broadcast once --------- */
 #define B2D_UNIQUE_ID_BYTES 128
 /* Channel c of n_channels lives on rank c % world (contiguous block alternative: see DESIGN.md). */

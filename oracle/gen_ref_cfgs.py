@@ -30,6 +30,9 @@ def main(outdir):
     with open(os.path.join(outdir, "cfgs_id.inc"), "w") as fh:
         for cid, (fi, fa, fo, ns, chn) in enumerate(rc.ID_CONFIGS):
             fh.write(f"X({cid}, {f(fi)}, {f(fa)}, {f(fo)}, {ns}, {chn})\n")
+    with open(os.path.join(outdir, "cfgs_mv.inc"), "w") as fh:
+        for cid, (maxs, taps, wt, fi, fo, fa, fc) in enumerate(rc.MV_CONFIGS):
+            fh.write(f"X({cid}, {maxs}, {taps}, {wt}, {f(fi)}, {f(fo)}, {f(fa)}, {f(fc)})\n")
     for mode in ("dec", "intr"):
         with open(os.path.join(outdir, f"cfgs_cic_{mode}.inc"), "w") as fh:
             for cid, c in enumerate(rc.CIC_CONFIGS):

@@ -514,6 +514,53 @@ class IdB:
             self.h = None
 
 
+WIN_MODES = ["AC_WIN", "AC_CLIP", "AC_MIRROR"]
+
+
+def mv_run_b(fin, fout, facc, fcoeff, taps, win, coeffs, x, n_sample):
+    """Oracle B ac_mv_avg (parity unpinned: ac_window restated): one run() call over whole bursts of n_sample samples."""
+    L = lib_b()
+    L.ob_mvavg_run.restype = C.c_long
+    L.ob_mvavg_run.argtypes = [C.POINTER(ObFmt)] * 4 + [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_long, C.c_long,
+                               C.POINTER(C.c_int64)]
+    a, b, c, d = _obfmt(fin), _obfmt(fout), _obfmt(facc), _obfmt(fcoeff)
+    x, h = _i64(x), _i64(coeffs)
+    out = np.empty(x.size + 1, dtype=np.int64)
+    w = WIN_MODES.index(win) if isinstance(win, str) else int(win)
+    n = L.ob_mvavg_run(C.byref(a), C.byref(b), C.byref(c), C.byref(d), int(taps), w, _p(h), _p(x), x.size, int(n_sample), _p(out))
+    if n < 0:
+        raise ValueError("bursts must be whole and at least TAPS samples long")
+    return out[:n].copy()
+
+
+class MvA:
+    """The unmodified reference ac_mv_avg for one compiled-in configuration (index into ref_configs.MV_CONFIGS), over the
+    restated ac_window_1d_flag of oracle/ac_shim/ac_window.h."""
+
+    def __init__(self, cfg_id, coeffs):
+        self.L = lib_a()
+        self.L.acref_mv_create.restype = C.c_void_p
+        self.L.acref_mv_create.argtypes = [C.c_int, C.POINTER(C.c_int64)]
+        self.L.acref_mv_run.restype = C.c_long
+        self.L.acref_mv_run.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_long, C.c_longlong, C.POINTER(C.c_int64)]
+        self.L.acref_mv_destroy.argtypes = [C.c_void_p]
+        h = _i64(coeffs)
+        self.h = self.L.acref_mv_create(int(cfg_id), _p(h))
+        if not self.h:
+            raise KeyError("configuration not instantiated in oracle/_ref")
+
+    def run(self, x, n_sample):
+        x = _i64(x)
+        out = np.empty(x.size + 1, dtype=np.int64)
+        n = self.L.acref_mv_run(self.h, _p(x), x.size, int(n_sample), _p(out))
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.acref_mv_destroy(self.h)
+            self.h = None
+
+
 class IdA:
     """The real reference ac_intg_dump for one compiled-in configuration (index into ref_configs.ID_CONFIGS)."""
 

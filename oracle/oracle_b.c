@@ -438,6 +438,38 @@ long ob_id_run(ob_id *f, const int64_t *in, long n, const int64_t *nsamp, long n
   return k == n ? nout : -1;
 }
 
+/* ------------------------------------------------------------------ ac_mv_avg -- PARITY UNPINNED */
+/* include/ac_dsp/ac_mv_avg.h:99-127,154-196: weighted moving average over a window of TAPS samples centred on the point
+ * being smoothed, burst by burst (n_sample samples per burst, the window restarts at every start-of-line flag):
+ *   acc = 0;  for j = -TAPS/2 .. TAPS/2:  acc = acc + (ACC_TYPE) w[j] * coeffs[j + TAPS/2];  out = acc     (:111-121)
+ * -- the sample is cast to ACC_TYPE BEFORE the multiply, the sum is re-quantised to ACC_TYPE at every tap.  w[j] comes
+ * from ac_window_1d_flag (ac_math's ac_window.h, absent here): restated from the manual's description (section 2.4):
+ * AC_CLIP repeats the edge sample, AC_MIRROR reflects about it, AC_WIN emits only the points whose window is full.
+ * win: 0 = AC_WIN, 1 = AC_CLIP, 2 = AC_MIRROR.  n must be a multiple of n_sample, n_sample >= taps.  Returns #outputs. */
+long ob_mvavg_run(const ob_fmt *in, const ob_fmt *out_f, const ob_fmt *acc, const ob_fmt *coeff, int taps, int win,
+                  const int64_t *c, const int64_t *x, long n, long n_sample, int64_t *out) {
+  const int Fin = F_of(in), Fa = F_of(acc), Fc = F_of(coeff), H = taps / 2;
+  if (n_sample < taps || n_sample < 1 || n % n_sample) return -1;
+  long nout = 0;
+  for (long b = 0; b < n / n_sample; b++) {
+    const int64_t *xb = x + b * n_sample;
+    const long lo = win == 0 ? H : 0, hi = win == 0 ? n_sample - 1 - H : n_sample - 1;
+    for (long i = lo; i <= hi; i++) {
+      w128 a = 0;
+      for (int j = -H; j <= H; j++) {
+        long k = i + j;
+        if (win == 1) { if (k < 0) k = 0; if (k > n_sample - 1) k = n_sample - 1; }
+        else if (win == 2) { if (k < 0) k = -k; if (k > n_sample - 1) k = 2 * (n_sample - 1) - k; }
+        const w128 s = ob_wrap((w128)xb[k], in->W, in->S);
+        const w128 cast = ob_convert(s, Fin, acc);                                        /* (ACC_TYPE) w[j] */
+        a = ob_macc(a, acc, cast * ob_wrap((w128)c[j + H], coeff->W, coeff->S), Fa + Fc);  /* acc_reg = acc_reg + ... */
+      }
+      out[nout++] = (int64_t)ob_convert(a, Fa, out_f);                                    /* data_out = acc_reg */
+    }
+  }
+  return nout;
+}
+
 /* ------------------------------------------------------------------ CIC */
 typedef struct {
   ob_fmt in, out, it;   /* it = lossless INT_TYPE */

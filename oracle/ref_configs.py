@@ -187,6 +187,22 @@ ID_CONFIGS = [
 ]
 
 
+# ac_mv_avg instantiations: (MAX_SAMPLE, TAPS, WIN_TYPE, in, out, acc, coeff).  Oracle A for these
+# is the unmodified ac_mv_avg.h over a RESTATED ac_window_1d_flag (oracle/ac_shim/ac_window.h): parity unpinned.
+MV_CONFIGS = [
+    (1024, 7, "AC_CLIP", fmt(16, 2), fmt(16, 2), fmt(16, 2), fmt(16, 2)),                 # the manual's usage example (pdf p.30)
+    (1024, 7, "AC_MIRROR", fmt(16, 2), fmt(16, 2), fmt(16, 2), fmt(16, 2)),
+    (1024, 7, "AC_WIN", fmt(16, 2), fmt(16, 2), fmt(16, 2), fmt(16, 2)),
+    (4096, 31, "AC_MIRROR", _Q15, _ACC40, _ACC40, _Q15),                                 # exact accumulation
+    (4096, 31, "AC_CLIP", _Q15, fmt(20, 3, True, RND, "AC_SAT"), fmt(28, 6, True, RND), fmt(12, 1)),
+    (500, 3, "AC_CLIP", fmt(12, 0, False), fmt(24, 8, False), fmt(24, 8, False), fmt(10, 2, False)),
+    (2000, 9, "AC_MIRROR", fmt(24, 8), fmt(20, 6, True, "AC_RND_CONV", "AC_SAT_SYM"), fmt(30, 10, True, "AC_TRN_ZERO", "AC_SAT"), fmt(16, 1)),
+    (300, 1, "AC_CLIP", _Q15, _ACC40, _ACC40, _Q15),                                      # TAPS = 1: a scaled copy
+    (64, 5, "AC_WIN", fmt(32, 16), fmt(64, 32), fmt(64, 32), fmt(32, 16)),
+    (8192, 63, "AC_CLIP", _Q15, _ACC40, fmt(18, 3), _Q15),                                 # the (ACC_TYPE) cast of the sample drops bits
+]
+
+
 def rs_ram_words(cfg):
     """Coefficient RAM words an instantiation reads (ac_fir_reg_share.h:122-133 and analogues)."""
     N, _fi, _fo, _fc, _fa, mww, bs, bo, ft = cfg

@@ -17,6 +17,7 @@
 #include <ac_dsp/ac_fir_reg_share.h>
 #include <ac_dsp/ac_poly_dec.h>
 #include <ac_dsp/ac_intg_dump.h>
+#include <ac_dsp/ac_mv_avg.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -188,6 +189,30 @@ static int run_intg_dump(const std::vector<long long> &x, const std::vector<long
   return 0;
 }
 
+// ac_mv_avg: the wrapper idiom of the manual (pdf p.30: the weights are a member of the DERIVED class), bursts of `chunk`
+// samples, the n_sample token written before the call
+template <int MAXS, int TAPS, ac_window_mode WT, class IN, class OUT, class ACC, class COEFF>
+class mv_wrapper : public ac_mv_avg<MAXS, TAPS, WT, IN, OUT, ACC, COEFF, ac_int<32, false> > {
+public:
+  COEFF coeffs[TAPS];
+  explicit mv_wrapper(const std::vector<long long> &c) : ac_mv_avg<MAXS, TAPS, WT, IN, OUT, ACC, COEFF, ac_int<32, false> >(coeffs) {
+    for (int i = 0; i < TAPS; i++) coeffs[i] = from_raw<COEFF>(c[i]);
+  }
+};
+template <int MAXS, int TAPS, ac_window_mode WT, class IN, class OUT, class ACC, class COEFF>
+static int run_mv_avg(const std::vector<long long> &x, const std::vector<long long> &c, size_t n_sample, std::vector<long long> &y) {
+  if (c.size() != TAPS || n_sample == 0) return 2;
+  mv_wrapper<MAXS, TAPS, WT, IN, OUT, ACC, COEFF> filter(c);
+  ac_channel<IN> in;
+  ac_channel<OUT> out;
+  ac_channel<ac_int<32, false> > ns;
+  for (size_t i = 0; i < x.size(); i++) in.write(from_raw<IN>(x[i]));
+  ns.write(ac_int<32, false>((unsigned)n_sample));
+  filter.run(in, out, ns);
+  drain_to(out, y);
+  return 0;
+}
+
 template <class FILTER, class IN, class OUT>
 static int run_cic(const std::vector<long long> &x, size_t chunk, std::vector<long long> &y) {
   FILTER filter;
@@ -256,6 +281,13 @@ int main(int argc, char **argv) {
       rc = run_intg_dump<ac_fixed<16, 1, true>, ac_fixed<32, 17, true>, ac_fixed<32, 17, true>, 64, 4>(x, c, y);
     else if (name == "id3")
       rc = run_intg_dump<ac_fixed<16, 1, true>, ac_fixed<24, 12, true>, ac_fixed<16, 8, true>, 16, 3>(x, c, y);
+    // ---- ac_mv_avg (oracle/ref_configs.py MV_CONFIGS 0, 3, 8); `chunk` carries n_sample
+    else if (name == "mv0")
+      rc = run_mv_avg<1024, 7, AC_CLIP, ac_fixed<16, 2, true>, ac_fixed<16, 2, true>, ac_fixed<16, 2, true>, ac_fixed<16, 2, true> >(x, c, chunk, y);
+    else if (name == "mv3")
+      rc = run_mv_avg<4096, 31, AC_MIRROR, ac_fixed<16, 1, true>, ac_fixed<40, 8, true>, ac_fixed<40, 8, true>, ac_fixed<16, 1, true> >(x, c, chunk, y);
+    else if (name == "mv8")
+      rc = run_mv_avg<64, 5, AC_WIN, ac_fixed<32, 16, true>, ac_fixed<64, 32, true>, ac_fixed<64, 32, true>, ac_fixed<32, 16, true> >(x, c, chunk, y);
     else
       std::fprintf(stderr, "unknown case %s\n", name.c_str());
   } catch (const b200dsp::engine_error &e) {

@@ -20,7 +20,8 @@ Fixtures (all raw two's-complement integers, int64):
       ac_firProgCoeffs_delay_line value; and of the UNMODIFIED ac_poly_dec (oracle/ref_driver_pd.cpp) for every
       configuration in PD_CONFIGS (samples, phase-ordered coefficients, outputs of three run batches), of the
       UNMODIFIED ac_poly_intr (oracle/ref_driver_pi.cpp) for every configuration in PI_CONFIGS (two coefficient /
-      control sets, the second loaded half way through the stream) and of ac_intg_dump (ID_CONFIGS).
+      control sets, the second loaded half way through the stream), of ac_intg_dump (ID_CONFIGS) and of ac_mv_avg
+      (MV_CONFIGS; the unmodified class over the RESTATED ac_window_1d_flag of oracle/ac_shim/ac_window.h: parity unpinned).
   ref_outputs.npz
       outputs of the UNMODIFIED reference classes (Oracle A) on seeded random inputs for every
       configuration in oracle/ref_configs.py x ftype (FIR) and every CIC configuration, fed in
@@ -173,6 +174,16 @@ def main():
             ys.append(f.run(x, ns)); xs.append(x); toks.append(ns)
         rs[f"id{cid}_x"], rs[f"id{cid}_ns"], rs[f"id{cid}_y"] = np.concatenate(xs), np.concatenate(toks), np.concatenate(ys)
         rs[f"id{cid}_xlen"] = np.array([v.size for v in xs], dtype=np.int64)
+    rng3 = np.random.default_rng(SEED + 4)                              # own stream: adding rows here leaves the others alone
+    for cid, (maxs, taps, wt, fi, fo, fa, fc) in enumerate(rc.MV_CONFIGS):   # ac_mv_avg (row N4): unmodified class over the RESTATED window
+        c = O.rand_raw(rng3, fc, taps)
+        f = O.MvA(cid, c)
+        ns1, ns2 = min(maxs, 3 * taps + 5), taps                        # two run() calls: three bursts, then two of the shortest legal length
+        x1, x2 = O.rand_raw(rng3, fi, 3 * ns1), O.rand_raw(rng3, fi, 2 * ns2)
+        x1[:2] = [O.rand_raw(rng3, fi, 1, "min")[0], O.rand_raw(rng3, fi, 1, "max")[0]]
+        rs[f"mv{cid}_c"], rs[f"mv{cid}_x1"], rs[f"mv{cid}_x2"] = c, x1, x2
+        rs[f"mv{cid}_ns"] = np.array([ns1, ns2], dtype=np.int64)
+        rs[f"mv{cid}_y1"], rs[f"mv{cid}_y2"] = f.run(x1, ns1), f.run(x2, ns2)
     for cid, cfg in enumerate(rc.PI_CONFIGS):                           # ac_poly_intr (row N2), same file
         fi, fc, fa, fo, nt, IF, ft = cfg
         f = O.PiA(cid)

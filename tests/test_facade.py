@@ -266,3 +266,15 @@ def test_facade_intg_dump(bench_exe, tmp_path, cid):
     p, y = run_case(bench_exe, tmp_path, f"id{cid}", g[f"id{cid}_x"], g[f"id{cid}_ns"])
     assert p.returncode == 0, p.stderr
     assert np.array_equal(y, g[f"id{cid}_y"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", [0, 3, 8])
+def test_facade_mv_avg(bench_exe, tmp_path, cid):
+    """ac_mv_avg through its facade class (wrapper idiom, n_sample token channel): equal to the unmodified reference
+    header driven over the restated window class (parity unpinned, oracle/ac_shim/ac_window.h)."""
+    g = np.load(os.path.join(GOLDEN, "rs_outputs.npz"))
+    for k in (1, 2):
+        p, y = run_case(bench_exe, tmp_path, f"mv{cid}", g[f"mv{cid}_x{k}"], g[f"mv{cid}_c"], chunk=int(g[f"mv{cid}_ns"][k - 1]))
+        assert p.returncode == 0, p.stderr
+        assert np.array_equal(y, g[f"mv{cid}_y{k}"])

@@ -729,6 +729,34 @@ def test_intg_dump_vs_reference_outputs(engine, cid, path):
     assert np.array_equal(np.concatenate(ys).astype(np.int64), g[f"id{cid}_y"])
 
 
+# ------------------------------------------------------------------------ ac_mv_avg (parity unpinned)
+@pytest.mark.parametrize("cid", range(len(rc.MV_CONFIGS)), ids=[f"mv{i}-{c[2]}-{c[1]}" for i, c in enumerate(rc.MV_CONFIGS)])
+def test_mv_avg_vs_reference_outputs(engine, oracle, cid):
+    """The engine against the committed outputs of the UNMODIFIED ac_mv_avg.h (driven over the restated window class):
+    several bursts per call, the shortest legal burst, every accumulator / output mode of the table; then a large
+    device-resident call against the restatement."""
+    import torch
+    g = golden("rs_outputs.npz")
+    maxs, taps, wt, fi, fo, fa, fc = rc.MV_CONFIGS[cid]
+    ns1, ns2 = (int(v) for v in g[f"mv{cid}_ns"])
+    f = engine.ac_mv_avg(maxs, taps, wt, fi, fo, fa, fc, g[f"mv{cid}_c"])
+    assert f.path == "mvavg_generic"
+    assert np.array_equal(f.run(g[f"mv{cid}_x1"], ns1).astype(np.int64), g[f"mv{cid}_y1"])
+    assert np.array_equal(f.run(g[f"mv{cid}_x2"], ns2).astype(np.int64), g[f"mv{cid}_y2"])      # nothing carries over
+    rng = np.random.default_rng(100 + cid)
+    x = oracle.rand_raw(rng, fi, 257 * maxs)
+    xin = torch.from_numpy(x.astype(f._in_dt)).cuda()
+    y = f.run(xin, maxs).cpu().numpy().astype(np.int64)
+    assert np.array_equal(y, oracle.mv_run_b(fi, fo, fa, fc, taps, wt, g[f"mv{cid}_c"], x, maxs))
+    with pytest.raises(engine.B2dError):
+        f.run(x[: maxs + 1], maxs)                       # not a whole number of bursts
+    with pytest.raises(engine.B2dError):
+        f.run(x[: 2 * (maxs + 1)], maxs + 1)             # burst longer than MAX_SAMPLE
+    if taps > 1:
+        with pytest.raises(engine.B2dError):
+            f.run(x[: taps - 1], taps - 1)               # window span above the burst length
+
+
 def test_intg_dump_regular_frames_device(engine, oracle):
     """Constant frame length (the streaming case): 4 channels x 64 samples per dump on the device path, and the
     argument check that stands in for the reference reading past the end of its channel."""

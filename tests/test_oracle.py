@@ -262,3 +262,48 @@ def test_intg_dump_restatement_vs_reference_outputs(oracle, cid):
     f = oracle.IdB(fi, fa, fo, NS, CHN)
     y = np.concatenate([f.run(x, ns) for x, ns in _id_calls(g, cid)])
     assert np.array_equal(y, g[f"id{cid}_y"])
+
+
+# ------------------------------------------------------------------------ ac_mv_avg (parity unpinned)
+MV_IDS = [f"mv{i}-{c[2]}-{c[1]}" for i, c in enumerate(rc.MV_CONFIGS)]
+
+
+@pytest.mark.parametrize("cid", range(len(rc.MV_CONFIGS)), ids=MV_IDS)
+def test_mv_avg_restatement_vs_reference_outputs(oracle, cid):
+    """Oracle B against the committed outputs of the UNMODIFIED ac_mv_avg.h driven over the restated window class."""
+    g = golden("rs_outputs.npz")
+    maxs, taps, wt, fi, fo, fa, fc = rc.MV_CONFIGS[cid]
+    ns1, ns2 = (int(v) for v in g[f"mv{cid}_ns"])
+    c = g[f"mv{cid}_c"]
+    assert np.array_equal(oracle.mv_run_b(fi, fo, fa, fc, taps, wt, c, g[f"mv{cid}_x1"], ns1), g[f"mv{cid}_y1"])
+    assert np.array_equal(oracle.mv_run_b(fi, fo, fa, fc, taps, wt, c, g[f"mv{cid}_x2"], ns2), g[f"mv{cid}_y2"])
+    assert g[f"mv{cid}_y1"].size == 3 * (ns1 - taps + 1 if wt == "AC_WIN" else ns1)
+
+
+def test_mv_avg_documented_behaviour(oracle):
+    """The manual's description (section 2.4.3), on the restatement: DC gain = sum of the weights everywhere (clip and
+    mirror keep a constant burst constant), an impulse in the middle returns the reversed weights, the two boundary
+    rules differ only within TAPS/2 of the burst edges, AC_WIN is the interior of either."""
+    Q = (16, 2)
+    A = (32, 6)
+    taps, n = 7, 50
+    c = np.array([3, -1, 4, 1, -5, 9, 2]) * 256
+    dc = np.full(n, 1 << 10)
+    for wt in ("AC_CLIP", "AC_MIRROR"):
+        y = oracle.mv_run_b(Q, A, A, Q, taps, wt, c, dc, n)
+        assert y.size == n and np.all(y == ((dc[0] * c) >> 2).sum())      # (x * 2^12 * c) >> 14 per tap: floor(x c / 4)
+    x = np.zeros(n, dtype=np.int64)
+    x[25] = 1 << 14
+    y = oracle.mv_run_b(Q, A, A, Q, taps, "AC_CLIP", c, x, n)
+    assert np.array_equal(y[22:29], c[::-1] * (1 << 14) >> 2)
+    rng = np.random.default_rng(8)
+    x = rng.integers(-30000, 30000, n)
+    yc, ym, yw = (oracle.mv_run_b(Q, A, A, Q, taps, wt, c, x, n) for wt in ("AC_CLIP", "AC_MIRROR", "AC_WIN"))
+    assert np.array_equal(yc[3:-3], ym[3:-3]) and np.array_equal(yw, yc[3:-3]) and not np.array_equal(yc[:3], ym[:3])
+    # the left edge by hand: clip repeats x[0], mirror reflects about it
+    k = 1
+    idx_c = [max(k + j, 0) for j in range(-3, 4)]
+    idx_m = [abs(k + j) for j in range(-3, 4)]
+    assert yc[k] == sum((int(x[i]) * int(w)) >> 2 for i, w in zip(idx_c, c)) and ym[k] == sum((int(x[i]) * int(w)) >> 2 for i, w in zip(idx_m, c))
+    with pytest.raises(ValueError):
+        oracle.mv_run_b(Q, A, A, Q, taps, "AC_CLIP", c, x[:6], 6)           # burst shorter than the window

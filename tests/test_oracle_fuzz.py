@@ -391,3 +391,51 @@ def test_reg_share_random_instantiation(rs_fuzz, i):
     assert np.array_equal(np.concatenate(ya), np.concatenate(yb)), cfgs[i]
     assert int(L.acref_rs_delay_out(ha)) == b.delay_out(), cfgs[i]
     L.acref_rs_destroy(ha)
+
+
+# ------------------------------------------------------------------------------------------ ac_mv_avg (parity unpinned)
+def draw_mv(rng, k):
+    """(MAX_SAMPLE, TAPS, WIN_TYPE, in, out, acc, coeff): the product is ACC_TYPE x COEFF_TYPE here (the sample is cast to
+    ACC_TYPE first), so the 128-bit budget bounds W_acc + W_coeff."""
+    cfgs = []
+    while len(cfgs) < k:
+        fi, fc, fa, fo = draw_mac_formats(rng)
+        if fa[0] + fc[0] > 96 or fa[0] + max(0, (fc[0] - fc[1])) > 110:
+            continue
+        taps = int(rng.integers(0, 8)) * 2 + 1
+        cfgs.append((taps + int(rng.integers(0, 40)), taps, ["AC_WIN", "AC_CLIP", "AC_MIRROR"][len(cfgs) % 3], fi, fo, fa, fc))
+    return cfgs
+
+
+@pytest.fixture(scope="module")
+def mv_fuzz(tmp_path_factory):
+    rng = np.random.default_rng(SEED + 17)
+    cfgs = draw_mv(rng, 9)
+    inc = "".join(f"X({i}, {maxs}, {taps}, {wt}, {cfmt(fi)}, {cfmt(fo)}, {cfmt(fa)}, {cfmt(fc)})\n" for i, (maxs, taps, wt, fi, fo, fa, fc) in enumerate(cfgs))
+    L = compile_driver(str(tmp_path_factory.mktemp("mvfuzz")), {"cfgs_mv.inc": inc}, [("ref_driver_mv.cpp", [])], "libmvfuzz.so")
+    P64 = C.POINTER(C.c_int64)
+    L.acref_mv_create.restype = C.c_void_p
+    L.acref_mv_create.argtypes = [C.c_int, P64]
+    L.acref_mv_run.restype = C.c_long
+    L.acref_mv_run.argtypes = [C.c_void_p, P64, C.c_long, C.c_longlong, P64]
+    L.acref_mv_destroy.argtypes = [C.c_void_p]
+    return L, cfgs
+
+
+@pytest.mark.parametrize("i", range(9))
+def test_mv_avg_random_instantiation(mv_fuzz, i):
+    """The unmodified ac_mv_avg.h (over the restated window class) == the plain-C restatement on drawn formats and modes:
+    pins the arithmetic of the class -- the ACC_TYPE cast before the multiply, the per-tap re-quantisation, the burst loop --
+    not the window's boundary rules, which both sides take from oracle/ac_shim/ac_window.h's reading of the manual."""
+    L, cfgs = mv_fuzz
+    maxs, taps, wt, fi, fo, fa, fc = cfgs[i]
+    rng = np.random.default_rng(SEED + 900 + i)
+    c = i64(O.rand_raw(rng, fc, taps))
+    ha = L.acref_mv_create(i, p64(c))
+    for ns in (taps, maxs):
+        x = i64(O.rand_raw(rng, fi, 3 * ns))
+        buf = np.empty(x.size + 1, dtype=np.int64)
+        ya = buf[:L.acref_mv_run(ha, p64(x), x.size, ns, p64(buf))].copy()
+        yb = O.mv_run_b(fi, fo, fa, fc, taps, wt, c, x, ns)
+        assert ya.size == yb.size and np.array_equal(ya, yb), (cfgs[i], ns)
+    L.acref_mv_destroy(ha)

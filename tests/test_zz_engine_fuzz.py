@@ -115,3 +115,14 @@ def test_intg_dump_random_formats(engine, oracle, i):
     want = np.asarray(oracle.IdB(fi, fa, fo, NS, CHN).run(x, tok)).reshape(-1)
     y = np.asarray(engine.ac_intg_dump(fi, fa, fo, NS, CHN).run(x, tok)).reshape(-1)
     assert np.array_equal(y.astype(np.int64), want), ((fi, fa, fo, NS, CHN),)
+
+
+@pytest.mark.parametrize("i", range(9))
+def test_mv_avg_random_formats(engine, oracle, i):
+    rng = np.random.default_rng(SEED + 9500 + i)
+    maxs, taps, wt, fi, fo, fa, fc = F.draw_mv(rng, 3)[i % 3]
+    c = oracle.rand_raw(rng, fc, taps)
+    f = engine.ac_mv_avg(maxs, taps, wt, fi, fo, fa, fc, c)
+    for ns in (taps, maxs):
+        x = oracle.rand_raw(rng, fi, 5 * ns)
+        assert np.array_equal(f.run(x, ns).astype(np.int64), oracle.mv_run_b(fi, fo, fa, fc, taps, wt, c, x, ns)), ((maxs, taps, wt, fi, fo, fa, fc), ns)
