@@ -67,7 +67,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    """libb200dsp.so of this tree; B2D_LIBRARY points at another build of it (kernel A/B runs: tools/build_variant.sh)."""
+    return os.environ.get("B2D_LIBRARY") or _build.LIB
 
 
 def load():

@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(kThreads) fir_q15_kernel(Q15Args a) {
 #pragma unroll
         for (int j = 0; j < kT; j++) { lo[j] = 0; hi[j] = 0; }
         const int kend = kb + KC < a.Npad ? kb + KC : a.Npad;
-#pragma unroll 1
+        // four chunks per trip: the loads use immediate offsets and the trip's address arithmetic (three IMAD.IADD on the
+        // DP2A pipe per chunk before) is paid once per 512 DP2A; r02 A/B on a B200: 33.27 -> 34.5 G IQ samples/s at 256 taps
+        // (unroll 2: 33.98, 8: 28.9, 16: 27.1 -- the loop body outgrows the instruction cache)
+#pragma unroll 4
         for (int k0 = kb; k0 < kend; k0 += kChunk) {
           uint32_t E[12], O[11], cwv[8];
           const uint4 v0 = x4[k0 / 8], v1 = x4[k0 / 8 + 1], v2 = x4[k0 / 8 + 2];
