@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(kUpThreads) upfir_q15_kernel(UpArgs a) {
 // of a period are stored straight from registers as 128-bit words: consecutive lanes write consecutive R*8-byte
 // groups, so a pair of store instructions covers 1 KB contiguously -- no staging tile, no copy-out pass, and one
 // barrier per tile (the sample double buffer).
-template <int R, int JT, int PLANES, int NARROW, bool PEEL = false, int MINB = 0>
-__global__ void __launch_bounds__(kUpThreads, MINB) upfir_lane_kernel(UpArgs a) {
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
+__global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int WPP = PLANES == 3 ? 2 : 1;
   constexpr int CW = R * WPP;                      // coefficient words per tap pair, all phases
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kUpThreads, MINB) upfir_lane_kernel(UpArgs a) 
           }
         };
         pair(0, std::true_type());
-#pragma unroll 2
+#pragma unroll 8
         for (int p = 1; p < TP; p++) pair(p, std::false_type());
       } else {
 #pragma unroll
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kUpThreads, MINB) upfir_lane_kernel(UpArgs a) 
 #pragma unroll
             for (int pl = 0; pl < PLANES; pl++) acc[j][ph][pl] = 0;
         const uint32_t *xq = xb + ((threadIdx.x & 1) ? XS : 0) + (threadIdx.x >> 1);   // period q = j*128 + tid: word q/2 + p
-#pragma unroll 2
+#pragma unroll 8
         for (int p = 0; p < TP; p++) {
           uint32_t w[CW];
           if (CW % 4 == 0) {
@@ -452,7 +452,7 @@ static int up_grid_waves() {
   return v < 1 ? 1 : (v > 64 ? 64 : v);
 }
 
-template <int R, int JT, int PLANES, int NARROW, bool PEEL = false, int MINB = 0>
+template <int R, int JT, int PLANES, int NARROW, bool PEEL = false>
 static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   constexpr int TILE = kUpThreads * JT;
   const long long kbase = a.out_first / R;
@@ -463,16 +463,16 @@ static cudaError_t launch_up_lane_n(UpArgs a, cudaStream_t st) {
   const int XS = ((((nxs + 1) / 2 + 1) + 31) & ~31) + 16;
   const size_t smem = (size_t)((ncw + 3) & ~3) * 4 + (size_t)4 * XS * 4 + (size_t)TILE * R * 8;
   a.ntiles = (nper + TILE - 1) / TILE;
-  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB>, kUpThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL>, kUpThreads, smem);
   if (per_sm < 1) per_sm = 1;
   long long gx = a.ntiles;
   const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, a.C);
-  upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL, MINB><<<grid, kUpThreads, smem, st>>>(a);
+  upfir_lane_kernel<R, JT, PLANES, NARROW, PEEL><<<grid, kUpThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -482,11 +482,10 @@ static cudaError_t launch_up_lane(const UpArgs &a, cudaStream_t st) {
   if (a.acc.W - a.lsh <= 40 && a.acc.W > 32 && a.lsh < 32) {
     // A/B switch (profiles/r01_source_level_notes.md): accumulators started by the first tap pair; instantiated for
     // the two bench geometries (R = 4, JT = 4, signed <40,8>-style accumulator) only
-    // three planes: +3 % with the peeled start (72 registers instead of 80); two planes: -6 % (70 instead of 54 registers)
+    // three planes: +3 % with the peeled start (72 registers instead of 80); two planes: -6 % (70 instead of 54 registers).
+    // Tap loop unrolled 8-fold: +1.8 % / +1.5 % over 2-fold on cicfir / polyintr (r02 A/B, gpurun_out/r02_m_*.json)
     const char *peel = getenv("B2D_UPFIR_PEEL");
     const bool use_peel = peel ? *peel == '1' : PLANES == 3;
-    const char *lb = getenv("B2D_UPFIR_LB6");       // A/B: __launch_bounds__(128, 6) keeps the prefetched samples out of local memory
-    if (R == 4 && JT == 4 && a.acc.S && use_peel && lb && *lb == '1') return launch_up_lane_n<4, 4, PLANES, 1, true, 6>(a, st);
     if (R == 4 && JT == 4 && a.acc.S && use_peel) return launch_up_lane_n<4, 4, PLANES, 1, true>(a, st);
     return a.acc.S ? launch_up_lane_n<R, JT, PLANES, 1>(a, st) : launch_up_lane_n<R, JT, PLANES, 2>(a, st);
   }
