@@ -393,7 +393,9 @@ __global__ void __launch_bounds__(kUpThreads) upfir_lane_kernel(UpArgs a) {
             // 32 < W_acc <= 40 + lsh: only the low W_acc - lsh bits of the sum count, so the upper planes combine modulo
             // 2^32 and the 64-bit sum, shift and sign extension are done on 32-bit halves (no IMAD.WIDE on the DP2A pipe)
             // (a 32-bit-only form -- low word (acc0 + (m << 8)) << lsh, high bits from m + (acc0 >> 8) -- saves four instructions
-            // per result but ptxas turns its shift-adds into IMADs on the DP2A pipe: 103.5 vs 111.3 G inputs/s, r02 A/B)
+            // per result but ptxas turns its shift-adds into IMADs on the DP2A pipe: 103.5 vs 111.3 G inputs/s; the same form
+            // forced onto the ALU pipe with funnel shifts and three-operand adds: 113.6 vs 113.2 G, not worth a second code
+            // path -- r02 A/B runs)
             const uint32_t m = PLANES == 3 ? (uint32_t)acc[j][ph][1] + ((uint32_t)acc[j][ph][2] << 8) : (uint32_t)acc[j][ph][1];
             uint32_t tl, th;
             asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(tl), "=r"(th)
