@@ -465,7 +465,6 @@ def measure(name, wl, args, ctx, want_cpu):
             tot = [int(v) for v in t.tolist()]
             parity = {"ranks": world, "windows": tot[2], "outputs_checked": tot[1], "mismatches": tot[0], "ok": tot[0] == 0,
                       "checker": mine["checker"]}
-    del y
 
     # ---- end to end through the C-ABI host-buffer call (page-locked host memory, copies inside the timed region)
     e2e = e2e_packed = None
@@ -517,12 +516,32 @@ def measure(name, wl, args, ctx, want_cpu):
             dt = float(tt.item())
             wb = lib.b2d_wire_bytes(W_out, wire)
             n_vals = no.value * (C if wl["kind"] != "intgdump" else 1)
+            # the bytes the host call delivered against the device-resident result of the same samples (an output depends on
+            # a finite window of inputs, so away from the start of the call the two must agree bit for bit)
+            same = None
+            if wl["kind"] == "fir" or (wl["kind"] == "cic" and wl["mode"] == "dec"):
+                Wn = 4096
+                per = no.value                                            # outputs per channel of one call
+                off = per // 2
+                if wl["kind"] == "fir" and il and C > 1:
+                    lo_e, cnt = off * C, Wn * C                           # interleaved: one contiguous run
+                    dev = y[off:off + Wn].reshape(-1)
+                else:
+                    lo_e, cnt = off, Wn                                   # planar: channel 0 of the call's output
+                    dev = (y.reshape(C, -1)[0] if C > 1 else y.reshape(-1))[off:off + Wn]
+                raw = yb[lo_e * wb:(lo_e + cnt) * wb]
+                if wire:
+                    host = np.empty(cnt, dtype={2: np.int16, 4: np.int32, 8: np.int64}[cbytes])
+                    assert lib.b2d_unpack_wire(raw.ctypes.data, cnt, W_out, 1, host.ctypes.data) == 0
+                else:
+                    host = raw.view({2: np.int16, 4: np.int32, 8: np.int64}[cbytes])
+                same = bool(np.array_equal(host.astype(np.int64), dev.cpu().numpy().astype(np.int64)))
             res = {"value": u2 * world * k2 / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xb.size),
                    "d2h_bytes_per_step": int(n_vals * wb), "steps": k2,
                    "api": f"b2d_{'cic' if wl['kind'] == 'cic' else wl['kind']}_run (C-ABI, page-locked host buffers from b2d_host_alloc, 3-slot copy/compute pipeline)",
                    "out_format": "B2D_WIRE_PACKED: %d bytes per ac_fixed<%d,.> value" % (wb, W_out) if wire else "containers: %d bytes per value" % cbytes,
                    "host_affinity": "NVML ideal CPUs of the GPU" if ctx["orig_affinity"] else "unchanged",
-                   "samples_per_step": u2,
+                   "samples_per_step": u2, "output_equals_device_path": same,
                    "note": "one step = one C-ABI call over %d units per GPU (the device-resident `value` runs %d per step)" % (u2, units_per_step)}
             ceil = pcie_ceiling(world, xb.size / u2, n_vals * wb / u2)
             if ceil:
@@ -535,6 +554,7 @@ def measure(name, wl, args, ctx, want_cpu):
             setw(f._h, 0)
         lib.b2d_host_free(xptr)
         lib.b2d_host_free(yptr)
+    del y
 
     res = {"name": name, "value": value, "ms_per_step": ms_per_step, "units_per_step": units_per_step, "path": path,
            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "parity": parity, "gpu_launches": launches_per_step * args.steps}
