@@ -58,7 +58,8 @@ __device__ __forceinline__ int q24_sample(const Q24Args &a, uint32_t c, long lon
 // LEAD = (-(N_TAPS - 1)) mod 4: where the first staged sample of a tile sits inside its 16-byte group (tiles are multiples
 // of 1024 outputs, so it is the same for every tile of a launch) -- a template parameter, so that picking four samples out
 // of two aligned 128-bit loads costs no moves.
-template <int LEAD>
+// ONE: the padded tap count fits one int32 accumulation block (<= 128 taps): no running 64-bit totals.
+template <int LEAD, bool ONE>
 __global__ void __launch_bounds__(kQ24Threads) fir_q24_kernel(Q24Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tile = kQ24Threads * kQ24T * a.passes;
@@ -103,15 +104,17 @@ __global__ void __launch_bounds__(kQ24Threads) fir_q24_kernel(Q24Args a) {
     const long long n0 = out0 + o;
     if ((size_t)n0 >= a.n) break;
     long long tot[kQ24T];
+    if (!ONE) {
 #pragma unroll
-    for (int j = 0; j < kQ24T; j++) tot[j] = 0;
-    for (int kb = 0; kb < a.Npad; kb += kQ24Block) {
+      for (int j = 0; j < kQ24T; j++) tot[j] = 0;
+    }
+    for (int kb = 0; kb < (ONE ? 1 : a.Npad); kb += kQ24Block) {
       int acc[3][kQ24T];
 #pragma unroll
       for (int p = 0; p < 3; p++)
 #pragma unroll
         for (int j = 0; j < kQ24T; j++) acc[p][j] = 0;
-      const int kend = kb + kQ24Block < a.Npad ? kb + kQ24Block : a.Npad;
+      const int kend = ONE ? a.Npad : (kb + kQ24Block < a.Npad ? kb + kQ24Block : a.Npad);
 #pragma unroll 1
       for (int k0 = kb; k0 < kend; k0 += kQ24Chunk) {
         uint32_t cwv[8];
@@ -143,7 +146,10 @@ __global__ void __launch_bounds__(kQ24Threads) fir_q24_kernel(Q24Args a) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < kQ24T; j++) tot[j] += (long long)acc[0][j] + ((long long)acc[1][j] << 8) + ((long long)acc[2][j] << 16);
+      for (int j = 0; j < kQ24T; j++) {
+        const long long blk = (long long)acc[0][j] + ((long long)acc[1][j] << 8) + ((long long)acc[2][j] << 16);
+        if (ONE) tot[j] = blk; else tot[j] += blk;
+      }
     }
     long long res[kQ24T];
 #pragma unroll
@@ -239,10 +245,16 @@ cudaError_t launch_fir_q24(const FirLaunch &p, cudaStream_t st) {
   dim3 grid((unsigned)((p.n + tile - 1) / tile), p.C);
   const int lead = (4 - ((p.n_taps - 1) & 3)) & 3;
   cudaError_t e = cudaSuccess;
+  const bool one = a.Npad <= kQ24Block;
 #define B2D_Q24_LAUNCH(L)                                                                                                    \
   do {                                                                                                                       \
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(fir_q24_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e == cudaSuccess) fir_q24_kernel<L><<<grid, kQ24Threads, smem, st>>>(a);                                             \
+    if (one) {                                                                                                               \
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(fir_q24_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e == cudaSuccess) fir_q24_kernel<L, true><<<grid, kQ24Threads, smem, st>>>(a);                                     \
+    } else {                                                                                                                 \
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(fir_q24_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e == cudaSuccess) fir_q24_kernel<L, false><<<grid, kQ24Threads, smem, st>>>(a);                                    \
+    }                                                                                                                        \
   } while (0)
   if (lead == 0) B2D_Q24_LAUNCH(0);
   else if (lead == 1) B2D_Q24_LAUNCH(1);
