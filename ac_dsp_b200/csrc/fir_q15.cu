@@ -149,7 +149,9 @@ __device__ __forceinline__ void stage_tile(const Q15Args &a, uint32_t c0, long l
 
 // XS / CS: samples / coefficients signed.  NP: planes per CTA (2 = interleaved IQ pair).
 // FASTOUT: OUT_TYPE == ACC_TYPE in an int64 container (the BASELINE configs): no conversion, 128-bit stores.
-template <int XS, int CS, int NP, bool FASTOUT>
+// ONE: the padded tap count fits one int32 accumulation block (<= 256 taps, 128 for unsigned samples): no running 64-bit
+// totals, 16 registers fewer.
+template <int XS, int CS, int NP, bool FASTOUT, bool ONE>
 __global__ void __launch_bounds__(kThreads) fir_q15_kernel(Q15Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tile = kThreads * kT * a.passes;
@@ -174,13 +176,15 @@ __global__ void __launch_bounds__(kThreads) fir_q15_kernel(Q15Args a) {
       const uint4 *x4 = (const uint4 *)(xs + (size_t)p * stride + o);
       const uint4 *c4 = (const uint4 *)(cw + (size_t)p * a.pkw);
       long long tot[kT];
+      if (!ONE) {
 #pragma unroll
-      for (int j = 0; j < kT; j++) tot[j] = 0;
-      for (int kb = 0; kb < a.Npad; kb += KC) {
+        for (int j = 0; j < kT; j++) tot[j] = 0;
+      }
+      for (int kb = 0; kb < (ONE ? 1 : a.Npad); kb += KC) {
         int lo[kT], hi[kT];
 #pragma unroll
         for (int j = 0; j < kT; j++) { lo[j] = 0; hi[j] = 0; }
-        const int kend = kb + KC < a.Npad ? kb + KC : a.Npad;
+        const int kend = ONE ? a.Npad : (kb + KC < a.Npad ? kb + KC : a.Npad);
         // four chunks per trip: the loads use immediate offsets and the trip's address arithmetic (three IMAD.IADD on the
         // DP2A pipe per chunk before) is paid once per 512 DP2A; r02 A/B on a B200: 33.27 -> 34.5 G IQ samples/s at 256 taps
         // (unroll 2: 33.98, 8: 28.9, 16: 27.1 -- the loop body outgrows the instruction cache)
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) fir_q15_kernel(Q15Args a) {
         for (int j = 0; j < kT; j++) {
           const long long l = XS ? (long long)lo[j] : (long long)(unsigned)lo[j];
           const long long h = (XS || CS) ? (long long)hi[j] : (long long)(unsigned)hi[j];
-          tot[j] += (h << 8) + l;
+          if (ONE) tot[j] = (h << 8) + l; else tot[j] += (h << 8) + l;
         }
       }
 #pragma unroll
@@ -318,14 +322,24 @@ void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uin
   }
 }
 
-template <int XS, int CS, int NP, bool FASTOUT>
-static cudaError_t launch_variant(const Q15Args &a, dim3 grid, size_t smem, cudaStream_t st) {
+template <int XS, int CS, int NP, bool FASTOUT, bool ONE>
+static cudaError_t launch_variant1(const Q15Args &a, dim3 grid, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(fir_q15_kernel<XS, CS, NP, FASTOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fir_q15_kernel<XS, CS, NP, FASTOUT, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  fir_q15_kernel<XS, CS, NP, FASTOUT><<<grid, kThreads, smem, st>>>(a);
+  static bool carved = false;    // per instantiation: ask for the largest shared-memory carve-out once (the tiles, not L1, hold the working set)
+  if (!carved) {
+    cudaFuncSetAttribute(fir_q15_kernel<XS, CS, NP, FASTOUT, ONE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    carved = true;
+  }
+  fir_q15_kernel<XS, CS, NP, FASTOUT, ONE><<<grid, kThreads, smem, st>>>(a);
   return cudaGetLastError();
+}
+template <int XS, int CS, int NP, bool FASTOUT>
+static cudaError_t launch_variant(const Q15Args &a, dim3 grid, size_t smem, cudaStream_t st) {
+  const bool one = a.Npad <= (XS ? 256 : 128);
+  return one ? launch_variant1<XS, CS, NP, FASTOUT, true>(a, grid, smem, st) : launch_variant1<XS, CS, NP, FASTOUT, false>(a, grid, smem, st);
 }
 
 template <int XS, int CS>
