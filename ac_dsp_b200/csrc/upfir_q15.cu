@@ -12,11 +12,10 @@
 //
 // Arithmetic: as in fir_q15.cu, DP2A on byte planes of the taps -- the composite taps need up to 24 bits, i.e. three
 // planes (unsigned low, unsigned middle, signed high byte), each exact in an int32 for <= 128 taps per phase.
-// A thread owns KT consecutive input periods (KT*R outputs), runs the R phases one after the other over the same
-// shared-memory sample window and parks the results in a shared staging tile, from which the CTA writes the tile's
-// outputs in order (a warp store covers 256 contiguous bytes whatever the alignment of the call's first output);
-// tap pairs are consumed four at a time with a 1..3 pair tail, so the taps per phase are padded to an even count
-// only.  CTAs are persistent; the next tile's samples are fetched into registers while the current one computes.
+// A lane owns one input period of each of JT groups of 128 periods (the lane-per-period kernel below; the round-1
+// thread-owns-8-periods kernel with a staging tile lost every A/B against it and was removed in round 2).  CTAs are
+// persistent over an 8-fold over-decomposed grid; the next tile's samples are fetched into registers while the current
+// one computes.
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -57,167 +56,8 @@ __device__ __forceinline__ int up_dp2a_hi_s(uint32_t a, uint32_t b, int c) {
 }
 
 // NPAIRS tap pairs starting at pair p0 for KT outputs: E words from shared memory, odd-aligned words by PRMT.
-// PLANES == 3: per pair words {lo0, lo1, mid0, mid1}, {hi0, hi1, 0, 0};  PLANES == 2: {lo0, lo1, hi0, hi1}.
-template <int KT, int PLANES, int NPAIRS>
-__device__ __forceinline__ void up_chunk(const uint32_t *xw, const uint32_t *cp, int (&a0)[KT], int (&a1)[KT], int (&a2)[KT]) {
-  constexpr int NE = NPAIRS + KT / 2;              // E[i] = samples (2i, 2i+1) of the window
-  uint32_t E[NE + 1], O[NE];
-  if (KT % 8 == 0) {                                // window start is 16-byte aligned
-#pragma unroll
-    for (int i = 0; i < (NE + 1 + 3) / 4; i++) {
-      const uint4 v = *(const uint4 *)(xw + 4 * i);
-      if (4 * i + 0 <= NE) E[4 * i + 0] = v.x;
-      if (4 * i + 1 <= NE) E[4 * i + 1] = v.y;
-      if (4 * i + 2 <= NE) E[4 * i + 2] = v.z;
-      if (4 * i + 3 <= NE) E[4 * i + 3] = v.w;
-    }
-  } else {                                          // KT = 4: 8-byte aligned
-#pragma unroll
-    for (int i = 0; i < (NE + 1 + 1) / 2; i++) {
-      const uint2 v = *(const uint2 *)(xw + 2 * i);
-      if (2 * i + 0 <= NE) E[2 * i + 0] = v.x;
-      if (2 * i + 1 <= NE) E[2 * i + 1] = v.y;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NE; i++) O[i] = __byte_perm(E[i], E[i + 1], 0x5432);
-#pragma unroll
-  for (int q = 0; q < NPAIRS; q++) {
-    const uint32_t wa = cp[q * (PLANES == 3 ? 2 : 1)];
-    const uint32_t wb = PLANES == 3 ? cp[q * 2 + 1] : 0u;
-#pragma unroll
-    for (int j = 0; j < KT; j++) {
-      const uint32_t s = (j & 1) ? O[q + j / 2] : E[q + j / 2];
-      a0[j] = up_dp2a_lo_u(s, wa, a0[j]);
-      if (PLANES == 3) { a1[j] = up_dp2a_hi_u(s, wa, a1[j]); a2[j] = up_dp2a_lo_s(s, wb, a2[j]); }
-      else a1[j] = up_dp2a_hi_s(s, wa, a1[j]);
-    }
-  }
-}
-
-template <int R, int KT, int PLANES>
-__global__ void __launch_bounds__(kUpThreads) upfir_q15_kernel(UpArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int WPP = PLANES == 3 ? 2 : 1;         // coefficient words per tap pair
-  constexpr int TILE = kUpThreads * KT;            // input periods per CTA and tile
-  constexpr int ROW = KT * R;                      // outputs per thread and tile
-  const int Tcp = 2 * a.TP;
-  const int ncw = R * a.TP * WPP;
-  const int ncw_pad = (ncw + 3) & ~3;
-  const int nxs = TILE + Tcp + 16;                               // samples staged per tile
-  const int xs_stride = (nxs + 7) & ~7;
-  uint32_t *cw = (uint32_t *)smem;                               // [R][TP][WPP]
-  int16_t *xs = (int16_t *)(smem + (size_t)ncw_pad * 4);         // two buffers; xb[i] = x[k_tile - (Tcp-1) + i]
-  // output staging: thread t's ROW results at ys[t * (ROW + 1) ..]; the odd row pitch keeps the 64-bit writes of a
-  // warp in distinct banks, and the copy-out below reads consecutive elements
-  long long *ys = (long long *)(smem + (size_t)ncw_pad * 4 + (size_t)2 * xs_stride * 2);
-  const uint32_t c = blockIdx.y;
-  const long long kbase = a.out_first / R;                       // first input period with an output in this call
-  const int16_t *xc = a.interleaved ? a.x + c : a.x + (size_t)c * a.n;
-  const size_t xstride = a.interleaved ? a.C : 1;
-  const long long lo = a.out_first, hi = a.out_first + (long long)a.n_out;
-  const int sh_dn = 64 - a.acc.W, sh_up = sh_dn + a.lsh;         // lsh < W_acc (host check): both below 64
-  const long long umask = (a.acc.S || a.acc.W >= 64) ? -1LL : (long long)((1ULL << a.acc.W) - 1);
-
-  for (int i = threadIdx.x; i < ncw; i += kUpThreads) cw[i] = a.cw[(size_t)c * ncw + i];
-
-  // samples of a tile, NL per thread, fetched one tile ahead (history for k < n_seen, zero past the end of the call)
-  constexpr int NL = (TILE + 256 + 16 + kUpThreads - 1) / kUpThreads;   // Tcp <= 256
-  int16_t pre[NL];
-  auto fetch = [&](long long tile) {
-    const long long k_tile = kbase + tile * TILE;
-    const long long l0 = k_tile - (Tcp - 1) - a.n_seen;          // index of xb[0] in this call's input
-#pragma unroll
-    for (int q = 0; q < NL; q++) pre[q] = 0;
-    if (l0 >= 0 && (size_t)(l0 + nxs) <= a.n) {                  // interior tile: no bounds, no history
-      const int16_t *xp = xc + (size_t)l0 * xstride;
-      if (xstride == 1) {
-#pragma unroll
-        for (int q = 0; q < NL; q++) { const int i = threadIdx.x + q * kUpThreads; if (i < nxs) pre[q] = xp[i]; }
-      } else {
-#pragma unroll
-        for (int q = 0; q < NL; q++) { const int i = threadIdx.x + q * kUpThreads; if (i < nxs) pre[q] = xp[(size_t)i * xstride]; }
-      }
-      return;
-    }
-#pragma unroll
-    for (int q = 0; q < NL; q++) {
-      const int i = threadIdx.x + q * kUpThreads;
-      const long long li = l0 + i;
-      if (i < nxs) {
-        if (li >= 0) { if ((size_t)li < a.n) pre[q] = xc[(size_t)li * xstride]; }
-        else if (li >= -(long long)a.H) pre[q] = a.tail[(size_t)c * a.H + (size_t)(a.H + li)];
-      }
-    }
-  };
-  if ((long long)blockIdx.x < a.ntiles) fetch(blockIdx.x);
-
-  int it = 0;
-  for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-    int16_t *xb = xs + (it & 1) * xs_stride;                     // double buffer
-#pragma unroll
-    for (int q = 0; q < NL; q++) {
-      const int i = threadIdx.x + q * kUpThreads;
-      if (i < nxs) xb[i] = pre[q];
-    }
-    __syncthreads();                                             // also: everyone finished copying out the previous tile
-    if (tile + gridDim.x < a.ntiles) fetch(tile + gridDim.x);
-
-    const long long k_tile = kbase + tile * TILE;
-    const int o = threadIdx.x * KT;                              // first period of this thread inside the tile
-    const long long o_tile = k_tile * R;                         // global index of the tile's first output
-    if (o_tile + (long long)o * R < hi) {
-      const uint32_t *xw = (const uint32_t *)(xb + o);           // window of output j starts at sample o + j
-      long long *yrow = ys + (size_t)threadIdx.x * (ROW + 1);
-#pragma unroll
-      for (int ph = 0; ph < R; ph++) {
-        int a0[KT], a1[KT], a2[KT];
-#pragma unroll
-        for (int j = 0; j < KT; j++) { a0[j] = 0; a1[j] = 0; a2[j] = 0; }
-        const uint32_t *cp = cw + ph * a.TP * WPP;
-        int p = 0;
-        for (; p + 4 <= a.TP; p += 4) up_chunk<KT, PLANES, 4>(xw + p, cp + p * WPP, a0, a1, a2);
-        const int rem = a.TP - p;
-        if (rem == 1) up_chunk<KT, PLANES, 1>(xw + p, cp + p * WPP, a0, a1, a2);
-        else if (rem == 2) up_chunk<KT, PLANES, 2>(xw + p, cp + p * WPP, a0, a1, a2);
-        else if (rem == 3) up_chunk<KT, PLANES, 3>(xw + p, cp + p * WPP, a0, a1, a2);
-#pragma unroll
-        for (int j = 0; j < KT; j++) {
-          long long tot;
-          if (PLANES == 3) tot = (long long)a0[j] + ((long long)a1[j] << 8) + ((long long)a2[j] << 16);
-          else tot = (long long)a0[j] + ((long long)a1[j] << 8);
-          // wrap_W(tot << lsh): push the kept bits to the top, pull them back down sign-extending
-          yrow[j * R + ph] = ((long long)((unsigned long long)tot << sh_up) >> sh_dn) & umask;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- copy out: consecutive threads write consecutive outputs (256 contiguous bytes per warp instruction)
-    if (a.fastout) {
-      long long *yc = (long long *)a.y + (size_t)c * a.n_out;
-      if (o_tile >= lo && o_tile + TILE * R <= hi) {             // whole tile inside this call's output: no checks
-        long long *yt = yc + (o_tile - lo);
-#pragma unroll 8
-        for (int e = threadIdx.x; e < TILE * R; e += kUpThreads) yt[e] = ys[e + e / ROW];
-      } else {
-        for (int e = threadIdx.x; e < TILE * R; e += kUpThreads) {
-          const long long og = o_tile + e;
-          if (og >= lo && og < hi) yc[og - lo] = ys[e + e / ROW];
-        }
-      }
-    } else {
-      for (int e = threadIdx.x; e < TILE * R; e += kUpThreads) {
-        const long long og = o_tile + e;
-        if (og >= lo && og < hi)
-          store_raw(a.y, (size_t)c * a.n_out + (size_t)(og - lo), a.out_bytes, convert((i128)ys[e + e / ROW], a.acc.F(), a.out));
-      }
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
-// Lane-per-period form (the default).  A lane owns ONE input period k of each of JT groups of 128 consecutive periods,
+// Lane-per-period form.  A lane owns ONE input period k of each of JT groups of 128 consecutive periods,
 // i.e. the R consecutive outputs k*R .. k*R+R-1, and keeps R * PLANES accumulators per group.  Its tap-pair operands
 // are the 32-bit words (x[k-(Tcp-1)+2p], x[k-(Tcp-1)+2p+1]); for odd k those straddle word boundaries, so the tile is
 // staged twice, the second copy shifted by one sample and placed 16 banks away: even lanes read word (q/2 + p) of the
@@ -536,29 +376,6 @@ void upfir_q15_pack(const int64_t *c, int taps_total, int R, int planes, uint32_
     }
 }
 
-template <int R, int KT, int PLANES>
-static cudaError_t launch_up(UpArgs a, cudaStream_t st) {
-  constexpr int TILE = kUpThreads * KT;
-  const long long kbase = a.out_first / R;
-  const long long klast = (a.out_first + (long long)a.n_out - 1) / R;
-  const long long nper = klast - kbase + 1;
-  const int ncw = R * a.TP * (PLANES == 3 ? 2 : 1);
-  const size_t nxs = (size_t)TILE + 2 * a.TP + 16;
-  const size_t smem = (size_t)((ncw + 3) & ~3) * 4 + 2 * ((nxs + 7) & ~(size_t)7) * 2 + (size_t)kUpThreads * (KT * R + 1) * 8;
-  a.ntiles = (nper + TILE - 1) / TILE;
-  cudaError_t e = cudaFuncSetAttribute(upfir_q15_kernel<R, KT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 4;                                                // persistent grid: what fits on the 148 SMs at once
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upfir_q15_kernel<R, KT, PLANES>, kUpThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  long long gx = a.ntiles;
-  const long long cap = (148LL * per_sm * up_grid_waves() + a.C - 1) / a.C;
-  if (gx > cap) gx = cap;
-  dim3 grid((unsigned)gx, a.C);
-  upfir_q15_kernel<R, KT, PLANES><<<grid, kUpThreads, smem, st>>>(a);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_upfir_q15(const UpLaunch &p, cudaStream_t st) {
   if (p.n_out == 0) return cudaSuccess;
   UpArgs a;
@@ -568,31 +385,14 @@ cudaError_t launch_upfir_q15(const UpLaunch &p, cudaStream_t st) {
   a.C = p.C; a.interleaved = p.interleaved && p.C > 1; a.lsh = p.lsh; a.acc = p.facc; a.out = p.fout;
   a.out_bytes = container_bytes(p.fout.W);
   a.fastout = (p.fout.W == p.facc.W && p.fout.I == p.facc.I && p.fout.S == p.facc.S && a.out_bytes == 8) ? 1 : 0;
-  const char *staged = getenv("B2D_UPFIR_STAGED");          // A/B switch: the thread-owns-8-periods kernel with a staging tile
-  if (!(staged && *staged == '1')) {
-    if (p.planes == 3) {
-      if (p.R == 2) return launch_up_lane<2, 4, 3>(a, st);
-      if (p.R == 4) {
-        const char *jt = getenv("B2D_UPFIR_JT");
-        if (jt && *jt == '1') return launch_up_lane<4, 1, 3>(a, st);
-        if (jt && *jt == '2') return launch_up_lane<4, 2, 3>(a, st);
-        return launch_up_lane<4, 4, 3>(a, st);
-      }
-      if (p.R == 8) return launch_up_lane<8, 2, 3>(a, st);
-    } else {
-      if (p.R == 2) return launch_up_lane<2, 8, 2>(a, st);
-      if (p.R == 4) return launch_up_lane<4, 4, 2>(a, st);
-      if (p.R == 8) return launch_up_lane<8, 2, 2>(a, st);
-    }
-  }
   if (p.planes == 3) {
-    if (p.R == 2) return launch_up<2, 8, 3>(a, st);
-    if (p.R == 4) return launch_up<4, 8, 3>(a, st);
-    if (p.R == 8) return launch_up<8, 4, 3>(a, st);
+    if (p.R == 2) return launch_up_lane<2, 4, 3>(a, st);
+    if (p.R == 4) return launch_up_lane<4, 4, 3>(a, st);
+    if (p.R == 8) return launch_up_lane<8, 2, 3>(a, st);
   } else {
-    if (p.R == 2) return launch_up<2, 8, 2>(a, st);
-    if (p.R == 4) return launch_up<4, 8, 2>(a, st);
-    if (p.R == 8) return launch_up<8, 4, 2>(a, st);
+    if (p.R == 2) return launch_up_lane<2, 8, 2>(a, st);
+    if (p.R == 4) return launch_up_lane<4, 4, 2>(a, st);
+    if (p.R == 8) return launch_up_lane<8, 2, 2>(a, st);
   }
   return cudaErrorNotSupported;
 }
