@@ -14,6 +14,8 @@
 //       IMAD.WIDE sliding-window block of fir_wide.cuh once per phase over that phase's plane and taps.
 //   polydec_generic_kernel     every Q / O mode: one thread per output, the reference's own order (phases DF-1 .. 0,
 //       taps upwards, partial accumulator added to the total with one more ACC_TYPE assignment), 128-bit intermediates.
+#include <cstdlib>
+
 #include "fir_wide.cuh"
 
 namespace b2d {
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(kWideThreads) polydec_wide_kernel(DecArgs a) {
   }
 }
 
+// W: intermediate width, i128 or int64_t (common.cuh: fits_i64)
+template <class W>
 __global__ void __launch_bounds__(256) polydec_generic_kernel(DecArgs a) {
   const size_t total = a.n_out * a.C;
   const int Fin = a.in.F(), Fc = a.coeff.F(), Fa = a.acc.F();
@@ -95,10 +99,10 @@ __global__ void __launch_bounds__(256) polydec_generic_kernel(DecArgs a) {
       const long long g = m * a.DF + (a.DF - 1 - df);              // newest sample when phase df is evaluated
       int64_t acc1 = 0;
       for (int tp = 0; tp < a.NT; tp++)
-        acc1 = macc(acc1, a.acc, (i128)dec_sample(a, c, g - (long long)tp * a.DF) * (i128)h[tp + a.NT * df], Fin + Fc);
-      acc = macc(acc, a.acc, (i128)acc1, Fa);                      // acc = acc + acc1[df]
+        acc1 = macc_t<W>(acc1, a.acc, (W)dec_sample(a, c, g - (long long)tp * a.DF) * (W)h[tp + a.NT * df], Fin + Fc);
+      acc = macc_t<W>(acc, a.acc, (W)acc1, Fa);                    // acc = acc + acc1[df]
     }
-    store_raw(a.y, (size_t)c * a.n_out + j, a.out_bytes, convert((i128)acc, Fa, a.out));
+    store_raw(a.y, (size_t)c * a.n_out + j, a.out_bytes, convert_t<W>((W)acc, Fa, a.out));
   }
 }
 
@@ -382,7 +386,12 @@ cudaError_t launch_polydec(const DecLaunch &p, cudaStream_t st) {
     const size_t total = p.n_out * p.C;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    polydec_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    const char *f128 = getenv("B2D_GENERIC_I128");
+    const int Wp = p.fin.W + (p.fin.S ? 0 : 1) + p.fcoeff.W + (p.fcoeff.S ? 0 : 1);
+    if (!(f128 && *f128 == '1') && fits_i64(p.facc, p.fout, Wp, p.fin.F() + p.fcoeff.F()))
+      polydec_generic_kernel<int64_t><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else
+      polydec_generic_kernel<i128><<<(unsigned)blocks, 256, 0, st>>>(a);
     return cudaGetLastError();
   }
   const int mode = polydec_wide_mode(p.fin, p.fcoeff, p.facc, p.nt, p.df);

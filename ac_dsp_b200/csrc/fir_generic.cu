@@ -12,6 +12,8 @@
 //   FOLD_ODD      :246-259  i = 0..(N-1)/2, fold = ACC_TYPE(reg[i]+reg[N-1-i]) (centre: reg[i]), acc += h[i]*fold
 //   TRANSPOSED    :265-278  y[n] = q(..q(q(x[n-N+1]h[N-1]) + x[n-N+2]h[N-2]).. + x[n]h[0])  (oldest first)
 // reg[k] is the sample k steps back; before the first sample of the stream it is 0 (:134-139).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b2d {
@@ -40,6 +42,8 @@ __device__ __forceinline__ int64_t fir_gen_sample(const FirGenArgs &a, uint32_t 
   return load_raw(a.tail, (size_t)c * T + (size_t)(T - (k - (int64_t)i)), a.in_bytes, a.in.S);
 }
 
+// W: intermediate width, i128 or int64_t (fir_generic_fits64: every product, shifted sum and conversion within 62 bits).
+template <class W>
 __global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
   const size_t total = a.n_limit * a.C;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -56,40 +60,62 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(FirGenArgs a) {
       case B2D_ROTATE_SHIFT:
       case B2D_TRANSPOSED:
         if (a.ascending) {
-          for (int k = 0; k < N; k++) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+          for (int k = 0; k < N; k++) acc = macc_t<W>(acc, a.acc, (W)fir_gen_sample(a, c, i, k) * (W)h[k], Fin + Fc);
         } else {
-          for (int k = N - 1; k >= 0; k--) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+          for (int k = N - 1; k >= 0; k--) acc = macc_t<W>(acc, a.acc, (W)fir_gen_sample(a, c, i, k) * (W)h[k], Fin + Fc);
         }
         break;
       case B2D_C_BUFF:
-        for (int k = 0; k < N; k++) acc = macc(acc, a.acc, (i128)fir_gen_sample(a, c, i, k) * (i128)h[k], Fin + Fc);
+        for (int k = 0; k < N; k++) acc = macc_t<W>(acc, a.acc, (W)fir_gen_sample(a, c, i, k) * (W)h[k], Fin + Fc);
         break;
       case B2D_FOLD_EVEN:
       case B2D_FOLD_EVEN_ANTI:
         for (int q = 0; q < N / 2; q++) {
           const int k = a.ascending ? q : N / 2 - 1 - q;
-          const i128 xb = (i128)fir_gen_sample(a, c, i, N - 1 - k);
-          const i128 pre = (i128)fir_gen_sample(a, c, i, k) + (anti ? -xb : xb);
-          acc = macc(acc, a.acc, (i128)h[k] * pre, Fin + Fc);
+          const W xb = (W)fir_gen_sample(a, c, i, N - 1 - k);
+          const W pre = (W)fir_gen_sample(a, c, i, k) + (anti ? -xb : xb);
+          acc = macc_t<W>(acc, a.acc, (W)h[k] * pre, Fin + Fc);
         }
         break;
       case B2D_FOLD_ODD:
       case B2D_FOLD_ODD_ANTI:
         for (int k = 0; k < (N - 1) / 2 + 1; k++) {
-          i128 pre = (i128)fir_gen_sample(a, c, i, k);
+          W pre = (W)fir_gen_sample(a, c, i, k);
           if (k != (N - 1) / 2) {
-            const i128 xb = (i128)fir_gen_sample(a, c, i, N - 1 - k);
+            const W xb = (W)fir_gen_sample(a, c, i, N - 1 - k);
             pre += anti ? -xb : xb;
           }
-          const int64_t fold = convert(pre, Fin, a.acc);
-          acc = macc(acc, a.acc, (i128)h[k] * (i128)fold, Fc + Fa);
+          const int64_t fold = convert_t<W>(pre, Fin, a.acc);
+          acc = macc_t<W>(acc, a.acc, (W)h[k] * (W)fold, Fc + Fa);
         }
         break;
       default: break;
     }
     if (a.acc_out) a.acc_out[(size_t)c * (N - 1) + i] = acc;
-    else store_raw(a.y, elem_index(i, c, a.n, a.C, a.interleaved), a.out_bytes, convert((i128)acc, Fa, a.out));
+    else store_raw(a.y, elem_index(i, c, a.n, a.C, a.interleaved), a.out_bytes, convert_t<W>((W)acc, Fa, a.out));
   }
+}
+
+// 64-bit intermediates suffice when every product, every shifted operand of `acc += p` and both conversions stay within
+// 62 bits (common.cuh: fits_i64); the folded forms multiply wider operands.
+bool fir_generic_fits64(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int ftype) {
+  const int Wi = in.W + (in.S ? 0 : 1), Wc = coeff.W + (coeff.S ? 0 : 1), Wa = acc.W + (acc.S ? 0 : 1);
+  switch (ftype) {
+    case B2D_FOLD_EVEN: case B2D_FOLD_EVEN_ANTI:
+      return fits_i64(acc, out, Wi + 1 + Wc, in.F() + coeff.F());
+    case B2D_FOLD_ODD: case B2D_FOLD_ODD_ANTI:
+      // fold = ACC_TYPE(a +- b): the pre-add shifted up to F_acc, then h * fold
+      if (Wi + 1 + (acc.F() > in.F() ? acc.F() - in.F() : 0) > 62) return false;
+      return fits_i64(acc, out, Wc + Wa, coeff.F() + acc.F());
+    default:
+      return fits_i64(acc, out, Wi + Wc, in.F() + coeff.F());
+  }
+}
+
+static void fir_generic_launch(const FirGenArgs &a, const FirLaunch &p, size_t blocks, cudaStream_t st) {
+  const char *f = getenv("B2D_GENERIC_I128");                 // A/B and test switch: always the 128-bit evaluation
+  if (!(f && *f == '1') && fir_generic_fits64(p.fin, p.fcoeff, p.facc, p.fout, a.ftype)) fir_generic_kernel<int64_t><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else fir_generic_kernel<i128><<<(unsigned)blocks, 256, 0, st>>>(a);
 }
 
 cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st) {
@@ -103,7 +129,7 @@ cudaError_t launch_fir_generic(const FirLaunch &p, cudaStream_t st) {
   const size_t total = p.n * p.C;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  fir_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  fir_generic_launch(a, p, blocks, st);
   return cudaGetLastError();
 }
 
@@ -124,7 +150,7 @@ cudaError_t launch_fir_pending(const FirLaunch &p, size_t n_limit, const int64_t
   const size_t total = n_limit * p.C;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  fir_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  fir_generic_launch(a, p, blocks, st);
   return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@
 // run() call (the reference constructs its core object inside run()), so every output is an independent function of one
 // burst: one thread per output, taps in the reference's order with its two quantisation points per tap (the ACC_TYPE cast
 // of the sample, the ACC_TYPE re-quantisation of the sum), 128-bit intermediates -- every Q / O mode.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b2d {
@@ -21,6 +23,8 @@ struct MvArgs {
   size_t n_sample, per, n_out;   // burst length, outputs per burst, outputs in all
 };
 
+// W: intermediate width, i128 or int64_t (common.cuh: fits_i64)
+template <class W>
 __global__ void __launch_bounds__(256) mvavg_kernel(MvArgs a) {
   const int H = a.taps / 2, Fin = a.in.F(), Fa = a.acc.F(), Fc = a.coeff.F();
   const long long last = (long long)a.n_sample - 1;
@@ -34,10 +38,10 @@ __global__ void __launch_bounds__(256) mvavg_kernel(MvArgs a) {
       if (a.win == B2D_CLIP) { k = k < 0 ? 0 : (k > last ? last : k); }
       else if (a.win == B2D_MIRROR) { if (k < 0) k = -k; if (k > last) k = 2 * last - k; }
       const int64_t s = load_raw(a.x, base + (size_t)k, a.in_bytes, a.in.S);
-      const int64_t cast = convert((i128)s, Fin, a.acc);                       // (ACC_TYPE) w[j]
-      acc = macc(acc, a.acc, (i128)cast * (i128)a.c[j + H], Fa + Fc);           // acc_reg = acc_reg + ... : re-quantised per tap
+      const int64_t cast = convert_t<W>((W)s, Fin, a.acc);                     // (ACC_TYPE) w[j]
+      acc = macc_t<W>(acc, a.acc, (W)cast * (W)a.c[j + H], Fa + Fc);            // acc_reg = acc_reg + ... : re-quantised per tap
     }
-    store_raw(a.y, o, a.out_bytes, convert((i128)acc, Fa, a.out));
+    store_raw(a.y, o, a.out_bytes, convert_t<W>((W)acc, Fa, a.out));
   }
 }
 
@@ -49,7 +53,12 @@ cudaError_t launch_mvavg(const MvLaunch &p, cudaStream_t st) {
   a.x = p.in; a.y = p.out; a.c = p.coeff64; a.n_sample = p.n_sample; a.per = p.per; a.n_out = p.n_out;
   size_t blocks = (p.n_out + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  mvavg_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  // 64-bit intermediates when the ACC_TYPE cast of the sample, the ACC x COEFF product and both conversions fit 62 bits
+  const int Wi = p.fin.W + (p.fin.S ? 0 : 1), Wa = p.facc.W + (p.facc.S ? 0 : 1), Wc = p.fcoeff.W + (p.fcoeff.S ? 0 : 1);
+  const bool small = Wi + (p.facc.F() > p.fin.F() ? p.facc.F() - p.fin.F() : 0) <= 62 && fits_i64(p.facc, p.fout, Wa + Wc, p.facc.F() + p.fcoeff.F());
+  const char *f128 = getenv("B2D_GENERIC_I128");
+  if (small && !(f128 && *f128 == '1')) mvavg_kernel<int64_t><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else mvavg_kernel<i128><<<(unsigned)blocks, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -29,6 +29,13 @@ def _container_dtype(fmt):
     return _NP_DT[L.load().b2d_container_bytes(fmt.W)]
 
 
+def _host_dtype(fmt):
+    """numpy dtype of host results: the container, read as unsigned for S = 0 formats (a full-width unsigned value,
+    e.g. ac_fixed<32,.,false>, has its top bit set in the container; torch results stay in the signed container)."""
+    dt = np.dtype(_container_dtype(fmt))
+    return dt if fmt.S else np.dtype(f"u{dt.itemsize}")
+
+
 def _get_state(h, prefix):
     lib = L.load()
     n = C.c_size_t(0)
@@ -61,7 +68,7 @@ class _Block:
         p = np.ascontiguousarray(packed, dtype=np.uint8)
         out = np.empty(p.shape[:-1], dtype=self._out_dt)
         L.check(L.load().b2d_unpack_wire(p.ctypes.data, out.size, self._out_W, self._out_S, out.ctypes.data))
-        return out
+        return out.view(self._host_dt)
 
     def _setup_io(self, fin, fout, n_channels, layout):
         self._wire = L.WIRE_CONTAINER
@@ -70,6 +77,7 @@ class _Block:
         self._layout = L.INTERLEAVED if layout in ("interleaved", L.INTERLEAVED) else L.PLANAR
         self._in_dt = _container_dtype(fin)
         self._out_dt = _container_dtype(fout)
+        self._host_dt = _host_dtype(fout)
 
     def _n_per_channel(self, shape):
         if self._C == 1:
@@ -122,7 +130,7 @@ class _Block:
             return yb[: self._C * n_out.value * pb].reshape(self._out_shape(n_out.value, rate_changing) + (pb,)).copy()
         y = np.empty(self._C * max(cap, 1), dtype=self._out_dt)
         L.check(fn_host(self._h, x.ctypes.data, n, y.ctypes.data, C.byref(n_out)))
-        return y[: self._C * n_out.value].reshape(self._out_shape(n_out.value, rate_changing)).copy()
+        return y[: self._C * n_out.value].reshape(self._out_shape(n_out.value, rate_changing)).copy().view(self._host_dt)
 
 
 class _Fir(_Block):
@@ -213,7 +221,7 @@ class ac_fir_load_coeffs(_Fir):
         if ld is not None and bool(ld) and coeffs_ch is not None and len(coeffs_ch) >= self.N_TAPS:
             self._load(np.asarray(coeffs_ch)[: self.N_TAPS], channel)
         if data_in is None or len(data_in) == 0:
-            return np.empty(0, dtype=self._out_dt)
+            return np.empty(0, dtype=self._host_dt)
         return self._process(data_in, out)
 
     def load(self, coeffs, channel=-1):
@@ -273,6 +281,7 @@ class ac_fir_reg_share(_Fir):
     def delay_line(self):
         y = np.zeros(self._C, dtype=self._out_dt)
         L.check(L.load().b2d_fir_delay_line_out(self._h, y.ctypes.data))
+        y = y.view(self._host_dt)
         return y if self._C > 1 else y[0]
 
     def run_window(self, reg):
@@ -281,6 +290,7 @@ class ac_fir_reg_share(_Fir):
             raise ValueError("window must hold n_channels * N_TAPS samples (reg[0] newest)")
         y = np.zeros(self._C, dtype=self._out_dt)
         L.check(L.load().b2d_fir_run_window(self._h, w.ctypes.data, y.ctypes.data))
+        y = y.view(self._host_dt)
         return y if self._C > 1 else y[0]
 
 
@@ -551,7 +561,7 @@ class ac_mv_avg:
         h = C.c_void_p()
         L.check(lib.b2d_mvavg_create(C.byref(h), C.byref(d), c.ctypes.data))
         self._h = h
-        self._in_dt, self._out_dt = _container_dtype(d.fin), _container_dtype(d.out)
+        self._in_dt, self._out_dt, self._host_dt = _container_dtype(d.fin), _container_dtype(d.out), _host_dtype(d.out)
 
     def run(self, data_in, n_sample):
         lib = L.load()
@@ -566,7 +576,7 @@ class ac_mv_avg:
         x = np.ascontiguousarray(np.asarray(data_in).astype(self._in_dt, copy=False)).reshape(-1)
         y = np.empty(max(x.size, 1), dtype=self._out_dt)
         L.check(lib.b2d_mvavg_run(self._h, x.ctypes.data, x.size, int(n_sample), y.ctypes.data, C.byref(n_out)))
-        return y[: n_out.value].copy()
+        return y[: n_out.value].copy().view(self._host_dt)
 
     @property
     def path(self):
@@ -596,7 +606,7 @@ class ac_intg_dump:
         L.check(lib.b2d_intgdump_create(C.byref(h), C.byref(d)))
         self._h = h
         self.NS, self.CHN = int(NS), int(CHN)
-        self._in_dt, self._out_dt = _container_dtype(d.fin), _container_dtype(d.out)
+        self._in_dt, self._out_dt, self._host_dt = _container_dtype(d.fin), _container_dtype(d.out), _host_dtype(d.out)
 
     def run(self, data_in, n_sample):
         lib = L.load()
@@ -612,7 +622,7 @@ class ac_intg_dump:
         x = np.ascontiguousarray(np.asarray(data_in).astype(self._in_dt, copy=False)).reshape(-1)
         y = np.empty((max(ns.size, 1), self.CHN), dtype=self._out_dt)
         L.check(lib.b2d_intgdump_run(self._h, x.ctypes.data, x.size, ns.ctypes.data, ns.size, y.ctypes.data, C.byref(n_out)))
-        return y[: n_out.value // self.CHN].copy()
+        return y[: n_out.value // self.CHN].copy().view(self._host_dt)
 
     @property
     def path(self):

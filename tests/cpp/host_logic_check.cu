@@ -235,6 +235,33 @@ static void check_upfir_pack() {
   EXPECT(!upfir_q15_geometry(3, 63, 24) && !upfir_q15_geometry(4, 63, 25) && !upfir_q15_geometry(4, 4 * 128 + 1, 24), "geometry limits");
 }
 
+// The 64-bit instantiation of the fixed-point primitives equals the 128-bit one wherever fits_i64 admits it.
+static void check_i64_primitives() {
+  const int Qs[] = {B2D_TRN, B2D_RND, B2D_TRN_ZERO, B2D_RND_ZERO, B2D_RND_INF, B2D_RND_MIN_INF, B2D_RND_CONV, B2D_RND_CONV_ODD};
+  const int Os[] = {B2D_WRAP, B2D_SAT, B2D_SAT_ZERO, B2D_SAT_SYM};
+  int admitted = 0;
+  for (int t = 0; t < 4000; t++) {
+    Fmt acc{8 + rand() % 50, 0, rand() % 4 ? 1 : 0, Qs[rand() % 8], Os[rand() % 4]};
+    acc.I = acc.W - (rand() % 40);
+    Fmt out{4 + rand() % 60, 0, rand() % 2, Qs[rand() % 8], Os[rand() % 4]};
+    out.I = out.W - (acc.F() - (rand() % 12) + 4);
+    const int Wp = 6 + rand() % 50, Fp = acc.F() + (rand() % 24) - 8;
+    if (!fits_i64(acc, out, Wp, Fp)) continue;
+    admitted++;
+    for (int k = 0; k < 24; k++) {
+      const long long a0 = wrap_bits(((long long)rand() << 32) ^ ((long long)rand() << 11) ^ rand(), acc.W, acc.S);
+      long long p = wrap_bits(((long long)rand() << 32) ^ ((long long)rand() << 9) ^ rand(), Wp, 1);
+      if (k == 0) p = -(1LL << (Wp - 1));
+      if (k == 1) p = (1LL << (Wp - 1)) - 1;
+      const int64_t r128 = macc_t<i128>(a0, acc, (i128)p, Fp), r64 = macc_t<int64_t>(a0, acc, (int64_t)p, Fp);
+      EXPECT(r128 == r64, "macc_t<int64_t> W %d I %d S %d Q %d O %d Wp %d Fp %d", acc.W, acc.I, acc.S, acc.Q, acc.O, Wp, Fp);
+      const int64_t o128 = convert_t<i128>((i128)r128, acc.F(), out), o64 = convert_t<int64_t>(r128, acc.F(), out);
+      EXPECT(o128 == o64, "convert_t<int64_t> acc F %d -> out W %d I %d S %d Q %d O %d", acc.F(), out.W, out.I, out.S, out.Q, out.O);
+    }
+  }
+  EXPECT(admitted > 500, "fits_i64 admitted only %d of 4000 draws", admitted);
+}
+
 static void check_support_tables() {
   const Fmt q15{16, 1, 1, B2D_TRN, B2D_WRAP}, acc40{40, 8, 1, B2D_TRN, B2D_WRAP};
   Fmt sat = acc40; sat.O = B2D_SAT;
@@ -260,6 +287,7 @@ int main() {
   check_upfir_pack();
   check_fir_wide_and_polydec_pack();
   check_fir_q24_pack();
+  check_i64_primitives();
   check_support_tables();
   std::printf("checks=%ld bad=%d\n", g_checks, g_bad);
   return g_bad != 0;
