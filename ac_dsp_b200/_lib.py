@@ -93,6 +93,7 @@ def load():
         "b2d_fir_reset": (C.c_int, [vp]), "b2d_fir_state_bytes": (C.c_int, [vp, psz]),
         "b2d_fir_get_state": (C.c_int, [vp, vp, sz]), "b2d_fir_set_state": (C.c_int, [vp, vp, sz]),
         "b2d_fir_path": (C.c_char_p, [vp]),
+        "b2d_fir_ovs_margin": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b2d_fir_load_blocked": (C.c_int, [vp, vp, sz, u32, u32, u32, i32]), "b2d_fir_delay_line_out": (C.c_int, [vp, vp]),
         "b2d_fir_run_window": (C.c_int, [vp, vp, vp]),
         "b2d_cic_create": (C.c_int, [C.POINTER(vp), C.POINTER(B2dCicDesc)]), "b2d_cic_destroy": (C.c_int, [vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200dsp.so")
-SOURCES = ["runtime.cu", "rt_fir.cu", "rt_cic.cu", "rt_poly.cu", "rt_intgdump.cu", "rt_mvavg.cu", "mv_avg.cu", "wire.cu", "fir_generic.cu", "fir_q15.cu", "fir_q24.cu", "fir_wide.cu", "fir_dec.cu", "fir_intr.cu", "intg_dump.cu", "upfir_q15.cu", "cic_generic.cu", "cic_fast.cu", "cic_intr_fast.cu", "nccl_dl.cpp"]
+SOURCES = ["runtime.cu", "rt_fir.cu", "rt_cic.cu", "rt_poly.cu", "rt_intgdump.cu", "rt_mvavg.cu", "mv_avg.cu", "wire.cu", "fir_generic.cu", "fir_q15.cu", "fir_ovs.cu", "fir_q24.cu", "fir_wide.cu", "fir_dec.cu", "fir_intr.cu", "intg_dump.cu", "upfir_q15.cu", "cic_generic.cu", "cic_fast.cu", "cic_intr_fast.cu", "nccl_dl.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -33,6 +33,15 @@ bool fir_q15_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fm
 void fir_q15_pack(const Fmt &coeff, const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);
 int fir_q15_pk_words(int n_taps, int ftype);
 cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st);
+// overlap-save path (fir_ovs.cu): q15 formats, long filters, FP64 FFT blocks of 4096 with an a-priori error bound < 1/2
+// evaluated on the loaded coefficients; tables and spectra are prepared by the host runtime at load time.
+void fir_effective_taps(const int64_t *c, int n_taps, int ftype, int64_t *eff);
+bool fir_ovs_geometry(int n_taps, uint32_t C, int interleaved);
+int fir_ovs_discard(int n_taps);
+double fir_ovs_error_bound(const Fmt &in, double l1);
+void fir_ovs_tables(double2 *tw1 /*[15][256]*/, double2 *tw2 /*[15][16]*/);
+void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs /*[16][256]*/);
+cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw /*[15][256] + [15][16]*/, const double2 *hs, double *resid, cudaStream_t st);
 // q24 path: W_in 17..24 in int32 containers, W_c <= 16: coefficient pairs in the DP2A 16-bit lanes, three sample byte planes.
 bool fir_q24_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
 void fir_q24_pack(const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);

@@ -215,6 +215,14 @@ struct b2d_fir {
   int pk_words = 0;
   int32_t *d_coeff32 = nullptr;
   int wide_words = 0, wide_mode = 0;
+  // overlap-save evaluation of long q15 filters (fir_ovs.cu): twiddle tables, per-channel spectra (prepared before the first
+  // long call after a load), the a-priori error bound of the loaded taps, the optional residual monitor
+  int ovs_mode = 0;               // 0: off, 1: long calls, 2: every call (B2D_FIR_OVS=2, tests)
+  double2 *d_tw = nullptr;        // [15][256] + [15][16]
+  double2 *d_hs = nullptr;        // [C][4096]
+  std::vector<char> hs_stale;     // per channel
+  double ovs_bound = 0.0;
+  double *d_resid = nullptr;
   void *d_tail[2] = {nullptr, nullptr};
   int cur = 0;
   b2d_comm *comm = nullptr;

@@ -61,6 +61,23 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
     h->pk_words = h->path == PATH_Q15 ? fir_q15_pk_words((int)N, desc->ftype) : fir_q24_pk_words((int)N);
     e = cudaMalloc(&h->d_coeff_pk, (size_t)C * h->pk_words * sizeof(uint32_t));
   }
+  if (e == cudaSuccess && h->path == PATH_Q15 && fir_ovs_geometry((int)N, C, desc->layout == B2D_INTERLEAVED)) {
+    const char *ov = getenv("B2D_FIR_OVS");        // 0: never, 2: every call whatever its length (tests), default: long calls
+    h->ovs_mode = ov ? (*ov == '0' ? 0 : (*ov == '2' ? 2 : 1)) : 1;
+    if (h->ovs_mode) {
+      std::vector<double2> tw(15 * 256 + 15 * 16);
+      fir_ovs_tables(tw.data(), tw.data() + 15 * 256);
+      e = cudaMalloc(&h->d_tw, tw.size() * sizeof(double2));
+      if (e == cudaSuccess) e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_hs, (size_t)C * 4096 * sizeof(double2));
+      const char *rs = getenv("B2D_OVS_RESID");
+      if (e == cudaSuccess && rs && *rs == '1') {
+        e = cudaMalloc(&h->d_resid, sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(h->d_resid, 0, sizeof(double));
+      }
+      h->hs_stale.assign(C, 1);
+    }
+  }
   if (e == cudaSuccess && desc->kind == B2D_FIR_REG_SHARE) {
     e = cudaMalloc(&h->d_dl, C * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemset(h->d_dl, 0, C * sizeof(int64_t));
@@ -88,6 +105,9 @@ extern "C" int b2d_fir_destroy(b2d_fir *h) {
   if (h->d_coeff_pk) cudaFree(h->d_coeff_pk);
   if (h->d_coeff32) cudaFree(h->d_coeff32);
   if (h->d_dl) cudaFree(h->d_dl);
+  if (h->d_tw) cudaFree(h->d_tw);
+  if (h->d_hs) cudaFree(h->d_hs);
+  if (h->d_resid) cudaFree(h->d_resid);
   if (h->d_win) cudaFree(h->d_win);
   if (h->e_hist) cudaEventDestroy(h->e_hist);
   for (int i = 0; i < 2; i++) { if (h->d_tail[i]) cudaFree(h->d_tail[i]); if (h->d_pend[i]) cudaFree(h->d_pend[i]); }
@@ -95,7 +115,44 @@ extern "C" int b2d_fir_destroy(b2d_fir *h) {
   return B2D_OK;
 }
 
-static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream_t st) {
+// Overlap-save is armed when every channel's loaded taps keep the FP64 error bound under 1/2 (and, for an interleaved IQ
+// pair, both channels carry the same taps: the pair is transformed as one complex sequence).
+static bool fir_ovs_armed(const b2d_fir *h) {
+  if (!h->ovs_mode || !h->d_hs) return false;
+  const size_t N = h->d.n_taps;
+  const uint32_t C = h->d.n_channels;
+  for (uint32_t c = 0; c < C; c++) if (!h->ch_loaded[c]) return false;
+  if (h->d.layout == B2D_INTERLEAVED && C == 2 && !std::equal(h->h_coeff.begin(), h->h_coeff.begin() + N, h->h_coeff.begin() + N)) return false;
+  return h->ovs_bound < 0.49;
+}
+static size_t fir_ovs_min_n(const b2d_fir *h) { return h->ovs_mode == 2 ? 1 : 4 * (size_t)(4096 - fir_ovs_discard((int)h->d.n_taps)); }
+
+// Spectra of channels whose taps changed since the last long call (host, extended precision; fir_ovs_spectrum).
+static int fir_ovs_prepare(b2d_fir *h, cudaStream_t st) {
+  const size_t N = h->d.n_taps;
+  bool any = false;
+  for (uint32_t c = 0; c < h->d.n_channels; c++) any = any || h->hs_stale[c];
+  if (!any) return B2D_OK;
+  CU(cudaStreamSynchronize(st));       // earlier launches on this stream may still read the spectra
+  std::vector<int64_t> eff(N);
+  std::vector<double2> hs(4096);
+  for (uint32_t c = 0; c < h->d.n_channels; c++) {
+    if (!h->hs_stale[c]) continue;
+    if (c && std::equal(h->h_coeff.begin() + (size_t)c * N, h->h_coeff.begin() + (size_t)(c + 1) * N, h->h_coeff.begin() + (size_t)(c - 1) * N) && !h->hs_stale[c - 1]) {
+      CU(cudaMemcpy(h->d_hs + (size_t)c * 4096, h->d_hs + (size_t)(c - 1) * 4096, 4096 * sizeof(double2), cudaMemcpyDeviceToDevice));
+    } else {
+      fir_effective_taps(h->h_coeff.data() + (size_t)c * N, (int)N, h->d.ftype, eff.data());
+      fir_ovs_spectrum(eff.data(), (int)N, hs.data());
+      CU(cudaMemcpy(h->d_hs + (size_t)c * 4096, hs.data(), 4096 * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    h->hs_stale[c] = 0;
+  }
+  return B2D_OK;
+}
+
+static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream_t st, bool allow_ovs = false) {
+  if (allow_ovs && h->path == PATH_Q15 && p.n >= fir_ovs_min_n(h) && fir_ovs_armed(h))
+    return launch_fir_ovs(p, h->d_tw, h->d_hs, h->d_resid, st);
   switch (h->path) {
     case PATH_Q15: return launch_fir_q15(p, st);
     case PATH_Q24: return launch_fir_q24(p, st);
@@ -106,7 +163,25 @@ static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream
 
 extern "C" const char *b2d_fir_path(b2d_fir *h) {
   static const char *names[] = {"fir_generic", "fir_q15", "fir_wide", "fir_q24"};
+  if (h && h->path == PATH_Q15 && fir_ovs_armed(h)) return "fir_ovs";   // calls of fir_ovs_min_n samples or more; shorter ones: fir_q15
   return !h ? "" : names[h->path];
+}
+
+// Overlap-save diagnostics: the a-priori bound of |FP64 result - exact sum| for the loaded taps (the path is armed below
+// 0.49) and, with B2D_OVS_RESID=1 in the environment at create time, the largest distance from an integer seen so far.
+extern "C" int b2d_fir_ovs_margin(b2d_fir *h, double *bound, double *resid) {
+  if (!h) return fail(B2D_EINVAL, "null handle");
+  if (bound) *bound = h->ovs_bound;
+  if (resid) {
+    *resid = -1.0;
+    if (h->d_resid) {
+      int st = use_device(h->device);
+      if (st) return st;
+      CU(cudaDeviceSynchronize());
+      CU(cudaMemcpy(resid, h->d_resid, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
+  return B2D_OK;
 }
 
 extern "C" int b2d_fir_set_comm(b2d_fir *h, b2d_comm *comm, int32_t root) {
@@ -183,11 +258,24 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
       else fir_q24_pack(v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
       CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    if (h->d_hs) h->hs_stale[c] = 1;
     if (h->path == PATH_WIDE) {
       std::vector<int32_t> w(h->wide_words, 0);
       fir_wide_pack(v.data(), (int)N, h->d.ftype, h->wide_mode, w.data(), h->wide_words);
       CU(cudaMemcpy(h->d_coeff32 + (size_t)c * h->wide_words, w.data(), h->wide_words * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
+  }
+  if (h->d_hs) {   // error bound of the overlap-save evaluation over the taps now loaded (largest 1-norm of any channel)
+    double l1max = 0.0;
+    std::vector<int64_t> eff(N);
+    for (uint32_t c = 0; c < C; c++) {
+      if (!h->ch_loaded[c]) continue;
+      fir_effective_taps(h->h_coeff.data() + (size_t)c * N, (int)N, h->d.ftype, eff.data());
+      double l1 = 0.0;
+      for (size_t i = 0; i < N; i++) l1 += std::fabs((double)eff[i]);
+      l1max = std::max(l1max, l1);
+    }
+    h->ovs_bound = fir_ovs_error_bound(h->fin, l1max);
   }
   return B2D_OK;
 }
@@ -203,7 +291,8 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
   int hs = hist_wait(h->e_hist, st);
   if (hs) return hs;
-  CU(fir_dispatch(h, p, st));
+  if (h->path == PATH_Q15 && n >= fir_ovs_min_n(h) && fir_ovs_armed(h) && (hs = fir_ovs_prepare(h, st))) return hs;
+  CU(fir_dispatch(h, p, st, true));
   if (h->pend_rem) {   // TRANSPOSED after a coefficient change: the first outputs start from the old taps' partial sums
     const size_t m = std::min(n, h->pend_rem);
     CU(launch_fir_pending(p, m, h->d_pend[h->pcur], nullptr, st));

@@ -156,8 +156,15 @@ class _Fir(_Block):
 
     @property
     def path(self):
-        """Kernel family serving this configuration ('fir_q15' or 'fir_generic')."""
+        """Kernel family serving this configuration (b200dsp.h: b2d_fir_path)."""
         return L.load().b2d_fir_path(self._h).decode()
+
+    def ovs_margin(self):
+        """(a-priori error bound of the overlap-save evaluation for the loaded taps, largest distance from an integer seen so
+        far or -1 when B2D_OVS_RESID=1 was not set at construction) -- b2d_fir_ovs_margin."""
+        b, r = C.c_double(0), C.c_double(0)
+        L.check(L.load().b2d_fir_ovs_margin(self._h, C.byref(b), C.byref(r)))
+        return b.value, r.value
 
     def _load(self, coeffs, channel=-1):
         lib = L.load()

@@ -158,8 +158,15 @@ int b2d_fir_get_state(b2d_fir *h, void *blob, size_t bytes);
 int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
 /* Name of the kernel family chosen for this descriptor: "fir_q15" (16-bit operands, DP2A byte planes), "fir_q24"
  * (samples of 17..24 bits, taps <= 16 bits: DP2A on three sample byte planes), "fir_wide" (operands <= 32 bits, wrapping
- * 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order). */
+ * 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order).  A "fir_q15" filter of 96..2049 taps
+ * reports "fir_ovs" once the loaded coefficients allow the overlap-save evaluation (blocks of 4096 samples through an FP64
+ * FFT whose a-priori error bound for THESE taps is below 1/2, so the rounded result is the exact integer sum); calls
+ * shorter than four blocks still run "fir_q15".  B2D_FIR_OVS=0 in the environment at create time turns it off. */
 const char *b2d_fir_path(b2d_fir *h);
+/* Overlap-save diagnostics: `bound` = the a-priori bound of |FP64 result - exact sum| for the loaded taps (armed below
+ * 0.49); `resid` = the largest distance of a result from an integer seen so far when B2D_OVS_RESID=1 was set at create
+ * time, else -1.  Either pointer may be NULL. */
+int b2d_fir_ovs_margin(b2d_fir *h, double *bound, double *resid);
 
 /* ---- CIC: ac_cic_dec_full / ac_cic_intr_full ---------------------------------------------- */
 /* Note on M > 2: the reference's comb shifts its delay line with an ascending copy loop (ac_cic_full_core.h:247-251),

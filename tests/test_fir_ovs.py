@@ -1,0 +1,156 @@
+"""The overlap-save FIR path (ac_dsp_b200/csrc/fir_ovs.cu): long 16-bit filters through blocks of 4096 samples and an FP64
+FFT, exact by an a-priori error bound evaluated on the loaded taps.
+
+CPU: tests/cpp/fir_ovs_check.cu runs the kernel's thread phases as loops over thread ids and compares the rounded results
+with a direct integer convolution (indexing, stream edges, the real-pair packing, the distance from an integer against
+the bound).  GPU: the selection rules and the kernel itself against Oracle B (tests/test_gpu_parity.py runs its long q15
+cases through both evaluations as well).
+"""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Q15, ACC40 = (16, 1), (40, 8)
+
+
+def test_phases_on_the_cpu_against_direct_convolution(engine, tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    libdir = os.path.join(ROOT, "ac_dsp_b200", "lib")
+    exe = str(tmp_path / "fir_ovs_check")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-w", f"-I{ROOT}/ac_dsp_b200/csrc", os.path.join(ROOT, "tests", "cpp", "fir_ovs_check.cu"),
+                           "-o", exe, f"-L{libdir}", "-lb200dsp", "-Xlinker", "-rpath", "-Xlinker", libdir])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    print(p.stdout)
+    assert p.returncode == 0 and "bad=0" in p.stdout, p.stdout[-3000:] + p.stderr[-1000:]
+
+
+def ofir(oracle, fi, fc, fa, fo, taps, ft, h, x):
+    b = oracle.FirB(fi, fc, fa, fo, taps, ft)
+    b.load(h)
+    return b.run(x)
+
+
+@pytest.fixture
+def forced(monkeypatch):
+    monkeypatch.setenv("B2D_FIR_OVS", "2")
+    monkeypatch.setenv("B2D_OVS_RESID", "1")
+
+
+@pytest.mark.gpu
+def test_selection_rules(engine, oracle, monkeypatch):
+    monkeypatch.delenv("B2D_FIR_OVS", raising=False)
+    rng = np.random.default_rng(1)
+    h = oracle.rand_raw(rng, Q15, 256)
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 256, "SHIFT_REG", n_channels=2, layout="interleaved")
+    f.load(h, channel=0)
+    f.load(h[::-1].copy(), channel=1)
+    assert f.path == "fir_q15"                      # an IQ pair is one complex sequence: both channels need the same taps
+    f.load(h, channel=1)
+    assert f.path == "fir_ovs" and 0 < f.ovs_margin()[0] < 0.49
+    # short calls still run the DP2A kernel, long ones overlap-save; the history crosses the switch in both directions
+    x = rng.integers(-32768, 32767, size=(60000, 2), endpoint=True).astype(np.int16)
+    y = np.concatenate([f.run(x[:100]), f.run(x[100:40000]), f.run(x[40000:40700]), f.run(x[40700:])])
+    for c in range(2):
+        assert np.array_equal(y[:, c], ofir(oracle, Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, x[:, c])), c
+    # fewer than 96 taps, formats outside the q15 family, order-dependent accumulators: never
+    assert engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 95, "SHIFT_REG", h[:95]).path == "fir_q15"
+    assert engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 96, "SHIFT_REG", h[:96]).path == "fir_ovs"
+    assert engine.ac_fir_const_coeffs((20, 5), ACC40, Q15, ACC40, 128, "SHIFT_REG", h[:128]).path == "fir_q24"
+    assert engine.ac_fir_const_coeffs(Q15, Q15, Q15, (24, 4, True, "AC_TRN", "AC_SAT"), 128, "SHIFT_REG", h[:128]).path == "fir_generic"
+    # taps whose 1-norm pushes the error bound past 1/2 are refused (2048 taps at full scale)
+    big = np.full(2048, -32768, dtype=np.int64)
+    g = engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 2048, "SHIFT_REG", big)
+    assert g.path == "fir_q15" and g.ovs_margin()[0] > 0.49
+    monkeypatch.setenv("B2D_FIR_OVS", "0")
+    assert engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 256, "SHIFT_REG", h).path == "fir_q15"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ft", ["SHIFT_REG", "ROTATE_SHIFT", "C_BUFF", "FOLD_EVEN", "FOLD_ODD", "TRANSPOSED"])
+@pytest.mark.parametrize("taps", [96, 255, 256, 257, 700, 1024])
+def test_every_architecture_chunked_with_reload(engine, oracle, forced, ft, taps):
+    if (ft == "FOLD_EVEN" and taps % 2) or (ft == "FOLD_ODD" and taps % 2 == 0):
+        pytest.skip("fold parity")
+    rng = np.random.default_rng(taps * 31 + len(ft))
+    n = 9000
+    x = oracle.rand_raw(rng, Q15, n)
+    h1, h2 = oracle.rand_raw(rng, Q15, taps), oracle.rand_raw(rng, (14, 1), taps)
+    b = oracle.FirB(Q15, Q15, ACC40, ACC40, taps, ft)
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, taps, ft)
+    want, got = [], []
+    for k, (lo, hi) in enumerate(((0, 1), (1, 4000), (4000, 4003), (4003, 8000), (8000, n))):
+        if k in (0, 3):
+            hh = h1 if k == 0 else h2
+            b.load(hh)
+            f.load(hh)
+        want.append(b.run(x[lo:hi]))
+        got.append(np.atleast_1d(f.run(x[lo:hi].astype(np.int16))))
+    assert f.path == "fir_ovs"
+    assert np.array_equal(np.concatenate(got).astype(np.int64), np.concatenate(want)), (ft, taps)
+    bound, resid = f.ovs_margin()
+    assert 0 <= resid < 0.01 and bound < 0.49, (bound, resid)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmts", [
+    ((16, 1), (16, 1), (40, 8), (18, 2, True, "AC_RND", "AC_SAT")),          # converting epilogue
+    ((16, 0, False), (16, 0, False), (48, 16, False), (48, 16, False)),      # unsigned samples and taps
+    ((16, 1), (12, 4, False), (36, 9), (36, 9)),                             # signed x unsigned, narrower accumulator (wraps)
+    ((12, 0, False), (14, 2), (30, 6), (20, 4)),                             # left shift into the accumulator
+    ((16, 1), (16, 1), (33, 1), (33, 1)),                                    # accumulator narrower than the sums: wraps
+])
+@pytest.mark.parametrize("layout,C", [("interleaved", 2), ("planar", 3), ("planar", 1)])
+def test_formats_layouts_and_extremes(engine, oracle, forced, fmts, layout, C):
+    fi, fc, fa, fo = fmts
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(str((fmts, layout, C)).encode()))
+    taps, n = 160, 9001
+    for kind in ("uniform", "min", "alt"):
+        x = np.stack([oracle.rand_raw(rng, fi, n, kind) for _ in range(C)])
+        hs = [oracle.rand_raw(rng, fc, taps, "min" if kind == "min" else "uniform") for _ in range(C)]
+        if layout == "interleaved":
+            hs = [hs[0]] * C
+        f = engine.ac_fir_prog_coeffs(fi, fo, fc, fa, taps, "SHIFT_REG", n_channels=C, layout=layout)
+        for c in range(C):
+            f.load(hs[c], channel=c)
+        assert f.path == "fir_ovs", (fmts, f.ovs_margin())
+        xin = x.astype(np.int16 if fi[0] <= 16 else np.int32)
+        xin = xin[0] if C == 1 else (np.ascontiguousarray(xin.T) if layout == "interleaved" else xin)
+        planar = layout == "planar" and C > 1
+        parts = [f.run(xin[:, :5000] if planar else xin[:5000]), f.run(xin[:, 5000:] if planar else xin[5000:])]
+        y = np.concatenate([np.atleast_1d(p_) for p_ in parts], axis=1 if planar else 0)
+        y = y.reshape(1, -1) if C == 1 else (y.T if layout == "interleaved" else y)
+        for c in range(C):
+            assert np.array_equal(y[c].astype(np.int64), ofir(oracle, fi, fc, fa, fo, taps, "SHIFT_REG", hs[c], x[c])), (fmts, layout, c, kind)
+        assert 0 <= f.ovs_margin()[1] < 0.01
+
+
+@pytest.mark.gpu
+def test_device_buffers_unaligned_views_and_state(engine, oracle, forced):
+    import torch
+    rng = np.random.default_rng(5)
+    taps, n = 300, 30011
+    x = rng.integers(-32768, 32767, size=(n, 2), endpoint=True).astype(np.int16)
+    h = oracle.rand_raw(rng, Q15, taps)
+    want = np.stack([ofir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, x[:, c]) for c in range(2)], axis=1)
+    f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, taps, "SHIFT_REG", n_channels=2, layout="interleaved")
+    f.load(h)
+    xd = torch.from_numpy(x).cuda()
+    y1 = f.run(xd[:7])                              # the next view starts 28 bytes into the allocation
+    y2 = f.run(xd[7:20001])
+    blob = f.get_state()
+    y3 = f.run(xd[20001:])
+    torch.cuda.synchronize()
+    assert np.array_equal(torch.cat([y1, y2, y3]).cpu().numpy(), want)
+    g = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, taps, "SHIFT_REG", n_channels=2, layout="interleaved")
+    g.load(h)
+    g.set_state(blob)
+    out = torch.empty((n - 20001 + 1, 2), dtype=torch.int64, device="cuda")
+    assert np.array_equal(g.run(xd[20001:], out=out.reshape(-1)[2:]).cpu().numpy(), want[20001:])   # output 16 bytes in: still aligned
+    assert g.path == "fir_ovs"

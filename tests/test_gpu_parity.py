@@ -46,6 +46,40 @@ def path(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(autouse=True)
+def _dp2a_unless_asked(monkeypatch):
+    """This module pins the DP2A kernel (fir_q15) unless a test asks for the `ovs` fixture: the overlap-save evaluation
+    would otherwise take every long call of a 96..2049-tap filter (tests/test_fir_ovs.py covers its own selection rules)."""
+    monkeypatch.setenv("B2D_FIR_OVS", "0")
+
+
+@pytest.fixture(params=["q15", "ovs"])
+def ovs(request, monkeypatch):
+    """Long 16-bit filters through both evaluations: the DP2A kernel, and overlap-save forced for every call length
+    (B2D_FIR_OVS=2) with the residual monitor on."""
+    monkeypatch.setenv("B2D_FIR_OVS", "2" if request.param == "ovs" else "0")
+    monkeypatch.setenv("B2D_OVS_RESID", "1")
+    return request.param
+
+
+@pytest.fixture(params=["q15", "auto"])
+def ovs_auto(request, monkeypatch):
+    """Full-size calls: the DP2A kernel, and the engine's own choice (overlap-save for long calls of long filters)."""
+    if request.param == "auto":
+        monkeypatch.delenv("B2D_FIR_OVS", raising=False)
+    return request.param
+
+
+def check_ovs(f, ovs, taps):
+    """Path name and exactness margin of a q15-format filter under the `ovs` fixture."""
+    bound, resid = f.ovs_margin()
+    if ovs == "ovs" and 96 <= taps <= 2049 and bound < 0.49:
+        assert f.path == "fir_ovs"
+        assert 0 <= resid < 0.01, (bound, resid)      # far inside the a-priori bound
+    else:
+        assert f.path == "fir_q15"
+
+
 @pytest.mark.parametrize("cfg", rc.fir_configs(), ids=lambda c: f"{c[1]}-{c[6]}")
 def test_fir_vs_reference_outputs(engine, ref_outputs, cfg, path):
     cid, _name, fi, fc, fa, fo, taps = cfg
@@ -114,18 +148,18 @@ def oracle_fir(O, fi, fc, fa, fo, taps, ft, coeffs, x):
 
 @pytest.mark.parametrize("taps,n", [(1, 100), (2, 1000), (16, 4096), (16, 1 << 20), (27, 5000), (63, 9999), (255, 8192),
                                     (256, 4095), (256, 70001), (1024, 20000), (2048, 9000)])
-def test_fir_q15_random(engine, oracle, taps, n):
+def test_fir_q15_random(engine, oracle, taps, n, ovs):
     rng = np.random.default_rng(taps * 7919 + n)
     x = oracle.rand_raw(rng, Q15, n)
     h = oracle.rand_raw(rng, Q15, taps)
     f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h)
-    assert f.path == "fir_q15"
     y = f.run(x.astype(np.int16))
     assert np.array_equal(y.astype(np.int64), oracle_fir(oracle, Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, x))
+    check_ovs(f, ovs, taps)
 
 
 @pytest.mark.parametrize("kind", ["min", "max", "alt"])
-def test_fir_q15_extremes_and_wrap(engine, oracle, kind):
+def test_fir_q15_extremes_and_wrap(engine, oracle, kind, ovs):
     """all-(-1.0) x all-(-1.0) over 256 taps reaches 2^40 and wraps to 0 in <40,8> (DERIVED KAT)."""
     rng = np.random.default_rng(3)
     for taps in (256, 1024):
@@ -138,7 +172,7 @@ def test_fir_q15_extremes_and_wrap(engine, oracle, kind):
             assert y[255] == 0 and y[254] == (255 << 32) - (1 << 40)
 
 
-def test_fir_q15_iq_interleaved_and_planar(engine, oracle):
+def test_fir_q15_iq_interleaved_and_planar(engine, oracle, ovs):
     rng = np.random.default_rng(11)
     n, taps = 40000 + 3, 256
     x = rng.integers(-32768, 32767, size=(n, 2), endpoint=True).astype(np.int16)
@@ -149,13 +183,15 @@ def test_fir_q15_iq_interleaved_and_planar(engine, oracle):
     assert y.shape == (n, 2) and y.dtype == np.int64
     for c in range(2):
         assert np.array_equal(y[:, c], want[c])
+    check_ovs(f, ovs, taps)
     f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h, n_channels=2, layout="planar")
     y = f.run(np.ascontiguousarray(x.T))
     for c in range(2):
         assert np.array_equal(y[c], want[c])
+    check_ovs(f, ovs, taps)
 
 
-def test_fir_per_channel_coefficients_and_layouts(engine, oracle):
+def test_fir_per_channel_coefficients_and_layouts(engine, oracle, ovs):
     """cfg 4 shape (scaled down): independent channels, a coefficient set per channel, 1024 taps."""
     rng = np.random.default_rng(12)
     C, n, taps = 5, 6001, 1024
@@ -231,7 +267,7 @@ def test_fir_formats_random(engine, oracle, fmts):
             assert np.array_equal(y.astype(np.int64), want), (fmts, taps, ft, f.path)
 
 
-def test_fir_device_path_and_state(engine, oracle):
+def test_fir_device_path_and_state(engine, oracle, ovs):
     import torch
     rng = np.random.default_rng(15)
     taps, n = 256, 50000
@@ -248,6 +284,7 @@ def test_fir_device_path_and_state(engine, oracle):
     g = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, taps, "SHIFT_REG", h)
     g.set_state(blob)                       # checkpoint / resume
     assert np.array_equal(g.run(xd[20000:]).cpu().numpy(), want[20000:])
+    check_ovs(g, ovs, taps)
 
 
 def test_fir_call_sequence_errors(engine):
@@ -372,7 +409,7 @@ def test_cic_intr_fast_path_device(engine, oracle, staged, N, M, fo, monkeypatch
 
 
 # ------------------------------------------------------------------------ full-size properties
-def test_full_size_fir_windows(engine, oracle):
+def test_full_size_fir_windows(engine, oracle, ovs_auto):
     """BASELINE config 2 at full size (2^30 IQ samples, 256 taps): an output depends on a 256-sample window only,
     so random windows of the device result are re-derived by the oracle from the same inputs."""
     import torch
@@ -382,10 +419,11 @@ def test_full_size_fir_windows(engine, oracle):
     rng = np.random.default_rng(20260101)
     h = oracle.rand_raw(rng, Q15, 256)
     f = make_fir(engine, "load", Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, n_channels=2, layout="interleaved")
+    assert f.path == ("fir_ovs" if ovs_auto == "auto" else "fir_q15")
     y = f.run(x)
     torch.cuda.synchronize()
     assert y.shape == (n, 2)
-    starts = [0, 1, 4096 - 300, n - 2000] + [int(v) for v in rng.integers(300, n - 3000, size=24)]
+    starts = [0, 1, 4096 - 300, 3840 - 100, n - 2000] + [int(v) for v in rng.integers(300, n - 3000, size=24)]
     for s in starts:
         lo = max(0, s - 255)
         xs = x[lo:s + 1500].cpu().numpy()
@@ -428,7 +466,7 @@ def test_full_size_cic_windows(engine, oracle):
     assert int(ydc[0, -1]) == 3 * 8 ** 4 and int(ydc[1, 1000]) == 3 * 8 ** 4
 
 
-def test_full_size_cascade_and_prog1024_windows(engine, oracle):
+def test_full_size_cascade_and_prog1024_windows(engine, oracle, ovs_auto):
     """BASELINE configs[4] (interpolator R=4 N=3 + 63-tap FIR, one channel of 2^26 inputs = one GPU's share) and
     configs[3] (1024 taps, one GPU's share: 8 channels x 2^27) at full size: random output windows re-derived by the
     oracle from the same inputs, plus output count and a zero-input / DC property."""
@@ -462,8 +500,8 @@ def test_full_size_cascade_and_prog1024_windows(engine, oracle):
     f = make_fir(engine, "prog", Q15, Q15, ACC40, ACC40, 1024, "SHIFT_REG", h, n_channels=C, layout="planar")
     y = f.run(x)
     torch.cuda.synchronize()
-    assert f.path == "fir_q15" and y.shape == (C, n)
-    for s in [0, n - 1500] + [int(v) for v in rng.integers(1100, n - 3000, size=10)]:
+    assert f.path == ("fir_ovs" if ovs_auto == "auto" and f.ovs_margin()[0] < 0.49 else "fir_q15") and y.shape == (C, n)
+    for s in [0, 3072 - 50, n - 1500] + [int(v) for v in rng.integers(1100, n - 3000, size=10)]:
         lo = max(0, s - 1023)
         c = int(rng.integers(0, C))
         want = oracle_fir(oracle, Q15, Q15, ACC40, ACC40, 1024, "SHIFT_REG", h, x[c, lo:s + 800].cpu().numpy())
