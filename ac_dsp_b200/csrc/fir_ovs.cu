@@ -49,6 +49,13 @@ __device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0,
 // Persistent CTA of two independent halves (256 threads each, own block buffer, own named barrier) that share one copy of
 // the twiddle tables in shared memory; half h of CTA b takes work items 2 b + h, 2 b + h + 2 gridDim.x, ...
 // A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one real channel (NP == 1).
+// The same value without the conversion instruction: v + 1.5 * 2^52 holds round(v) in the low bits of its mantissa (two's
+// complement, |v| < 2^51), and the accumulator keeps fewer than 52 of them (a.magic_shl >= 13 pushes exponent and bit 51 out).
+__device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
+  const long long b = __double_as_longlong(d + 6755399441055744.0) << a.magic_shl;
+  return a.acc.S ? (b >> a.wrap_shr) : (long long)((unsigned long long)b >> a.wrap_shr);
+}
+
 template <int NP, bool FASTOUT>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
@@ -63,6 +70,19 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     const uint32_t c0 = NP == 2 ? 0 : item / a.per_channel;
     const long long blk = NP == 2 ? item : item % a.per_channel;
     const bool interior = block_interior<NP>(a, blk);
+    {  // the samples of this half's next item on their way into L2 while this one is transformed (one 128-byte line per thread)
+      const unsigned nx = item + 2 * gridDim.x;
+      if (nx < a.items) {
+        if (NP == 2) {
+          const long long g = (long long)nx * a.L - a.D + 32 * tid;
+          if (tid < 128 && g >= 0 && (size_t)g < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint32_t *)a.x + g));
+        } else {
+          const uint32_t cn = nx / a.per_channel;
+          const long long g = 2 * (long long)(nx % a.per_channel) * a.L - a.D + 64 * tid;
+          if (tid < 128 && g >= 0 && (size_t)g < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint16_t *)a.x + (size_t)cn * a.n + g));
+        }
+      }
+    }
     if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
     else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
@@ -84,21 +104,41 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     if (FASTOUT && interior) {      // every kept output lands inside the call: one base pointer, immediate offsets
       if (NP == 2) {
         long long *yp = (long long *)a.y + 2 * (blk * a.L - a.D + tid);
+        if (a.magic_shl) {
 #pragma unroll
-        for (int k = 1; k < 16; k++) {
-          OVS_FENCE();
-          if (k < k0) continue;
-          longlong2 o; o.x = ovs_to_acc(v[k].x, a); o.y = ovs_to_acc(v[k].y, a);
-          *(longlong2 *)(yp + 512 * k) = o;
+          for (int k = 1; k < 16; k++) {
+            if (k % 5 == 1) OVS_FENCE();
+            if (k < k0) continue;
+            longlong2 o; o.x = ovs_to_acc_magic(v[k].x, a); o.y = ovs_to_acc_magic(v[k].y, a);
+            *(longlong2 *)(yp + 512 * k) = o;
+          }
+        } else {
+#pragma unroll
+          for (int k = 1; k < 16; k++) {
+            if (k % 5 == 1) OVS_FENCE();
+            if (k < k0) continue;
+            longlong2 o; o.x = ovs_to_acc(v[k].x, a); o.y = ovs_to_acc(v[k].y, a);
+            *(longlong2 *)(yp + 512 * k) = o;
+          }
         }
       } else {
         long long *yp = (long long *)a.y + (size_t)c0 * a.n + (2 * blk * a.L - a.D + tid);
+        if (a.magic_shl) {
 #pragma unroll
-        for (int k = 1; k < 16; k++) {
-          OVS_FENCE();
-          if (k < k0) continue;
-          yp[256 * k] = ovs_to_acc(v[k].x, a);
-          yp[256 * k + a.L] = ovs_to_acc(v[k].y, a);
+          for (int k = 1; k < 16; k++) {
+            if (k % 5 == 1) OVS_FENCE();
+            if (k < k0) continue;
+            yp[256 * k] = ovs_to_acc_magic(v[k].x, a);
+            yp[256 * k + a.L] = ovs_to_acc_magic(v[k].y, a);
+          }
+        } else {
+#pragma unroll
+          for (int k = 1; k < 16; k++) {
+            if (k % 5 == 1) OVS_FENCE();
+            if (k < k0) continue;
+            yp[256 * k] = ovs_to_acc(v[k].x, a);
+            yp[256 * k + a.L] = ovs_to_acc(v[k].y, a);
+          }
         }
       }
     } else if (NP == 2) {
@@ -236,6 +276,9 @@ cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 
   a.acc = p.facc; a.out = p.fout; a.out_bytes = container_bytes(p.fout.W);
   a.fastout = (p.fout.W == p.facc.W && p.fout.I == p.facc.I && p.fout.S == p.facc.S && a.out_bytes == 8 && (((uintptr_t)p.out) & 15) == 0) ? 1 : 0;
   a.resid = resid;
+  // the bit-pattern conversion needs every kept bit of the sum inside the mantissa window: W_acc - lsh <= 51
+  a.magic_shl = 0; a.wrap_shr = 0;
+  if (p.facc.W <= 64 && p.facc.W - a.lsh <= 51 && p.facc.W - a.lsh >= 1) { a.magic_shl = a.lsh + 64 - p.facc.W; a.wrap_shr = 64 - p.facc.W; }
   const size_t blocks = (p.n + a.L - 1) / a.L;
   if (p.interleaved && p.C == 2) {
     if (blocks > 0xFFFFFFF0u) return cudaErrorInvalidValue;

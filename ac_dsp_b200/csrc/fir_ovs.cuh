@@ -53,6 +53,7 @@ struct Args {
   unsigned items, per_channel;   // work items of the launch (blocks, or block pairs x channels), items per channel
   int xs;                 // samples signed
   int lsh;                // exact left shift of the dot product into ACC_TYPE
+  int magic_shl, wrap_shr; // > 0: ACC_TYPE raw = (bits(v + 1.5 * 2^52) << magic_shl) >> wrap_shr (arithmetic if ACC_TYPE is signed)
   Fmt acc, out;
   int out_bytes, fastout;
   double *resid;          // optional: max |v - rint(v)| over the launch (tests), as the bits of a non-negative double
@@ -256,27 +257,27 @@ __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, do
 }
 
 // ---- phase C: pass 3 (16 consecutive points), times H, first backward pass, in registers.
-// H comes from L2 (64 KB per channel, read once per block): the loads run one group of four ahead of their use, the
-// first group is issued before the butterfly.
+// H comes from L2 (64 KB per channel, read once per block): two groups of four loads are in flight at any time, the
+// first two are issued before the butterfly.
 __host__ __device__ __forceinline__ void phase_c(const Args &a, uint32_t c0, int tid, double2 *sm) {
   double2 v[16];
   double2 *s0 = sm + 17 * tid;
   const double2 *hs = a.hs + (size_t)c0 * kN + tid;
   double2 h[2][4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) h[0][j] = ld_stream(hs + j * 256);
+  for (int j = 0; j < 8; j++) h[j >> 2][j & 3] = ld_stream(hs + j * 256);
 #pragma unroll
   for (int k = 0; k < 16; k++) v[k] = s0[k];
   dft16_nat2perm<false>(v);
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    OVS_FENCE();
-    if (q < 3) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) h[(q + 1) & 1][j] = ld_stream(hs + (4 * q + 4 + j) * 256);
-    }
 #pragma unroll
     for (int j = 0; j < 4; j++) v[perm(4 * q + j)] = cmul<false>(v[perm(4 * q + j)], h[q & 1][j].x, h[q & 1][j].y);
+    OVS_FENCE();
+    if (q < 2) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) h[q & 1][j] = ld_stream(hs + (4 * q + 8 + j) * 256);
+    }
   }
   OVS_FENCE();
   dft16_perm2nat<true>(v);
