@@ -56,7 +56,10 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
   return a.acc.S ? (b >> a.wrap_shr) : (long long)((unsigned long long)b >> a.wrap_shr);
 }
 
-template <int NP, bool FASTOUT>
+// VAR: A/B variants of the kernel, B2D_OVS_VARIANT in the environment picks one (default: the best measured).
+//   bit 0: the packed samples of a half's next item are loaded into registers before the epilogue of the current one;
+//   bit 1: the first eight spectrum values of phase C are loaded before the barrier that precedes it.
+template <int NP, bool FASTOUT, int VAR>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
   double2 *tw1 = smem, *tw2 = smem + 15 * 256;
@@ -66,6 +69,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   double2 *sm = smem + kTwElems + half * kSmElems;
   const int k0 = a.D >> 8;
   double rmax = 0.0;
+  uint32_t raw[16];
+  if ((VAR & 1) && 2 * blockIdx.x + half < a.items) {
+    const unsigned it = 2 * blockIdx.x + half;
+    const uint32_t c0 = NP == 2 ? 0 : it / a.per_channel;
+    const long long blk = NP == 2 ? it : it % a.per_channel;
+    if (block_interior<NP>(a, blk)) load_block<NP, true>(a, c0, blk, tid, raw);
+    else load_block<NP, false>(a, c0, blk, tid, raw);
+  }
   for (unsigned item = 2 * blockIdx.x + half; item < a.items; item += 2 * gridDim.x) {
     const uint32_t c0 = NP == 2 ? 0 : item / a.per_channel;
     const long long blk = NP == 2 ? item : item % a.per_channel;
@@ -83,18 +94,35 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         }
       }
     }
-    if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
+    if (VAR & 1) phase_a_raw(a, tw1, tid, raw, sm);
+    else if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
     else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
     phase_b(tw2, tid, sm);
-    half_sync(half);
-    phase_c(a, c0, tid, sm);
+    if (VAR & 2) {
+      double2 h8[8];
+      load_h8(a, c0, tid, h8);
+      half_sync(half);
+      phase_c_h8(a, c0, tid, h8, sm);
+    } else {
+      half_sync(half);
+      phase_c(a, c0, tid, sm);
+    }
     half_sync(half);
     phase_d(tw2, tid, sm);
     half_sync(half);
     double2 v[16];
     phase_e(tw1, tid, sm, v);
     half_sync(half);            // the buffer is free for the next item's phase A
+    if (VAR & 1) {
+      const unsigned nx = item + 2 * gridDim.x;
+      if (nx < a.items) {
+        const uint32_t cn = NP == 2 ? 0 : nx / a.per_channel;
+        const long long bn = NP == 2 ? nx : nx % a.per_channel;
+        if (block_interior<NP>(a, bn)) load_block<NP, true>(a, cn, bn, tid, raw);
+        else load_block<NP, false>(a, cn, bn, tid, raw);
+      }
+    }
 
     if (a.resid) {
 #pragma unroll
@@ -253,17 +281,26 @@ void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
     }
 }
 
+template <int NP, bool FASTOUT, int VAR>
+static cudaError_t launch_var(const Args &a, unsigned ctas, cudaStream_t st) {
+  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return e;
+  fir_ovs_kernel<NP, FASTOUT, VAR><<<ctas, kCtaThreads, kSmemBytes, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <int NP>
 static cudaError_t launch_np(const Args &a, cudaStream_t st) {
-  const cudaError_t e = a.fastout ? cudaFuncSetAttribute(fir_ovs_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)
-                                  : cudaFuncSetAttribute(fir_ovs_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-  if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned ctas = std::min<unsigned>((a.items + 1) / 2, (unsigned)sms);
-  if (a.fastout) fir_ovs_kernel<NP, true><<<ctas, kCtaThreads, kSmemBytes, st>>>(a);
-  else fir_ovs_kernel<NP, false><<<ctas, kCtaThreads, kSmemBytes, st>>>(a);
-  return cudaGetLastError();
+  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt), G samples/s for variants 0 / 1 / 2 / 3: IQ pair, 256 taps 93.4 / 97.2 /
+  // 110.6 / 99.6; real channels, 1024 taps 156.2 / 123.4 / 150.0 / 123.5
+  static const int var = [] { const char *v = getenv("B2D_OVS_VARIANT"); return v ? atoi(v) : (NP == 2 ? 2 : 0); }();
+  if (var == 1) return a.fastout ? launch_var<NP, true, 1>(a, ctas, st) : launch_var<NP, false, 1>(a, ctas, st);
+  if (var == 2) return a.fastout ? launch_var<NP, true, 2>(a, ctas, st) : launch_var<NP, false, 2>(a, ctas, st);
+  if (var == 3) return a.fastout ? launch_var<NP, true, 3>(a, ctas, st) : launch_var<NP, false, 3>(a, ctas, st);
+  return a.fastout ? launch_var<NP, true, 0>(a, ctas, st) : launch_var<NP, false, 0>(a, ctas, st);
 }
 
 cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 *hs, double *resid, cudaStream_t st) {

@@ -233,6 +233,67 @@ __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *t
   }
 }
 
+// The same phase in two steps, for a kernel that loads the next item's samples before the epilogue of the current one:
+// load_block fetches the 16 complex samples of one thread as packed 16-bit pairs (low half: real part), phase_a_raw converts
+// and transforms them.
+template <int NP, bool INTERIOR>
+__host__ __device__ __forceinline__ void load_block(const Args &a, uint32_t c0, long long blk, int tid, uint32_t (&raw)[16]) {
+  if (INTERIOR && NP == 2) {
+    const uint32_t *p = (const uint32_t *)a.x + (blk * a.L - a.D + tid);
+#pragma unroll
+    for (int k = 0; k < 16; k++) raw[k] = ld_stream(p + 256 * k);
+  } else if (INTERIOR) {
+    const uint16_t *p = (const uint16_t *)a.x + (size_t)c0 * a.n + (2 * blk * a.L - a.D + tid);
+#pragma unroll
+    for (int k = 0; k < 16; k++) raw[k] = (uint32_t)ld_stream(p + 256 * k) | ((uint32_t)ld_stream(p + a.L + 256 * k) << 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < (NP == 2 ? 1 : 2); e++) {
+        const long long g = (NP == 2 ? blk : 2 * blk + e) * a.L - a.D + tid + 256 * k;
+        if (NP == 2) {
+          const uint16_t *t16 = (const uint16_t *)a.tail;
+          if (g < 0) { if (g + a.T >= 0) w = (uint32_t)t16[(size_t)(a.T + g)] | ((uint32_t)t16[(size_t)a.T + (size_t)(a.T + g)] << 16); }
+          else if ((size_t)g < a.n) w = ld_stream((const uint32_t *)a.x + g);
+        } else {
+          const uint16_t *t16 = (const uint16_t *)a.tail + (size_t)c0 * a.T;
+          uint32_t s = 0;
+          if (g < 0) { if (g + a.T >= 0) s = t16[(size_t)(a.T + g)]; }
+          else if ((size_t)g < a.n) s = ld_stream((const uint16_t *)a.x + (size_t)c0 * a.n + g);
+          w |= s << (16 * e);
+        }
+      }
+      raw[k] = w;
+    }
+  }
+}
+__host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double2 *tw1, int tid, const uint32_t (&raw)[16], double2 *sm) {
+  double2 v[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t w = raw[k];
+    const int vi = a.xs ? (int)(int16_t)(w & 0xFFFF) : (int)(w & 0xFFFF);
+    const int vq = a.xs ? ((int)w >> 16) : (int)(w >> 16);
+    v[k] = make_double2((double)vi, (double)vq);
+  }
+  dft16_nat2perm<false>(v);
+  double2 *s0 = sm + tid + (tid >> 4);
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    OVS_FENCE();
+#pragma unroll
+    for (int j = q; j < q + 4; j++) {
+      if (j) {
+        const double2 w = tw1[(j - 1) * 256 + tid];
+        v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
+      }
+      s0[272 * j] = v[perm(j)];
+    }
+  }
+}
+
 // ---- phase B: pass 2 (stride 16 inside each block of 256), twiddle W_256^(u*j).
 // position 256 b + u + 16 k -> shared-memory index 272 b + u + 17 k
 __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, double2 *sm) {
@@ -279,6 +340,41 @@ __host__ __device__ __forceinline__ void phase_c(const Args &a, uint32_t c0, int
       for (int j = 0; j < 4; j++) h[q & 1][j] = ld_stream(hs + (4 * q + 8 + j) * 256);
     }
   }
+  OVS_FENCE();
+  dft16_perm2nat<true>(v);
+#pragma unroll
+  for (int k = 0; k < 16; k++) s0[k] = v[k];
+}
+
+// The same phase with the first eight spectrum values loaded before the barrier that precedes it (load_h8) and the other
+// eight in two groups of four right after the butterfly has freed its temporaries.
+__host__ __device__ __forceinline__ void load_h8(const Args &a, uint32_t c0, int tid, double2 (&h)[8]) {
+  const double2 *hs = a.hs + (size_t)c0 * kN + tid;
+#pragma unroll
+  for (int j = 0; j < 8; j++) h[j] = ld_stream(hs + j * 256);
+}
+__host__ __device__ __forceinline__ void phase_c_h8(const Args &a, uint32_t c0, int tid, double2 (&h)[8], double2 *sm) {
+  double2 v[16];
+  double2 *s0 = sm + 17 * tid;
+  const double2 *hs = a.hs + (size_t)c0 * kN + tid;
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] = s0[k];
+  dft16_nat2perm<false>(v);
+  OVS_FENCE();
+  double2 g[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) g[j] = ld_stream(hs + (8 + j) * 256);
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[perm(j)] = cmul<false>(v[perm(j)], h[j].x, h[j].y);
+  OVS_FENCE();
+#pragma unroll
+  for (int j = 0; j < 4; j++) h[j] = ld_stream(hs + (12 + j) * 256);
+#pragma unroll
+  for (int j = 4; j < 8; j++) v[perm(j)] = cmul<false>(v[perm(j)], h[j].x, h[j].y);
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[perm(8 + j)] = cmul<false>(v[perm(8 + j)], g[j].x, g[j].y);
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[perm(12 + j)] = cmul<false>(v[perm(12 + j)], h[j].x, h[j].y);
   OVS_FENCE();
   dft16_perm2nat<true>(v);
 #pragma unroll
