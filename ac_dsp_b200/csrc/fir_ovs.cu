@@ -58,7 +58,9 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
 
 // VAR: A/B variants of the kernel, B2D_OVS_VARIANT in the environment picks one (default: the best measured).
 //   bit 0: the packed samples of a half's next item are loaded into registers before the epilogue of the current one;
-//   bit 1: the first eight spectrum values of phase C are loaded before the barrier that precedes it.
+//   bit 1: the first eight spectrum values of phase C are loaded before the barrier that precedes it;
+//   bit 2: twiddle / shared-memory loads of the passes in groups of eight instead of four;
+//   bit 3: no scheduling fences in the interior epilogue.
 template <int NP, bool FASTOUT, int VAR>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   const int half = threadIdx.x >> 8, tid = threadIdx.x & (kThreads - 1);
   double2 *sm = smem + kTwElems + half * kSmElems;
   const int k0 = a.D >> 8;
+  constexpr int GQ = (VAR & 4) ? 8 : 4;
   double rmax = 0.0;
   uint32_t raw[16];
   if ((VAR & 1) && 2 * blockIdx.x + half < a.items) {
@@ -94,11 +97,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         }
       }
     }
-    if (VAR & 1) phase_a_raw(a, tw1, tid, raw, sm);
-    else if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
-    else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
+    if (VAR & 1) phase_a_raw<GQ>(a, tw1, tid, raw, sm);
+    else if (interior) phase_a<NP, true, GQ>(a, tw1, c0, blk, tid, sm);
+    else phase_a<NP, false, GQ>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
-    phase_b(tw2, tid, sm);
+    phase_b<GQ>(tw2, tid, sm);
     if (VAR & 2) {
       double2 h8[8];
       load_h8(a, c0, tid, h8);
@@ -109,10 +112,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
       phase_c(a, c0, tid, sm);
     }
     half_sync(half);
-    phase_d(tw2, tid, sm);
+    phase_d<GQ>(tw2, tid, sm);
     half_sync(half);
     double2 v[16];
-    phase_e(tw1, tid, sm, v);
+    phase_e<GQ>(tw1, tid, sm, v);
     half_sync(half);            // the buffer is free for the next item's phase A
     if (VAR & 1) {
       const unsigned nx = item + 2 * gridDim.x;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         if (a.magic_shl) {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (k % 5 == 1) OVS_FENCE();
+            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             longlong2 o; o.x = ovs_to_acc_magic(v[k].x, a); o.y = ovs_to_acc_magic(v[k].y, a);
             *(longlong2 *)(yp + 512 * k) = o;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         } else {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (k % 5 == 1) OVS_FENCE();
+            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             longlong2 o; o.x = ovs_to_acc(v[k].x, a); o.y = ovs_to_acc(v[k].y, a);
             *(longlong2 *)(yp + 512 * k) = o;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         if (a.magic_shl) {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (k % 5 == 1) OVS_FENCE();
+            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             yp[256 * k] = ovs_to_acc_magic(v[k].x, a);
             yp[256 * k + a.L] = ovs_to_acc_magic(v[k].y, a);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         } else {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (k % 5 == 1) OVS_FENCE();
+            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             yp[256 * k] = ovs_to_acc(v[k].x, a);
             yp[256 * k + a.L] = ovs_to_acc(v[k].y, a);
@@ -297,9 +300,9 @@ static cudaError_t launch_np(const Args &a, cudaStream_t st) {
   // r02 A/B on a B200 (profiles/r02_ovs_variants.txt), G samples/s for variants 0 / 1 / 2 / 3: IQ pair, 256 taps 93.4 / 97.2 /
   // 110.6 / 99.6; real channels, 1024 taps 156.2 / 123.4 / 150.0 / 123.5
   static const int var = [] { const char *v = getenv("B2D_OVS_VARIANT"); return v ? atoi(v) : (NP == 2 ? 2 : 0); }();
-  if (var == 1) return a.fastout ? launch_var<NP, true, 1>(a, ctas, st) : launch_var<NP, false, 1>(a, ctas, st);
-  if (var == 2) return a.fastout ? launch_var<NP, true, 2>(a, ctas, st) : launch_var<NP, false, 2>(a, ctas, st);
-  if (var == 3) return a.fastout ? launch_var<NP, true, 3>(a, ctas, st) : launch_var<NP, false, 3>(a, ctas, st);
+#define OVS_CASE(V) if (var == V) return a.fastout ? launch_var<NP, true, V>(a, ctas, st) : launch_var<NP, false, V>(a, ctas, st);
+  OVS_CASE(1) OVS_CASE(2) OVS_CASE(3) OVS_CASE(4) OVS_CASE(6) OVS_CASE(8) OVS_CASE(10) OVS_CASE(12) OVS_CASE(14)
+#undef OVS_CASE
   return a.fastout ? launch_var<NP, true, 0>(a, ctas, st) : launch_var<NP, false, 0>(a, ctas, st);
 }
 

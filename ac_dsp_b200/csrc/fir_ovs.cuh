@@ -194,7 +194,7 @@ __host__ __device__ __forceinline__ double2 load_point(const Args &a, uint32_t c
 // ---- phase A: samples -> registers, pass 1 (stride 256), twiddle W_4096^(t*j), to shared memory.
 // INTERIOR: every sample of the block lies inside this call's input (no history, no stream end): plain strided loads.
 // Shared-memory index of position i: pad(i) = i + (i >> 4); for i = tid + 256 j that is tid + (tid >> 4) + 272 j.
-template <int NP, bool INTERIOR>
+template <int NP, bool INTERIOR, int GQ = 4>
 __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *tw1, uint32_t c0, long long blk, int tid, double2 *sm) {
   double2 v[16];
   if (INTERIOR && NP == 2) {
@@ -220,10 +220,10 @@ __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *t
   dft16_nat2perm<false>(v);
   double2 *s0 = sm + tid + (tid >> 4);
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
+  for (int q = 0; q < 16; q += GQ) {
     OVS_FENCE();
 #pragma unroll
-    for (int j = q; j < q + 4; j++) {
+    for (int j = q; j < q + GQ; j++) {
       if (j) {
         const double2 w = tw1[(j - 1) * 256 + tid];
         v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
@@ -269,6 +269,7 @@ __host__ __device__ __forceinline__ void load_block(const Args &a, uint32_t c0, 
     }
   }
 }
+template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double2 *tw1, int tid, const uint32_t (&raw)[16], double2 *sm) {
   double2 v[16];
 #pragma unroll
@@ -281,10 +282,10 @@ __host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double
   dft16_nat2perm<false>(v);
   double2 *s0 = sm + tid + (tid >> 4);
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
+  for (int q = 0; q < 16; q += GQ) {
     OVS_FENCE();
 #pragma unroll
-    for (int j = q; j < q + 4; j++) {
+    for (int j = q; j < q + GQ; j++) {
       if (j) {
         const double2 w = tw1[(j - 1) * 256 + tid];
         v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
@@ -296,6 +297,7 @@ __host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double
 
 // ---- phase B: pass 2 (stride 16 inside each block of 256), twiddle W_256^(u*j).
 // position 256 b + u + 16 k -> shared-memory index 272 b + u + 17 k
+template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, double2 *sm) {
   const int u = tid & 15;
   double2 *s0 = sm + (tid >> 4) * 272 + u;
@@ -304,10 +306,10 @@ __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, do
   for (int k = 0; k < 16; k++) v[k] = s0[17 * k];
   dft16_nat2perm<false>(v);
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
+  for (int q = 0; q < 16; q += GQ) {
     OVS_FENCE();
 #pragma unroll
-    for (int j = q; j < q + 4; j++) {
+    for (int j = q; j < q + GQ; j++) {
       if (j) {
         const double2 w = tw2[(j - 1) * 16 + u];
         v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
@@ -382,14 +384,15 @@ __host__ __device__ __forceinline__ void phase_c_h8(const Args &a, uint32_t c0, 
 }
 
 // ---- phase D: backward pass 2
+template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_d(const double2 *tw2, int tid, double2 *sm) {
   const int u = tid & 15;
   double2 *s0 = sm + (tid >> 4) * 272 + u;
   double2 v[16];
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
+  for (int q = 0; q < 16; q += GQ) {
 #pragma unroll
-    for (int j = q; j < q + 4; j++) {
+    for (int j = q; j < q + GQ; j++) {
       if (j) {
         const double2 w = tw2[(j - 1) * 16 + u];
         v[perm(j)] = cmul<true>(s0[17 * j], w.x, w.y);
@@ -405,12 +408,13 @@ __host__ __device__ __forceinline__ void phase_d(const double2 *tw2, int tid, do
 }
 
 // ---- phase E: backward pass 1 into registers: v[k] = block position tid + 256*k (first D positions are discarded)
+template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_e(const double2 *tw1, int tid, const double2 *sm, double2 (&v)[16]) {
   const double2 *s0 = sm + tid + (tid >> 4);
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
+  for (int q = 0; q < 16; q += GQ) {
 #pragma unroll
-    for (int j = q; j < q + 4; j++) {
+    for (int j = q; j < q + GQ; j++) {
       if (j) {
         const double2 w = tw1[(j - 1) * 256 + tid];
         v[perm(j)] = cmul<true>(s0[272 * j], w.x, w.y);

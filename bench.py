@@ -334,6 +334,9 @@ def parity_probe(wl, x, y, n, C, il, h, rank):
         T = wl["taps"] - 1
         infmt = wl.get("infmt", Q15)
         offs = [0, int(rng.integers(T + 1, n - W - 1)), n - W]
+        Lb = 4096 - ((T + 255) // 256) * 256       # outputs per block of the overlap-save path: one window straddles a block seam
+        if n > 4 * Lb:
+            offs.insert(2, int(rng.integers(1, n // Lb - 1)) * Lb - W // 2)
         for off in offs:
             for c in sorted(set((0, C - 1))):
                 col = (lambda a, lo, hi: a[lo:hi, c] if il and C > 1 else (a[c, lo:hi] if C > 1 else a[lo:hi]))
@@ -566,6 +569,8 @@ def measure(name, wl, args, ctx, want_cpu):
         for tp in ("r02_traffic.json", "r01_traffic.json"):
             tp = os.path.join(ROOT, "profiles", tp)
             t = json.load(open(tp)).get(name) if os.path.exists(tp) else None
+            if t and t.get("path", path) != path:
+                t = None                      # the capture belongs to another kernel family than the one that ran
             if t:   # measured DRAM bytes per unit (one ncu --set full capture) scaled to this launch's units
                 traffic = t["dram_bytes_per_unit"] * units_per_step
                 traffic_src = f"{t['source']}: {t['dram_bytes']} B measured at {t['capture_units']} units/launch, scaled"
@@ -581,6 +586,10 @@ def measure(name, wl, args, ctx, want_cpu):
             roof["int_pipe"] = {"achieved_tmac_s": tmacs, "ceiling_tmac_s": 148 * 64 * sm_mhz * 1e6 / 1e12,
                                 "frac": tmacs / (148 * 64 * sm_mhz * 1e6 / 1e12),
                                 "note": "CUDA-core IDP.2A issue ceiling at the sampled SM clock (tensor cores excluded by the north star)"}
+        if wl["macs_per_unit"] and path == "fir_ovs":
+            roof["note"] = ("overlap-save: 4096-point FP64 FFT blocks in registers and shared memory (about 80 FP64 instructions and 200 bytes of "
+                            "shared-memory traffic per complex sample whatever the tap count), exact by an a-priori error bound on the loaded taps; "
+                            "B2D_FIR_OVS=0 selects the tap-by-tap DP2A kernel (fir_q15)")
         res["roofline"] = roof
         if want_cpu:
             if ctx["orig_affinity"]:
