@@ -9,12 +9,13 @@
 // Error bound.  With u = 2^-53, block length N = 4096, |x| <= xmax per component,
 // every radix-16 pass is 4 levels of additions (u each, normwise), one internal and one external twiddle
 // multiplication ((sqrt(5) + 1) u each: Brent-Percival-Zimmermann bound plus the rounding of the tabulated twiddle),
-// 10.5 u in all; the pass without external twiddle 7.3 u: forward and backward transform 28.3 u each.  H is computed in
-// extended precision on the host and rounded once (|dH_k| <= 1.1 u ||h||_1), the pointwise product adds sqrt(5) u.
-// In the 2-norm the exact transform passes are unitary up to scale, so the relative errors add:
-//     ||y_computed - y||_inf <= ||.||_2 <= 61 u * ||x||_2 * ||h||_1 <= 61 u * sqrt(2 N) xmax ||h||_1 .
-// kErrK = 64 is used.  For 256 full-scale Q15 taps (||h||_1 <= 2^23) the bound is 0.27; typical measured residuals
-// |v - rint(v)| are below 1e-3 (tests/test_fir_ovs.py prints them).
+// 10.5 u in all; nine of the fifteen external twiddles are applied as two factors (fir_ovs.cuh: Tw6), one more
+// (sqrt(5) + 1) u: 13.8 u for the four passes with external twiddles, 7.3 u for the two without: 69.8 u for both
+// transforms.  H is computed in extended precision on the host and rounded once (|dH_k| <= 1.1 u ||h||_1), the pointwise
+// product adds sqrt(5) u.  In the 2-norm the exact transform passes are unitary up to scale, so the relative errors add:
+//     ||y_computed - y||_inf <= ||.||_2 <= 73.2 u * ||x||_2 * ||h||_1 <= 73.2 u * sqrt(2 N) xmax ||h||_1 .
+// kErrK = 76 is used.  For 256 full-scale Q15 taps (||h||_1 <= 2^23) the bound is 0.21; measured residuals
+// |v - rint(v)| stay below 1e-4 (tests/test_fir_ovs.py, tests/cpp/fir_ovs_check.cu print them).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -27,7 +28,7 @@ namespace b2d {
 
 using namespace ovs;
 
-constexpr double kErrK = 64.0;
+constexpr double kErrK = 76.0;
 constexpr int kMinTaps = 96;          // below this the DP2A kernel is faster
 constexpr int kMaxTapsOvs = 2049;     // D <= N / 2
 
@@ -40,15 +41,12 @@ __host__ __device__ __forceinline__ int64_t ovs_to_acc(double d, const Args &a) 
   return wrap_bits((int64_t)((uint64_t)s << a.lsh), a.acc.W, a.acc.S);
 }
 
-constexpr int kTwElems = 15 * 256 + 15 * 16;
+constexpr int kTwElems = 6 * 256 + 6 * 16;
 constexpr int kCtaThreads = 2 * kThreads;
-constexpr size_t kSmemBytes = (size_t)(kTwElems + 2 * kSmElems) * sizeof(double2);   // 204,544 bytes: one CTA per SM
+constexpr size_t kSmemBytes = (size_t)(kTwElems + kN + 2 * kSmElems) * sizeof(double2);   // 230,912 bytes: one CTA per SM
 
 __device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kThreads) : "memory"); }
 
-// Persistent CTA of two independent halves (256 threads each, own block buffer, own named barrier) that share one copy of
-// the twiddle tables in shared memory; half h of CTA b takes work items 2 b + h, 2 b + h + 2 gridDim.x, ...
-// A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one real channel (NP == 1).
 // The same value without the conversion instruction: v + 1.5 * 2^52 holds round(v) in the low bits of its mantissa (two's
 // complement, |v| < 2^51), and the accumulator keeps fewer than 52 of them (a.magic_shl >= 13 pushes exponent and bit 51 out).
 __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
@@ -56,76 +54,50 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
   return a.acc.S ? (b >> a.wrap_shr) : (long long)((unsigned long long)b >> a.wrap_shr);
 }
 
-// VAR: A/B variants of the kernel, B2D_OVS_VARIANT in the environment picks one (default: the best measured).
-//   bit 0: the packed samples of a half's next item are loaded into registers before the epilogue of the current one;
-//   bit 1: the first eight spectrum values of phase C are loaded before the barrier that precedes it;
-//   bit 2: twiddle / shared-memory loads of the passes in groups of eight instead of four;
-//   bit 3: no scheduling fences in the interior epilogue.
-template <int NP, bool FASTOUT, int VAR>
+// Persistent CTA of two independent halves (256 threads each, own block buffer, own named barrier) that share one copy of
+// the twiddle tables and of ONE channel's spectrum in shared memory -- the transform reads nothing but its samples from
+// global memory.  blockIdx.y is the channel (0 for an IQ pair); half h of CTA b takes the channel's work items 2 b + h,
+// 2 b + h + 2 gridDim.x, ...  A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one
+// real channel (NP == 1).
+template <int NP, bool FASTOUT>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
-  double2 *tw1 = smem, *tw2 = smem + 15 * 256;
+  double2 *tw1 = smem, *tw2 = smem + 6 * 256, *hsm = smem + kTwElems;
+  const uint32_t c0 = blockIdx.y;
   for (int i = threadIdx.x; i < kTwElems; i += kCtaThreads) smem[i] = a.tw[i];
+  for (int i = threadIdx.x; i < kN; i += kCtaThreads) hsm[i] = a.hs[(size_t)c0 * kN + i];
   __syncthreads();
   const int half = threadIdx.x >> 8, tid = threadIdx.x & (kThreads - 1);
-  double2 *sm = smem + kTwElems + half * kSmElems;
+  double2 *sm = smem + kTwElems + kN + half * kSmElems;
   const int k0 = a.D >> 8;
-  constexpr int GQ = (VAR & 4) ? 8 : 4;
   double rmax = 0.0;
-  uint32_t raw[16];
-  if ((VAR & 1) && 2 * blockIdx.x + half < a.items) {
-    const unsigned it = 2 * blockIdx.x + half;
-    const uint32_t c0 = NP == 2 ? 0 : it / a.per_channel;
-    const long long blk = NP == 2 ? it : it % a.per_channel;
-    if (block_interior<NP>(a, blk)) load_block<NP, true>(a, c0, blk, tid, raw);
-    else load_block<NP, false>(a, c0, blk, tid, raw);
-  }
-  for (unsigned item = 2 * blockIdx.x + half; item < a.items; item += 2 * gridDim.x) {
-    const uint32_t c0 = NP == 2 ? 0 : item / a.per_channel;
-    const long long blk = NP == 2 ? item : item % a.per_channel;
+  for (unsigned item = 2 * blockIdx.x + half; item < a.per_channel; item += 2 * gridDim.x) {
+    const long long blk = item;
     const bool interior = block_interior<NP>(a, blk);
     {  // the samples of this half's next item on their way into L2 while this one is transformed (one 128-byte line per thread)
       const unsigned nx = item + 2 * gridDim.x;
-      if (nx < a.items) {
+      if (nx < a.per_channel) {
         if (NP == 2) {
           const long long g = (long long)nx * a.L - a.D + 32 * tid;
           if (tid < 128 && g >= 0 && (size_t)g < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint32_t *)a.x + g));
         } else {
-          const uint32_t cn = nx / a.per_channel;
-          const long long g = 2 * (long long)(nx % a.per_channel) * a.L - a.D + 64 * tid;
-          if (tid < 128 && g >= 0 && (size_t)g < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint16_t *)a.x + (size_t)cn * a.n + g));
+          const long long g = 2 * (long long)nx * a.L - a.D + 64 * tid;
+          if (tid < 128 && g >= 0 && (size_t)g < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint16_t *)a.x + (size_t)c0 * a.n + g));
         }
       }
     }
-    if (VAR & 1) phase_a_raw<GQ>(a, tw1, tid, raw, sm);
-    else if (interior) phase_a<NP, true, GQ>(a, tw1, c0, blk, tid, sm);
-    else phase_a<NP, false, GQ>(a, tw1, c0, blk, tid, sm);
+    if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
+    else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
-    phase_b<GQ>(tw2, tid, sm);
-    if (VAR & 2) {
-      double2 h8[8];
-      load_h8(a, c0, tid, h8);
-      half_sync(half);
-      phase_c_h8(a, c0, tid, h8, sm);
-    } else {
-      half_sync(half);
-      phase_c(a, c0, tid, sm);
-    }
+    phase_b(tw2, tid, sm);
     half_sync(half);
-    phase_d<GQ>(tw2, tid, sm);
+    phase_c(hsm, tid, sm);
+    half_sync(half);
+    phase_d(tw2, tid, sm);
     half_sync(half);
     double2 v[16];
-    phase_e<GQ>(tw1, tid, sm, v);
+    phase_e(tw1, tid, sm, v);
     half_sync(half);            // the buffer is free for the next item's phase A
-    if (VAR & 1) {
-      const unsigned nx = item + 2 * gridDim.x;
-      if (nx < a.items) {
-        const uint32_t cn = NP == 2 ? 0 : nx / a.per_channel;
-        const long long bn = NP == 2 ? nx : nx % a.per_channel;
-        if (block_interior<NP>(a, bn)) load_block<NP, true>(a, cn, bn, tid, raw);
-        else load_block<NP, false>(a, cn, bn, tid, raw);
-      }
-    }
 
     if (a.resid) {
 #pragma unroll
@@ -138,7 +110,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         if (a.magic_shl) {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
+            if (k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             longlong2 o; o.x = ovs_to_acc_magic(v[k].x, a); o.y = ovs_to_acc_magic(v[k].y, a);
             *(longlong2 *)(yp + 512 * k) = o;
@@ -146,7 +118,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         } else {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
+            if (k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             longlong2 o; o.x = ovs_to_acc(v[k].x, a); o.y = ovs_to_acc(v[k].y, a);
             *(longlong2 *)(yp + 512 * k) = o;
@@ -157,7 +129,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         if (a.magic_shl) {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
+            if (k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             yp[256 * k] = ovs_to_acc_magic(v[k].x, a);
             yp[256 * k + a.L] = ovs_to_acc_magic(v[k].y, a);
@@ -165,7 +137,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         } else {
 #pragma unroll
           for (int k = 1; k < 16; k++) {
-            if (!(VAR & 8) && k % 5 == 1) OVS_FENCE();
+            if (k % 5 == 1) OVS_FENCE();
             if (k < k0) continue;
             yp[256 * k] = ovs_to_acc(v[k].x, a);
             yp[256 * k + a.L] = ovs_to_acc(v[k].y, a);
@@ -236,17 +208,19 @@ double fir_ovs_error_bound(const Fmt &in, double l1) {
   return kErrK * std::ldexp(1.0, -53) * std::sqrt(2.0 * kN) * xmax * l1;
 }
 
-// Twiddle tables, rounded from extended precision: tw1[j-1][t] = W_4096^(t*j), tw2[j-1][u] = W_256^(u*j).
+// Twiddle tables, rounded from extended precision (fir_ovs.cuh: Tw6): tw1[i][t], t < 256, i = 0..2: W_4096^(t (i + 1)),
+// i = 3..5: W_4096^(4 t (i - 2)); tw2[i][u], u < 16: the same of W_256.
 void fir_ovs_tables(double2 *tw1, double2 *tw2) {
   const long double tau = 6.283185307179586476925286766559005768L;
-  for (int j = 1; j < 16; j++) {
+  for (int i = 0; i < 6; i++) {
+    const int mul = i < 3 ? i + 1 : 4 * (i - 2);
     for (int t = 0; t < 256; t++) {
-      const long double ang = tau * (long double)((t * j) % kN) / (long double)kN;
-      tw1[(j - 1) * 256 + t] = make_double2((double)cosl(ang), (double)-sinl(ang));
+      const long double ang = tau * (long double)((t * mul) % kN) / (long double)kN;
+      tw1[i * 256 + t] = make_double2((double)cosl(ang), (double)-sinl(ang));
     }
     for (int u = 0; u < 16; u++) {
-      const long double ang = tau * (long double)((u * j) % 256) / 256.0L;
-      tw2[(j - 1) * 16 + u] = make_double2((double)cosl(ang), (double)-sinl(ang));
+      const long double ang = tau * (long double)((u * mul) % 256) / 256.0L;
+      tw2[i * 16 + u] = make_double2((double)cosl(ang), (double)-sinl(ang));
     }
   }
 }
@@ -284,26 +258,12 @@ void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
     }
 }
 
-template <int NP, bool FASTOUT, int VAR>
-static cudaError_t launch_var(const Args &a, unsigned ctas, cudaStream_t st) {
-  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+template <int NP, bool FASTOUT>
+static cudaError_t launch_k(const Args &a, dim3 grid, cudaStream_t st) {
+  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
-  fir_ovs_kernel<NP, FASTOUT, VAR><<<ctas, kCtaThreads, kSmemBytes, st>>>(a);
+  fir_ovs_kernel<NP, FASTOUT><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
   return cudaGetLastError();
-}
-
-template <int NP>
-static cudaError_t launch_np(const Args &a, cudaStream_t st) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned ctas = std::min<unsigned>((a.items + 1) / 2, (unsigned)sms);
-  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt), G samples/s for variants 0 / 1 / 2 / 3: IQ pair, 256 taps 93.4 / 97.2 /
-  // 110.6 / 99.6; real channels, 1024 taps 156.2 / 123.4 / 150.0 / 123.5
-  static const int var = [] { const char *v = getenv("B2D_OVS_VARIANT"); return v ? atoi(v) : (NP == 2 ? 2 : 0); }();
-#define OVS_CASE(V) if (var == V) return a.fastout ? launch_var<NP, true, V>(a, ctas, st) : launch_var<NP, false, V>(a, ctas, st);
-  OVS_CASE(1) OVS_CASE(2) OVS_CASE(3) OVS_CASE(4) OVS_CASE(6) OVS_CASE(8) OVS_CASE(10) OVS_CASE(12) OVS_CASE(14)
-#undef OVS_CASE
-  return a.fastout ? launch_var<NP, true, 0>(a, ctas, st) : launch_var<NP, false, 0>(a, ctas, st);
 }
 
 cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 *hs, double *resid, cudaStream_t st) {
@@ -319,16 +279,19 @@ cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 
   // the bit-pattern conversion needs every kept bit of the sum inside the mantissa window: W_acc - lsh <= 51
   a.magic_shl = 0; a.wrap_shr = 0;
   if (p.facc.W <= 64 && p.facc.W - a.lsh <= 51 && p.facc.W - a.lsh >= 1) { a.magic_shl = a.lsh + 64 - p.facc.W; a.wrap_shr = 64 - p.facc.W; }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t blocks = (p.n + a.L - 1) / a.L;
-  if (p.interleaved && p.C == 2) {
-    if (blocks > 0xFFFFFFF0u) return cudaErrorInvalidValue;
-    a.items = (unsigned)blocks; a.per_channel = a.items;
-    return launch_np<2>(a, st);
-  }
-  const size_t pairs = (blocks + 1) / 2;
-  if (pairs * p.C > 0xFFFFFFF0u) return cudaErrorInvalidValue;
-  a.per_channel = (unsigned)pairs; a.items = (unsigned)(pairs * p.C);
-  return launch_np<1>(a, st);
+  const bool iq = p.interleaved && p.C == 2;
+  const size_t per_channel = iq ? blocks : (blocks + 1) / 2;
+  const uint32_t chans = iq ? 1 : p.C;
+  if (per_channel > 0xFFFFFFF0u || chans > 65535) return cudaErrorInvalidValue;
+  a.per_channel = (unsigned)per_channel;
+  // a CTA is bound to one channel (its spectrum sits in shared memory): the SMs are divided among the channels
+  const unsigned per_ch_ctas = (unsigned)std::min<size_t>((per_channel + 1) / 2, std::max<unsigned>(1u, (unsigned)sms / chans));
+  const dim3 grid(per_ch_ctas, chans);
+  if (iq) return a.fastout ? launch_k<2, true>(a, grid, st) : launch_k<2, false>(a, grid, st);
+  return a.fastout ? launch_k<1, true>(a, grid, st) : launch_k<1, false>(a, grid, st);
 }
 
 }  // namespace b2d

@@ -22,9 +22,9 @@
 #else
 #define OVS_LDG(p) (*(p))
 #endif
-// The compiler may not move memory operations across this point: the twiddle / spectrum loads of a phase are issued four at
-// a time next to their use.  Hoisted above the butterflies (what the scheduler does when left alone) they cost 60 more
-// live registers and the kernel spilled 500 bytes per thread at its 128-register budget (2 CTAs per SM).
+// The compiler may not move memory operations across this point: the shared-memory loads of a phase are issued four at a
+// time next to their use.  Hoisted above the butterflies (what the scheduler does when left alone) they cost up to 60 more
+// live registers and the kernel spills at its 128-register budget (512 threads per SM).
 #define OVS_FENCE() asm volatile("" ::: "memory")
 
 namespace b2d {
@@ -45,12 +45,12 @@ struct Args {
   const void *x;          // input samples (int16 containers)
   void *y;                // output containers
   const void *tail;       // [C][T] history, planar
-  const double2 *tw;      // [15][256]: W_4096^(t*j), j = 1..15, then [15][16]: W_256^(u*j); the kernel keeps a copy in shared memory
+  const double2 *tw;      // [6][256]: W_4096^(t b), b = 1..3, W_4096^(4 t a), a = 1..3; then [6][16]: the same of W_256 (fir_ovs_tables)
   const double2 *hs;      // [C][16][256]: spectrum of the taps / 4096 at position 16*c + j, stored [j][c]
   size_t n;               // samples per channel in this call
   int T, D, L;            // history length (n_taps - 1), discarded head of a block (multiple of 256, >= T), L = kN - D
   uint32_t C;
-  unsigned items, per_channel;   // work items of the launch (blocks, or block pairs x channels), items per channel
+  unsigned per_channel;   // work items per channel (blocks of an IQ pair, or block pairs of a real channel)
   int xs;                 // samples signed
   int lsh;                // exact left shift of the dot product into ACC_TYPE
   int magic_shl, wrap_shr; // > 0: ACC_TYPE raw = (bits(v + 1.5 * 2^52) << magic_shl) >> wrap_shr (arithmetic if ACC_TYPE is signed)
@@ -59,8 +59,7 @@ struct Args {
   double *resid;          // optional: max |v - rint(v)| over the launch (tests), as the bits of a non-negative double
 };
 
-// Table entries that are read once per block (the spectrum) or once per launch (samples) bypass L1 so that the 64 KB of
-// twiddles, read twice per block by every CTA, stay resident there.
+// Samples are read once per launch: no L1 allocation.
 __host__ __device__ __forceinline__ double2 ld_stream(const double2 *p) {
 #if defined(__CUDA_ARCH__)
   double2 v;
@@ -191,10 +190,30 @@ __host__ __device__ __forceinline__ double2 load_point(const Args &a, uint32_t c
   }
 }
 
+// Twiddles of a pass, factored: output j = 4 a + b of a radix-16 butterfly is multiplied by W^(x j) = W^(x b) * W^(4 x a),
+// x the thread's index in the pass.  A thread reads six table values per pass (tw[0..2] = W^(x b), b = 1..3, and
+// tw[3..5] = W^(4 x a), a = 1..3, `stride` elements apart) instead of fifteen: the table of the first pass shrinks from 60 KB
+// to 24 KB, which is what lets the spectrum live in shared memory next to both block buffers; nine of the fifteen outputs
+// pay a second complex multiplication (FP64 has the headroom, the shared-memory pipe has not).
+struct Tw6 { double2 w[6]; };
+__host__ __device__ __forceinline__ Tw6 load_tw6(const double2 *tw, int stride, int x) {
+  Tw6 t;
+#pragma unroll
+  for (int i = 0; i < 6; i++) t.w[i] = tw[i * stride + x];
+  return t;
+}
+template <bool INV>
+__host__ __device__ __forceinline__ double2 twiddle_j(double2 v, const Tw6 &t, int j) {
+  const int a = j >> 2, b = j & 3;
+  if (b) v = cmul<INV>(v, t.w[b - 1].x, t.w[b - 1].y);
+  if (a) v = cmul<INV>(v, t.w[2 + a].x, t.w[2 + a].y);
+  return v;
+}
+
 // ---- phase A: samples -> registers, pass 1 (stride 256), twiddle W_4096^(t*j), to shared memory.
 // INTERIOR: every sample of the block lies inside this call's input (no history, no stream end): plain strided loads.
 // Shared-memory index of position i: pad(i) = i + (i >> 4); for i = tid + 256 j that is tid + (tid >> 4) + 272 j.
-template <int NP, bool INTERIOR, int GQ = 4>
+template <int NP, bool INTERIOR>
 __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *tw1, uint32_t c0, long long blk, int tid, double2 *sm) {
   double2 v[16];
   if (INTERIOR && NP == 2) {
@@ -218,86 +237,15 @@ __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *t
     for (int k = 0; k < 16; k++) v[k] = load_point<NP>(a, c0, blk, tid + 256 * k);
   }
   dft16_nat2perm<false>(v);
+  OVS_FENCE();
+  const Tw6 t = load_tw6(tw1, 256, tid);
   double2 *s0 = sm + tid + (tid >> 4);
 #pragma unroll
-  for (int q = 0; q < 16; q += GQ) {
-    OVS_FENCE();
-#pragma unroll
-    for (int j = q; j < q + GQ; j++) {
-      if (j) {
-        const double2 w = tw1[(j - 1) * 256 + tid];
-        v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
-      }
-      s0[272 * j] = v[perm(j)];
-    }
-  }
-}
-
-// The same phase in two steps, for a kernel that loads the next item's samples before the epilogue of the current one:
-// load_block fetches the 16 complex samples of one thread as packed 16-bit pairs (low half: real part), phase_a_raw converts
-// and transforms them.
-template <int NP, bool INTERIOR>
-__host__ __device__ __forceinline__ void load_block(const Args &a, uint32_t c0, long long blk, int tid, uint32_t (&raw)[16]) {
-  if (INTERIOR && NP == 2) {
-    const uint32_t *p = (const uint32_t *)a.x + (blk * a.L - a.D + tid);
-#pragma unroll
-    for (int k = 0; k < 16; k++) raw[k] = ld_stream(p + 256 * k);
-  } else if (INTERIOR) {
-    const uint16_t *p = (const uint16_t *)a.x + (size_t)c0 * a.n + (2 * blk * a.L - a.D + tid);
-#pragma unroll
-    for (int k = 0; k < 16; k++) raw[k] = (uint32_t)ld_stream(p + 256 * k) | ((uint32_t)ld_stream(p + a.L + 256 * k) << 16);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      uint32_t w = 0;
-#pragma unroll
-      for (int e = 0; e < (NP == 2 ? 1 : 2); e++) {
-        const long long g = (NP == 2 ? blk : 2 * blk + e) * a.L - a.D + tid + 256 * k;
-        if (NP == 2) {
-          const uint16_t *t16 = (const uint16_t *)a.tail;
-          if (g < 0) { if (g + a.T >= 0) w = (uint32_t)t16[(size_t)(a.T + g)] | ((uint32_t)t16[(size_t)a.T + (size_t)(a.T + g)] << 16); }
-          else if ((size_t)g < a.n) w = ld_stream((const uint32_t *)a.x + g);
-        } else {
-          const uint16_t *t16 = (const uint16_t *)a.tail + (size_t)c0 * a.T;
-          uint32_t s = 0;
-          if (g < 0) { if (g + a.T >= 0) s = t16[(size_t)(a.T + g)]; }
-          else if ((size_t)g < a.n) s = ld_stream((const uint16_t *)a.x + (size_t)c0 * a.n + g);
-          w |= s << (16 * e);
-        }
-      }
-      raw[k] = w;
-    }
-  }
-}
-template <int GQ = 4>
-__host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double2 *tw1, int tid, const uint32_t (&raw)[16], double2 *sm) {
-  double2 v[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const uint32_t w = raw[k];
-    const int vi = a.xs ? (int)(int16_t)(w & 0xFFFF) : (int)(w & 0xFFFF);
-    const int vq = a.xs ? ((int)w >> 16) : (int)(w >> 16);
-    v[k] = make_double2((double)vi, (double)vq);
-  }
-  dft16_nat2perm<false>(v);
-  double2 *s0 = sm + tid + (tid >> 4);
-#pragma unroll
-  for (int q = 0; q < 16; q += GQ) {
-    OVS_FENCE();
-#pragma unroll
-    for (int j = q; j < q + GQ; j++) {
-      if (j) {
-        const double2 w = tw1[(j - 1) * 256 + tid];
-        v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
-      }
-      s0[272 * j] = v[perm(j)];
-    }
-  }
+  for (int j = 0; j < 16; j++) s0[272 * j] = twiddle_j<false>(v[perm(j)], t, j);
 }
 
 // ---- phase B: pass 2 (stride 16 inside each block of 256), twiddle W_256^(u*j).
 // position 256 b + u + 16 k -> shared-memory index 272 b + u + 17 k
-template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, double2 *sm) {
   const int u = tid & 15;
   double2 *s0 = sm + (tid >> 4) * 272 + u;
@@ -305,78 +253,29 @@ __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, do
 #pragma unroll
   for (int k = 0; k < 16; k++) v[k] = s0[17 * k];
   dft16_nat2perm<false>(v);
+  OVS_FENCE();
+  const Tw6 t = load_tw6(tw2, 16, u);
 #pragma unroll
-  for (int q = 0; q < 16; q += GQ) {
-    OVS_FENCE();
-#pragma unroll
-    for (int j = q; j < q + GQ; j++) {
-      if (j) {
-        const double2 w = tw2[(j - 1) * 16 + u];
-        v[perm(j)] = cmul<false>(v[perm(j)], w.x, w.y);
-      }
-      s0[17 * j] = v[perm(j)];
-    }
-  }
+  for (int j = 0; j < 16; j++) s0[17 * j] = twiddle_j<false>(v[perm(j)], t, j);
 }
 
 // ---- phase C: pass 3 (16 consecutive points), times H, first backward pass, in registers.
-// H comes from L2 (64 KB per channel, read once per block): two groups of four loads are in flight at any time, the
-// first two are issued before the butterfly.
-__host__ __device__ __forceinline__ void phase_c(const Args &a, uint32_t c0, int tid, double2 *sm) {
+// hsm: this channel's spectrum in shared memory, [16][256], value for position 16 tid + j at hsm[256 j + tid].
+__host__ __device__ __forceinline__ void phase_c(const double2 *hsm, int tid, double2 *sm) {
   double2 v[16];
   double2 *s0 = sm + 17 * tid;
-  const double2 *hs = a.hs + (size_t)c0 * kN + tid;
-  double2 h[2][4];
-#pragma unroll
-  for (int j = 0; j < 8; j++) h[j >> 2][j & 3] = ld_stream(hs + j * 256);
 #pragma unroll
   for (int k = 0; k < 16; k++) v[k] = s0[k];
   dft16_nat2perm<false>(v);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) v[perm(4 * q + j)] = cmul<false>(v[perm(4 * q + j)], h[q & 1][j].x, h[q & 1][j].y);
+  for (int q = 0; q < 16; q += 4) {
     OVS_FENCE();
-    if (q < 2) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) h[q & 1][j] = ld_stream(hs + (4 * q + 8 + j) * 256);
+    for (int j = q; j < q + 4; j++) {
+      const double2 h = hsm[256 * j + tid];
+      v[perm(j)] = cmul<false>(v[perm(j)], h.x, h.y);
     }
   }
-  OVS_FENCE();
-  dft16_perm2nat<true>(v);
-#pragma unroll
-  for (int k = 0; k < 16; k++) s0[k] = v[k];
-}
-
-// The same phase with the first eight spectrum values loaded before the barrier that precedes it (load_h8) and the other
-// eight in two groups of four right after the butterfly has freed its temporaries.
-__host__ __device__ __forceinline__ void load_h8(const Args &a, uint32_t c0, int tid, double2 (&h)[8]) {
-  const double2 *hs = a.hs + (size_t)c0 * kN + tid;
-#pragma unroll
-  for (int j = 0; j < 8; j++) h[j] = ld_stream(hs + j * 256);
-}
-__host__ __device__ __forceinline__ void phase_c_h8(const Args &a, uint32_t c0, int tid, double2 (&h)[8], double2 *sm) {
-  double2 v[16];
-  double2 *s0 = sm + 17 * tid;
-  const double2 *hs = a.hs + (size_t)c0 * kN + tid;
-#pragma unroll
-  for (int k = 0; k < 16; k++) v[k] = s0[k];
-  dft16_nat2perm<false>(v);
-  OVS_FENCE();
-  double2 g[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) g[j] = ld_stream(hs + (8 + j) * 256);
-#pragma unroll
-  for (int j = 0; j < 4; j++) v[perm(j)] = cmul<false>(v[perm(j)], h[j].x, h[j].y);
-  OVS_FENCE();
-#pragma unroll
-  for (int j = 0; j < 4; j++) h[j] = ld_stream(hs + (12 + j) * 256);
-#pragma unroll
-  for (int j = 4; j < 8; j++) v[perm(j)] = cmul<false>(v[perm(j)], h[j].x, h[j].y);
-#pragma unroll
-  for (int j = 0; j < 4; j++) v[perm(8 + j)] = cmul<false>(v[perm(8 + j)], g[j].x, g[j].y);
-#pragma unroll
-  for (int j = 0; j < 4; j++) v[perm(12 + j)] = cmul<false>(v[perm(12 + j)], h[j].x, h[j].y);
   OVS_FENCE();
   dft16_perm2nat<true>(v);
 #pragma unroll
@@ -384,22 +283,15 @@ __host__ __device__ __forceinline__ void phase_c_h8(const Args &a, uint32_t c0, 
 }
 
 // ---- phase D: backward pass 2
-template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_d(const double2 *tw2, int tid, double2 *sm) {
   const int u = tid & 15;
   double2 *s0 = sm + (tid >> 4) * 272 + u;
+  const Tw6 t = load_tw6(tw2, 16, u);
   double2 v[16];
 #pragma unroll
-  for (int q = 0; q < 16; q += GQ) {
+  for (int q = 0; q < 16; q += 4) {
 #pragma unroll
-    for (int j = q; j < q + GQ; j++) {
-      if (j) {
-        const double2 w = tw2[(j - 1) * 16 + u];
-        v[perm(j)] = cmul<true>(s0[17 * j], w.x, w.y);
-      } else {
-        v[0] = s0[0];
-      }
-    }
+    for (int j = q; j < q + 4; j++) v[perm(j)] = twiddle_j<true>(s0[17 * j], t, j);
     OVS_FENCE();
   }
   dft16_perm2nat<true>(v);
@@ -408,20 +300,13 @@ __host__ __device__ __forceinline__ void phase_d(const double2 *tw2, int tid, do
 }
 
 // ---- phase E: backward pass 1 into registers: v[k] = block position tid + 256*k (first D positions are discarded)
-template <int GQ = 4>
 __host__ __device__ __forceinline__ void phase_e(const double2 *tw1, int tid, const double2 *sm, double2 (&v)[16]) {
   const double2 *s0 = sm + tid + (tid >> 4);
+  const Tw6 t = load_tw6(tw1, 256, tid);
 #pragma unroll
-  for (int q = 0; q < 16; q += GQ) {
+  for (int q = 0; q < 16; q += 4) {
 #pragma unroll
-    for (int j = q; j < q + GQ; j++) {
-      if (j) {
-        const double2 w = tw1[(j - 1) * 256 + tid];
-        v[perm(j)] = cmul<true>(s0[272 * j], w.x, w.y);
-      } else {
-        v[0] = s0[0];
-      }
-    }
+    for (int j = q; j < q + 4; j++) v[perm(j)] = twiddle_j<true>(s0[272 * j], t, j);
     OVS_FENCE();
   }
   dft16_perm2nat<true>(v);

@@ -39,9 +39,9 @@ void fir_effective_taps(const int64_t *c, int n_taps, int ftype, int64_t *eff);
 bool fir_ovs_geometry(int n_taps, uint32_t C, int interleaved);
 int fir_ovs_discard(int n_taps);
 double fir_ovs_error_bound(const Fmt &in, double l1);
-void fir_ovs_tables(double2 *tw1 /*[15][256]*/, double2 *tw2 /*[15][16]*/);
+void fir_ovs_tables(double2 *tw1 /*[6][256]*/, double2 *tw2 /*[6][16]*/);
 void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs /*[16][256]*/);
-cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw /*[15][256] + [15][16]*/, const double2 *hs, double *resid, cudaStream_t st);
+cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw /*[6][256] + [6][16]*/, const double2 *hs, double *resid, cudaStream_t st);
 // q24 path: W_in 17..24 in int32 containers, W_c <= 16: coefficient pairs in the DP2A 16-bit lanes, three sample byte planes.
 bool fir_q24_supported(const Fmt &in, const Fmt &coeff, const Fmt &acc, const Fmt &out, int n_taps, int ftype);
 void fir_q24_pack(const int64_t *c, int n_taps, int ftype, uint32_t *pk, int pk_words);

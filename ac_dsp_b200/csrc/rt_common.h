@@ -218,7 +218,7 @@ struct b2d_fir {
   // overlap-save evaluation of long q15 filters (fir_ovs.cu): twiddle tables, per-channel spectra (prepared before the first
   // long call after a load), the a-priori error bound of the loaded taps, the optional residual monitor
   int ovs_mode = 0;               // 0: off, 1: long calls, 2: every call (B2D_FIR_OVS=2, tests)
-  double2 *d_tw = nullptr;        // [15][256] + [15][16]
+  double2 *d_tw = nullptr;        // [6][256] + [6][16]
   double2 *d_hs = nullptr;        // [C][4096]
   std::vector<char> hs_stale;     // per channel
   double ovs_bound = 0.0;

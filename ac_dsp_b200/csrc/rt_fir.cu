@@ -65,8 +65,8 @@ extern "C" int b2d_fir_create(b2d_fir **out, const b2d_fir_desc *desc) {
     const char *ov = getenv("B2D_FIR_OVS");        // 0: never, 2: every call whatever its length (tests), default: long calls
     h->ovs_mode = ov ? (*ov == '0' ? 0 : (*ov == '2' ? 2 : 1)) : 1;
     if (h->ovs_mode) {
-      std::vector<double2> tw(15 * 256 + 15 * 16);
-      fir_ovs_tables(tw.data(), tw.data() + 15 * 256);
+      std::vector<double2> tw(6 * 256 + 6 * 16);
+      fir_ovs_tables(tw.data(), tw.data() + 6 * 256);
       e = cudaMalloc(&h->d_tw, tw.size() * sizeof(double2));
       if (e == cudaSuccess) e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice);
       if (e == cudaSuccess) e = cudaMalloc(&h->d_hs, (size_t)C * 4096 * sizeof(double2));

@@ -47,7 +47,7 @@ static void run_case(const char *name, int np, uint32_t C, int n_taps, size_t n,
     for (size_t i = 0; i < n; i++) xin[np == 2 ? i * 2 + c : (size_t)c * n + i] = (uint16_t)x[c][i];
     for (int i = 0; i < T; i++) tail[(size_t)c * T + i] = (uint16_t)tl[c][i];
   }
-  std::vector<double2> tw1(15 * 256), tw2(15 * 16), hs((size_t)C * kN);
+  std::vector<double2> tw1(6 * 256), tw2(6 * 16), hs((size_t)C * kN);
   fir_ovs_tables(tw1.data(), tw2.data());
   double l1max = 0;
   for (uint32_t c = 0; c < C; c++) {
@@ -79,7 +79,7 @@ static void run_case(const char *name, int np, uint32_t C, int n_taps, size_t n,
         else { if (in) phase_a<1, true>(a, tw1.data(), c0, (long long)blk, t, sm.data()); else phase_a<1, false>(a, tw1.data(), c0, (long long)blk, t, sm.data()); }
       }
       for (int t = 0; t < kThreads; t++) phase_b(tw2.data(), t, sm.data());
-      for (int t = 0; t < kThreads; t++) phase_c(a, np == 2 ? 0 : c0, t, sm.data());
+      for (int t = 0; t < kThreads; t++) phase_c(hs.data() + (size_t)(np == 2 ? 0 : c0) * kN, t, sm.data());
       for (int t = 0; t < kThreads; t++) phase_d(tw2.data(), t, sm.data());
       for (int t = 0; t < kThreads; t++) {
         double2 v[16];
