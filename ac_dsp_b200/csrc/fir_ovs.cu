@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     half_sync(half);
     double2 v[16];
     phase_e(tw1, tid, sm, v);
-    half_sync(half);            // the buffer is free for the next item's phase A
+    // no barrier here: phase A of the next item writes exactly the shared-memory elements this thread has just read
+    // (positions tid + 256 j in both), and nobody else touches them before the barrier that follows phase A
 
     if (a.resid) {
 #pragma unroll
@@ -199,7 +200,8 @@ int fir_ovs_discard(int n_taps) { return n_taps <= 1 ? 256 : ((n_taps - 1 + 255)
 
 bool fir_ovs_geometry(int n_taps, uint32_t C, int interleaved) {
   if (n_taps < kMinTaps || n_taps > kMaxTapsOvs) return false;
-  return !interleaved || C == 1 || C == 2;
+  if (interleaved && C == 2) return true;              // one IQ pair = one complex sequence
+  return (!interleaved || C == 1) && C <= 65535;       // planar real channels: one grid row per channel
 }
 
 // Upper bound of |computed - exact| for samples of format `in` and taps of 1-norm l1 (see the header of this file).
