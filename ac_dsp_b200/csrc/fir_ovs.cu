@@ -59,7 +59,9 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
 // global memory.  blockIdx.y is the channel (0 for an IQ pair); half h of CTA b takes the channel's work items 2 b + h,
 // 2 b + h + 2 gridDim.x, ...  A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one
 // real channel (NP == 1).
-template <int NP, bool FASTOUT>
+// RAW (IQ pairs only, A/B switch B2D_OVS_RAW): the samples of a half's next item are loaded into registers before the epilogue
+// of the current one when that item is an interior block.
+template <int NP, bool FASTOUT, bool RAW>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
   double2 *tw1 = smem, *tw2 = smem + 6 * 256, *hsm = smem + kTwElems;
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   double2 *sm = smem + kTwElems + kN + half * kSmElems;
   const int k0 = a.D >> 8;
   double rmax = 0.0;
+  uint32_t raw[16];
+  bool have_raw = false;
   for (unsigned item = 2 * blockIdx.x + half; item < a.per_channel; item += 2 * gridDim.x) {
     const long long blk = item;
     const bool interior = block_interior<NP>(a, blk);
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         }
       }
     }
-    if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
+    if (RAW && have_raw) phase_a_raw(a, tw1, tid, raw, sm);
+    else if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
     else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
     phase_b(tw2, tid, sm);
@@ -99,6 +104,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     phase_e(tw1, tid, sm, v);
     // no barrier here: phase A of the next item writes exactly the shared-memory elements this thread has just read
     // (positions tid + 256 j in both), and nobody else touches them before the barrier that follows phase A
+    if (RAW) {
+      const unsigned nx = item + 2 * gridDim.x;
+      have_raw = nx < a.per_channel && block_interior<NP>(a, (long long)nx);
+      if (have_raw) load_block(a, (long long)nx, tid, raw);
+    }
 
     if (a.resid) {
 #pragma unroll
@@ -260,11 +270,11 @@ void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
     }
 }
 
-template <int NP, bool FASTOUT>
+template <int NP, bool FASTOUT, bool RAW = false>
 static cudaError_t launch_k(const Args &a, dim3 grid, cudaStream_t st) {
-  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
-  fir_ovs_kernel<NP, FASTOUT><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  fir_ovs_kernel<NP, FASTOUT, RAW><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -292,6 +302,9 @@ cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 
   // a CTA is bound to one channel (its spectrum sits in shared memory): the SMs are divided among the channels
   const unsigned per_ch_ctas = (unsigned)std::min<size_t>((per_channel + 1) / 2, std::max<unsigned>(1u, (unsigned)sms / chans));
   const dim3 grid(per_ch_ctas, chans);
+  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt): 123.9 vs 122.5 G IQ samples/s at 256 taps; B2D_OVS_RAW=0 turns it off
+  static const bool raw = [] { const char *v = getenv("B2D_OVS_RAW"); return !(v && *v == '0'); }();
+  if (iq && raw) return a.fastout ? launch_k<2, true, true>(a, grid, st) : launch_k<2, false, true>(a, grid, st);
   if (iq) return a.fastout ? launch_k<2, true>(a, grid, st) : launch_k<2, false>(a, grid, st);
   return a.fastout ? launch_k<1, true>(a, grid, st) : launch_k<1, false>(a, grid, st);
 }
