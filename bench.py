@@ -390,7 +390,7 @@ def measure(name, wl, args, ctx, want_cpu):
         f = E.ac_fir_load_coeffs(infmt, ACC40, Q15, ACC40, wl["taps"], "SHIFT_REG", n_channels=C, layout=wl["layout"],
                                  device=local, comm=comm, root=0)
         f.load(h if rank == 0 else None)     # rank 0 owns the set: one ncclBroadcast (the only collective on this path)
-        launches_per_step = 2          # fir_q15_kernel + history carry
+        launches_per_step = 2          # fir_ovs_kernel (or fir_q15_kernel) + history carry
     elif wl["kind"] == "intgdump":
         class _Id:   # adapter: fixed token array, out= ignored (outputs are 1/64 of the input)
             def __init__(self):
@@ -568,8 +568,9 @@ def measure(name, wl, args, ctx, want_cpu):
         traffic, traffic_src = None, None
         for tp in ("r02_traffic.json", "r01_traffic.json"):
             tp = os.path.join(ROOT, "profiles", tp)
-            t = json.load(open(tp)).get(name) if os.path.exists(tp) else None
-            if t and t.get("path", path) != path:
+            tab = json.load(open(tp)) if os.path.exists(tp) else {}
+            t = tab.get(f"{name}@{path}") or tab.get(name)
+            if t and t.get("path", "fir_q15" if wl["kind"] == "fir" else path) != path:
                 t = None                      # the capture belongs to another kernel family than the one that ran
             if t:   # measured DRAM bytes per unit (one ncu --set full capture) scaled to this launch's units
                 traffic = t["dram_bytes_per_unit"] * units_per_step
@@ -587,6 +588,17 @@ def measure(name, wl, args, ctx, want_cpu):
                                 "frac": tmacs / (148 * 64 * sm_mhz * 1e6 / 1e12),
                                 "note": "CUDA-core IDP.2A issue ceiling at the sampled SM clock (tensor cores excluded by the north star)"}
         if wl["macs_per_unit"] and path == "fir_ovs":
+            # FP64 instructions per complex point of a 4096-point block, counted by ncu on the final kernel
+            # (profiles/r02_fir_ovs_ncu_summary.json: 1310 per thread and block of 16 points); FP64 issue ceiling of sm_100a:
+            # 64 lanes / clk / SM (ncu: sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained)
+            T_ = wl["taps"] - 1
+            Lb = 4096 - ((T_ + 255) // 256) * 256
+            points = units_per_step * (1.0 if wl["unit_is_iq"] else 0.5) * 4096.0 / Lb
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            tinst = 81.9 * points / (ms_per_step * 1e-3) / 1e12
+            roof["fp64_pipe"] = {"achieved_tinst_s": tinst, "ceiling_tinst_s": 148 * 64 * sm_mhz * 1e6 / 1e12,
+                                 "frac": tinst / (148 * 64 * sm_mhz * 1e6 / 1e12),
+                                 "note": "81.9 FP64 instructions per complex point (ncu), blocks of 4096 points yield %d outputs" % Lb}
             roof["note"] = ("overlap-save: 4096-point FP64 FFT blocks in registers and shared memory (about 80 FP64 instructions and 200 bytes of "
                             "shared-memory traffic per complex sample whatever the tap count), exact by an a-priori error bound on the loaded taps; "
                             "B2D_FIR_OVS=0 selects the tap-by-tap DP2A kernel (fir_q15)")
