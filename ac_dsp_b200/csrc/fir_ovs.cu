@@ -54,6 +54,42 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
   return a.acc.S ? (b >> a.wrap_shr) : (long long)((unsigned long long)b >> a.wrap_shr);
 }
 
+// Phase E and the interior epilogue in one: the last butterfly stage is done one group of four at a time, each group converted
+// and stored while the next one is computed (A/B switch B2D_OVS_FUSE).
+template <int NP>
+__device__ __forceinline__ void phase_e_store(const Args &a, const double2 *tw1, uint32_t c0, long long blk, int tid, const double2 *sm, int k0) {
+  double2 v[16];
+  const double2 *s0 = sm + tid + (tid >> 4);
+  const Tw6 t = load_tw6(tw1, 256, tid);
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+#pragma unroll
+    for (int j = q; j < q + 4; j++) v[perm(j)] = twiddle_j<true>(s0[272 * j], t, j);
+    OVS_FENCE();
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) bfly4<true>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  twiddle16<true>(v);
+  long long *yp = NP == 2 ? (long long *)a.y + 2 * (blk * a.L - a.D + tid) : (long long *)a.y + (size_t)c0 * a.n + (2 * blk * a.L - a.D + tid);
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    bfly4<true>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int k = 4 * q + b;
+      if (k == 0 || k < k0) continue;
+      if (NP == 2) {
+        longlong2 o; o.x = ovs_to_acc_magic(v[k].x, a); o.y = ovs_to_acc_magic(v[k].y, a);
+        *(longlong2 *)(yp + 512 * k) = o;
+      } else {
+        yp[256 * k] = ovs_to_acc_magic(v[k].x, a);
+        yp[256 * k + a.L] = ovs_to_acc_magic(v[k].y, a);
+      }
+    }
+    OVS_FENCE();
+  }
+}
+
 // Persistent CTA of two independent halves (256 threads each, own block buffer, own named barrier) that share one copy of
 // the twiddle tables and of ONE channel's spectrum in shared memory -- the transform reads nothing but its samples from
 // global memory.  blockIdx.y is the channel (0 for an IQ pair); half h of CTA b takes the channel's work items 2 b + h,
@@ -61,7 +97,7 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
 // real channel (NP == 1).
 // RAW (IQ pairs only, A/B switch B2D_OVS_RAW): the samples of a half's next item are loaded into registers before the epilogue
 // of the current one when that item is an interior block.
-template <int NP, bool FASTOUT, bool RAW>
+template <int NP, bool FASTOUT, bool RAW, bool FUSE>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   extern __shared__ __align__(16) double2 smem[];
   double2 *tw1 = smem, *tw2 = smem + 6 * 256, *hsm = smem + kTwElems;
@@ -100,6 +136,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     half_sync(half);
     phase_d(tw2, tid, sm);
     half_sync(half);
+    if (FUSE && FASTOUT && interior && a.magic_shl && !a.resid) {
+      phase_e_store<NP>(a, tw1, c0, blk, tid, sm, k0);
+      if (RAW) {
+        const unsigned nx = item + 2 * gridDim.x;
+        have_raw = nx < a.per_channel && block_interior<NP>(a, (long long)nx);
+        if (have_raw) load_block(a, (long long)nx, tid, raw);
+      }
+      continue;
+    }
     double2 v[16];
     phase_e(tw1, tid, sm, v);
     // no barrier here: phase A of the next item writes exactly the shared-memory elements this thread has just read
@@ -270,12 +315,20 @@ void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
     }
 }
 
+template <int NP, bool FASTOUT, bool RAW, bool FUSE>
+static cudaError_t launch_k2(const Args &a, dim3 grid, cudaStream_t st) {
+  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, RAW, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return e;
+  fir_ovs_kernel<NP, FASTOUT, RAW, FUSE><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return cudaGetLastError();
+}
 template <int NP, bool FASTOUT, bool RAW = false>
 static cudaError_t launch_k(const Args &a, dim3 grid, cudaStream_t st) {
-  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-  if (e != cudaSuccess) return e;
-  fir_ovs_kernel<NP, FASTOUT, RAW><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return cudaGetLastError();
+  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt): real channels, 1024 taps 188.8 vs 184.4 G samples/s; IQ pair, 256 taps
+  // 121.8 vs 123.9 -- on by default for the real-channel kernel only
+  static const bool fuse = [] { const char *v = getenv("B2D_OVS_FUSE"); return v ? *v == '1' : NP == 1; }();
+  if (FASTOUT && fuse) return launch_k2<NP, FASTOUT, RAW, true>(a, grid, st);
+  return launch_k2<NP, FASTOUT, RAW, false>(a, grid, st);
 }
 
 cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 *hs, double *resid, cudaStream_t st) {

@@ -679,7 +679,7 @@ def test_reg_share_vs_reference_outputs(engine, cid, path):
         assert int(f.run_window(reg)) == int(want[n]), n
 
 
-def test_reg_share_random_and_errors(engine, oracle):
+def test_reg_share_random_and_errors(engine, oracle, ovs):
     rng = np.random.default_rng(41)
     for N, ft, fc in ((256, "FOLD_EVEN_ANTI", (15, 1)), (255, "FOLD_ODD_ANTI", (15, 1)), (256, "FOLD_EVEN_ANTI", Q15), (64, "SHIFT_REG", Q15)):
         f = engine.ac_fir_reg_share(N, Q15, ACC40, fc, ACC40, 1, 1, 0, ft, n_channels=2, layout="interleaved")
@@ -692,6 +692,8 @@ def test_reg_share_random_and_errors(engine, oracle):
             assert np.array_equal(y[:, c].astype(np.int64), ob[c].run(x[:, c], ram)), (N, ft, c)
         dl = f.delay_line()
         assert [int(v) for v in dl] == [ob[c].delay_out() for c in range(2)]
+        if f.path != "fir_wide":
+            check_ovs(f, ovs, N)                  # the anti-symmetric folds through the overlap-save evaluation as well
     with pytest.raises(engine.B2dError):      # ac_fir_reg_share does not dispatch TRANSPOSED
         engine.ac_fir_reg_share(16, Q15, ACC40, Q15, ACC40, 1, 1, 0, "TRANSPOSED")
     with pytest.raises(engine.B2dError):      # ... and the const / load / prog classes do not dispatch _ANTI
