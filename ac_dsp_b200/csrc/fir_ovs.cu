@@ -17,6 +17,7 @@
 // kErrK = 76 is used.  For 256 full-scale Q15 taps (||h||_1 <= 2^23) the bound is 0.21; measured residuals
 // |v - rint(v)| stay below 1e-4 (tests/test_fir_ovs.py, tests/cpp/fir_ovs_check.cu print them).
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -286,6 +287,7 @@ void fir_ovs_tables(double2 *tw1, double2 *tw2) {
 // hs[j * 256 + c] = H[spectrum_index(16 c + j)] / 4096.  Direct sums in extended precision, blocked (16 taps per partial
 // sum) so that the accumulated rounding stays below 2^-56 ||h||_1; real taps: H[N - f] = conj(H[f]).
 void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
+  static_assert(LDBL_MANT_DIG >= 64, "the spectrum is summed in extended precision (x87 80-bit or IEEE binary128)");
   const long double tau = 6.283185307179586476925286766559005768L;
   std::vector<long double> wr(kN), wi(kN);
   for (int m = 0; m < kN; m++) {

@@ -154,3 +154,69 @@ def test_device_buffers_unaligned_views_and_state(engine, oracle, forced):
     out = torch.empty((n - 20001 + 1, 2), dtype=torch.int64, device="cuda")
     assert np.array_equal(g.run(xd[20001:], out=out.reshape(-1)[2:]).cpu().numpy(), want[20001:])   # output 16 bytes in: still aligned
     assert g.path == "fir_ovs"
+
+
+FUZZ_SEED = int(os.environ.get("B2D_FUZZ_SEED", "0"))
+Q_MODES = ["AC_TRN", "AC_RND", "AC_TRN_ZERO", "AC_RND_ZERO", "AC_RND_INF", "AC_RND_MIN_INF", "AC_RND_CONV", "AC_RND_CONV_ODD"]
+O_MODES = ["AC_WRAP", "AC_SAT", "AC_SAT_ZERO", "AC_SAT_SYM"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(12))
+def test_random_q15_family_draws(engine, oracle, forced, i):
+    """Random members of the format family the path serves (samples and taps of up to 16 bits, signed or not, an
+    accumulator that takes the products without dropping bits and wraps, any OUT_TYPE incl. every Q / O mode), random tap
+    counts 96..2048, layouts, chunkings and a coefficient change: engine == Oracle B.  B2D_FUZZ_SEED draws again."""
+    rng = np.random.default_rng(FUZZ_SEED * 1000 + 77 + i)
+    Wi, Wc = int(rng.integers(2, 17)), int(rng.integers(2, 17))
+    fi = (Wi, int(rng.integers(-2, Wi + 3)), bool(rng.integers(0, 2)))
+    fc = (Wc, int(rng.integers(-2, Wc + 3)), bool(rng.integers(0, 2)))
+    Fp = (fi[0] - fi[1]) + (fc[0] - fc[1])
+    Fa = Fp + int(rng.integers(0, 5))                                        # exact left shift into the accumulator
+    Wa = int(rng.integers(12, 65))
+    fa = (Wa, Wa - Fa, bool(rng.integers(0, 4)), ["AC_TRN", "AC_RND"][int(rng.integers(0, 2))], "AC_WRAP")
+    Wo = int(rng.integers(4, 65))
+    fo = (Wo, Wo - (Fa - int(rng.integers(0, 10))), bool(rng.integers(0, 2)), Q_MODES[int(rng.integers(0, 8))], O_MODES[int(rng.integers(0, 4))])
+    if i % 3 == 0:
+        fo = fa
+    taps = int(rng.choice([96, 100, 128, 255, 256, 257, 511, 512, 513, 1000, 1024, 1500, 2048]))
+    ft = ["SHIFT_REG", "C_BUFF", "TRANSPOSED", "FOLD_EVEN", "FOLD_ODD"][int(rng.integers(0, 5))]
+    if ft == "FOLD_EVEN" and taps % 2:
+        taps += 1
+    if ft == "FOLD_ODD" and taps % 2 == 0:
+        taps -= 1
+    if ft == "FOLD_ODD" and not (fa[2] and Fa >= fi[0] - fi[1] and fi[0] + 2 + (Fa - (fi[0] - fi[1])) <= fa[0]):
+        ft = "SHIFT_REG"                                                     # the pre-add must be exact in ACC_TYPE for the q15 family
+    layout, C = [("interleaved", 2), ("planar", 1), ("planar", 2), ("planar", 5)][int(rng.integers(0, 4))]
+    n = int(rng.integers(1, 4)) * 4096 + int(rng.integers(0, 4096))
+    x = np.stack([oracle.rand_raw(rng, fi, n) for _ in range(C)])
+    hs1 = [oracle.rand_raw(rng, fc, taps) for _ in range(C)]
+    hs2 = [oracle.rand_raw(rng, fc, taps) for _ in range(C)]
+    if layout == "interleaved":
+        hs1, hs2 = [hs1[0]] * C, [hs2[0]] * C
+    f = engine.ac_fir_load_coeffs(fi, fo, fc, fa, taps, ft, n_channels=C, layout=layout)
+    obs = [oracle.FirB(fi, fc, fa, fo, taps, ft) for _ in range(C)]
+    cut1, cut2 = int(rng.integers(1, n // 2)), int(rng.integers(n // 2, n))
+    want = [[] for _ in range(C)]
+    got = []
+    for k, (lo, hi) in enumerate(((0, cut1), (cut1, cut2), (cut2, n))):
+        if k in (0, 2):
+            for c in range(C):
+                hh = (hs1 if k == 0 else hs2)[c]
+                obs[c].load(hh)
+                f.load(hh, channel=c)
+        for c in range(C):
+            want[c].append(obs[c].run(x[c, lo:hi]))
+        seg = x[:, lo:hi].astype(np.int16)
+        seg = seg[0] if C == 1 else (np.ascontiguousarray(seg.T) if layout == "interleaved" else np.ascontiguousarray(seg))
+        y = f.run(seg)
+        got.append(y.reshape(1, -1) if C == 1 else (y.T if layout == "interleaved" else y))
+    bound, resid = f.ovs_margin()
+    info = (fi, fc, fa, fo, taps, ft, layout, C, n, f.path, bound, resid)
+    if f.path == "fir_ovs":
+        assert 0 <= resid < 0.01, info
+    else:
+        assert f.path == "fir_q15" and bound >= 0.49, info                    # refused by the error bound only
+    y = np.concatenate(got, axis=1).astype(np.int64)
+    for c in range(C):
+        assert np.array_equal(y[c], np.concatenate(want[c])), (info, c)
