@@ -56,7 +56,7 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
 }
 
 // Phase E and the interior epilogue in one: the last butterfly stage is done one group of four at a time, each group converted
-// and stored while the next one is computed (A/B switch B2D_OVS_FUSE).
+// and stored while the next one is computed (used by the real-channel kernel).
 template <int NP>
 __device__ __forceinline__ void phase_e_store(const Args &a, const double2 *tw1, uint32_t c0, long long blk, int tid, const double2 *sm, int k0) {
   double2 v[16];
@@ -96,10 +96,14 @@ __device__ __forceinline__ void phase_e_store(const Args &a, const double2 *tw1,
 // global memory.  blockIdx.y is the channel (0 for an IQ pair); half h of CTA b takes the channel's work items 2 b + h,
 // 2 b + h + 2 gridDim.x, ...  A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one
 // real channel (NP == 1).
-// RAW (IQ pairs only, A/B switch B2D_OVS_RAW): the samples of a half's next item are loaded into registers before the epilogue
-// of the current one when that item is an interior block.
-template <int NP, bool FASTOUT, bool RAW, bool FUSE>
+// Two choices were A/B-ed on a B200 and are fixed per instantiation (profiles/r02_ovs_variants.txt):
+//   RAW (IQ pairs): the samples of a half's next interior item are loaded into registers before the epilogue of the current one
+//       (123.9 vs 122.5 G IQ samples/s at 256 taps; with the 2-byte loads of real channels it loses);
+//   FUSE (real channels): the last butterfly stage is interleaved with the interior epilogue (188.8 vs 184.4 G real samples/s at
+//       1024 taps; IQ pairs: 121.8 vs 123.9).
+template <int NP, bool FASTOUT>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
+  constexpr bool RAW = NP == 2, FUSE = NP == 1;
   extern __shared__ __align__(16) double2 smem[];
   double2 *tw1 = smem, *tw2 = smem + 6 * 256, *hsm = smem + kTwElems;
   const uint32_t c0 = blockIdx.y;
@@ -131,10 +135,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     else if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
     else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
+    // passes 2, 3 and their mirrors exchange data inside groups of 16 threads only (positions 256 b + ..., b = tid >> 4: a thread
+    // of phase C reads what the threads of its own group wrote in phase B, and so on): a warp-level barrier is enough
     phase_b(tw2, tid, sm);
-    half_sync(half);
+    __syncwarp();
     phase_c(hsm, tid, sm);
-    half_sync(half);
+    __syncwarp();
     phase_d(tw2, tid, sm);
     half_sync(half);
     if (FUSE && FASTOUT && interior && a.magic_shl && !a.resid) {
@@ -317,20 +323,12 @@ void fir_ovs_spectrum(const int64_t *eff, int n_taps, double2 *hs) {
     }
 }
 
-template <int NP, bool FASTOUT, bool RAW, bool FUSE>
-static cudaError_t launch_k2(const Args &a, dim3 grid, cudaStream_t st) {
-  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT, RAW, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-  if (e != cudaSuccess) return e;
-  fir_ovs_kernel<NP, FASTOUT, RAW, FUSE><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return cudaGetLastError();
-}
-template <int NP, bool FASTOUT, bool RAW = false>
+template <int NP, bool FASTOUT>
 static cudaError_t launch_k(const Args &a, dim3 grid, cudaStream_t st) {
-  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt): real channels, 1024 taps 188.8 vs 184.4 G samples/s; IQ pair, 256 taps
-  // 121.8 vs 123.9 -- on by default for the real-channel kernel only
-  static const bool fuse = [] { const char *v = getenv("B2D_OVS_FUSE"); return v ? *v == '1' : NP == 1; }();
-  if (FASTOUT && fuse) return launch_k2<NP, FASTOUT, RAW, true>(a, grid, st);
-  return launch_k2<NP, FASTOUT, RAW, false>(a, grid, st);
+  const cudaError_t e = cudaFuncSetAttribute(fir_ovs_kernel<NP, FASTOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return e;
+  fir_ovs_kernel<NP, FASTOUT><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 *hs, double *resid, cudaStream_t st) {
@@ -357,9 +355,6 @@ cudaError_t launch_fir_ovs(const FirLaunch &p, const double2 *tw, const double2 
   // a CTA is bound to one channel (its spectrum sits in shared memory): the SMs are divided among the channels
   const unsigned per_ch_ctas = (unsigned)std::min<size_t>((per_channel + 1) / 2, std::max<unsigned>(1u, (unsigned)sms / chans));
   const dim3 grid(per_ch_ctas, chans);
-  // r02 A/B on a B200 (profiles/r02_ovs_variants.txt): 123.9 vs 122.5 G IQ samples/s at 256 taps; B2D_OVS_RAW=0 turns it off
-  static const bool raw = [] { const char *v = getenv("B2D_OVS_RAW"); return !(v && *v == '0'); }();
-  if (iq && raw) return a.fastout ? launch_k<2, true, true>(a, grid, st) : launch_k<2, false, true>(a, grid, st);
   if (iq) return a.fastout ? launch_k<2, true>(a, grid, st) : launch_k<2, false>(a, grid, st);
   return a.fastout ? launch_k<1, true>(a, grid, st) : launch_k<1, false>(a, grid, st);
 }
