@@ -249,6 +249,8 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
   }
   for (uint32_t c = 0; c < C; c++) {
     if (channel >= 0 && (uint32_t)channel != c) continue;
+    // re-loading the taps a channel already has (ac_fir_prog_coeffs passes its array on every call) keeps its spectrum
+    const bool same = h->ch_loaded[c] && std::equal(v.begin(), v.end(), h->h_coeff.begin() + c * N);
     std::copy(v.begin(), v.end(), h->h_coeff.begin() + c * N);
     h->ch_loaded[c] = 1;
     CU(cudaMemcpy(h->d_coeff64 + c * N, v.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -258,7 +260,7 @@ extern "C" int b2d_fir_load(b2d_fir *h, const void *coeff_raw, size_t n, int32_t
       else fir_q24_pack(v.data(), (int)N, h->d.ftype, pk.data(), h->pk_words);
       CU(cudaMemcpy(h->d_coeff_pk + (size_t)c * h->pk_words, pk.data(), h->pk_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
-    if (h->d_hs) h->hs_stale[c] = 1;
+    if (h->d_hs && !same) h->hs_stale[c] = 1;
     if (h->path == PATH_WIDE) {
       std::vector<int32_t> w(h->wide_words, 0);
       fir_wide_pack(v.data(), (int)N, h->d.ftype, h->wide_mode, w.data(), h->wide_words);
