@@ -56,7 +56,7 @@ __device__ __forceinline__ int64_t ovs_to_acc_magic(double d, const Args &a) {
 }
 
 // Phase E and the interior epilogue in one: the last butterfly stage is done one group of four at a time, each group converted
-// and stored while the next one is computed (used by the real-channel kernel).
+// and stored while the next one is computed.
 template <int NP>
 __device__ __forceinline__ void phase_e_store(const Args &a, const double2 *tw1, uint32_t c0, long long blk, int tid, const double2 *sm, int k0) {
   double2 v[16];
@@ -96,14 +96,11 @@ __device__ __forceinline__ void phase_e_store(const Args &a, const double2 *tw1,
 // global memory.  blockIdx.y is the channel (0 for an IQ pair); half h of CTA b takes the channel's work items 2 b + h,
 // 2 b + h + 2 gridDim.x, ...  A work item is one block of an IQ pair (NP == 2) or a pair of consecutive blocks of one
 // real channel (NP == 1).
-// Two choices were A/B-ed on a B200 and are fixed per instantiation (profiles/r02_ovs_variants.txt):
-//   RAW (IQ pairs): the samples of a half's next interior item are loaded into registers before the epilogue of the current one
-//       (123.9 vs 122.5 G IQ samples/s at 256 taps; with the 2-byte loads of real channels it loses);
-//   FUSE (real channels): the last butterfly stage is interleaved with the interior epilogue (188.8 vs 184.4 G real samples/s at
-//       1024 taps; IQ pairs: 121.8 vs 123.9).
+// Interior blocks whose accumulator takes the bit-pattern conversion run phase E fused with the epilogue (phase_e_store).
+// Measured and dropped (profiles/r02_ovs_variants.txt): the next block's samples carried in registers across the epilogue
+// (+1 % before the warp-level barriers, -3 % after), no L2 prefetch (-6 % on real channels).
 template <int NP, bool FASTOUT>
 __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
-  constexpr bool RAW = NP == 2, FUSE = NP == 1;
   extern __shared__ __align__(16) double2 smem[];
   double2 *tw1 = smem, *tw2 = smem + 6 * 256, *hsm = smem + kTwElems;
   const uint32_t c0 = blockIdx.y;
@@ -114,8 +111,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
   double2 *sm = smem + kTwElems + kN + half * kSmElems;
   const int k0 = a.D >> 8;
   double rmax = 0.0;
-  uint32_t raw[16];
-  bool have_raw = false;
   for (unsigned item = 2 * blockIdx.x + half; item < a.per_channel; item += 2 * gridDim.x) {
     const long long blk = item;
     const bool interior = block_interior<NP>(a, blk);
@@ -131,8 +126,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
         }
       }
     }
-    if (RAW && have_raw) phase_a_raw(a, tw1, tid, raw, sm);
-    else if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
+    if (interior) phase_a<NP, true>(a, tw1, c0, blk, tid, sm);
     else phase_a<NP, false>(a, tw1, c0, blk, tid, sm);
     half_sync(half);
     // passes 2, 3 and their mirrors exchange data inside groups of 16 threads only (positions 256 b + ..., b = tid >> 4: a thread
@@ -143,24 +137,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) fir_ovs_kernel(Args a) {
     __syncwarp();
     phase_d(tw2, tid, sm);
     half_sync(half);
-    if (FUSE && FASTOUT && interior && a.magic_shl && !a.resid) {
+    if (FASTOUT && interior && a.magic_shl && !a.resid) {
       phase_e_store<NP>(a, tw1, c0, blk, tid, sm, k0);
-      if (RAW) {
-        const unsigned nx = item + 2 * gridDim.x;
-        have_raw = nx < a.per_channel && block_interior<NP>(a, (long long)nx);
-        if (have_raw) load_block(a, (long long)nx, tid, raw);
-      }
       continue;
     }
     double2 v[16];
     phase_e(tw1, tid, sm, v);
     // no barrier here: phase A of the next item writes exactly the shared-memory elements this thread has just read
     // (positions tid + 256 j in both), and nobody else touches them before the barrier that follows phase A
-    if (RAW) {
-      const unsigned nx = item + 2 * gridDim.x;
-      have_raw = nx < a.per_channel && block_interior<NP>(a, (long long)nx);
-      if (have_raw) load_block(a, (long long)nx, tid, raw);
-    }
 
     if (a.resid) {
 #pragma unroll

@@ -244,31 +244,6 @@ __host__ __device__ __forceinline__ void phase_a(const Args &a, const double2 *t
   for (int j = 0; j < 16; j++) s0[272 * j] = twiddle_j<false>(v[perm(j)], t, j);
 }
 
-// The same phase in two steps, for a kernel that loads the next item's samples before the epilogue of the current one:
-// load_block fetches the 16 complex samples of one thread of an INTERIOR block of an IQ pair as packed 16-bit pairs,
-// phase_a_raw converts and transforms them.
-__host__ __device__ __forceinline__ void load_block(const Args &a, long long blk, int tid, uint32_t (&raw)[16]) {
-  const uint32_t *p = (const uint32_t *)a.x + (blk * a.L - a.D + tid);
-#pragma unroll
-  for (int k = 0; k < 16; k++) raw[k] = ld_stream(p + 256 * k);
-}
-__host__ __device__ __forceinline__ void phase_a_raw(const Args &a, const double2 *tw1, int tid, const uint32_t (&raw)[16], double2 *sm) {
-  double2 v[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const uint32_t w = raw[k];
-    const int vi = a.xs ? (int)(int16_t)(w & 0xFFFF) : (int)(w & 0xFFFF);
-    const int vq = a.xs ? ((int)w >> 16) : (int)(w >> 16);
-    v[k] = make_double2((double)vi, (double)vq);
-  }
-  dft16_nat2perm<false>(v);
-  OVS_FENCE();
-  const Tw6 t = load_tw6(tw1, 256, tid);
-  double2 *s0 = sm + tid + (tid >> 4);
-#pragma unroll
-  for (int j = 0; j < 16; j++) s0[272 * j] = twiddle_j<false>(v[perm(j)], t, j);
-}
-
 // ---- phase B: pass 2 (stride 16 inside each block of 256), twiddle W_256^(u*j).
 // position 256 b + u + 16 k -> shared-memory index 272 b + u + 17 k
 __host__ __device__ __forceinline__ void phase_b(const double2 *tw2, int tid, double2 *sm) {

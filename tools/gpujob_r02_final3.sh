@@ -2,7 +2,8 @@
 # line, launch list + ncu --set full captures of fir_ovs (IQ pair and real channels), compute-sanitizer over the new kernel.
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/r02_pytest_gpu_final.txt
-for seed in 41 42 43; do B2D_FUZZ_SEED=$seed timeout 600 python -m pytest tests/test_zz_engine_fuzz.py -m gpu -q 2>&1 | tail -1; done | tee gpurun_out/r02_fuzz_41_43.txt
+for seed in 7 8 9; do B2D_FUZZ_SEED=$seed timeout 600 python -m pytest tests/test_fir_ovs.py -m gpu -q -k random_q15_family 2>&1 | tail -1; done | tee gpurun_out/r02_ovs_family_fuzz.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/r02_smoke.txt
 timeout 600 python bench.py > gpurun_out/r02_bench_fir256.json 2> gpurun_out/r02_bench_fir256.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err
 timeout 300 python bench.py --workload fir1024 --no-cpu --steps 20 --warmup 5 > gpurun_out/r02_bench_fir1024.json 2> gpurun_out/r02_bench_fir1024.err
