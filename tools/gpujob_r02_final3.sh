@@ -33,4 +33,4 @@ ls -la gpurun_out/r02_fir_ovs*_full.ncu-rep
 CS=/usr/local/cuda/bin/compute-sanitizer
 timeout 900 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_fir_ovs.py -x -q -m gpu -k "selection or device_buffers or (every_architecture and 257) or (formats and fmts0)" > gpurun_out/r02_sanitize_ovs_memcheck.log 2>&1; echo "fir_ovs memcheck rc=$?" | tee gpurun_out/r02_sanitize_ovs_summary.txt
 timeout 900 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_fir_ovs.py -x -q -m gpu -k "device_buffers or (every_architecture and 257 and SHIFT) or (formats and fmts0 and planar-3)" > gpurun_out/r02_sanitize_ovs_racecheck.log 2>&1; echo "fir_ovs racecheck rc=$?" | tee -a gpurun_out/r02_sanitize_ovs_summary.txt
-tail -3 gpurun_out/r02_sanitize_ovs_memcheck.log gpurun_out/r02_sanitize_ovs_racecheck.log
+tail -n 3 gpurun_out/r02_sanitize_ovs_memcheck.log; tail -n 3 gpurun_out/r02_sanitize_ovs_racecheck.log
