@@ -125,7 +125,14 @@ static bool fir_ovs_armed(const b2d_fir *h) {
   if (h->d.layout == B2D_INTERLEAVED && C == 2 && !std::equal(h->h_coeff.begin(), h->h_coeff.begin() + N, h->h_coeff.begin() + N)) return false;
   return h->ovs_bound < 0.49;
 }
-static size_t fir_ovs_min_n(const b2d_fir *h) { return h->ovs_mode == 2 ? 1 : 4 * (size_t)(4096 - fir_ovs_discard((int)h->d.n_taps)); }
+// Is a call of n samples per channel worth the overlap-save evaluation?  From four blocks per channel on.  Measured kernel
+// durations on a B200 (profiles/r02_ovs_crossover.txt): a single wave of the DP2A kernel takes 30 us at 256 taps (49 us at
+// 1024) however short the call, one round of overlap-save blocks 22 us, so the transform wins from the first full wave; below
+// four blocks the DP2A kernel runs a fraction of a tile.  B2D_FIR_OVS=2 takes every call (tests).
+static bool fir_ovs_worth(const b2d_fir *h, size_t n) {
+  if (h->ovs_mode == 2) return n > 0;
+  return n >= 4 * (size_t)(4096 - fir_ovs_discard((int)h->d.n_taps));
+}
 
 // Spectra of channels whose taps changed since the last long call (host, extended precision; fir_ovs_spectrum).
 static int fir_ovs_prepare(b2d_fir *h, cudaStream_t st) {
@@ -151,7 +158,7 @@ static int fir_ovs_prepare(b2d_fir *h, cudaStream_t st) {
 }
 
 static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream_t st, bool allow_ovs = false) {
-  if (allow_ovs && h->path == PATH_Q15 && p.n >= fir_ovs_min_n(h) && fir_ovs_armed(h))
+  if (allow_ovs && h->path == PATH_Q15 && fir_ovs_worth(h, p.n) && fir_ovs_armed(h))
     return launch_fir_ovs(p, h->d_tw, h->d_hs, h->d_resid, st);
   switch (h->path) {
     case PATH_Q15: return launch_fir_q15(p, st);
@@ -163,7 +170,7 @@ static cudaError_t fir_dispatch(const b2d_fir *h, const FirLaunch &p, cudaStream
 
 extern "C" const char *b2d_fir_path(b2d_fir *h) {
   static const char *names[] = {"fir_generic", "fir_q15", "fir_wide", "fir_q24"};
-  if (h && h->path == PATH_Q15 && fir_ovs_armed(h)) return "fir_ovs";   // calls of fir_ovs_min_n samples or more; shorter ones: fir_q15
+  if (h && h->path == PATH_Q15 && fir_ovs_armed(h)) return "fir_ovs";   // calls long enough to be worth it (fir_ovs_worth); shorter ones: fir_q15
   return !h ? "" : names[h->path];
 }
 
@@ -293,7 +300,7 @@ static int fir_launch(b2d_fir *h, const void *d_in, size_t n, void *d_out, cudaS
   p.coeff64 = h->d_coeff64; p.coeff_pk = h->d_coeff_pk; p.pk_words = h->pk_words; p.coeff32 = h->d_coeff32;
   int hs = hist_wait(h->e_hist, st);
   if (hs) return hs;
-  if (h->path == PATH_Q15 && n >= fir_ovs_min_n(h) && fir_ovs_armed(h) && (hs = fir_ovs_prepare(h, st))) return hs;
+  if (h->path == PATH_Q15 && fir_ovs_worth(h, n) && fir_ovs_armed(h) && (hs = fir_ovs_prepare(h, st))) return hs;
   CU(fir_dispatch(h, p, st, true));
   if (h->pend_rem) {   // TRANSPOSED after a coefficient change: the first outputs start from the old taps' partial sums
     const size_t m = std::min(n, h->pend_rem);

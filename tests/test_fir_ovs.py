@@ -56,6 +56,7 @@ def resid_ok(f, forced):
 @pytest.mark.gpu
 def test_selection_rules(engine, oracle, monkeypatch):
     monkeypatch.delenv("B2D_FIR_OVS", raising=False)
+    monkeypatch.setenv("B2D_OVS_RESID", "1")
     rng = np.random.default_rng(1)
     h = oracle.rand_raw(rng, Q15, 256)
     f = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 256, "SHIFT_REG", n_channels=2, layout="interleaved")
@@ -66,7 +67,12 @@ def test_selection_rules(engine, oracle, monkeypatch):
     assert f.path == "fir_ovs" and 0 < f.ovs_margin()[0] < 0.49
     # short calls still run the DP2A kernel, long ones overlap-save; the history crosses the switch in both directions
     x = rng.integers(-32768, 32767, size=(60000, 2), endpoint=True).astype(np.int16)
-    y = np.concatenate([f.run(x[:100]), f.run(x[100:40000]), f.run(x[40000:40700]), f.run(x[40700:])])
+    parts = [f.run(x[:100]), f.run(x[100:10000])]
+    assert f.ovs_margin()[1] == 0.0                 # the residual monitor has seen no overlap-save launch so far
+    parts += [f.run(x[10000:40000])]
+    assert 0 < f.ovs_margin()[1] < 0.01             # ... and now it has
+    parts += [f.run(x[40000:40700]), f.run(x[40700:])]
+    y = np.concatenate(parts)
     for c in range(2):
         assert np.array_equal(y[:, c], ofir(oracle, Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, x[:, c])), c
     # fewer than 96 taps, formats outside the q15 family, order-dependent accumulators: never
