@@ -360,8 +360,14 @@ cudaError_t launch_fir_q15(const FirLaunch &p, cudaStream_t st) {
   const int np = (p.interleaved && p.C == 2) ? 2 : 1;
   const bool fastout = p.fout.W == p.facc.W && p.fout.I == p.facc.I && p.fout.S == p.facc.S && a.out_bytes == 8;
   const size_t per_pass = (size_t)kThreads * kT;
-  size_t passes = (p.n + per_pass - 1) / per_pass;
+  // tile = 1..4 passes of 1024 outputs: four amortise the staged halo best (the tuned shape of the long calls), but a CTA walks
+  // its passes one after the other, so a call too short to fill the GPU with four-pass tiles (25 CTAs for 10^5 samples: a
+  // 30 us wave at 256 taps whatever the length, profiles/r02_ovs_crossover.txt) takes fewer passes per tile instead
+  const size_t ctas_per_wave = 148 * 9;
+  const size_t chans = (p.interleaved && p.C == 2) ? 1 : p.C;
+  size_t passes = (p.n * chans + per_pass * ctas_per_wave - 1) / (per_pass * ctas_per_wave);
   if (passes > 4) passes = 4;
+  if (passes < 1) passes = 1;
   a.passes = (int)passes;
   const size_t tile = per_pass * passes;
   const size_t stride = (tile + a.Npad + 8 + 7) & ~(size_t)7;

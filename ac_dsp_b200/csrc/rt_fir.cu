@@ -125,13 +125,27 @@ static bool fir_ovs_armed(const b2d_fir *h) {
   if (h->d.layout == B2D_INTERLEAVED && C == 2 && !std::equal(h->h_coeff.begin(), h->h_coeff.begin() + N, h->h_coeff.begin() + N)) return false;
   return h->ovs_bound < 0.49;
 }
-// Is a call of n samples per channel worth the overlap-save evaluation?  From four blocks per channel on.  Measured kernel
-// durations on a B200 (profiles/r02_ovs_crossover.txt): a single wave of the DP2A kernel takes 30 us at 256 taps (49 us at
-// 1024) however short the call, one round of overlap-save blocks 22 us, so the transform wins from the first full wave; below
-// four blocks the DP2A kernel runs a fraction of a tile.  B2D_FIR_OVS=2 takes every call (tests).
+// Is a call of n samples per channel worth the overlap-save evaluation?  Kernel durations measured on a B200
+// (profiles/r02_ovs_crossover.txt, microseconds): the DP2A kernel takes 5.5 + 0.0095 taps for its first wave plus its MACs at
+// 17.8 T/s; overlap-save comes in rounds of one block per CTA half, 13 + 9.1 per round of 296 blocks (IQ pair) or of
+// 2 * (148 / C) block pairs per real channel.  256 taps on an IQ pair: from about 5 * 10^5 samples per call; 1024 taps on
+// eight real channels: from about 2.5 * 10^4 per channel.  B2D_FIR_OVS=2 takes every call (tests).
 static bool fir_ovs_worth(const b2d_fir *h, size_t n) {
   if (h->ovs_mode == 2) return n > 0;
-  return n >= 4 * (size_t)(4096 - fir_ovs_discard((int)h->d.n_taps));
+  const size_t L = 4096 - (size_t)fir_ovs_discard((int)h->d.n_taps);
+  if (n < L) return false;
+  const uint32_t C = h->d.n_channels;
+  const double taps = (double)h->d.n_taps;
+  const double t_dp2a = 5.5 + 0.0095 * taps + (double)n * C * taps / 17.8e6;
+  const size_t blocks = (n + L - 1) / L;
+  size_t rounds;
+  if (h->d.layout == B2D_INTERLEAVED && C == 2) rounds = (blocks + 295) / 296;
+  else {
+    const size_t halves = 2 * std::max<size_t>(1, 148 / C);          // per channel
+    const size_t waves = (C + 147) / 148;                            // more channels than SMs: the grid rows queue up
+    rounds = (((blocks + 1) / 2 + halves - 1) / halves) * waves;
+  }
+  return 13.0 + 9.1 * (double)rounds < t_dp2a;
 }
 
 // Spectra of channels whose taps changed since the last long call (host, extended precision; fir_ovs_spectrum).

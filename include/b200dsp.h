@@ -161,7 +161,8 @@ int b2d_fir_set_state(b2d_fir *h, const void *blob, size_t bytes);
  * 64-bit accumulator) or "fir_generic" (every format and mode, reference tap order).  A "fir_q15" filter of 96..2049 taps
  * reports "fir_ovs" once the loaded coefficients allow the overlap-save evaluation (blocks of 4096 samples through an FP64
  * FFT whose a-priori error bound for THESE taps is below 1/2, so the rounded result is the exact integer sum); calls
- * shorter than four blocks (15360 samples per channel at 256 taps) still run "fir_q15".  B2D_FIR_OVS=0 in the
+ * too short to repay a round of blocks (under about 5 * 10^5 IQ samples at 256 taps, 2.5 * 10^4 per channel at 1024 taps on
+ * eight channels) still run "fir_q15".  B2D_FIR_OVS=0 in the
  * environment at create time turns it off. */
 const char *b2d_fir_path(b2d_fir *h);
 /* Overlap-save diagnostics: `bound` = the a-priori bound of |FP64 result - exact sum| for the loaded taps (armed below

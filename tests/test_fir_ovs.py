@@ -65,16 +65,21 @@ def test_selection_rules(engine, oracle, monkeypatch):
     assert f.path == "fir_q15"                      # an IQ pair is one complex sequence: both channels need the same taps
     f.load(h, channel=1)
     assert f.path == "fir_ovs" and 0 < f.ovs_margin()[0] < 0.49
-    # short calls still run the DP2A kernel, long ones overlap-save; the history crosses the switch in both directions
-    x = rng.integers(-32768, 32767, size=(60000, 2), endpoint=True).astype(np.int16)
-    parts = [f.run(x[:100]), f.run(x[100:10000])]
-    assert f.ovs_margin()[1] == 0.0                 # the residual monitor has seen no overlap-save launch so far
-    parts += [f.run(x[10000:40000])]
-    assert 0 < f.ovs_margin()[1] < 0.01             # ... and now it has
-    parts += [f.run(x[40000:40700]), f.run(x[40700:])]
+    # short calls still run the DP2A kernel, long ones overlap-save (1024 taps: from about 5 * 10^4 samples per call of an IQ
+    # pair); the history crosses the switch in both directions
+    h4 = oracle.rand_raw(rng, Q15, 1024)
+    f4 = engine.ac_fir_load_coeffs(Q15, ACC40, Q15, ACC40, 1024, "SHIFT_REG", n_channels=2, layout="interleaved")
+    f4.load(h4)
+    assert f4.path == "fir_ovs"
+    x = rng.integers(-32768, 32767, size=(160000, 2), endpoint=True).astype(np.int16)
+    parts = [f4.run(x[:100]), f4.run(x[100:20000])]
+    assert f4.ovs_margin()[1] == 0.0                # the residual monitor has seen no overlap-save launch so far
+    parts += [f4.run(x[20000:130000])]
+    assert 0 < f4.ovs_margin()[1] < 0.01            # ... and now it has
+    parts += [f4.run(x[130000:130700]), f4.run(x[130700:])]
     y = np.concatenate(parts)
     for c in range(2):
-        assert np.array_equal(y[:, c], ofir(oracle, Q15, Q15, ACC40, ACC40, 256, "SHIFT_REG", h, x[:, c])), c
+        assert np.array_equal(y[:, c], ofir(oracle, Q15, Q15, ACC40, ACC40, 1024, "SHIFT_REG", h4, x[:, c])), c
     # fewer than 96 taps, formats outside the q15 family, order-dependent accumulators: never
     assert engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 95, "SHIFT_REG", h[:95]).path == "fir_q15"
     assert engine.ac_fir_const_coeffs(Q15, ACC40, Q15, ACC40, 96, "SHIFT_REG", h[:96]).path == "fir_ovs"
