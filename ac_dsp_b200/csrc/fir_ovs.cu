@@ -1,8 +1,9 @@
 // fir_ovs.cu -- overlap-save evaluation of long FIR filters on 16-bit samples (BASELINE configs 1 and 3: 256 and
 // 1024 taps, ac_fixed<16,1> x ac_fixed<16,1> -> <40,8>).  See fir_ovs.cuh for the transform and the phases.
 //
-// Taken instead of fir_q15 when (fir_ovs_usable) the call is long enough, the filter has at least kMinTaps taps and
-// the a-priori error bound of the FP64 evaluation is below 1/2 for the COEFFICIENTS ACTUALLY LOADED, so that the
+// Taken instead of fir_q15 when the call is long enough to repay a round of blocks (rt_fir.cu: fir_ovs_worth), the filter has
+// at least kMinTaps taps and the a-priori error bound of the FP64 evaluation is below 1/2 for the COEFFICIENTS ACTUALLY
+// LOADED (rt_fir.cu: fir_ovs_armed, evaluated at b2d_fir_load with fir_ovs_error_bound below), so that the
 // nearest integer is the exact dot product  sum_i x[n-i]*h[i]  the reference's loop accumulates
 // (ac_fir_load_coeffs.h:180-278; same exactness argument as fir_q15: s <= 0, ACC_TYPE wraps).
 //
