@@ -236,8 +236,10 @@ cudaError_t launch_fir_q24(const FirLaunch &p, cudaStream_t st) {
   a.fastout = (p.fout.W == p.facc.W && p.fout.I == p.facc.I && p.fout.S == p.facc.S && a.out_bytes == 8) ? 1 : 0;
   a.vec_ok = (((uintptr_t)p.in) & 15) == 0;
   const size_t per_pass = (size_t)kQ24Threads * kQ24T;
-  size_t passes = (p.n + per_pass - 1) / per_pass;
+  // as in launch_fir_q15: a call too short to fill the GPU with four-pass tiles takes fewer passes per tile
+  size_t passes = (p.n * p.C + per_pass * (148 * 9) - 1) / (per_pass * (148 * 9));
   if (passes > 4) passes = 4;
+  if (passes < 1) passes = 1;
   a.passes = (int)passes;
   const size_t tile = per_pass * passes;
   const size_t stride = (tile + a.Npad + 16 + 15) & ~(size_t)15;
