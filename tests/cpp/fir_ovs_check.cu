@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "fir_ovs.cuh"
@@ -112,7 +113,28 @@ static void run_case(const char *name, int np, uint32_t C, int n_taps, size_t n,
   if (bad || resid > bound || resid > 0.05) g_bad++;
 }
 
-int main() {
+// `dump FILE`: the twiddle tables and the spectrum of a fixed tap set as raw doubles, for tests/test_fir_ovs.py to compare with
+// a multi-precision evaluation (the error analysis assumes correctly rounded tables and |dH_k| <= 1.1 u ||h||_1 / 4096).
+static int dump(const char *path) {
+  std::vector<double2> tw1(6 * 256), tw2(6 * 16), hs(kN);
+  fir_ovs_tables(tw1.data(), tw2.data());
+  std::vector<int64_t> h(1000);
+  for (size_t i = 0; i < h.size(); i++) h[i] = (int64_t)(rnd() % 65536) - 32768;
+  fir_ovs_spectrum(h.data(), (int)h.size(), hs.data());
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return 2;
+  const int64_t n = (int64_t)h.size();
+  std::fwrite(&n, sizeof(n), 1, f);
+  std::fwrite(h.data(), sizeof(int64_t), h.size(), f);
+  std::fwrite(tw1.data(), sizeof(double2), tw1.size(), f);
+  std::fwrite(tw2.data(), sizeof(double2), tw2.size(), f);
+  std::fwrite(hs.data(), sizeof(double2), hs.size(), f);
+  std::fclose(f);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc == 3 && std::string(argv[1]) == "dump") return dump(argv[2]);
   run_case("iq256 random", 2, 2, 256, 4 * 3840 + 77, 1, 0, true);
   run_case("iq256 unsigned", 2, 2, 256, 3 * 3840 + 1, 0, 0, true);
   run_case("iq256 largest sums", 2, 2, 256, 3840 + 5, 1, 1, true);

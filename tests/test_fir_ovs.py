@@ -30,6 +30,63 @@ def test_phases_on_the_cpu_against_direct_convolution(engine, tmp_path):
     assert p.returncode == 0 and "bad=0" in p.stdout, p.stdout[-3000:] + p.stderr[-1000:]
 
 
+def test_tables_and_spectrum_against_multiprecision(engine, tmp_path):
+    """What the error bound assumes about the prepared constants: every twiddle component is the correctly rounded value
+    (within 0.51 ulp) and every spectrum value is within 1.1 * 2^-53 * ||h||_1 / 4096 of the exact one."""
+    mp = pytest.importorskip("mpmath")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    libdir = os.path.join(ROOT, "ac_dsp_b200", "lib")
+    exe, blob = str(tmp_path / "fir_ovs_check"), str(tmp_path / "tables.bin")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-w", f"-I{ROOT}/ac_dsp_b200/csrc", os.path.join(ROOT, "tests", "cpp", "fir_ovs_check.cu"),
+                           "-o", exe, f"-L{libdir}", "-lb200dsp", "-Xlinker", "-rpath", "-Xlinker", libdir])
+    subprocess.check_call([exe, "dump", blob])
+    raw = open(blob, "rb").read()
+    n = int(np.frombuffer(raw, dtype=np.int64, count=1)[0])
+    h = np.frombuffer(raw, dtype=np.int64, count=n, offset=8)
+    off = 8 + 8 * n
+    tw1 = np.frombuffer(raw, dtype=np.float64, count=2 * 6 * 256, offset=off).reshape(6, 256, 2)
+    off += tw1.nbytes
+    tw2 = np.frombuffer(raw, dtype=np.float64, count=2 * 6 * 16, offset=off).reshape(6, 16, 2)
+    off += tw2.nbytes
+    hs = np.frombuffer(raw, dtype=np.float64, count=2 * 4096, offset=off).reshape(16, 256, 2)
+    mp.mp.prec = 200
+    u = mp.mpf(2) ** -53
+
+    def ulp_err(got, exact):
+        if exact == 0:
+            return abs(mp.mpf(got))
+        e = mp.floor(mp.log(abs(exact), 2))                 # 2^e <= |exact| < 2^(e+1): spacing of doubles there is 2^(e-52)
+        return abs(mp.mpf(got) - exact) / mp.mpf(2) ** (e - 52)
+
+    worst = mp.mpf(0)
+    for i in range(6):
+        mul = i + 1 if i < 3 else 4 * (i - 2)
+        for tab, size, N in ((tw1, 256, 4096), (tw2, 16, 256)):
+            for t in range(0, size, 1 if size == 16 else 5):
+                ang = 2 * mp.pi * ((t * mul) % N) / N
+                for got, exact in ((tab[i, t, 0], mp.cos(ang)), (tab[i, t, 1], -mp.sin(ang))):
+                    if abs(exact) < mp.mpf(2) ** -60:                       # cos / sin of a multiple of pi / 2: an exact zero is expected
+                        assert abs(got) < 1e-16
+                    else:
+                        worst = max(worst, ulp_err(got, exact))
+    assert worst <= mp.mpf("0.51"), worst
+    l1 = mp.mpf(int(np.abs(h).sum()))
+    budget = mp.mpf("1.1") * u * l1 / 4096
+    # position p = 16 c + j of the forward passes' output holds frequency (p >> 8) + 16 ((p >> 4) & 15) + 256 (p & 15); hs is stored [j][c]
+    rng = np.random.default_rng(3)
+    for p in [0, 1, 16, 255, 256, 4095] + [int(v) for v in rng.integers(0, 4096, size=40)]:
+        f = (p >> 8) + 16 * ((p >> 4) & 15) + 256 * (p & 15)
+        exact = mp.mpc(0)
+        for k in range(n):
+            ang = -2 * mp.pi * ((f * k) % 4096) / 4096
+            exact += int(h[k]) * mp.mpc(mp.cos(ang), mp.sin(ang))
+        exact /= 4096
+        got = hs[p & 15, p >> 4]
+        assert abs(mp.mpc(float(got[0]), float(got[1])) - exact) <= budget, (p, f)
+
+
 def ofir(oracle, fi, fc, fa, fo, taps, ft, h, x):
     b = oracle.FirB(fi, fc, fa, fo, taps, ft)
     b.load(h)
