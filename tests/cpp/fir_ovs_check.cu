@@ -133,8 +133,56 @@ static int dump(const char *path) {
   return 0;
 }
 
+// `stress N`: N single blocks of an IQ pair with every sample and every one of 256 taps at +-full scale, signs drawn at random
+// (the largest ||x||_2 ||h||_1 the format allows): the largest distance of a result from an integer, against the bound 0.21.
+static int stress(int blocks) {
+  const int n_taps = 256, T = n_taps - 1;
+  std::vector<double2> tw1(6 * 256), tw2(6 * 16), hs(kN), sm(kSmElems);
+  fir_ovs_tables(tw1.data(), tw2.data());
+  double worst = 0;
+  size_t wrong = 0;
+  for (int b = 0; b < blocks; b++) {
+    std::vector<int64_t> h(n_taps);
+    for (auto &v : h) v = (rnd() & 1) ? -32768 : 32767;
+    fir_ovs_spectrum(h.data(), n_taps, hs.data());
+    const size_t n = 3840;
+    std::vector<uint16_t> xin(2 * n), tail(2 * T);
+    for (auto &v : xin) v = (uint16_t)((rnd() & 1) ? -32768 : 32767);
+    for (auto &v : tail) v = (uint16_t)((rnd() & 1) ? -32768 : 32767);
+    Args a;
+    a.x = xin.data(); a.y = nullptr; a.tail = tail.data(); a.tw = nullptr; a.hs = hs.data();
+    a.n = n; a.T = T; a.D = 256; a.L = kN - 256; a.C = 2; a.xs = 1; a.lsh = 0; a.resid = nullptr;
+    for (int t = 0; t < kThreads; t++) phase_a<2, false>(a, tw1.data(), 0, 0, t, sm.data());
+    for (int t = 0; t < kThreads; t++) phase_b(tw2.data(), t, sm.data());
+    for (int t = 0; t < kThreads; t++) phase_c(hs.data(), t, sm.data());
+    for (int t = 0; t < kThreads; t++) phase_d(tw2.data(), t, sm.data());
+    for (int t = 0; t < kThreads; t++) {
+      double2 v[16];
+      phase_e(tw1.data(), t, sm.data(), v);
+      for (int k = 1; k < 16; k++)
+        for (int e = 0; e < 2; e++) {
+          const double d = e ? v[k].y : v[k].x;
+          worst = std::fmax(worst, std::fabs(d - std::rint(d)));
+          const long long g = t + 256 * k - 256;                // output index; exact sum over the history and this block
+          if (b % 16 == 0 && (t + k) % 37 == 0) {
+            long long sum = 0;
+            for (int i = 0; i < n_taps; i++) {
+              const long long idx = g - i;
+              const int xv = (int)(int16_t)(idx >= 0 ? xin[2 * idx + e] : tail[(size_t)e * T + (size_t)(T + idx)]);
+              sum += (long long)xv * h[i];
+            }
+            if (sum != llrint(d)) wrong++;
+          }
+        }
+    }
+  }
+  std::printf("stress: %d blocks of full-scale +-1 patterns, largest |v - rint(v)| %.3e, spot-checked sums wrong: %zu\n", blocks, worst, wrong);
+  return (worst > 1e-3 || wrong) ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
   if (argc == 3 && std::string(argv[1]) == "dump") return dump(argv[2]);
+  if (argc == 3 && std::string(argv[1]) == "stress") return stress(std::atoi(argv[2]));
   run_case("iq256 random", 2, 2, 256, 4 * 3840 + 77, 1, 0, true);
   run_case("iq256 unsigned", 2, 2, 256, 3 * 3840 + 1, 0, 0, true);
   run_case("iq256 largest sums", 2, 2, 256, 3840 + 5, 1, 1, true);

@@ -28,6 +28,10 @@ def test_phases_on_the_cpu_against_direct_convolution(engine, tmp_path):
     p = subprocess.run([exe], capture_output=True, text=True)
     print(p.stdout)
     assert p.returncode == 0 and "bad=0" in p.stdout, p.stdout[-3000:] + p.stderr[-1000:]
+    # 500 blocks of +-full-scale samples against +-full-scale taps (random signs): the largest ||x||_2 ||h||_1 of the format
+    p = subprocess.run([exe, "stress", "500"], capture_output=True, text=True)
+    print(p.stdout)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-1000:]
 
 
 def test_tables_and_spectrum_against_multiprecision(engine, tmp_path):
